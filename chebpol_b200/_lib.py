@@ -1,0 +1,284 @@
+"""ctypes binding of libchebpol_cuda (include/chebpol_cuda.h).
+
+This is the only way the package computes anything: there is no CPU
+evaluation path.  If the shared library is missing, or no B200 is visible,
+the calls raise -- they never fall back.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libchebpol_cuda.so")
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+_dpp = C.POINTER(_dp)
+_vp = C.c_void_p
+
+# option / query keys (include/chebpol_cuda.h)
+OPT_KERNEL, OPT_BLEND, OPT_CHUNK_POINTS, OPT_VARIANT = 1, 2, 3, 4
+GET_KERNEL_USED, GET_LAUNCHES, GET_TENSOR_BYTES, GET_DEVICE, GET_SMEM_BYTES, GET_GRID = 101, 102, 103, 104, 105, 106
+KERNEL_AUTO, KERNEL_STRICT, KERNEL_FAST = 0, 1, 2
+KERNEL_NAMES = {
+    0: "none", 10: "cheb_strict", 11: "cheb_slab", 20: "mlip_strict", 21: "mlip_pair",
+    30: "fh_strict", 31: "fh_slab",
+}
+
+EXPORTS = [
+    "chebpol_cuda_strerror", "chebpol_cuda_last_error", "chebpol_cuda_device_count",
+    "chebpol_cuda_version", "chebpol_cuda_evalcheb", "chebpol_cuda_evalmlip", "chebpol_cuda_fh",
+    "chebpol_cuda_plan_cheb", "chebpol_cuda_plan_mlip", "chebpol_cuda_plan_fh",
+    "chebpol_cuda_plan_destroy", "chebpol_cuda_plan_eval_device", "chebpol_cuda_plan_eval_host",
+    "chebpol_cuda_plan_set", "chebpol_cuda_plan_get", "chebpol_cuda_fp64_peak",
+    "chebpol_cuda_launch_count",
+]
+
+
+class ChebpolCudaError(RuntimeError):
+    def __init__(self, code: int, what: str, detail: str):
+        super().__init__(f"libchebpol_cuda: {what} (code {code}){': ' + detail if detail else ''}")
+        self.code = code
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load libchebpol_cuda.so; raise loudly if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(or `make -C chebpol_b200/csrc`). chebpol_b200 has no CPU fallback."
+        )
+    L = C.CDLL(LIB_PATH)
+    L.chebpol_cuda_strerror.restype = C.c_char_p
+    L.chebpol_cuda_strerror.argtypes = [C.c_int]
+    L.chebpol_cuda_last_error.restype = C.c_char_p
+    L.chebpol_cuda_last_error.argtypes = []
+    L.chebpol_cuda_device_count.argtypes = [_ip]
+    L.chebpol_cuda_version.argtypes = []
+    L.chebpol_cuda_evalcheb.argtypes = [_vp, _ip, C.c_int, _vp, C.c_int64, _vp, _vp, _vp, C.c_int, _vp]
+    L.chebpol_cuda_evalmlip.argtypes = [_dpp, _ip, C.c_int, _vp, _vp, C.c_int64, C.c_int, C.c_int, _vp]
+    L.chebpol_cuda_fh.argtypes = [_vp, _dpp, _dpp, _ip, C.c_int, _vp, C.c_int64, C.c_int, _vp]
+    L.chebpol_cuda_plan_cheb.argtypes = [_vp, _ip, C.c_int, _vp, _vp, _vp, C.c_int, C.POINTER(_vp)]
+    L.chebpol_cuda_plan_mlip.argtypes = [_dpp, _ip, C.c_int, _vp, C.c_int, C.c_int, C.POINTER(_vp)]
+    L.chebpol_cuda_plan_fh.argtypes = [_vp, _dpp, _dpp, _ip, C.c_int, C.c_int, C.POINTER(_vp)]
+    L.chebpol_cuda_plan_destroy.restype = None
+    L.chebpol_cuda_plan_destroy.argtypes = [_vp]
+    L.chebpol_cuda_plan_eval_device.argtypes = [_vp, _vp, C.c_int64, _vp, _vp]
+    L.chebpol_cuda_plan_eval_host.argtypes = [_vp, _vp, C.c_int64, _vp]
+    L.chebpol_cuda_plan_set.argtypes = [_vp, C.c_int, C.c_int64]
+    L.chebpol_cuda_plan_get.argtypes = [_vp, C.c_int, C.POINTER(C.c_int64)]
+    L.chebpol_cuda_fp64_peak.argtypes = [C.c_int, C.c_int, _dp]
+    L.chebpol_cuda_launch_count.restype = C.c_int64
+    L.chebpol_cuda_launch_count.argtypes = []
+    _lib = L
+    return L
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        L = lib()
+        raise ChebpolCudaError(rc, L.chebpol_cuda_strerror(rc).decode(), L.chebpol_cuda_last_error().decode())
+
+
+def device_count() -> int:
+    n = C.c_int(0)
+    rc = lib().chebpol_cuda_device_count(C.byref(n))
+    if rc != 0:
+        return 0
+    return n.value
+
+
+def launch_count() -> int:
+    return int(lib().chebpol_cuda_launch_count())
+
+
+def fp64_peak_tflops(device: int = 0, repeats: int = 5) -> float:
+    v = C.c_double(0.0)
+    check(lib().chebpol_cuda_fp64_peak(device, repeats, C.byref(v)))
+    return v.value
+
+
+# ---- helpers -----------------------------------------------------------------
+def f64(a, order="C"):
+    return np.require(a, dtype=np.float64, requirements=["C" if order == "C" else "F", "A"])
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _addr(a) -> int:
+    return a.ctypes.data if a is not None else 0
+
+
+def ptr_list(arrs):
+    keep = [f64(np.asarray(a).ravel()) for a in arrs]
+    arr = (_dp * len(keep))(*[k.ctypes.data_as(_dp) for k in keep])
+    return arr, keep
+
+
+def as_points(x, rank: int) -> np.ndarray:
+    """Coerce to the (P, K) point-major layout of R's K x P column-major matrix.
+
+    Accepts what the reference's closures accept (R/tools.R:9-20): a K x P
+    matrix (numpy shape (K, P), any memory order -- a Fortran-ordered one is
+    passed through without a copy), or a length-K vector.
+    """
+    x = np.asarray(x, dtype=np.float64)
+    if x.ndim == 1:
+        if rank == 1:
+            return f64(x.reshape(-1, 1))
+        if x.size == rank:
+            return f64(x.reshape(1, rank))
+        raise ValueError(f"Function should take {rank} arguments, you supplied a vector of length {x.size}")
+    if x.ndim != 2 or x.shape[0] != rank:
+        raise ValueError(f"argument must be a {rank} x P matrix, got shape {x.shape}")
+    return f64(x.T)  # (P, K) C-contiguous == K x P column-major
+
+
+class Plan:
+    """A fitted interpolant resident on one GPU (chebpol_cuda_plan)."""
+
+    def __init__(self, handle: int, rank: int, kind: str):
+        self._h = _vp(handle)
+        self.rank = rank
+        self.kind = kind
+
+    # -- constructors ----------------------------------------------------------
+    @staticmethod
+    def cheb(coef, mid=None, ispan=None, ugm_n=None, device: int = 0) -> "Plan":
+        coef = np.asarray(coef, dtype=np.float64)
+        dims = _i32(coef.shape)
+        cf = f64(coef, order="F")
+        mid_a = f64(mid) if mid is not None else None
+        isp_a = f64(ispan) if ispan is not None else None
+        ugm_a = _i32(ugm_n) if ugm_n is not None else None
+        h = _vp()
+        check(lib().chebpol_cuda_plan_cheb(_addr(cf), dims.ctypes.data_as(_ip), coef.ndim, _addr(mid_a),
+                                           _addr(isp_a), _addr(ugm_a), device, C.byref(h)))
+        return Plan(h.value, coef.ndim, "cheb")
+
+    @staticmethod
+    def mlip(grid, values, blend: int = 0, device: int = 0) -> "Plan":
+        dims = _i32([len(g) for g in grid])
+        vals = f64(np.asarray(values, dtype=np.float64).ravel(order="F"))
+        if vals.size != int(np.prod(dims.astype(np.int64))):
+            raise ValueError(f"grid has size {int(np.prod(dims.astype(np.int64)))}, you supplied {vals.size} values")
+        gl, keep = ptr_list(grid)
+        h = _vp()
+        check(lib().chebpol_cuda_plan_mlip(gl, dims.ctypes.data_as(_ip), len(grid), _addr(vals), blend, device,
+                                           C.byref(h)))
+        return Plan(h.value, len(grid), "mlip")
+
+    @staticmethod
+    def fh(vals, grid, weights, device: int = 0) -> "Plan":
+        dims = _i32([len(g) for g in grid])
+        v = f64(np.asarray(vals, dtype=np.float64).ravel(order="F"))
+        if v.size != int(np.prod(dims.astype(np.int64))):
+            raise ValueError(f"coefficient length({v.size}) does not match data length({int(np.prod(dims.astype(np.int64)))})")
+        gl, k1 = ptr_list(grid)
+        wl, k2 = ptr_list(weights)
+        h = _vp()
+        check(lib().chebpol_cuda_plan_fh(_addr(v), gl, wl, dims.ctypes.data_as(_ip), len(grid), device, C.byref(h)))
+        return Plan(h.value, len(grid), "fh")
+
+    # -- evaluation --------------------------------------------------------------
+    def eval_host(self, x_pk: np.ndarray, out: np.ndarray | None = None) -> np.ndarray:
+        """x_pk: (P, K) C-contiguous float64 host array (pinned or pageable)."""
+        assert x_pk.dtype == np.float64 and x_pk.flags.c_contiguous and x_pk.shape[1] == self.rank
+        n = x_pk.shape[0]
+        if out is None:
+            out = np.empty(n, dtype=np.float64)
+        check(lib().chebpol_cuda_plan_eval_host(self._h, _addr(x_pk), n, _addr(out)))
+        return out
+
+    def eval_host_ptr(self, x_ptr: int, npts: int, out_ptr: int) -> None:
+        check(lib().chebpol_cuda_plan_eval_host(self._h, x_ptr, npts, out_ptr))
+
+    def eval_device_ptr(self, x_ptr: int, npts: int, out_ptr: int, stream: int = 0) -> None:
+        check(lib().chebpol_cuda_plan_eval_device(self._h, x_ptr, npts, out_ptr, stream))
+
+    def eval_torch(self, x, out=None):
+        """x: CUDA float64 tensor of shape (P, K), contiguous, on the plan's device."""
+        import torch
+
+        assert x.is_cuda and x.dtype == torch.float64 and x.is_contiguous() and x.shape[1] == self.rank
+        if out is None:
+            out = torch.empty(x.shape[0], dtype=torch.float64, device=x.device)
+        stream = torch.cuda.current_stream(x.device).cuda_stream
+        self.eval_device_ptr(x.data_ptr(), x.shape[0], out.data_ptr(), stream)
+        return out
+
+    # -- options -------------------------------------------------------------------
+    def set(self, option: int, value: int) -> "Plan":
+        check(lib().chebpol_cuda_plan_set(self._h, option, value))
+        return self
+
+    def get(self, what: int) -> int:
+        v = C.c_int64(0)
+        check(lib().chebpol_cuda_plan_get(self._h, what, C.byref(v)))
+        return v.value
+
+    @property
+    def kernel_used(self) -> str:
+        return KERNEL_NAMES.get(self.get(GET_KERNEL_USED), "?")
+
+    def close(self) -> None:
+        if self._h:
+            lib().chebpol_cuda_plan_destroy(self._h)
+            self._h = _vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# ---- stateless entry points (what the R .Call glue binds) -------------------------
+def evalcheb(coef, x_pk, mid=None, ispan=None, ugm_n=None, ngpus: int = 0) -> np.ndarray:
+    coef = np.asarray(coef, dtype=np.float64)
+    dims = _i32(coef.shape)
+    cf = f64(coef, order="F")
+    x_pk = f64(x_pk)
+    out = np.empty(x_pk.shape[0], dtype=np.float64)
+    mid_a = f64(mid) if mid is not None else None
+    isp_a = f64(ispan) if ispan is not None else None
+    ugm_a = _i32(ugm_n) if ugm_n is not None else None
+    check(lib().chebpol_cuda_evalcheb(_addr(cf), dims.ctypes.data_as(_ip), coef.ndim, _addr(x_pk), x_pk.shape[0],
+                                      _addr(mid_a), _addr(isp_a), _addr(ugm_a), ngpus, _addr(out)))
+    return out
+
+
+def evalmlip(grid, values, x_pk, blend: int = 0, ngpus: int = 0) -> np.ndarray:
+    dims = _i32([len(g) for g in grid])
+    vals = f64(np.asarray(values, dtype=np.float64).ravel(order="F"))
+    if vals.size != int(np.prod(dims.astype(np.int64))):
+        raise ValueError(f"grid has size {int(np.prod(dims.astype(np.int64)))}, you supplied {vals.size} values")
+    x_pk = f64(x_pk)
+    out = np.empty(x_pk.shape[0], dtype=np.float64)
+    gl, keep = ptr_list(grid)
+    check(lib().chebpol_cuda_evalmlip(gl, dims.ctypes.data_as(_ip), len(grid), _addr(vals), _addr(x_pk),
+                                      x_pk.shape[0], blend, ngpus, _addr(out)))
+    return out
+
+
+def fh(vals, grid, weights, x_pk, ngpus: int = 0) -> np.ndarray:
+    dims = _i32([len(g) for g in grid])
+    v = f64(np.asarray(vals, dtype=np.float64).ravel(order="F"))
+    x_pk = f64(x_pk)
+    out = np.empty(x_pk.shape[0], dtype=np.float64)
+    gl, k1 = ptr_list(grid)
+    wl, k2 = ptr_list(weights)
+    check(lib().chebpol_cuda_fh(_addr(v), gl, wl, dims.ctypes.data_as(_ip), len(grid), _addr(x_pk), x_pk.shape[0],
+                                ngpus, _addr(out)))
+    return out

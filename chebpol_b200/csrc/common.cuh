@@ -1,0 +1,119 @@
+// common.cuh -- shared declarations of libchebpol_cuda (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/chebpol_cuda.h"
+
+#define CP_MAXR 32  // CHEBPOL_CUDA_MAXRANK + 1
+
+// Pre-map applied to every coordinate before evaluation (Chebyshev plans):
+//   bit 0: x <- (x - mid)*ispan                 R/chebyshev.R:223-227 (imap)
+//   bit 1: x <- sin(0.5*pi*x*(1-n)/n)           R/uniform.R:6 (ugm)
+struct PreMap {
+    int mode;
+    double mid[CP_MAXR];
+    double ispan[CP_MAXR];
+    double nd[CP_MAXR];
+};
+
+__device__ __forceinline__ double premap_coord(const PreMap &pm, int d, double v)
+{
+    if (pm.mode & 1) v = (v - pm.mid[d]) * pm.ispan[d];
+    if (pm.mode & 2) {
+        // R evaluates 0.5*pi*x*(1-n)/n left to right
+        const double n = pm.nd[d];
+        v = sin(0.5 * 3.141592653589793 * v * (1.0 - n) / n);
+    }
+    return v;
+}
+
+// ---- kernel ids reported through CHEBPOL_CUDA_GET_KERNEL_USED ------------
+enum KernelId {
+    K_NONE = 0,
+    K_CHEB_STRICT = 10,  // thread-per-point Clenshaw, reference op order, no FMA
+    K_CHEB_SLAB = 11,    // basis-in-registers contraction, TMA-streamed slabs
+    K_MLIP_STRICT = 20,  // thread-per-point, reference op order
+    K_MLIP_PAIR = 21,    // lane-pair gather kernel
+    K_FH_STRICT = 30,    // thread-per-point nested barycentric, reference op order
+    K_FH_SLAB = 31,      // barycentric-basis contraction, TMA-streamed slabs
+};
+
+// ---- launch descriptors filled by api.cu, consumed by the kernel TUs -------
+struct ChebStrictArgs {
+    const double *cf;  // original layout (R array)
+    int rank;
+    int dims[CP_MAXR];
+    int64_t stride[CP_MAXR];
+    const double *x;
+    int64_t npts;
+    double *out;
+    PreMap pm;
+};
+
+struct MlipArgs {
+    const double *values;
+    const double *grid;  // all knot vectors, concatenated
+    int goff[CP_MAXR];   // offset of grid d in `grid`
+    int rank;
+    int dims[CP_MAXR];
+    int64_t stride[CP_MAXR];
+    int blend;
+    const double *x;
+    int64_t npts;
+    double *out;
+};
+
+struct FhArgs {
+    const double *vals;
+    const double *grid;     // concatenated knots
+    const double *weights;  // concatenated weights, same offsets
+    int goff[CP_MAXR];
+    int rank;
+    int dims[CP_MAXR];
+    int64_t stride[CP_MAXR];
+    const double *x;
+    int64_t npts;
+    double *out;
+};
+
+// Slab-streamed contraction kernels (Chebyshev fast path, FH fast path).
+// The tensor is stored padded: dim 0 rounded up to an even length n0p so
+// every row is 16-byte aligned; a slab is the sub-tensor spanned by the first
+// `depth` dims (slab_elems doubles); slabs are consumed last-to-first.
+struct SlabArgs {
+    const double *cf;  // padded tensor
+    int rank;
+    int depth;         // dims inside a slab (1..3)
+    int n0, n0p;
+    int dims[CP_MAXR];
+    int slab_elems;
+    int nslabs;        // < 2^31 (R arrays have < 2^31 elements)
+    int ns;            // ring stages in shared memory
+    int stage_stride;  // bytes between stages (slab bytes rounded up to 128)
+    int resident;      // nslabs <= ns: every slab loaded once per CTA
+    unsigned cum[CP_MAXR];  // cum[L] = prod_{j=depth..L} dims[j], L >= depth
+    const double *x;
+    int64_t npts;
+    double *out;
+    PreMap pm;
+    // FH only
+    const double *grid;
+    const double *weights;
+    int goff[CP_MAXR];
+};
+
+// Launchers implemented in the kernel TUs.  Each returns cudaGetLastError().
+struct LaunchInfo {
+    int grid, block, smem, kernel;
+};
+cudaError_t launch_cheb_strict(const ChebStrictArgs &a, cudaStream_t s, LaunchInfo *li);
+cudaError_t launch_mlip_strict(const MlipArgs &a, cudaStream_t s, LaunchInfo *li);
+cudaError_t launch_fh_strict(const FhArgs &a, cudaStream_t s, LaunchInfo *li);
+// returns cudaErrorNotSupported when the shape has no fast instantiation
+cudaError_t launch_cheb_slab(const SlabArgs &a, int variant, int num_sms, cudaStream_t s, LaunchInfo *li);
+bool cheb_slab_supported(int n0, int rank, const int *dims);
+cudaError_t launch_mlip_pair(const MlipArgs &a, int variant, int num_sms, cudaStream_t s, LaunchInfo *li);
+bool mlip_pair_supported(int rank, int blend);
+cudaError_t launch_fh_fast(const FhArgs &a, int variant, int num_sms, cudaStream_t s, LaunchInfo *li);
+bool fh_fast_supported(int rank, const int *dims);
+cudaError_t run_fp64_peak(int num_sms, int repeats, cudaStream_t s, double *tflops);

@@ -1,0 +1,375 @@
+"""Host-side mirror of chebpol's R interface for the batched-evaluation path.
+
+R is not available in the build image, so the drop-in boundary that can be
+executed is the C ABI (include/chebpol_cuda.h); this module reproduces, in
+Python, the R layer that sits above it so that tests and users can drive the
+GPU engine exactly the way the R closures would:
+
+    ip = ipol(val, dims=..., intervals=..., grid=..., k=..., method=...)
+    y  = ip(x, threads=...)            # x: K x P matrix or length-K vector
+
+Reference (all under /root/reference/R): ipol.R:108-239 (method switch),
+chebyshev.R:201-233 (chebappx.real, imap), multilinear.R:49-70 (mlappx.real,
+blend names), floater-hormann.R:55-70 (fhappx.real), uniform.R:6,58-77
+(ugm, ucappx.real), tools.R:2-25 (vectorfun argument coercion).
+
+Evaluation always goes through libchebpol_cuda; the fit-side helpers
+(chebcoef, fhweights, chebknots, evalongrid) run once per interpolant on the
+host in numpy and are not part of the accelerated path (SURVEY.md section 2,
+rows 8-10).
+"""
+from __future__ import annotations
+
+import warnings
+from typing import Callable, Sequence
+
+import numpy as np
+
+from . import _lib
+
+__all__ = [
+    "ipol", "chebappx", "chebappxf", "mlappx", "fhappx", "ucappx", "ucappxf", "chebeval",
+    "chebknots", "chebcoef", "evalongrid", "fhweights", "Interpolant",
+]
+
+BLENDS = {"linear": 0, "sigmoid": 1, "parodic": 2, "cubic": 3, "square": 4}  # R/multilinear.R:64-65
+
+
+# ------------------------------------------------------------------ fit side
+def _chebknots1(n: int, interval=None) -> np.ndarray:
+    """R/chebyshev.R:4-9."""
+    kn = np.cos(np.pi * (np.arange(1, n + 1) - 0.5) / n)
+    if n % 2 == 1:
+        kn[(n + 1) // 2 - 1] = 0.0
+    if interval is None:
+        return kn
+    a, b = float(interval[0]), float(interval[1])
+    return kn * (b - a) / 2 + (a + b) / 2
+
+
+def chebknots(dims, intervals=None) -> list[np.ndarray]:
+    """Chebyshev grid on a hypercube (R/chebyshev.R:41-51)."""
+    dims = [int(d) for d in np.atleast_1d(dims)]
+    if intervals is None:
+        return [_chebknots1(d) for d in dims]
+    if len(dims) == 1 and np.isscalar(intervals[0]):
+        intervals = [intervals]
+    return [_chebknots1(d, iv) for d, iv in zip(dims, intervals)]
+
+
+def evalongrid(fun: Callable, dims=None, intervals=None, grid=None) -> np.ndarray:
+    """Evaluate fun on a tensor grid (R/tools.R:122-128); array in R (Fortran) order."""
+    if grid is None:
+        grid = chebknots(dims, intervals)
+    grid = [np.asarray(g, dtype=np.float64) for g in grid]
+    shape = tuple(len(g) for g in grid)
+    out = np.empty(shape, dtype=np.float64, order="F")
+    flat = out.reshape(-1, order="F")
+    idx = np.zeros(len(grid), dtype=np.int64)
+    arg = np.array([g[0] for g in grid])
+    for j in range(flat.size):
+        flat[j] = fun(arg.copy())
+        for d in range(len(grid)):  # odometer, dim 0 fastest
+            idx[d] += 1
+            if idx[d] < shape[d]:
+                arg[d] = grid[d][idx[d]]
+                break
+            idx[d] = 0
+            arg[d] = grid[d][0]
+    return flat.reshape(shape, order="F")
+
+
+def chebcoef(val, dct: bool = False) -> np.ndarray:
+    """Chebyshev coefficients of values on a Chebyshev grid (R/chebyshev.R:82-84,
+    src/chebpol.c:8-141): DCT-II per dimension scaled by 1/prod(dims), index-0
+    hyperplanes halved.  Fit side: host numpy/scipy."""
+    from scipy.fft import dctn
+
+    val = np.asarray(val, dtype=np.float64)
+    if val.ndim == 0:
+        val = val.reshape(1)
+    F = dctn(val, type=2)
+    if dct:
+        return np.asfortranarray(F)
+    F = F / val.size
+    for d in range(val.ndim):
+        sl = [slice(None)] * val.ndim
+        sl[d] = 0
+        F[tuple(sl)] *= 0.5
+    return np.asfortranarray(F)
+
+
+def fhweights(grid: Sequence[np.ndarray], d) -> list[np.ndarray]:
+    """Floater-Hormann weights, eq. (18) of the FH paper (src/chebpol.c:267-282)."""
+    dd = np.broadcast_to(np.asarray(d, dtype=np.int64), (len(grid),)) if np.ndim(d) == 0 else np.resize(
+        np.asarray(d, dtype=np.int64), len(grid))
+    out = []
+    for g, deg in zip(grid, dd):
+        g = np.asarray(g, dtype=np.float64)
+        n = g.size - 1
+        deg = int(deg)
+        w = np.empty(n + 1)
+        for k in range(n + 1):
+            lo = 0 if k < deg else k - deg
+            hi = k if k < n - deg else n - deg
+            s = 0.0
+            for i in range(lo, hi + 1):
+                prod = 1.0
+                for j in range(i, i + deg + 1):
+                    if j != k:
+                        prod *= g[k] - g[j]
+                s += 1.0 / abs(prod)
+            w[k] = s * (-1.0 if (k % 2 != deg % 2) else 1.0)
+        out.append(w)
+    return out
+
+
+def _unsorted(g: np.ndarray) -> bool:
+    d = np.diff(g)
+    return not (np.all(d > 0) or np.all(d < 0))
+
+
+# --------------------------------------------------------------- interpolant
+class Interpolant:
+    """The closure ipol() returns: call it on a K x P matrix or a length-K vector.
+
+    ``threads`` is accepted for signature compatibility (R/interpolant.R:9-11)
+    and ignored: points are spread over GPU threads, and over ``ngpus`` GPUs.
+    """
+
+    def __init__(self, kind: str, arity: int, domain, **tensors):
+        self.kind = kind
+        self.arity = arity
+        self.domain = domain
+        self.t = tensors
+        self._plans: dict[int, _lib.Plan] = {}
+        self.kernel = _lib.KERNEL_AUTO
+
+    # device-resident copy, re-creatable from the host tensors at any time
+    def plan(self, device: int = 0) -> _lib.Plan:
+        p = self._plans.get(device)
+        if p is None:
+            t = self.t
+            if self.kind in ("chebyshev", "uniform"):
+                p = _lib.Plan.cheb(t["coef"], t.get("mid"), t.get("ispan"), t.get("ugm_n"), device)
+            elif self.kind == "multilinear":
+                p = _lib.Plan.mlip(t["grid"], t["values"], 0, device)
+            elif self.kind == "fh":
+                p = _lib.Plan.fh(t["values"], t["grid"], t["weights"], device)
+            else:
+                raise ValueError(self.kind)
+            self._plans[device] = p
+        p.set(_lib.OPT_KERNEL, self.kernel)
+        return p
+
+    def _coerce(self, x) -> tuple[np.ndarray, bool]:
+        """vectorfun, R/tools.R:9-20."""
+        x = np.asarray(x, dtype=np.float64)
+        K = self.arity
+        if x.ndim == 2:
+            if x.shape[0] != K:
+                raise ValueError(f"coeffcient rank({K}) must match number of rows({x.shape[0]})")
+            return _lib.f64(x.T), False
+        x = x.ravel()
+        if x.size == K:
+            return _lib.f64(x.reshape(1, K)), True
+        if K == 1:
+            return _lib.f64(x.reshape(-1, 1)), False
+        if x.size % K == 0:
+            numvec = x.size // K
+            if numvec > 1:
+                warnings.warn(f"Coercing vector of length {x.size} into {K}x{numvec} matrix")
+            return _lib.f64(x.reshape(numvec, K)), False
+        raise ValueError(f"Function should take {K} arguments, you supplied a vector of length {x.size}")
+
+    def __call__(self, x, threads=None, blend: str | int = "linear", ngpus: int = 1, device: int = 0):
+        xp, _single = self._coerce(x)
+        if self.kind == "multilinear":
+            b = BLENDS[blend] if isinstance(blend, str) else int(blend)
+        if ngpus != 1:
+            t = self.t
+            if self.kind in ("chebyshev", "uniform"):
+                return _lib.evalcheb(t["coef"], xp, t.get("mid"), t.get("ispan"), t.get("ugm_n"), ngpus)
+            if self.kind == "multilinear":
+                return _lib.evalmlip(t["grid"], t["values"], xp, b, ngpus)
+            return _lib.fh(t["values"], t["grid"], t["weights"], xp, ngpus)
+        p = self.plan(device)
+        if self.kind == "multilinear":
+            p.set(_lib.OPT_BLEND, b)
+        return p.eval_host(xp)
+
+    def close(self):
+        for p in self._plans.values():
+            p.close()
+        self._plans.clear()
+
+
+# --------------------------------------------------------------- constructors
+def chebappx(val, intervals=None) -> Interpolant:
+    """chebappx.real, R/chebyshev.R:201-233."""
+    val = np.asarray(val, dtype=np.float64)
+    if val.ndim == 0:
+        val = val.reshape(1)
+    K = val.ndim
+    if intervals is not None and np.ndim(intervals) == 1 and len(intervals) == 2 and np.isscalar(intervals[0]):
+        intervals = [intervals]
+    cf = chebcoef(val)
+    if intervals is None:
+        return Interpolant("chebyshev", K, [(-1.0, 1.0)] * K, coef=cf)
+    if any(len(iv) != 2 for iv in intervals):
+        raise ValueError("interval elements should have length 2")
+    if len(intervals) != K:
+        raise ValueError(f"values should have the same dimension as intervals {len(intervals)} {K}")
+    ispan = np.array([2.0 / (float(iv[1]) - float(iv[0])) for iv in intervals])
+    mid = np.array([(float(iv[0]) + float(iv[1])) / 2.0 for iv in intervals])
+    return Interpolant("chebyshev", K, [tuple(iv) for iv in intervals], coef=cf, mid=mid, ispan=ispan)
+
+
+def chebappxf(fun, dims, intervals=None) -> Interpolant:
+    """chebappxf.real, R/chebyshev.R:243-245."""
+    dims = [int(d) for d in np.atleast_1d(dims)]
+    if intervals is not None and np.ndim(intervals) == 1 and len(intervals) == 2 and np.isscalar(intervals[0]):
+        intervals = [intervals]
+    return chebappx(evalongrid(fun, dims, intervals), intervals)
+
+
+def chebeval(x, coef, intervals=None, threads=None):
+    """chebeval, R/chebyshev.R:126-130."""
+    coef = np.asarray(coef, dtype=np.float64)
+    ip = Interpolant("chebyshev", coef.ndim, None, coef=np.asfortranarray(coef))
+    if intervals is not None:
+        ip.t["mid"] = np.array([np.mean(iv) for iv in intervals])
+        ip.t["ispan"] = np.array([2.0 / (iv[1] - iv[0]) for iv in intervals])
+    try:
+        return ip(x)
+    finally:
+        ip.close()
+
+
+def mlappx(val, grid) -> Interpolant:
+    """mlappx.real, R/multilinear.R:49-70."""
+    if np.isscalar(grid[0]):
+        grid = [grid]
+    grid = [np.asarray(g, dtype=np.float64) for g in grid]
+    if any(np.any(np.diff(g) < 0) for g in grid):
+        if not callable(val):
+            raise ValueError("Grid points must be ordered in increasing order")
+        grid = [np.sort(g) for g in grid]
+    if callable(val):
+        val = evalongrid(val, grid=grid)
+    val = np.asarray(val, dtype=np.float64)
+    gl = int(np.prod([len(g) for g in grid]))
+    if val.size != gl:
+        raise ValueError(f"length of values {val.size} do not match size of grid {gl}")
+    values = val.ravel(order="F") if val.ndim > 1 else val
+    return Interpolant("multilinear", len(grid), [(g.min(), g.max()) for g in grid], grid=grid,
+                       values=np.ascontiguousarray(values))
+
+
+def fhappx(val, grid=None, d=1) -> Interpolant:
+    """fhappx.real, R/floater-hormann.R:55-70."""
+    if grid is None:
+        raise ValueError("Must specify grid")
+    if np.isscalar(grid[0]):
+        grid = [grid]
+    grid = [np.asarray(g, dtype=np.float64) for g in grid]
+    if callable(val):
+        val = evalongrid(val, grid=grid)
+    val = np.asarray(val, dtype=np.float64)
+    shape = tuple(len(g) for g in grid)
+    if val.shape != shape:
+        val = val.reshape(shape, order="F")
+    dd = np.resize(np.asarray(d, dtype=np.int64), len(grid))
+    weights = fhweights(grid, dd)
+    return Interpolant("fh", len(grid), [(g.min(), g.max()) for g in grid], grid=grid,
+                       values=np.asfortranarray(val), weights=weights)
+
+
+def ucappx(val, intervals=None) -> Interpolant:
+    """ucappx.real, R/uniform.R:58-77: Chebyshev series of the values with the
+    per-coordinate map x -> sin(0.5*pi*x*(1-n)/n) (ugm, R/uniform.R:6) applied,
+    after the optional interval map, on every call -- here inside the kernel."""
+    val = np.asarray(val, dtype=np.float64)
+    if val.ndim == 0:
+        val = val.reshape(1)
+    dims = val.shape
+    cf = chebcoef(val)
+    K = val.ndim
+    if intervals is None:
+        return Interpolant("uniform", K, [(-1.0, 1.0)] * K, coef=cf, ugm_n=np.array(dims, dtype=np.int32))
+    if np.ndim(intervals) == 1 and len(intervals) == 2 and np.isscalar(intervals[0]):
+        intervals = [intervals]
+    mid = np.array([(float(iv[0]) + float(iv[1])) / 2.0 for iv in intervals])
+    ispan = np.array([2.0 / (float(iv[1]) - float(iv[0])) for iv in intervals])
+    return Interpolant("uniform", K, [tuple(iv) for iv in intervals], coef=cf, mid=mid, ispan=ispan,
+                       ugm_n=np.array(dims, dtype=np.int32))
+
+
+def ucappxf(fun, dims, intervals=None) -> Interpolant:
+    """ucappxf.real, R/uniform.R:86-96."""
+    dims = [int(d) for d in np.atleast_1d(dims)]
+    if intervals is None:
+        return ucappx(evalongrid(fun, grid=[np.linspace(-1, 1, d) for d in dims]))
+    if np.ndim(intervals) == 1 and len(intervals) == 2 and np.isscalar(intervals[0]):
+        intervals = [intervals]
+    grid = [np.linspace(min(iv), max(iv), d) for d, iv in zip(dims, intervals)]
+    return ucappx(evalongrid(fun, grid=grid), intervals)
+
+
+_METHODS = ["chebyshev", "multilinear", "fh", "uniform", "general", "polyharmonic", "simplexlinear",
+            "hstalker", "stalker", "crbf", "oldstalker"]
+_ON_PATH = {"chebyshev", "multilinear", "fh", "uniform"}
+
+
+def ipol(val, dims=None, intervals=None, grid=None, knots=None, k=None, method="chebyshev", **kw) -> Interpolant:
+    """ipol, R/ipol.R:108-239, for the four evaluators on the accelerated path."""
+    cand = [m for m in _METHODS if m.startswith(method)]  # match.arg partial matching
+    if method in _METHODS:
+        cand = [method]
+    if len(cand) != 1:
+        raise ValueError(f"Unknown interpolation method: {method}")
+    method = cand[0]
+    if method not in _ON_PATH:
+        raise NotImplementedError(
+            f"method '{method}' is outside the GPU evaluation path (SURVEY.md section 2); use the R package")
+    if method == "chebyshev":
+        if callable(val):
+            if dims is None:
+                raise ValueError("dims must be specified")
+            return chebappxf(val, dims, intervals)
+        val = np.asarray(val, dtype=np.float64)
+        if val.ndim <= 1 and dims is not None:
+            val = val.reshape(tuple(int(d) for d in np.atleast_1d(dims)), order="F")
+        return chebappx(val, intervals)
+    if method == "multilinear":
+        if grid is None:
+            raise ValueError("grid must be specified for multi linear interpolation")
+        if np.isscalar(grid[0]):
+            grid = [grid]
+        grid = [np.asarray(g, dtype=np.float64) for g in grid]
+        if any(_unsorted(g) for g in grid):
+            raise ValueError("grid must be distinct ordered values")
+        return mlappx(val, grid)
+    if method == "fh":
+        if grid is None:
+            raise ValueError("grid must be specified for Floater-Hormann interpolation")
+        if np.isscalar(grid[0]):
+            grid = [grid]
+        grid = [np.asarray(g, dtype=np.float64) for g in grid]
+        if any(_unsorted(g) for g in grid):
+            raise ValueError("grid must be distinct ordered values")
+        if k is None:
+            k = [min(4, len(g) - 1) for g in grid]
+        return fhappx(val, grid, d=k)
+    # uniform
+    if callable(val) and dims is None:
+        raise ValueError("Must specify dims for uniform intervals")
+    if intervals is None and grid is not None:
+        intervals = [(np.min(g), np.max(g)) for g in grid]
+        warnings.warn("intervals constructed from ranges of grid-argument")
+    if callable(val):
+        return ucappxf(val, dims, intervals)
+    val = np.asarray(val, dtype=np.float64)
+    if val.ndim <= 1 and dims is not None:
+        val = val.reshape(tuple(int(d) for d in np.atleast_1d(dims)), order="F")
+    return ucappx(val, intervals)

@@ -1,0 +1,150 @@
+/* chebpol_cuda.h -- C ABI of libchebpol_cuda, the B200 (sm_100a) batched
+ * evaluation engine behind chebpol's interpolant closures.
+ *
+ * Plain pointers and sizes only; no R, torch or C++ types.  Every function
+ * returns 0 on success or a CHEBPOL_CUDA_E* code; nothing longjmps, nothing
+ * calls back into R, and there is no CPU fallback: without a usable CUDA
+ * device every compute entry point fails with CHEBPOL_CUDA_ENODEV.
+ *
+ * Conventions shared with the reference (/root/reference/src/chebpol.c):
+ *  - tensors (coef / values / vals) are R arrays: column-major, dim 0 fastest;
+ *  - points are the K x P column-major matrix R passes to .Call, i.e. point i
+ *    occupies x[i*rank .. i*rank+rank-1] (reference: `xp+i*rank`, :377);
+ *  - results are a length-P vector of doubles (reference: NEW_NUMERIC(numvec)).
+ * Differences, all deliberate: point counts are int64_t (the reference's `int`
+ * index overflows once P*K >= 2^31, src/chebpol.c:368,376-377); NaN
+ * coordinates give NaN results instead of the endless loop of the reference's
+ * binsearch (src/chebpol.c:547-554).
+ */
+#ifndef CHEBPOL_CUDA_H
+#define CHEBPOL_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define CHEBPOL_CUDA_API __attribute__((visibility("default")))
+#else
+#define CHEBPOL_CUDA_API
+#endif
+
+#define CHEBPOL_CUDA_MAXRANK 31
+
+/* ---- error codes ------------------------------------------------------- */
+#define CHEBPOL_CUDA_OK 0
+#define CHEBPOL_CUDA_EINVAL 1  /* NULL pointer / negative count / bad option        */
+#define CHEBPOL_CUDA_ERANK 2   /* rank <= 0 or > MAXRANK (ref: "rank must be positive") */
+#define CHEBPOL_CUDA_ESIZE 3   /* a dimension <= 0 or product overflows              */
+#define CHEBPOL_CUDA_EBLEND 4  /* blend not in 0..5 (src/chebpol.h:24-45)            */
+#define CHEBPOL_CUDA_ENODEV 5  /* no CUDA device / requested device absent           */
+#define CHEBPOL_CUDA_ENOMEM 6  /* device or pinned-host allocation failed            */
+#define CHEBPOL_CUDA_ECUDA 7   /* any other CUDA runtime failure (see last_error)    */
+#define CHEBPOL_CUDA_EARCH 8   /* device is not compute capability 10.x              */
+
+CHEBPOL_CUDA_API const char *chebpol_cuda_strerror(int code);
+/* detail text of the calling thread's most recent failure ("" if none) */
+CHEBPOL_CUDA_API const char *chebpol_cuda_last_error(void);
+CHEBPOL_CUDA_API int chebpol_cuda_device_count(int *count);
+/* version of this ABI: major*10000 + minor*100 + patch */
+CHEBPOL_CUDA_API int chebpol_cuda_version(void);
+
+/* ---- stateless entry points: host pointers in, host pointers out --------
+ * These are what the .Call glue binds (csrc/r_glue.c); one call replaces
+ * one call of the reference routine named beside it.  The tensor is uploaded
+ * (replicated on each GPU used), the point batch is split into contiguous
+ * ranges over `ngpus` devices (<=0: all visible), streamed through each GPU
+ * in chunks, and every GPU writes its own slice of `out`.  No state survives
+ * the call, as in the reference (tensors live in the R closure environment).
+ */
+
+/* Replaces R_evalcheb (src/chebpol.c:340-381) + C_evalcheb (:314-338), and
+ * the R-level pre-maps that run on every call of the closure:
+ *   mid/ispan != NULL : x <- (x - mid)*ispan          imap, R/chebyshev.R:223-227
+ *   ugm_n     != NULL : x <- sin(0.5*pi*x*(1-n)/n)    ugm,  R/uniform.R:6,63-73
+ *                       (applied after the interval map, as ucappx.real does)
+ * dims[rank] are the dims of `coef`; length(coef) == prod(dims). */
+CHEBPOL_CUDA_API int chebpol_cuda_evalcheb(const double *coef, const int *dims, int rank,
+                          const double *x, int64_t npts,
+                          const double *mid, const double *ispan, const int *ugm_n,
+                          int ngpus, double *out);
+
+/* Replaces R_evalmlip (src/chebpol.c:670-707) + C_evalmlip (:617-667),
+ * binsearch (:543-556) and blendfun (src/chebpol.h:24-45).
+ * grid[d] has dims[d] strictly increasing knots; blend: 0 linear, 1 sigmoid,
+ * 2 parodic, 3 cubic, 4 square/step, 5 mean (R/multilinear.R:64-65). */
+CHEBPOL_CUDA_API int chebpol_cuda_evalmlip(const double *const *grid, const int *dims, int rank,
+                          const double *values, const double *x, int64_t npts,
+                          int blend, int ngpus, double *out);
+
+/* Replaces R_FH (src/chebpol.c:220-265) + FH (:182-218).  weights[d] are the
+ * Floater-Hormann weights of grid[d] (reference: C_FHweights, :267-312);
+ * grids may be increasing or decreasing. */
+CHEBPOL_CUDA_API int chebpol_cuda_fh(const double *vals, const double *const *grid,
+                    const double *const *weights, const int *dims, int rank,
+                    const double *x, int64_t npts, int ngpus, double *out);
+
+/* ---- plans: a fitted interpolant resident on one GPU --------------------
+ * For callers that evaluate the same interpolant repeatedly, and for
+ * device-resident benchmarking.  A plan owns the device copy of the tensor
+ * (re-laid-out for the kernels), knot/weight vectors and pre-map constants.
+ */
+typedef struct chebpol_cuda_plan chebpol_cuda_plan;
+
+CHEBPOL_CUDA_API int chebpol_cuda_plan_cheb(const double *coef, const int *dims, int rank,
+                           const double *mid, const double *ispan, const int *ugm_n,
+                           int device, chebpol_cuda_plan **plan);
+CHEBPOL_CUDA_API int chebpol_cuda_plan_mlip(const double *const *grid, const int *dims, int rank,
+                           const double *values, int blend, int device,
+                           chebpol_cuda_plan **plan);
+CHEBPOL_CUDA_API int chebpol_cuda_plan_fh(const double *vals, const double *const *grid,
+                         const double *const *weights, const int *dims, int rank,
+                         int device, chebpol_cuda_plan **plan);
+CHEBPOL_CUDA_API void chebpol_cuda_plan_destroy(chebpol_cuda_plan *plan);
+
+/* d_x (rank*npts doubles, point-major) and d_out (npts doubles) are DEVICE
+ * pointers on the plan's device; `stream` is a cudaStream_t (NULL = default
+ * stream).  Asynchronous: returns after enqueueing. */
+CHEBPOL_CUDA_API int chebpol_cuda_plan_eval_device(chebpol_cuda_plan *plan, const double *d_x,
+                                  int64_t npts, double *d_out, void *stream);
+/* Host pointers (pinned or pageable); chunked, double-buffered H2D -> kernel
+ * -> D2H pipeline on the plan's device.  Synchronous. */
+CHEBPOL_CUDA_API int chebpol_cuda_plan_eval_host(chebpol_cuda_plan *plan, const double *x,
+                                int64_t npts, double *out);
+
+/* plan options (set) and facts (get) */
+#define CHEBPOL_CUDA_OPT_KERNEL 1      /* see CHEBPOL_CUDA_KERNEL_*                       */
+#define CHEBPOL_CUDA_OPT_BLEND 2       /* multilinear plans: blend 0..5                   */
+#define CHEBPOL_CUDA_OPT_CHUNK_POINTS 3 /* eval_host chunk size in points (0 = auto)      */
+#define CHEBPOL_CUDA_OPT_VARIANT 4     /* tuning knob of the fast kernels (0 = auto)      */
+#define CHEBPOL_CUDA_GET_KERNEL_USED 101  /* kernel id of the most recent eval            */
+#define CHEBPOL_CUDA_GET_LAUNCHES 102     /* kernels launched by this plan so far         */
+#define CHEBPOL_CUDA_GET_TENSOR_BYTES 103 /* device bytes of the resident tensor          */
+#define CHEBPOL_CUDA_GET_DEVICE 104
+#define CHEBPOL_CUDA_GET_SMEM_BYTES 105   /* dynamic smem of the most recent launch       */
+#define CHEBPOL_CUDA_GET_GRID 106         /* grid size of the most recent launch          */
+
+/* kernel selection.  AUTO picks the fastest kernel that supports the shape.
+ * STRICT is the reference's operation order with no fused multiply-add:
+ * bit-identical to the reference C (up to libm exp/sin for blends 1,2 and the
+ * uniform map).  The others are IEEE FP64 kernels that reorder the sums
+ * (basis-contraction instead of Clenshaw, FMA), within 1e-12*max|f|. */
+#define CHEBPOL_CUDA_KERNEL_AUTO 0
+#define CHEBPOL_CUDA_KERNEL_STRICT 1
+#define CHEBPOL_CUDA_KERNEL_FAST 2
+CHEBPOL_CUDA_API int chebpol_cuda_plan_set(chebpol_cuda_plan *plan, int option, int64_t value);
+CHEBPOL_CUDA_API int chebpol_cuda_plan_get(chebpol_cuda_plan *plan, int what, int64_t *value);
+
+/* ---- diagnostics -------------------------------------------------------- */
+/* Register-resident DFMA chain on every SM of `device`: the FP64 roofline
+ * denominator (MEASURED_PEAKS.json has none).  Returns TFLOP/s (2 flop/FMA). */
+CHEBPOL_CUDA_API int chebpol_cuda_fp64_peak(int device, int repeats, double *tflops);
+/* total kernels launched by this library in this process */
+CHEBPOL_CUDA_API int64_t chebpol_cuda_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CHEBPOL_CUDA_H */

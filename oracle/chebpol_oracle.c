@@ -1,0 +1,371 @@
+/* oracle/chebpol_oracle.c -- TEST INFRASTRUCTURE ONLY; never linked into or
+ * called from the product (chebpol_b200/, libchebpol_cuda).
+ *
+ * A CPU restatement, in plain C, of the arithmetic of chebpol's batched
+ * evaluation path.  It is written from the reference's behaviour, not from
+ * its text: every routine is iterative where the reference recurses, but the
+ * floating-point operations are issued in the reference's order so that the
+ * results are bit-identical to the reference C compiled without FMA
+ * contraction (checked against oracle/_ref/libchebpol_ref.so -- the
+ * reference's own src/chebpol.c compiled through oracle/shim -- by
+ * tests/test_oracle.py, and against the golden values of the reference's
+ * saved test output, tests/all.Rout.save and
+ * tests/Examples/chebpol-Ex.Rout.save).  Parity status: PINNED.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * --impl reference legs may load this library.
+ *
+ * Build: see oracle/Makefile (gcc -O2 -fopenmp -ffp-contract=off).
+ */
+#include <math.h>
+#include <float.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define API __attribute__((visibility("default")))
+#define ORACLE_MAXRANK 32
+
+/* ------------------------------------------------------------------------
+ * Chebyshev series, nested Clenshaw.
+ * Follows C_evalcheb, /root/reference/src/chebpol.c:314-338:
+ *  - dimension rank-1 is the outermost recurrence, dimension 0 the innermost;
+ *  - innermost (:324-330): b = 2x*b1 - b2 + c[i] for i = N-1..1, result
+ *    x*b - b1 + c[0];
+ *  - outer levels (:332-337): b = 2x*b1 - b2 + (value of sub-tensor i) for
+ *    i = N-1..0, result b - x*b1.
+ * The c[0] coefficients carry no 1/2 factor (chebcoef folds it in, :126-140).
+ * ------------------------------------------------------------------------ */
+static inline double cheb_row(const double *c, int n, double x0)
+{
+    const double two_x = 2.0 * x0;
+    double b = 0.0, b1 = 0.0, b2;
+    for (int i = n - 1; i >= 1; --i) {
+        b2 = b1;
+        b1 = b;
+        b = two_x * b1 - b2 + c[i];
+    }
+    return x0 * b - b1 + c[0];
+}
+
+static double cheb_point(const double *cf, const double *x, const int *dims, int rank,
+                         const int64_t *stride)
+{
+    if (rank == 0) return cf[0];
+    if (rank == 1) return cheb_row(cf, dims[0], x[0]);
+    int idx[ORACLE_MAXRANK];
+    double b[ORACLE_MAXRANK], b1[ORACLE_MAXRANK];
+    int64_t off = 0;
+    for (int l = 1; l < rank; ++l) {
+        idx[l] = dims[l] - 1;
+        b[l] = b1[l] = 0.0;
+        off += (int64_t)idx[l] * stride[l];
+    }
+    for (;;) {
+        double v = cheb_row(cf + off, dims[0], x[0]);
+        int l = 1;
+        for (;;) {
+            const double b2 = b1[l];
+            b1[l] = b[l];
+            b[l] = 2.0 * x[l] * b1[l] - b2 + v;
+            if (idx[l] > 0) {
+                --idx[l];
+                off -= stride[l];
+                break;
+            }
+            v = b[l] - x[l] * b1[l];
+            b[l] = b1[l] = 0.0;
+            idx[l] = dims[l] - 1;
+            off += (int64_t)idx[l] * stride[l];
+            if (++l == rank) return v;
+        }
+    }
+}
+
+/* Batch driver: the loop of R_evalcheb, src/chebpol.c:375-378, with a 64-bit
+ * point index.  x is K x P column-major, i.e. point i at x + i*rank. */
+API int oracle_evalcheb(const double *cf, const int *dims, int rank, const double *x,
+                        int64_t npts, int threads, double *out)
+{
+    if (rank < 0 || rank > ORACLE_MAXRANK) return 1;
+    int64_t stride[ORACLE_MAXRANK + 1];
+    stride[0] = 1;
+    for (int l = 0; l < rank; ++l) stride[l + 1] = stride[l] * dims[l];
+#pragma omp parallel for num_threads(threads) schedule(static) if (npts > 1 && threads > 1)
+    for (int64_t i = 0; i < npts; ++i)
+        out[i] = cheb_point(cf, x + i * rank, dims, rank, stride);
+    return 0;
+}
+
+/* ------------------------------------------------------------------------
+ * R-level pre-maps that run on every call of the closure.
+ *  imap: (x - mid) * ispan           R/chebyshev.R:223-227
+ *  ugm : sin(0.5*pi*x*(1-n)/n)       R/uniform.R:6, applied per coordinate
+ *        after the optional interval map is*(xi-mid), R/uniform.R:63-72.
+ * R evaluates 0.5*pi*x*(1-n)/n left to right in doubles.
+ * ------------------------------------------------------------------------ */
+API void oracle_imap(const double *x, int rank, int64_t npts, const double *mid,
+                     const double *ispan, int threads, double *out)
+{
+#pragma omp parallel for num_threads(threads) schedule(static) if (npts > 1 && threads > 1)
+    for (int64_t i = 0; i < npts; ++i)
+        for (int d = 0; d < rank; ++d)
+            out[i * rank + d] = (x[i * rank + d] - mid[d]) * ispan[d];
+}
+
+API void oracle_ugm(const double *x, int rank, int64_t npts, const int *n, const double *mid,
+                    const double *ispan, int threads, double *out)
+{
+    const double pi = 3.141592653589793;
+#pragma omp parallel for num_threads(threads) schedule(static) if (npts > 1 && threads > 1)
+    for (int64_t i = 0; i < npts; ++i)
+        for (int d = 0; d < rank; ++d) {
+            double t = x[i * rank + d];
+            if (mid) t = ispan[d] * (t - mid[d]);
+            const double nd = (double)n[d];
+            out[i * rank + d] = sin(0.5 * pi * t * (1.0 - nd) / nd);
+        }
+}
+
+/* ------------------------------------------------------------------------
+ * Multilinear interpolation with blending.
+ * Follows binsearch (src/chebpol.c:543-556), blendfun (src/chebpol.h:24-45)
+ * and C_evalmlip (src/chebpol.c:617-667).
+ * ------------------------------------------------------------------------ */
+/* smallest index with arr[idx] >= val, clamped to [1, n-1] (comment at
+ * src/chebpol.c:537-542).  Unlike the reference loop (:547-554) this one
+ * terminates on NaN: NaN compares false, so it is treated as "too small". */
+static inline int cell_upper(int n, const double *arr, double val)
+{
+    int lo = 0, hi = n - 1;
+    while (lo + 1 < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (arr[mid] >= val) hi = mid;
+        else lo = mid;
+    }
+    return hi;
+}
+
+static inline double blend_weight(double w, int blend)
+{
+    switch (blend) {
+    case 1: return w < 0.5 ? 0.5 * exp(2 - 1 / w) : 1 - 0.5 * exp(2 - 1 / (1 - w));
+    case 2: return w < 0.5 ? 0.5 * exp(4 - 1 / (w * w)) : 1 - 0.5 * exp(4 - 1 / ((1 - w) * (1 - w)));
+    case 3: return (-2 * w + 3) * w * w;
+    case 4: return (w < 0.5) ? 0 : 1;
+    case 5: return 0.5;
+    default: return w; /* 0 = linear */
+    }
+}
+
+static double mlip_point(int rank, const double *x, const double *const *grid, const int *dims,
+                         const double *values, int blend)
+{
+    double w[ORACLE_MAXRANK];
+    int64_t stride[ORACLE_MAXRANK];
+    int64_t top = 0, s = 1;
+    for (int d = 0; d < rank; ++d) {
+        const double *g = grid[d];
+        const int gp = cell_upper(dims[d], g, x[d]);
+        w[d] = (x[d] - g[gp - 1]) / (g[gp] - g[gp - 1]);
+        stride[d] = s;
+        top += s * gp;
+        s *= dims[d];
+    }
+    double wsum = 0.0, acc = 0.0;
+    const unsigned long ncorner = 1ul << rank;
+    for (unsigned long corner = 0; corner < ncorner; ++corner) {
+        int64_t pos = top;
+        double cw = 1;
+        for (int d = 0; d < rank; ++d) {
+            if (corner & (1ul << d)) {
+                cw *= blend_weight(w[d], blend);
+            } else {
+                cw *= blend_weight(1 - w[d], blend);
+                pos -= stride[d];
+            }
+        }
+        wsum += cw;
+        acc += cw * values[pos];
+    }
+    return acc / wsum;
+}
+
+API int oracle_evalmlip(int rank, const double *const *grid, const int *dims, const double *values,
+                        const double *x, int64_t npts, int blend, int threads, double *out)
+{
+    if (rank < 1 || rank > ORACLE_MAXRANK - 1) return 1;
+#pragma omp parallel for num_threads(threads) schedule(static) if (npts > 1 && threads > 1)
+    for (int64_t i = 0; i < npts; ++i)
+        out[i] = mlip_point(rank, x + i * rank, grid, dims, values, blend);
+    return 0;
+}
+
+API double oracle_blendfun(double w, int blend) { return blend_weight(w, blend); }
+API int oracle_binsearch(int n, const double *arr, double val) { return cell_upper(n, arr, val); }
+
+/* ------------------------------------------------------------------------
+ * Floater-Hormann rational interpolation, nested barycentric form.
+ * Follows FH, src/chebpol.c:182-218: dimension rank-1 outermost; at each
+ * level, first i with |x - knot_i| < 10*DBL_EPSILON (absolute) short-cuts to
+ * slice i (:195-197); otherwise sum(pole*val)/sum(pole) with
+ * pole = w_i/(x - knot_i), accumulated for i ascending (:211-217).
+ * Iterative: an explicit frame per level replaces the recursion.
+ * ------------------------------------------------------------------------ */
+static double fh_point(const double *fv, const double *x, const double *const *knots,
+                       const int *dims, int rank, const double *const *weights,
+                       const int64_t *stride)
+{
+    if (rank == 0) return fv[0];
+    /* frame of level l (the recursion with rank == l+1) */
+    int i[ORACLE_MAXRANK], hit[ORACLE_MAXRANK];
+    double num[ORACLE_MAXRANK], den[ORACLE_MAXRANK];
+    const double *base[ORACLE_MAXRANK];
+    int l = rank - 1;
+    base[l] = fv;
+    double ret = 0.0;
+    int entering = 1;
+    for (;;) {
+        if (entering) {
+            /* open level l on sub-tensor base[l] */
+            const double xx = x[l];
+            const double *kn = knots[l];
+            hit[l] = -1;
+            for (int k = 0; k < dims[l]; ++k)
+                if (fabs(xx - kn[k]) < 10.0 * DBL_EPSILON) { hit[l] = k; break; }
+            num[l] = den[l] = 0.0;
+            i[l] = (hit[l] >= 0) ? hit[l] : 0;
+            if (l == 0) {
+                if (hit[0] >= 0) {
+                    ret = base[0][hit[0]];
+                } else {
+                    double nu = 0, de = 0;
+                    const double *w = weights[0];
+                    for (int k = 0; k < dims[0]; ++k) {
+                        const double val = base[0][k];
+                        const double pole = w[k] / (xx - kn[k]);
+                        nu += pole * val;
+                        de += pole;
+                    }
+                    ret = nu / de;
+                }
+                entering = 0;
+                ++l;
+                if (l == rank) return ret;
+                continue;
+            }
+            base[l - 1] = base[l] + (int64_t)i[l] * stride[l];
+            --l;
+            continue;
+        }
+        /* returning into level l with the value `ret` of slice i[l] */
+        if (hit[l] >= 0) {
+            /* knot hit: the level's value is the slice value */
+        } else {
+            const double pole = weights[l][i[l]] / (x[l] - knots[l][i[l]]);
+            num[l] += pole * ret;
+            den[l] += pole;
+            if (++i[l] < dims[l]) {
+                base[l - 1] = base[l] + (int64_t)i[l] * stride[l];
+                --l;
+                entering = 1;
+                continue;
+            }
+            ret = num[l] / den[l];
+        }
+        ++l;
+        if (l == rank) return ret;
+    }
+}
+
+API int oracle_fh(const double *vals, const double *x, const double *const *knots, const int *dims,
+                  int rank, const double *const *weights, int64_t npts, int threads, double *out)
+{
+    if (rank < 0 || rank > ORACLE_MAXRANK) return 1;
+    int64_t stride[ORACLE_MAXRANK + 1];
+    stride[0] = 1;
+    for (int l = 0; l < rank; ++l) stride[l + 1] = stride[l] * dims[l];
+#pragma omp parallel for num_threads(threads) schedule(static) if (npts > 1 && threads > 1)
+    for (int64_t p = 0; p < npts; ++p)
+        out[p] = fh_point(vals, x + p * rank, knots, dims, rank, weights, stride);
+    return 0;
+}
+
+/* ------------------------------------------------------------------------
+ * Fit-side helpers (fixtures only; not on the timed path).
+ * ------------------------------------------------------------------------ */
+/* Floater-Hormann weights, eq. (18) of the FH paper, as fhweights at
+ * src/chebpol.c:267-282 computes them: for knot k (0..n, n = nknots-1)
+ *   w_k = (-1)^(k-d) * sum_{i=max(0,k-d)}^{min(k,n-d)} 1/prod_{j=i..i+d, j!=k} |x_k-x_j|
+ * where the product is taken signed and its absolute value inverted. */
+API void oracle_fhweights(int nknots, const double *grid, int d, double *w)
+{
+    const int n = nknots - 1;
+    for (int k = 0; k <= n; ++k) {
+        const int lo = (k < d) ? 0 : k - d;
+        const int hi = (k < n - d) ? k : n - d;
+        double sum = 0.0;
+        for (int i = lo; i <= hi; ++i) {
+            double prod = 1.0;
+            for (int j = i; j <= i + d; ++j)
+                if (j != k) prod *= grid[k] - grid[j];
+            sum += 1.0 / fabs(prod);
+        }
+        w[k] = sum * ((k % 2 != d % 2) ? -1.0 : 1.0);
+    }
+}
+
+/* cos(pi*x), exact at multiples of 1/2 (R's cospi, used at src/chebpol.c:94) */
+static double cos_pi(double x)
+{
+    x = fmod(fabs(x), 2.0);
+    if (fmod(x, 1.0) == 0.5) return 0.0;
+    if (x == 1.0) return -1.0;
+    if (x == 0.0) return 1.0;
+    return cos(M_PI * x);
+}
+
+/* Chebyshev coefficients from values on the Chebyshev grid: the matrix path
+ * of chebcoef, src/chebpol.c:65-140.  Per dimension (last first, :109):
+ *   out[k] = alpha * sum_i cos(pi*k*(i+0.5)/N) * in[i],  alpha = 2/N (2 if dct)
+ * and afterwards, unless dct, every index-0 hyperplane is halved (:126-140).
+ * The transform of one dimension rotates it to the front, exactly as the
+ * reference's dgemm("T","T") call does (:119), so after `rank` steps the
+ * array is back in its original order and the roundings match. */
+API void oracle_chebcoef(const double *val, const int *dims, int rank, double *F, int dct)
+{
+    int64_t siz = 1;
+    for (int i = 0; i < rank; ++i) siz *= dims[i];
+    double *a = (double *)malloc(sizeof(double) * siz);
+    double *b = (double *)malloc(sizeof(double) * siz);
+    memcpy(a, val, sizeof(double) * siz);
+    for (int d = rank - 1; d >= 0; --d) {
+        const int N = dims[d];
+        const int64_t rest = siz / N;
+        const double alpha = dct ? 2.0 : 2.0 / N;
+        double *cm = (double *)malloc(sizeof(double) * N * N);
+        for (int k = 0; k < N; ++k)
+            for (int i = 0; i < N; ++i) cm[i + (int64_t)k * N] = cos_pi(k * (i + 0.5) / N);
+        /* a is (rest x N) column-major with the transformed dim last; b becomes (N x rest) */
+        for (int64_t j = 0; j < rest; ++j)
+            for (int k = 0; k < N; ++k) {
+                double s = 0.0;
+                for (int i = 0; i < N; ++i) s += cm[i + (int64_t)k * N] * a[j + (int64_t)i * rest];
+                b[k + (int64_t)j * N] = alpha * s;
+            }
+        free(cm);
+        double *t = a; a = b; b = t;
+    }
+    memcpy(F, a, sizeof(double) * siz);
+    free(a);
+    free(b);
+    if (!dct) {
+        int64_t blocklen = 1, stride = 1;
+        for (int i = 0; i < rank; ++i) {
+            stride *= dims[i];
+            for (int64_t j = 0; j < siz; j += stride)
+                for (int64_t s = 0; s < blocklen; ++s) F[j + s] *= 0.5;
+            blocklen = stride;
+        }
+    }
+}

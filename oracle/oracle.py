@@ -1,0 +1,193 @@
+"""oracle/oracle.py -- TEST INFRASTRUCTURE ONLY.
+
+ctypes front-end to the two CPU checkers:
+
+* ``Oracle("port")``      -> oracle/liboracle.so, the C restatement
+  (oracle/chebpol_oracle.c);
+* ``Oracle("reference")`` -> oracle/_ref/libchebpol_ref.so, the reference's own
+  src/chebpol.c compiled through the R-API shim (oracle/ref_wrap.c).
+
+Only tests/, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline /
+``--impl reference`` legs may import this module.  The product
+(``chebpol_b200``) never does.
+
+Points are passed the way R hands them to ``.Call``: a K x P column-major
+matrix, i.e. a C-contiguous ``(P, K)`` numpy array (point-major).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+_dpp = C.POINTER(_dp)
+
+
+def build(verbose: bool = False) -> None:
+    """Compile liboracle.so and (if /root/reference is present) _ref."""
+    r = subprocess.run(["make", "-C", _HERE, "all"], capture_output=True, text=True)
+    if verbose or r.returncode != 0:
+        print(r.stdout, r.stderr)
+    if r.returncode != 0:
+        raise RuntimeError("oracle build failed")
+
+
+def _as_pts(x, rank):
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    if x.ndim == 1:
+        x = x.reshape(1, -1) if x.size == rank else x.reshape(-1, rank)
+    assert x.shape[1] == rank, (x.shape, rank)
+    return x
+
+
+def _ptr(a):
+    return a.ctypes.data_as(_dp)
+
+
+def _ptr_list(arrs):
+    keep = [np.ascontiguousarray(a, dtype=np.float64) for a in arrs]
+    arr = (_dp * len(keep))(*[_ptr(a) for a in keep])
+    return arr, keep
+
+
+class Oracle:
+    def __init__(self, kind: str = "port"):
+        self.kind = kind
+        if kind == "port":
+            path = os.path.join(_HERE, "liboracle.so")
+            self.pfx = "oracle_"
+        elif kind == "reference":
+            path = os.path.join(_HERE, "_ref", "libchebpol_ref.so")
+            self.pfx = "ref_"
+        else:
+            raise ValueError(kind)
+        if not os.path.exists(path):
+            build()
+        if not os.path.exists(path):
+            raise FileNotFoundError(path)
+        self.lib = C.CDLL(path)
+        self.path = path
+
+    @staticmethod
+    def available(kind: str) -> bool:
+        p = "liboracle.so" if kind == "port" else os.path.join("_ref", "libchebpol_ref.so")
+        return os.path.exists(os.path.join(_HERE, p))
+
+    # -- Chebyshev ---------------------------------------------------------
+    def evalcheb(self, coef, x, threads: int = 1):
+        """coef: numpy array in R layout (Fortran order, dim 0 fastest)."""
+        coef = np.asfortranarray(coef, dtype=np.float64)
+        dims = np.array(coef.shape, dtype=np.int32)
+        rank = coef.ndim
+        x = _as_pts(x, rank)
+        out = np.empty(x.shape[0], dtype=np.float64)
+        f = getattr(self.lib, self.pfx + "evalcheb")
+        f.restype = None if self.kind == "reference" else C.c_int
+        f.argtypes = [_dp, _ip, C.c_int, _dp, C.c_int64, C.c_int, _dp]
+        f(coef.ctypes.data_as(_dp), dims.ctypes.data_as(_ip), rank, _ptr(x), x.shape[0], threads, _ptr(out))
+        return out
+
+    def imap(self, x, mid, ispan, threads: int = 1):
+        rank = len(mid)
+        x = _as_pts(x, rank)
+        if self.kind == "reference":  # R code, not in the C reference: same restatement
+            return (x - np.asarray(mid, dtype=np.float64)) * np.asarray(ispan, dtype=np.float64)
+        out = np.empty_like(x)
+        mid = np.ascontiguousarray(mid, dtype=np.float64)
+        ispan = np.ascontiguousarray(ispan, dtype=np.float64)
+        f = self.lib.oracle_imap
+        f.restype = None
+        f.argtypes = [_dp, C.c_int, C.c_int64, _dp, _dp, C.c_int, _dp]
+        f(_ptr(x), rank, x.shape[0], _ptr(mid), _ptr(ispan), threads, _ptr(out))
+        return out
+
+    def ugm(self, x, n, mid=None, ispan=None, threads: int = 1):
+        """R/uniform.R:6,63-72 (only in the port; the C reference has no such routine)."""
+        lib = Oracle("port").lib if self.kind == "reference" else self.lib
+        n = np.ascontiguousarray(n, dtype=np.int32)
+        rank = n.size
+        x = _as_pts(x, rank)
+        out = np.empty_like(x)
+        f = lib.oracle_ugm
+        f.restype = None
+        f.argtypes = [_dp, C.c_int, C.c_int64, _ip, _dp, _dp, C.c_int, _dp]
+        if mid is None:
+            f(_ptr(x), rank, x.shape[0], n.ctypes.data_as(_ip), None, None, threads, _ptr(out))
+        else:
+            mid = np.ascontiguousarray(mid, dtype=np.float64)
+            ispan = np.ascontiguousarray(ispan, dtype=np.float64)
+            f(_ptr(x), rank, x.shape[0], n.ctypes.data_as(_ip), _ptr(mid), _ptr(ispan), threads, _ptr(out))
+        return out
+
+    # -- multilinear -------------------------------------------------------
+    def evalmlip(self, grid, values, x, blend: int = 0, threads: int = 1):
+        rank = len(grid)
+        dims = np.array([len(g) for g in grid], dtype=np.int32)
+        values = np.ascontiguousarray(np.asarray(values, dtype=np.float64).ravel(order="F"))
+        assert values.size == int(np.prod(dims.astype(np.int64)))
+        x = _as_pts(x, rank)
+        out = np.empty(x.shape[0], dtype=np.float64)
+        gl, keep = _ptr_list(grid)
+        f = getattr(self.lib, self.pfx + "evalmlip")
+        f.restype = None if self.kind == "reference" else C.c_int
+        f.argtypes = [C.c_int, _dpp, _ip, _dp, _dp, C.c_int64, C.c_int, C.c_int, _dp]
+        f(rank, gl, dims.ctypes.data_as(_ip), _ptr(values), _ptr(x), x.shape[0], blend, threads, _ptr(out))
+        return out
+
+    def blendfun(self, w: float, blend: int) -> float:
+        f = getattr(self.lib, self.pfx + "blendfun")
+        f.restype = C.c_double
+        f.argtypes = [C.c_double, C.c_int]
+        return f(w, blend)
+
+    def binsearch(self, arr, val: float) -> int:
+        arr = np.ascontiguousarray(arr, dtype=np.float64)
+        f = getattr(self.lib, self.pfx + "binsearch")
+        f.restype = C.c_int
+        f.argtypes = [C.c_int, _dp, C.c_double]
+        return f(arr.size, _ptr(arr), val)
+
+    # -- Floater-Hormann -----------------------------------------------------
+    def fh(self, vals, grid, weights, x, threads: int = 1):
+        vals = np.asfortranarray(vals, dtype=np.float64)
+        rank = len(grid)
+        dims = np.array([len(g) for g in grid], dtype=np.int32)
+        assert vals.size == int(np.prod(dims.astype(np.int64)))
+        x = _as_pts(x, rank)
+        out = np.empty(x.shape[0], dtype=np.float64)
+        gl, k1 = _ptr_list(grid)
+        wl, k2 = _ptr_list(weights)
+        f = getattr(self.lib, self.pfx + "fh")
+        f.restype = None if self.kind == "reference" else C.c_int
+        f.argtypes = [_dp, _dp, _dpp, _ip, C.c_int, _dpp, C.c_int64, C.c_int, _dp]
+        f(vals.ctypes.data_as(_dp), _ptr(x), gl, dims.ctypes.data_as(_ip), rank, wl, x.shape[0], threads, _ptr(out))
+        return out
+
+    # -- fit side (fixtures) -------------------------------------------------
+    def fhweights(self, grid, d):
+        d = np.broadcast_to(np.asarray(d, dtype=np.int64), (len(grid),))
+        f = getattr(self.lib, self.pfx + "fhweights")
+        f.restype = None
+        f.argtypes = [C.c_int, _dp, C.c_int, _dp]
+        out = []
+        for g, dd in zip(grid, d):
+            g = np.ascontiguousarray(g, dtype=np.float64)
+            w = np.empty_like(g)
+            f(g.size, _ptr(g), int(dd), _ptr(w))
+            out.append(w)
+        return out
+
+    def chebcoef(self, val, dct: bool = False):
+        val = np.asfortranarray(val, dtype=np.float64)
+        dims = np.array(val.shape, dtype=np.int32)
+        F = np.empty(val.shape, dtype=np.float64, order="F")
+        f = getattr(self.lib, self.pfx + "chebcoef")
+        f.restype = None
+        f.argtypes = [_dp, _ip, C.c_int, _dp, C.c_int]
+        f(val.ctypes.data_as(_dp), dims.ctypes.data_as(_ip), val.ndim, F.ctypes.data_as(_dp), int(dct))
+        return F

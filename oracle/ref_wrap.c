@@ -1,0 +1,149 @@
+/* oracle/ref_wrap.c -- TEST INFRASTRUCTURE ONLY; never linked into the product.
+ *
+ * Builds oracle/_ref/libchebpol_ref.so from the reference's OWN source file,
+ * compiled where it lies (the Makefile passes -I$(REF)/src; nothing is copied
+ * into this repository).  Because this TU #includes the reference .c file,
+ * its `static` per-point kernels are reachable directly:
+ *   C_evalcheb  src/chebpol.c:314-338     FH         src/chebpol.c:182-218
+ *   C_evalmlip  src/chebpol.c:617-667     fhweights  src/chebpol.c:267-282
+ *   chebcoef    src/chebpol.c:8-141 (BLAS-matrix path, :65-122)
+ * The batch drivers below repeat the reference's outer loops
+ * (src/chebpol.c:375-378, :701-704, :259-262) with 64-bit point indices
+ * (the reference's `int i`, `i*rank` overflow once P*K >= 2^31).
+ *
+ * Everything the R API would provide is a stub that aborts when executed:
+ * the numeric kernels never call into R.
+ */
+#include <stdio.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include "chebpol.c" /* resolved through -I/root/reference/src at build time */
+
+/* ---- R API link-time stubs (never executed on the paths we call) ---- */
+#undef error
+#undef warning
+#undef length
+#define SHIM_DIE(name) do { fprintf(stderr, "oracle shim: R API '%s' called\n", name); abort(); } while (0)
+SEXP R_NilValue, R_DimSymbol, R_DimNamesSymbol, R_BaseEnv;
+double R_NaReal;
+double *REAL(SEXP s) { (void)s; SHIM_DIE("REAL"); }
+int *INTEGER(SEXP s) { (void)s; SHIM_DIE("INTEGER"); }
+int *LOGICAL(SEXP s) { (void)s; SHIM_DIE("LOGICAL"); }
+int LENGTH(SEXP s) { (void)s; SHIM_DIE("LENGTH"); }
+R_xlen_t XLENGTH(SEXP s) { (void)s; SHIM_DIE("XLENGTH"); }
+int Rf_length(SEXP s) { (void)s; SHIM_DIE("length"); }
+SEXP Rf_getAttrib(SEXP a, SEXP b) { (void)a; (void)b; SHIM_DIE("getAttrib"); }
+SEXP Rf_setAttrib(SEXP a, SEXP b, SEXP c) { (void)a; (void)b; (void)c; SHIM_DIE("setAttrib"); }
+int Rf_isNull(SEXP s) { (void)s; SHIM_DIE("isNull"); }
+int Rf_isLogical(SEXP s) { (void)s; SHIM_DIE("isLogical"); }
+int Rf_isMatrix(SEXP s) { (void)s; SHIM_DIE("isMatrix"); }
+int Rf_isFunction(SEXP s) { (void)s; SHIM_DIE("isFunction"); }
+int Rf_isReal(SEXP s) { (void)s; SHIM_DIE("isReal"); }
+int Rf_nrows(SEXP s) { (void)s; SHIM_DIE("nrows"); }
+int Rf_ncols(SEXP s) { (void)s; SHIM_DIE("ncols"); }
+SEXP Rf_protect(SEXP s) { (void)s; SHIM_DIE("PROTECT"); }
+void Rf_unprotect(int n) { (void)n; SHIM_DIE("UNPROTECT"); }
+SEXP Rf_allocVector(unsigned int t, R_xlen_t n) { (void)t; (void)n; SHIM_DIE("allocVector"); }
+SEXP Rf_allocMatrix(unsigned int t, int a, int b) { (void)t; (void)a; (void)b; SHIM_DIE("allocMatrix"); }
+SEXP VECTOR_ELT(SEXP s, R_xlen_t i) { (void)s; (void)i; SHIM_DIE("VECTOR_ELT"); }
+SEXP SET_VECTOR_ELT(SEXP s, R_xlen_t i, SEXP v) { (void)s; (void)i; (void)v; SHIM_DIE("SET_VECTOR_ELT"); }
+SEXP Rf_coerceVector(SEXP s, unsigned int t) { (void)s; (void)t; SHIM_DIE("coerceVector"); }
+SEXP Rf_eval(SEXP a, SEXP b) { (void)a; (void)b; SHIM_DIE("eval"); }
+SEXP Rf_lang2(SEXP a, SEXP b) { (void)a; (void)b; SHIM_DIE("lang2"); }
+SEXP SETCADR(SEXP a, SEXP b) { (void)a; (void)b; SHIM_DIE("SETCADR"); }
+SEXP Rf_ScalarLogical(int v) { (void)v; SHIM_DIE("ScalarLogical"); }
+SEXP Rf_ScalarReal(double v) { (void)v; SHIM_DIE("ScalarReal"); }
+int MAYBE_REFERENCED(SEXP s) { (void)s; SHIM_DIE("MAYBE_REFERENCED"); }
+int R_registerRoutines(DllInfo *d, const void *a, const R_CallMethodDef *b, const void *c, const void *e)
+{ (void)d; (void)a; (void)b; (void)c; (void)e; SHIM_DIE("R_registerRoutines"); }
+int R_useDynamicSymbols(DllInfo *d, int v) { (void)d; (void)v; SHIM_DIE("R_useDynamicSymbols"); }
+void R_RegisterCCallable(const char *a, const char *b, DL_FUNC f) { (void)a; (void)b; (void)f; SHIM_DIE("R_RegisterCCallable"); }
+void Rf_error(const char *fmt, ...) {
+  va_list ap; va_start(ap, fmt); fprintf(stderr, "oracle shim: error(): "); vfprintf(stderr, fmt, ap);
+  fprintf(stderr, "\n"); va_end(ap); abort();
+}
+void Rf_warning(const char *fmt, ...) {
+  va_list ap; va_start(ap, fmt); fprintf(stderr, "oracle shim: warning(): "); vfprintf(stderr, fmt, ap);
+  fprintf(stderr, "\n"); va_end(ap);
+}
+/* entry points of the reference's other TU (src/stalker.c), named by the
+ * registration table only */
+SEXP R_evalstalker(SEXP a, SEXP b, SEXP c, SEXP d, SEXP e) { (void)a;(void)b;(void)c;(void)d;(void)e; SHIM_DIE("R_evalstalker"); }
+SEXP R_makehyp(SEXP a, SEXP b) { (void)a;(void)b; SHIM_DIE("R_makehyp"); }
+SEXP R_evalhyp(SEXP a, SEXP b, SEXP c, SEXP d) { (void)a;(void)b;(void)c;(void)d; SHIM_DIE("R_evalhyp"); }
+SEXP R_makestalk(SEXP a, SEXP b) { (void)a;(void)b; SHIM_DIE("R_makestalk"); }
+SEXP R_evalstalk(SEXP a, SEXP b, SEXP c, SEXP d) { (void)a;(void)b;(void)c;(void)d; SHIM_DIE("R_evalstalk"); }
+SEXP havegsl(void) { SHIM_DIE("havegsl"); }
+void dgetrf_(const int *a, const int *b, double *c, const int *d, int *e, int *f)
+{ (void)a;(void)b;(void)c;(void)d;(void)e;(void)f; SHIM_DIE("dgetrf"); }
+void dgetrs_(const char *t, const int *a, const int *b, const double *c, const int *d, const int *e, double *f, const int *g, int *h)
+{ (void)t;(void)a;(void)b;(void)c;(void)d;(void)e;(void)f;(void)g;(void)h; SHIM_DIE("dgetrs"); }
+
+/* ---- the three non-stub services chebcoef's matrix path needs ---- */
+/* R_alloc: transient storage R frees at .Call exit; here a small arena the
+ * wrapper resets after each call. */
+static char **arena = NULL; static int arena_n = 0, arena_cap = 0;
+char *R_alloc(size_t n, int size) {
+  if (arena_n == arena_cap) { arena_cap = arena_cap ? 2 * arena_cap : 16; arena = realloc(arena, arena_cap * sizeof(char *)); }
+  char *p = malloc(n * (size_t)size + 16); arena[arena_n++] = p; return p;
+}
+static void arena_reset(void) { for (int i = 0; i < arena_n; i++) free(arena[i]); arena_n = 0; }
+/* R's cospi(x) = cos(pi*x) with exact values at multiples of 1/2 */
+double cospi(double x) {
+  x = fmod(fabs(x), 2.0);
+  if (fmod(x, 1.0) == 0.5) return 0.0;
+  if (x == 1.0) return -1.0;
+  if (x == 0.0) return 1.0;
+  return cos(M_PI * x);
+}
+double R_pow_di(double x, int n) { return pow(x, (double)n); }
+/* dgemm, only the ("T","T") case reached from src/chebpol.c:119:
+ * C(MxN) = alpha * A^T * B^T + beta*C, column-major, A is KxM (lda), B is NxK (ldb) */
+void dgemm_(const char *ta, const char *tb, const int *M, const int *N, const int *K,
+            const double *alpha, const double *A, const int *lda, const double *B, const int *ldb,
+            const double *beta, double *C, const int *ldc) {
+  if (ta[0] != 'T' || tb[0] != 'T') SHIM_DIE("dgemm (non T,T)");
+  for (int j = 0; j < *N; j++)
+    for (int i = 0; i < *M; i++) {
+      double s = 0.0;
+      for (int k = 0; k < *K; k++) s += A[k + (size_t)i * *lda] * B[j + (size_t)k * *ldb];
+      C[i + (size_t)j * *ldc] = *alpha * s + (*beta == 0.0 ? 0.0 : *beta * C[i + (size_t)j * *ldc]);
+    }
+}
+
+/* ---- exported batch drivers over the reference's own kernels ---- */
+#define EXPORT __attribute__((visibility("default")))
+
+EXPORT void ref_evalcheb(const double *cf, const int *dims, int rank, const double *x,
+                         int64_t npts, int threads, double *out) {
+#pragma omp parallel for num_threads(threads) schedule(static) if (npts > 1 && threads > 1)
+  for (int64_t i = 0; i < npts; i++)
+    out[i] = C_evalcheb((double *)cf, (double *)x + i * rank, (int *)dims, rank);
+}
+
+EXPORT void ref_evalmlip(int rank, const double *const *grid, const int *dims, const double *values,
+                         const double *x, int64_t npts, int blend, int threads, double *out) {
+#pragma omp parallel for num_threads(threads) schedule(static) if (npts > 1 && threads > 1)
+  for (int64_t i = 0; i < npts; i++)
+    out[i] = C_evalmlip(rank, (double *)x + i * rank, (double **)grid, (int *)dims, (double *)values, blend);
+}
+
+EXPORT void ref_fh(const double *vals, const double *x, const double *const *knots, const int *dims,
+                   int rank, const double *const *weights, int64_t npts, int threads, double *out) {
+#pragma omp parallel for num_threads(threads) schedule(static) if (npts > 1 && threads > 1)
+  for (int64_t i = 0; i < npts; i++)
+    out[i] = FH((double *)vals, (double *)x + i * rank, (double **)knots, (int *)dims, rank, (double **)weights);
+}
+
+EXPORT void ref_chebcoef(const double *val, const int *dims, int rank, double *F, int dct) {
+  chebcoef((double *)val, (int *)dims, rank, F, dct, 1);
+  arena_reset();
+}
+
+/* n = number of knots (the reference is called with dims[r]-1, src/chebpol.c:307) */
+EXPORT void ref_fhweights(int nknots, const double *grid, int d, double *w) {
+  fhweights(nknots - 1, grid, d, w, 1);
+}
+
+EXPORT double ref_blendfun(double w, int blend) { return blendfun(w, blend); }
+EXPORT int ref_binsearch(int n, const double *arr, double val) { return binsearch(n, (double *)arr, val); }

@@ -1,0 +1,6 @@
+/* oracle/shim/Rmath.h -- TEST INFRASTRUCTURE ONLY (see R.h). */
+#ifndef CHEBPOL_ORACLE_SHIM_RMATH_H
+#define CHEBPOL_ORACLE_SHIM_RMATH_H
+double cospi(double);
+double R_pow_di(double, int);
+#endif
