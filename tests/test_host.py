@@ -1,0 +1,177 @@
+"""CPU tests (no GPU): the C-ABI library loads and exports every symbol the header
+declares; argument validation that precedes device selection mirrors the reference's
+entry checks; the package fails loudly -- never falls back -- without a GPU; the
+host mirror of the R interface coerces arguments as R/tools.R:9-20 does; and the
+multi-rank point partition tiles the batch (world_size-2 gloo run)."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import chebpol_b200 as cb
+from chebpol_b200 import _lib, shard
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    txt = open(os.path.join(ROOT, "include", "chebpol_cuda.h")).read()
+    return sorted(set(re.findall(r"CHEBPOL_CUDA_API[^;(]*?\b(chebpol_cuda_\w+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol():
+    L = _lib.lib()
+    syms = header_symbols()
+    assert len(syms) >= 17
+    for s in syms:
+        assert getattr(L, s) is not None, s
+    assert sorted(_lib.EXPORTS) == syms
+    # and nothing from the oracle is linked into the product
+    out = subprocess.run(["nm", "-D", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "oracle_" not in out and "ref_evalcheb" not in out
+
+
+def test_strerror_and_version():
+    L = _lib.lib()
+    assert L.chebpol_cuda_version() >= 100
+    assert L.chebpol_cuda_strerror(0) == b"success"
+    for code in range(1, 9):
+        assert len(L.chebpol_cuda_strerror(code)) > 0
+    assert b"unknown" in L.chebpol_cuda_strerror(99)
+
+
+def test_argument_validation_precedes_device():
+    """Mirrors 'rank must be positive' (src/chebpol.c:352,232) and the size checks."""
+    L = _lib.lib()
+    h = C.c_void_p()
+    cf = np.zeros(4)
+    d = np.array([2, 2], dtype=np.int32)
+    dp = d.ctypes.data_as(C.POINTER(C.c_int))
+    assert L.chebpol_cuda_plan_cheb(cf.ctypes.data, dp, 0, None, None, None, 0, C.byref(h)) == 2
+    assert b"rank must be positive" in L.chebpol_cuda_last_error()
+    assert L.chebpol_cuda_plan_cheb(cf.ctypes.data, dp, 40, None, None, None, 0, C.byref(h)) == 2
+    assert L.chebpol_cuda_plan_cheb(None, dp, 2, None, None, None, 0, C.byref(h)) == 1
+    bad = np.array([2, 0], dtype=np.int32)
+    assert L.chebpol_cuda_plan_cheb(cf.ctypes.data, bad.ctypes.data_as(C.POINTER(C.c_int)), 2, None, None, None, 0,
+                                    C.byref(h)) == 3
+    huge = np.array([65536, 65536], dtype=np.int32)
+    assert L.chebpol_cuda_plan_cheb(cf.ctypes.data, huge.ctypes.data_as(C.POINTER(C.c_int)), 2, None, None, None, 0,
+                                    C.byref(h)) == 3
+    mid = np.zeros(2)
+    assert L.chebpol_cuda_plan_cheb(cf.ctypes.data, dp, 2, mid.ctypes.data, None, None, 0, C.byref(h)) == 1
+    g = [np.linspace(0, 1, 2), np.linspace(0, 1, 2)]
+    gl, keep = _lib.ptr_list(g)
+    assert L.chebpol_cuda_plan_mlip(gl, dp, 2, cf.ctypes.data, 9, 0, C.byref(h)) == 4  # EBLEND
+    assert L.chebpol_cuda_plan_eval_host(None, None, 1, None) == 1
+
+
+@pytest.mark.skipif(_lib.device_count() > 0, reason="a GPU is visible")
+def test_no_cpu_fallback_without_gpu():
+    cf = np.ones((3, 3))
+    with pytest.raises(cb.ChebpolCudaError) as e:
+        _lib.Plan.cheb(cf)
+    assert e.value.code == 5  # ENODEV
+    ip = cb.chebappx(np.ones((3, 3)))
+    with pytest.raises(cb.ChebpolCudaError):
+        ip(np.array([0.1, 0.2]))
+    with pytest.raises(cb.ChebpolCudaError):
+        _lib.evalcheb(cf, np.zeros((4, 2)))
+
+
+def test_missing_library_is_loud(tmp_path, monkeypatch):
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(ImportError):
+        _lib.lib()
+
+
+def test_vectorfun_coercion_rules():
+    """R/tools.R:9-20 via Interpolant._coerce (no device needed)."""
+    ip = cb.Interpolant("chebyshev", 3, None, coef=np.zeros((2, 2, 2)))
+    x, _ = ip._coerce(np.arange(6.0).reshape(3, 2))  # K x P matrix
+    assert x.shape == (2, 3) and np.array_equal(x[1], [1, 3, 5])
+    x, single = ip._coerce([1.0, 2.0, 3.0])
+    assert x.shape == (1, 3) and single
+    with pytest.warns(UserWarning):
+        x, _ = ip._coerce(np.arange(6.0))
+    assert x.shape == (2, 3) and np.array_equal(x[0], [0, 1, 2])  # dim(x) <- c(arity, numvec)
+    with pytest.raises(ValueError):
+        ip._coerce(np.arange(4.0))
+    with pytest.raises(ValueError):
+        ip._coerce(np.zeros((2, 5)))
+    ip1 = cb.Interpolant("chebyshev", 1, None, coef=np.zeros(4))
+    x, _ = ip1._coerce(np.arange(5.0))
+    assert x.shape == (5, 1)
+
+
+def test_ipol_front_end_checks():
+    with pytest.raises(ValueError):
+        cb.ipol(lambda x: 0.0, method="chebyshev")  # dims must be specified
+    with pytest.raises(ValueError):
+        cb.ipol(np.zeros(4), method="multilinear")  # grid must be specified
+    with pytest.raises(ValueError):
+        cb.ipol(np.zeros(3), grid=[np.array([0.0, 2.0, 1.0])], method="fh")  # unsorted
+    with pytest.raises(NotImplementedError):
+        cb.ipol(np.zeros(4), knots=np.zeros((2, 2)), method="polyharmonic")
+    ip = cb.ipol(np.zeros(9), grid=[np.linspace(0, 1, 3)] * 2, method="multi")  # partial match
+    assert ip.kind == "multilinear" and ip.arity == 2
+    ip = cb.ipol(np.arange(24.0), dims=[2, 3, 4], method="cheb")
+    assert ip.t["coef"].shape == (2, 3, 4)
+    ip = cb.ipol(np.zeros((5, 5)), grid=[np.linspace(0, 1, 5)[::-1], np.linspace(0, 1, 5)], method="fh")
+    assert [len(w) for w in ip.t["weights"]] == [5, 5]  # decreasing grids are legal (R/ipol.R:241-243)
+    ip = cb.ipol(np.zeros(15), method="uniform")
+    assert ip.kind == "uniform" and list(ip.t["ugm_n"]) == [15]
+
+
+def test_shard_range_tiles_the_batch():
+    for npts in [0, 1, 7, 1000, 10**9 + 7]:
+        for world in [1, 2, 3, 4, 8]:
+            prev = 0
+            for r in range(world):
+                lo, hi = shard.shard_range(npts, r, world)
+                assert lo == prev and hi >= lo
+                prev = hi
+            assert prev == npts
+    with pytest.raises(ValueError):
+        shard.shard_range(10, 2, 2)
+
+
+_WORKER = r"""
+import os, sys
+sys.path.insert(0, {root!r})
+import numpy as np, torch, torch.distributed as dist
+from chebpol_b200 import shard
+rank, local, world = shard.init_process_group("gloo")
+assert world == 2
+npts = 1001
+lo, hi = shard.shard_range(npts, rank, world)
+# every rank owns a slice; the slices' sizes sum to P; MAX reduction picks the slower rank
+tot = shard.sum_over_ranks(hi - lo)
+assert tot == npts, tot
+shard.barrier()
+mx = shard.max_over_ranks(10.0 + rank)
+assert mx == 11.0, mx
+# a replicated "tensor" evaluated on each rank's slice, gathered: equals the whole
+x = np.linspace(-1, 1, npts)
+mine = torch.zeros(npts, dtype=torch.float64)
+mine[lo:hi] = torch.from_numpy(np.polynomial.chebyshev.chebval(x[lo:hi], [1.0, 0.5, 0.25]))
+dist.all_reduce(mine)
+assert np.allclose(mine.numpy(), np.polynomial.chebyshev.chebval(x, [1.0, 0.5, 0.25]))
+dist.destroy_process_group()
+print("rank", rank, "ok")
+"""
+
+
+def test_two_rank_gloo_partition(tmp_path):
+    script = tmp_path / "w.py"
+    script.write_text(_WORKER.format(root=ROOT))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29611", str(script)],
+                       capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "rank 0 ok" in r.stdout and "rank 1 ok" in r.stdout

@@ -1,0 +1,308 @@
+"""GPU parity tests (run with -m gpu on a B200): libchebpol_cuda, called through its
+C ABI, against the CPU oracle on the same seeded inputs.
+
+Bars (BASELINE.json north_star: "at most 1e-12 relative to max|f|, or a few ULPs
+accounting for summation order"):
+  * STRICT kernels (reference operation order, no FMA): BIT-IDENTICAL to the oracle,
+    which is itself bit-identical to the reference C (tests/test_oracle.py);
+    where libm is involved (exp in blends 1/2, sin in the uniform map) 1e-14 relative.
+  * fast kernels (basis contraction + FMA, pair-wise gathers): |diff| <= TOL_REL * scale,
+    TOL_REL = 1e-12, scale = max|f| over the evaluated points for fitted interpolants;
+    for the adversarial "stress" tensor (slowly decaying random coefficients, points
+    outside the domain) scale = sum|c| * max_k|T_k(x)|, the natural conditioning bound.
+"""
+import numpy as np
+import pytest
+
+import cases
+import chebpol_b200 as cb
+from chebpol_b200 import _lib
+
+pytestmark = pytest.mark.gpu
+TOL_REL = 1e-12
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype=np.float64).view(np.uint64)
+
+
+def eval_plan(plan, x, kernel):
+    plan.set(_lib.OPT_KERNEL, kernel)
+    out = plan.eval_host(np.ascontiguousarray(x))
+    return out, plan.kernel_used
+
+
+# ----------------------------------------------------------------- Chebyshev
+CHEB_SHAPES = [(7,), (20, 20), (8, 7, 6), (10, 10, 10), (5, 4, 3, 2), (10,) * 5, (3, 3, 3, 3, 3, 3), (1, 4), (4, 1, 3),
+               (2,) * 7, (33, 5), (12, 12, 12, 3), (17, 9), (31, 2, 3)]
+
+
+@pytest.mark.parametrize("dims", CHEB_SHAPES)
+def test_cheb_strict_bit_exact(gpu_ok, port, dims):
+    cf = cases.cheb_stress(dims)
+    x = cases.points(3001, len(dims), lo=-1.3, hi=1.3)
+    plan = _lib.Plan.cheb(cf)
+    got, k = eval_plan(plan, x, _lib.KERNEL_STRICT)
+    assert k == "cheb_strict"
+    want = port.evalcheb(cf, x, threads=4)
+    assert np.array_equal(bits(got), bits(want))
+    plan.close()
+
+
+@pytest.mark.parametrize("dims", CHEB_SHAPES)
+def test_cheb_fast_fitted(gpu_ok, port, dims):
+    cf = cases.cheb_fitted(dims)
+    x = cases.points(20011, len(dims))
+    plan = _lib.Plan.cheb(cf)
+    got, k = eval_plan(plan, x, _lib.KERNEL_AUTO)
+    assert k == ("cheb_slab" if dims[0] <= 32 else "cheb_strict")
+    want = port.evalcheb(cf, x, threads=4)
+    scale = np.abs(want).max()
+    assert np.abs(got - want).max() <= TOL_REL * scale, (np.abs(got - want).max(), scale)
+    plan.close()
+
+
+@pytest.mark.parametrize("dims", [(20, 20), (10,) * 5, (12, 12, 12, 3), (6, 5, 4, 3, 2, 2)])
+def test_cheb_fast_stress_outside_domain(gpu_ok, port, dims):
+    cf = cases.cheb_stress(dims)
+    x = cases.points(5003, len(dims), lo=-1.2, hi=1.2)
+    plan = _lib.Plan.cheb(cf)
+    got, k = eval_plan(plan, x, _lib.KERNEL_AUTO)
+    assert k == "cheb_slab"
+    want = port.evalcheb(cf, x, threads=4)
+    # conditioning bound: sum|c| * prod_d max_k |T_k(x_d)|, |T_k(1.2)| <= cosh(k*acosh(1.2))
+    tmax = np.prod([np.cosh((n - 1) * np.arccosh(1.2)) for n in dims])
+    scale = np.abs(cf).sum() * tmax
+    assert np.abs(got - want).max() <= TOL_REL * scale
+    plan.close()
+
+
+def test_cheb_intervals_and_uniform_premaps(gpu_ok, port):
+    dims = (9, 8, 7)
+    iv = [(1.0, 2.0), (1.0, 4.0), (-3.0, 3.0)]
+    grids = cb.chebknots(dims, iv)
+    cf = cb.chebcoef(cases.grid_values(grids))
+    mid = np.array([np.mean(i) for i in iv])
+    ispan = np.array([2.0 / (i[1] - i[0]) for i in iv])
+    rng = np.random.default_rng(3)
+    x = np.ascontiguousarray(np.stack([rng.uniform(a, b, 4000) for a, b in iv], axis=1))
+    for kernel, exact in [(_lib.KERNEL_STRICT, True), (_lib.KERNEL_AUTO, False)]:
+        plan = _lib.Plan.cheb(cf, mid=mid, ispan=ispan)
+        got, _ = eval_plan(plan, x, kernel)
+        want = port.evalcheb(cf, port.imap(x, mid, ispan))
+        if exact:
+            assert np.array_equal(bits(got), bits(want))
+        else:
+            assert np.abs(got - want).max() <= TOL_REL * np.abs(want).max()
+        plan.close()
+        # uniform evaluator: ugm after the interval map (R/uniform.R:68)
+        plan = _lib.Plan.cheb(cf, mid=mid, ispan=ispan, ugm_n=dims)
+        got, _ = eval_plan(plan, x, kernel)
+        want = port.evalcheb(cf, port.ugm(x, dims, mid=mid, ispan=ispan))
+        # device sin vs glibc sin: <= 1 ulp in the mapped coordinate
+        assert np.abs(got - want).max() <= 1e-13 * np.abs(want).max()
+        plan.close()
+        plan = _lib.Plan.cheb(cf, ugm_n=dims)
+        xu = cases.points(4000, 3)
+        got, _ = eval_plan(plan, xu, kernel)
+        want = port.evalcheb(cf, port.ugm(xu, dims))
+        assert np.abs(got - want).max() <= 1e-13 * np.abs(want).max()
+        plan.close()
+
+
+def test_cheb_long_1d_golden(gpu_ok):
+    """tests/all.R:10-13 -> all.Rout.save:57 through the GPU path (n = 50000 falls to the strict kernel)."""
+    n = 50000
+    kn = cb.chebknots([n])[0]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        val = np.where(kn == 0, 0.0, np.sin(1.0 / kn))
+    ch = cb.ipol(val, dims=n, method="chebyshev")
+    got = ch(np.array([0.03, 0.031]))
+    assert abs(got[0] - 0.9400964) < 5e-8 and abs(got[1] - 0.7465345) < 5e-8
+
+
+def test_cheb_goldens_through_ipol(gpu_ok):
+    """all.Rout.save:69,71 and :74 via the host mirror of the R interface."""
+    f = lambda x: np.exp(-np.sum(x ** 2))
+    ch = cb.ipol(f, dims=[8, 7, 6], intervals=[(1, 2), (1, 4), (1, 3)], method="chebyshev")
+    for kern in (_lib.KERNEL_AUTO, _lib.KERNEL_STRICT):
+        ch.kernel = kern
+        s = np.array([1.4, 2.3, 1.9])
+        assert abs((ch(s)[0] - f(s)) - (-3.115592e-06)) < 5e-13
+        a = np.array([1.01, 1.01, 1.01])
+        assert abs((ch(a)[0] - f(a)) - 0.0001730159) < 5e-11
+    ch.close()
+
+
+# --------------------------------------------------------------- multilinear
+@pytest.mark.parametrize("blend", [0, 1, 2, 3, 4, 5])
+@pytest.mark.parametrize("dims", [(10,), (7, 9), (11, 11, 11), (16, 16, 16, 16), (5, 4, 3, 6, 4), (3, 4, 3, 2, 5, 3), (3,) * 8])
+def test_mlip_strict(gpu_ok, port, dims, blend):
+    grid, values = cases.mlip_case(dims, uniform=False)
+    x = cases.points(4001, len(dims), lo=-1.2, hi=1.2)
+    plan = _lib.Plan.mlip(grid, values, blend)
+    got, k = eval_plan(plan, x, _lib.KERNEL_STRICT)
+    assert k == "mlip_strict"
+    want = port.evalmlip(grid, values, x, blend=blend, threads=4)
+    if blend in (1, 2):  # device exp vs glibc exp
+        assert np.abs(got - want).max() <= 1e-14 * np.abs(want).max()
+    else:
+        assert np.array_equal(bits(got), bits(want))
+    plan.close()
+
+
+@pytest.mark.parametrize("blend", [0, 1, 2, 3, 4, 5])
+@pytest.mark.parametrize("dims", [(10,), (7, 9), (11, 11, 11), (16, 16, 16, 16), (5, 4, 3, 6, 4), (3, 4, 3, 2, 5, 3)])
+def test_mlip_fast(gpu_ok, port, dims, blend):
+    grid, values = cases.mlip_case(dims, uniform=(len(dims) % 2 == 0))
+    x = cases.points(20001, len(dims), lo=-1.2, hi=1.2)
+    # points exactly on knots and on the domain edge
+    x[:50, 0] = np.resize(grid[0], 50)
+    plan = _lib.Plan.mlip(grid, values, blend)
+    got, k = eval_plan(plan, x, _lib.KERNEL_AUTO)
+    assert k == "mlip_pair"
+    want = port.evalmlip(grid, values, x, blend=blend, threads=4)
+    assert np.abs(got - want).max() <= TOL_REL * np.abs(want).max()
+    plan.close()
+
+
+def test_mlip_golden_and_blend_names(gpu_ok):
+    """chebpol-Ex.Rout.save:451-452: ml1(su) - exp(su)."""
+    import math
+
+    su = np.array([i * (1.0 / 9.0) for i in range(10)])
+    su[-1] = 1.0
+    s = np.array([math.pow(v, 3.0) for v in su])
+    ml1 = cb.ipol(np.array([math.exp(v) for v in s]), grid=[s], method="multilin")
+    want = [0.0, 0.0007963441, 0.0023666771, 0.0036681447, 0.0028930495, 0.0111173403, 0.0064666457, 0.0191999204,
+            0.0246303860, 0.0]
+    assert np.allclose(ml1(su) - np.exp(su), want, rtol=0, atol=6e-11)
+    for name in cb.interp.BLENDS:
+        assert np.all(np.isfinite(ml1(su, blend=name)))
+    ml1.close()
+
+
+def test_mlip_nan_terminates(gpu_ok):
+    grid, values = cases.mlip_case((6, 5))
+    for kern in (_lib.KERNEL_AUTO, _lib.KERNEL_STRICT):
+        plan = _lib.Plan.mlip(grid, values, 0)
+        x = np.array([[np.nan, 0.1], [0.2, np.nan], [0.3, 0.4]])
+        got, _ = eval_plan(plan, x, kern)
+        assert np.isnan(got[0]) and np.isnan(got[1]) and np.isfinite(got[2])
+        plan.close()
+
+
+# ------------------------------------------------------------ Floater-Hormann
+@pytest.mark.parametrize("dims,kind,d", [((10,), "uniform", 4), ((12, 9), "mixed", 3), ((10, 8, 7), "mixed", 3),
+                                         ((50, 30, 20), "mixed", 4), ((5, 4, 3, 4), "uniform", 2), ((40, 40, 40), "uniform", 4)])
+def test_fh_strict_bit_exact(gpu_ok, port, dims, kind, d):
+    vals, grid, weights = cases.fh_case(dims, d=d, kind=kind)
+    x = cases.points(1501, len(dims), lo=-1.05, hi=1.05)
+    for j in range(60):  # exact and near knot hits (absolute 10*eps test, src/chebpol.c:195-197)
+        dd = j % len(dims)
+        x[j, dd] = grid[dd][j % len(grid[dd])] + (0.0, 1e-16, -1e-15, 3e-15)[j % 4]
+    plan = _lib.Plan.fh(vals, grid, weights)
+    got, k = eval_plan(plan, x, _lib.KERNEL_STRICT)
+    assert k == "fh_strict"
+    want = port.fh(vals, grid, weights, x, threads=4)
+    assert np.array_equal(bits(got), bits(want))
+    plan.close()
+
+
+def test_fh_goldens_through_ipol(gpu_ok):
+    """chebpol-Ex.Rout.save:416-424 (set.seed(1)): ip(c(0.3,0.8)) and six more values."""
+    from r_rng import RRng
+
+    r = RRng(1)
+    g = np.array([i * (1.0 / 9.0) for i in range(10)])
+    g[-1] = 1.0
+    val = r.runif(100).reshape((10, 10), order="F")
+    ip = cb.ipol(val, grid=[g, g], method="fh")
+    assert abs(ip(np.array([0.3, 0.8]))[0] - 0.2284498) < 5e-8
+    x = r.runif(12).reshape((2, 6), order="F")
+    got = ip(x, threads=2)
+    assert np.allclose(got, [0.74713282, 0.83340490, 0.00568654, 0.70100518, 0.39261432, 0.71810846], rtol=0, atol=5e-9)
+    ip.close()
+
+
+# ----------------------------------------------------- boundary / host pipeline
+def test_stateless_entry_points_and_chunking(gpu_ok, port):
+    dims = (10, 10, 10)
+    cf = cases.cheb_fitted(dims)
+    x = cases.points(300007, 3)
+    want = port.evalcheb(cf, x, threads=8)
+    got = _lib.evalcheb(cf, x, ngpus=1)
+    assert np.abs(got - want).max() <= TOL_REL * np.abs(want).max()
+    # many small chunks through the double-buffered pipeline, odd tail
+    plan = _lib.Plan.cheb(cf)
+    plan.set(_lib.OPT_CHUNK_POINTS, 4099)
+    got2 = plan.eval_host(x)
+    assert np.array_equal(bits(got), bits(got2))
+    assert plan.get(_lib.GET_LAUNCHES) == (300007 + 4098) // 4099
+    plan.close()
+    grid, values = cases.mlip_case((9, 8, 7))
+    xm = cases.points(100003, 3)
+    assert np.abs(_lib.evalmlip(grid, values, xm, 0, 1) - port.evalmlip(grid, values, xm, threads=8)).max() <= 1e-14
+    vals, g, w = cases.fh_case((9, 8, 7))
+    assert np.array_equal(bits(_lib.fh(vals, g, w, xm[:5000], 1)), bits(port.fh(vals, g, w, xm[:5000], threads=8))) or \
+        np.abs(_lib.fh(vals, g, w, xm[:5000], 1) - port.fh(vals, g, w, xm[:5000], threads=8)).max() <= 1e-12
+
+
+def test_empty_and_single_point(gpu_ok, port):
+    cf = cases.cheb_fitted((6, 5))
+    plan = _lib.Plan.cheb(cf)
+    assert plan.eval_host(np.empty((0, 2))).shape == (0,)
+    one = plan.eval_host(np.array([[0.25, -0.5]]))
+    assert abs(one[0] - port.evalcheb(cf, np.array([[0.25, -0.5]]))[0]) <= 1e-14
+    plan.close()
+    ip = cb.chebappx(cases.grid_values(cb.chebknots([6, 5])))
+    assert ip(np.array([0.25, -0.5])).shape == (1,)
+    with pytest.raises(ValueError):
+        ip(np.array([0.1, 0.2, 0.3]))
+    with pytest.warns(UserWarning):
+        assert ip(np.array([0.1, 0.2, 0.3, 0.4])).shape == (2,)
+    ip.close()
+
+
+def test_device_resident_torch(gpu_ok, port):
+    import torch
+
+    dims = (10,) * 5
+    cf = cases.cheb_fitted(dims)
+    x = cases.points(50000, 5)
+    plan = _lib.Plan.cheb(cf)
+    xd = torch.from_numpy(x).cuda()
+    out = plan.eval_torch(xd)
+    torch.cuda.synchronize()
+    want = port.evalcheb(cf, x, threads=8)
+    assert np.abs(out.cpu().numpy() - want).max() <= TOL_REL * np.abs(want).max()
+    assert plan.kernel_used == "cheb_slab"
+    plan.close()
+
+
+def test_full_size_properties(gpu_ok, port):
+    """BASELINE-size shapes: properties that need no full CPU pass.
+    cfg2 tensor (10^5), 2e6 points: (a) partition independence -- evaluating two halves
+    equals evaluating the whole, bitwise; (b) linearity in the coefficients;
+    (c) a strided sample of 2000 points against the oracle."""
+    import torch
+
+    dims = (10,) * 5
+    cf = cases.cheb_fitted(dims)
+    g = torch.Generator(device="cuda").manual_seed(42)
+    xd = torch.rand((2_000_000, 5), generator=g, device="cuda", dtype=torch.float64) * 2 - 1
+    plan = _lib.Plan.cheb(cf)
+    whole = plan.eval_torch(xd)
+    a = plan.eval_torch(xd[:777_777].contiguous())
+    b = plan.eval_torch(xd[777_777:].contiguous())
+    torch.cuda.synchronize()
+    assert torch.equal(whole, torch.cat([a, b]))
+    plan2 = _lib.Plan.cheb(2.0 * cf)
+    twice = plan2.eval_torch(xd)
+    torch.cuda.synchronize()
+    assert torch.equal(twice, 2.0 * whole)  # scaling by 2 is exact in binary FP
+    idx = torch.arange(0, 2_000_000, 1000, device="cuda")
+    want = port.evalcheb(cf, xd[idx].cpu().numpy(), threads=8)
+    assert np.abs(whole[idx].cpu().numpy() - want).max() <= TOL_REL * np.abs(want).max()
+    plan.close()
+    plan2.close()
