@@ -103,9 +103,14 @@ struct chebpol_cuda_plan {
     int kernel_opt = CHEBPOL_CUDA_KERNEL_AUTO;
     int variant = 0;
     int64_t chunk_points = 0;
-    // slab configuration (Chebyshev fast path)
+    // slab configuration (Chebyshev DFMA fast path)
     bool slab_ok = false;
     SlabArgs slab;
+    // DMMA contraction engine (Chebyshev and Floater-Hormann)
+    bool mma_ok = false;
+    MmaArgs mma;
+    double *d_mma = nullptr;  // [nrest][rs] padded rows
+    int *d_ktab = nullptr;    // [kp][3] folded-dim digit rows
     // statistics
     LaunchInfo last = {0, 0, 0, 0};
     int64_t launches = 0;
@@ -164,6 +169,7 @@ static chebpol_cuda_plan *new_plan(int kind, int device, int num_sms, const int 
     }
     memset(&p->pm, 0, sizeof p->pm);
     memset(&p->slab, 0, sizeof p->slab);
+    memset(&p->mma, 0, sizeof p->mma);
     return p;
 }
 
@@ -192,6 +198,8 @@ extern "C" void chebpol_cuda_plan_destroy(chebpol_cuda_plan *p)
     }
     cudaFree(p->d_tensor);
     cudaFree(p->d_padded);
+    cudaFree(p->d_mma);
+    cudaFree(p->d_ktab);
     cudaFree(p->d_grid);
     cudaFree(p->d_weights);
     delete p;
@@ -264,6 +272,54 @@ static void configure_slab(chebpol_cuda_plan *p)
     p->slab_ok = true;
 }
 
+// Row-padded copy of the tensor for the DMMA engine: row r holds the K entries of the
+// folded leading dims (contiguous in the R layout) followed by zeros up to rs.
+static int configure_mma(chebpol_cuda_plan *p, int kind, const double *host_tensor)
+{
+    p->mma_ok = false;
+    int kc = 0;
+    if (!mma_configure(p->mma, kind, p->rank, p->dims, &kc)) return CHEBPOL_CUDA_OK;
+    MmaArgs &m = p->mma;
+    m.pm = p->pm;
+    const size_t rows = (size_t)m.nrest, rs = (size_t)m.rs, K = (size_t)m.K;
+    std::vector<double> padded(rows * rs, 0.0);
+    for (size_t r = 0; r < rows; ++r) {
+        memcpy(&padded[r * rs], host_tensor + r * K, sizeof(double) * K);
+        // basis-table rows (boff[d] + digit_d) of the rest-level digits of r, as int32
+        int *info = reinterpret_cast<int *>(&padded[r * rs + m.kp]);
+        size_t rem = r;
+        for (int l = 0; l < m.nlev; ++l) {
+            const int d = m.nfold + l;
+            info[l] = m.boff[d] + (int)(rem % (size_t)m.dims[d]);
+            rem /= (size_t)m.dims[d];
+        }
+    }
+    std::vector<int> ktab((size_t)m.kp * 3, -1);
+    for (int k = 0; k < m.K; ++k) {
+        int rem = k;
+        for (int l = 0; l < m.nfold; ++l) {
+            ktab[(size_t)k * 3 + l] = m.boff[l] + rem % m.dims[l];
+            rem /= m.dims[l];
+        }
+    }
+    cudaError_t ek = cudaMalloc(&p->d_ktab, sizeof(int) * ktab.size());
+    if (ek != cudaSuccess) return cuda_fail(ek, "cudaMalloc(ktab)");
+    ek = cudaMemcpy(p->d_ktab, ktab.data(), sizeof(int) * ktab.size(), cudaMemcpyHostToDevice);
+    if (ek != cudaSuccess) return cuda_fail(ek, "cudaMemcpy(ktab)");
+    m.ktab = p->d_ktab;
+    cudaError_t e = cudaMalloc(&p->d_mma, sizeof(double) * rows * rs);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(mma tensor)");
+    e = cudaMemcpy(p->d_mma, padded.data(), sizeof(double) * rows * rs, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpy(mma tensor)");
+    m.tensor = p->d_mma;
+    m.grid = p->d_grid;
+    m.weights = p->d_weights;
+    for (int d = 0; d < p->rank; ++d) m.goff[d] = p->goff[d];
+    p->tensor_bytes += sizeof(double) * rows * rs;
+    p->mma_ok = true;
+    return CHEBPOL_CUDA_OK;
+}
+
 extern "C" int chebpol_cuda_plan_cheb(const double *coef, const int *dims, int rank, const double *mid,
                                       const double *ispan, const int *ugm_n, int device,
                                       chebpol_cuda_plan **plan)
@@ -314,6 +370,8 @@ extern "C" int chebpol_cuda_plan_cheb(const double *coef, const int *dims, int r
         p->slab.cf = p->d_padded;
         p->tensor_bytes += sizeof(double) * rows * n0p;
     }
+    rc = configure_mma(p, 0, coef);
+    if (rc) return bail(rc);
     *plan = p;
     return CHEBPOL_CUDA_OK;
 }
@@ -369,6 +427,8 @@ extern "C" int chebpol_cuda_plan_fh(const double *vals, const double *const *gri
     e = cudaMemcpy(p->d_tensor, vals, sizeof(double) * nelem, cudaMemcpyHostToDevice);
     if (e != cudaSuccess) return bail(cuda_fail(e, "cudaMemcpy(vals)"));
     p->tensor_bytes = sizeof(double) * nelem;
+    rc = configure_mma(p, 1, vals);
+    if (rc) return bail(rc);
     *plan = p;
     return CHEBPOL_CUDA_OK;
 }
@@ -421,8 +481,19 @@ static int launch_plan(chebpol_cuda_plan *p, const double *d_x, int64_t npts, do
     LaunchInfo li = {0, 0, 0, 0};
     const bool want_fast = p->kernel_opt != CHEBPOL_CUDA_KERNEL_STRICT;
     const bool aligned16 = (((uintptr_t)d_x) & 15) == 0;
+    // variant: 0 auto (DMMA engine, else DFMA slab kernel, else strict); 1..99999 tuning
+    // code of the DFMA slab kernel; >= 100000 DMMA engine with tuning code variant-100000
+    const bool force_slab = p->variant > 0 && p->variant < 100000;
+    const int mma_variant = p->variant >= 100000 ? p->variant - 100000 : 0;
     if (p->kind == PLAN_CHEB) {
-        if (want_fast && p->slab_ok) {
+        if (want_fast && p->mma_ok && !force_slab) {
+            MmaArgs a = p->mma;
+            a.x = d_x;
+            a.npts = npts;
+            a.out = d_out;
+            e = launch_contract_mma(a, mma_variant, p->num_sms, s, &li);
+        }
+        if (e == cudaErrorNotSupported && want_fast && p->slab_ok && p->variant < 100000) {
             SlabArgs a = p->slab;
             a.x = d_x;
             a.npts = npts;
@@ -469,8 +540,13 @@ static int launch_plan(chebpol_cuda_plan *p, const double *d_x, int64_t npts, do
         a.x = d_x;
         a.npts = npts;
         a.out = d_out;
-        if (want_fast && fh_fast_supported(p->rank, p->dims))
-            e = launch_fh_fast(a, p->variant, p->num_sms, s, &li);
+        if (want_fast && p->mma_ok) {
+            MmaArgs m = p->mma;
+            m.x = d_x;
+            m.npts = npts;
+            m.out = d_out;
+            e = launch_contract_mma(m, mma_variant, p->num_sms, s, &li);
+        }
         if (e == cudaErrorNotSupported) {
             if (p->kernel_opt == CHEBPOL_CUDA_KERNEL_FAST)
                 return fail(CHEBPOL_CUDA_EINVAL, "no fast Floater-Hormann kernel for this shape");

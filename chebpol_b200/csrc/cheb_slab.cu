@@ -80,6 +80,37 @@ struct RowEval {
             for (int p = 0; p < PT; ++p) v[p] = fma(T[p][2 * k + 1], c[k].y, v[p]);
         }
     }
+
+    // two rows at once: 2*PT independent accumulation chains per thread, so one warp
+    // alone covers the DFMA dependent-issue latency
+    __device__ __forceinline__ void dot2(const double *row_a, const double *row_b, double (&va)[PT],
+                                         double (&vb)[PT]) const
+    {
+        const double2 *ra = reinterpret_cast<const double2 *>(row_a);
+        const double2 *rb = reinterpret_cast<const double2 *>(row_b);
+#pragma unroll
+        for (int k = 0; k < N0P / 2; ++k) {
+            const double2 ca = ra[k], cb = rb[k];
+            if (k == 0) {
+#pragma unroll
+                for (int p = 0; p < PT; ++p) {
+                    va[p] = T[p][0] * ca.x;
+                    vb[p] = T[p][0] * cb.x;
+                }
+            } else {
+#pragma unroll
+                for (int p = 0; p < PT; ++p) {
+                    va[p] = fma(T[p][2 * k], ca.x, va[p]);
+                    vb[p] = fma(T[p][2 * k], cb.x, vb[p]);
+                }
+            }
+#pragma unroll
+            for (int p = 0; p < PT; ++p) {
+                va[p] = fma(T[p][2 * k + 1], ca.y, va[p]);
+                vb[p] = fma(T[p][2 * k + 1], cb.y, vb[p]);
+            }
+        }
+    }
 };
 
 // Clenshaw step for PT points: b <- tx*b + (v - b1), b1 <- old b
@@ -104,7 +135,42 @@ __device__ __forceinline__ void clenshaw_finish(const double (&b)[PT], const dou
     for (int p = 0; p < PT; ++p) v[p] = fma(-0.5 * tx[p], b1[p], b[p]);
 }
 
-template <int N0P, int PT, int NW, int MINB>
+// Clenshaw over the n1 rows ending at row_top (row n1-1), descending; RB rows per step
+template <int N0P, int PT, int RB>
+__device__ __forceinline__ void level1_eval(const RowEval<N0P, PT> &re, const double *row_top, int n1,
+                                            const double (&tx1)[PT], double (&v)[PT])
+{
+    double b[PT], b1[PT];
+#pragma unroll
+    for (int p = 0; p < PT; ++p) b[p] = b1[p] = 0.0;
+    const double *row = row_top;
+    int i = n1;
+    if constexpr (RB == 2) {
+        if (i & 1) {
+            double r[PT];
+            re.dot(row, r);
+            clenshaw_step<PT>(b, b1, tx1, r);
+            row -= N0P;
+            --i;
+        }
+        for (; i > 0; i -= 2, row -= 2 * N0P) {
+            double r0[PT], r1[PT];
+            re.dot2(row, row - N0P, r0, r1);
+            clenshaw_step<PT>(b, b1, tx1, r0);
+            clenshaw_step<PT>(b, b1, tx1, r1);
+        }
+    } else {
+#pragma unroll 2
+        for (; i > 0; --i, row -= N0P) {
+            double r[PT];
+            re.dot(row, r);
+            clenshaw_step<PT>(b, b1, tx1, r);
+        }
+    }
+    clenshaw_finish<PT>(b, b1, tx1, v);
+}
+
+template <int N0P, int PT, int NW, int MINB, int RB>
 __global__ void __launch_bounds__(NW * 32, MINB) cheb_slab_kernel(const __grid_constant__ SlabArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -183,34 +249,15 @@ __global__ void __launch_bounds__(NW * 32, MINB) cheb_slab_kernel(const __grid_c
             if (depth == 1) {
                 re.dot(slab, v);
             } else if (depth == 2) {
-                double b[PT], b1[PT];
-#pragma unroll
-                for (int p = 0; p < PT; ++p) b[p] = b1[p] = 0.0;
-                const double *row = slab + (size_t)(n1 - 1) * N0P;
-#pragma unroll 2
-                for (int i1 = n1 - 1; i1 >= 0; --i1, row -= N0P) {
-                    double r[PT];
-                    re.dot(row, r);
-                    clenshaw_step<PT>(b, b1, tx1, r);
-                }
-                clenshaw_finish<PT>(b, b1, tx1, v);
+                level1_eval<N0P, PT, RB>(re, slab + (size_t)(n1 - 1) * N0P, n1, tx1, v);
             } else {
                 double c[PT], c1[PT];
 #pragma unroll
                 for (int p = 0; p < PT; ++p) c[p] = c1[p] = 0.0;
-                const double *row = slab + ((size_t)n2 * n1 - 1) * N0P;
-                for (int i2 = n2 - 1; i2 >= 0; --i2) {
-                    double b[PT], b1[PT];
-#pragma unroll
-                    for (int p = 0; p < PT; ++p) b[p] = b1[p] = 0.0;
-#pragma unroll 2
-                    for (int i1 = n1 - 1; i1 >= 0; --i1, row -= N0P) {
-                        double r[PT];
-                        re.dot(row, r);
-                        clenshaw_step<PT>(b, b1, tx1, r);
-                    }
+                const double *top = slab + ((size_t)n2 * n1 - 1) * N0P;
+                for (int i2 = n2 - 1; i2 >= 0; --i2, top -= (size_t)n1 * N0P) {
                     double w[PT];
-                    clenshaw_finish<PT>(b, b1, tx1, w);
+                    level1_eval<N0P, PT, RB>(re, top, n1, tx1, w);
                     clenshaw_step<PT>(c, c1, tx2, w);
                 }
                 clenshaw_finish<PT>(c, c1, tx2, v);
@@ -270,10 +317,10 @@ __global__ void __launch_bounds__(NW * 32, MINB) cheb_slab_kernel(const __grid_c
     }
 }
 
-template <int N0P, int PT, int NW, int MINB>
+template <int N0P, int PT, int NW, int MINB, int RB = 1>
 cudaError_t launch_one(const SlabArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li)
 {
-    auto kern = cheb_slab_kernel<N0P, PT, NW, MINB>;
+    auto kern = cheb_slab_kernel<N0P, PT, NW, MINB, RB>;
     const int smem = kBarBytes + a.ns * a.stage_stride;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
@@ -310,10 +357,21 @@ bool cheb_slab_supported(int n0, int rank, const int *dims)
 cudaError_t launch_cheb_slab(const SlabArgs &a, int variant, int num_sms, cudaStream_t s, LaunchInfo *li)
 {
 #define CASE(N0P, PT, NW, MINB) return launch_one<N0P, PT, NW, MINB>(a, num_sms, s, li)
+    if (variant == 1) variant = 0;  // "the DFMA slab kernel, default tuning"
     if (variant != 0 && (a.n0p == 10 || a.n0p == 12)) {
-        const int pt = variant / 100, nw = variant % 100;
+        const int rb = variant / 10000 ? variant / 10000 : 1;
+        const int pt = (variant % 10000) / 100, nw = variant % 100;
 #define TUNE(N0P)                                        \
-    if (a.n0p == N0P) {                                  \
+    if (a.n0p == N0P && rb == 2) {                       \
+        if (pt == 3 && nw == 8) return launch_one<N0P, 3, 8, 1, 2>(a, num_sms, s, li); \
+        if (pt == 4 && nw == 8) return launch_one<N0P, 4, 8, 1, 2>(a, num_sms, s, li); \
+        if (pt == 5 && nw == 8) return launch_one<N0P, 5, 8, 1, 2>(a, num_sms, s, li); \
+        if (pt == 6 && nw == 8) return launch_one<N0P, 6, 8, 1, 2>(a, num_sms, s, li); \
+        if (pt == 4 && nw == 4) return launch_one<N0P, 4, 4, 2, 2>(a, num_sms, s, li); \
+        if (pt == 6 && nw == 4) return launch_one<N0P, 6, 4, 1, 2>(a, num_sms, s, li); \
+        if (pt == 3 && nw == 12) return launch_one<N0P, 3, 12, 1, 2>(a, num_sms, s, li); \
+    }                                                    \
+    if (a.n0p == N0P && rb == 1) {                       \
         if (pt == 2 && nw == 8) CASE(N0P, 2, 8, 1);      \
         if (pt == 3 && nw == 8) CASE(N0P, 3, 8, 1);      \
         if (pt == 4 && nw == 8) CASE(N0P, 4, 8, 1);      \

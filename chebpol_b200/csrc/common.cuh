@@ -31,11 +31,12 @@ __device__ __forceinline__ double premap_coord(const PreMap &pm, int d, double v
 enum KernelId {
     K_NONE = 0,
     K_CHEB_STRICT = 10,  // thread-per-point Clenshaw, reference op order, no FMA
-    K_CHEB_SLAB = 11,    // basis-in-registers contraction, TMA-streamed slabs
+    K_CHEB_SLAB = 11,    // basis-in-registers DFMA contraction, TMA-streamed slabs
+    K_CHEB_MMA = 12,     // DMMA (FP64 tensor core) contraction, TMA-streamed rows
     K_MLIP_STRICT = 20,  // thread-per-point, reference op order
     K_MLIP_PAIR = 21,    // lane-pair gather kernel
     K_FH_STRICT = 30,    // thread-per-point nested barycentric, reference op order
-    K_FH_SLAB = 31,      // barycentric-basis contraction, TMA-streamed slabs
+    K_FH_MMA = 32,       // barycentric-basis DMMA contraction, TMA-streamed rows
 };
 
 // ---- launch descriptors filled by api.cu, consumed by the kernel TUs -------
@@ -102,10 +103,42 @@ struct SlabArgs {
     int goff[CP_MAXR];
 };
 
-// Launchers implemented in the kernel TUs.  Each returns cudaGetLastError().
 struct LaunchInfo {
     int grid, block, smem, kernel;
 };
+
+// DMMA contraction engine (contract_mma.cu): f(x) = sum_r W_r(x) * sum_k A_k(x) * C[r][k]
+// where k runs over the first `nfold` dims (folded into the MMA K dimension), r over
+// the remaining dims, A_k / W_r are products of per-dimension basis values
+// (Chebyshev T_i(x_d), or Floater-Hormann barycentric weights).
+struct MmaArgs {
+    const double *tensor;  // [nrest][rs] doubles: row r = the K leading-dim entries of rest index r, zero padded
+    int kind;              // 0 Chebyshev basis, 1 Floater-Hormann basis
+    int rank;
+    int dims[CP_MAXR];
+    int boff[CP_MAXR];     // row offset of dim d in the shared-memory basis table (prefix sum of dims)
+    int sumn;              // sum of dims
+    int nfold;             // leading dims folded into K
+    int K;                 // prod of folded dims
+    int rs;                // row stride in doubles (== 4 or 12 mod 16: conflict-free B loads)
+    int kp;                // 4*KC: padded K; the row's rest-level table offsets (int32) start there
+    int nlev;              // rank - nfold: number of rest levels
+    const int *ktab;       // [kp][3] basis-table rows of the folded dims for each k (-1: padding)
+    int nrest;             // prod of the remaining dims (1 if none)
+    int rows_per_slab;     // multiple of 16
+    int nslabs, ns, stage_bytes, resident;
+    const double *x;
+    int64_t npts;
+    double *out;
+    PreMap pm;
+    const double *grid;    // FH: concatenated knots / weights
+    const double *weights;
+    int goff[CP_MAXR];
+};
+bool mma_configure(MmaArgs &a, int kind, int rank, const int *dims, int *kc_out);
+cudaError_t launch_contract_mma(const MmaArgs &a, int variant, int num_sms, cudaStream_t s, LaunchInfo *li);
+
+// Launchers implemented in the kernel TUs.  Each returns cudaGetLastError().
 cudaError_t launch_cheb_strict(const ChebStrictArgs &a, cudaStream_t s, LaunchInfo *li);
 cudaError_t launch_mlip_strict(const MlipArgs &a, cudaStream_t s, LaunchInfo *li);
 cudaError_t launch_fh_strict(const FhArgs &a, cudaStream_t s, LaunchInfo *li);
@@ -114,6 +147,4 @@ cudaError_t launch_cheb_slab(const SlabArgs &a, int variant, int num_sms, cudaSt
 bool cheb_slab_supported(int n0, int rank, const int *dims);
 cudaError_t launch_mlip_pair(const MlipArgs &a, int variant, int num_sms, cudaStream_t s, LaunchInfo *li);
 bool mlip_pair_supported(int rank, int blend);
-cudaError_t launch_fh_fast(const FhArgs &a, int variant, int num_sms, cudaStream_t s, LaunchInfo *li);
-bool fh_fast_supported(int rank, const int *dims);
 cudaError_t run_fp64_peak(int num_sms, int repeats, cudaStream_t s, double *tflops);

@@ -26,8 +26,20 @@ def bits(a):
     return np.ascontiguousarray(a, dtype=np.float64).view(np.uint64)
 
 
-def eval_plan(plan, x, kernel):
+def assert_close(got, want, tol_rel):
+    """Finite results within tol_rel*max|finite want|; non-finite results (blends 1/2 overflow
+    when extrapolating: exp(2 - 1/w) with w < 0) must be non-finite on both sides."""
+    fin = np.isfinite(want)
+    assert np.array_equal(fin, np.isfinite(got))
+    assert np.array_equal(np.isnan(want), np.isnan(got))
+    if fin.any():
+        scale = np.abs(want[fin]).max()
+        assert np.abs(got[fin] - want[fin]).max() <= tol_rel * scale, (np.abs(got[fin] - want[fin]).max(), scale)
+
+
+def eval_plan(plan, x, kernel, variant=0):
     plan.set(_lib.OPT_KERNEL, kernel)
+    plan.set(_lib.OPT_VARIANT, variant)
     out = plan.eval_host(np.ascontiguousarray(x))
     return out, plan.kernel_used
 
@@ -49,26 +61,39 @@ def test_cheb_strict_bit_exact(gpu_ok, port, dims):
     plan.close()
 
 
+FAST = [("mma", _lib.VARIANT_MMA), ("slab", _lib.VARIANT_SLAB)]
+
+
+def expected_kernel(family, dims):
+    """DMMA engine when dims[0] <= 192 (the folded K), DFMA slab kernel when dims[0] <= 32,
+    otherwise the strict kernel serves the shape (csrc/api.cu: launch_plan)."""
+    if family == "mma":
+        return "cheb_mma" if dims[0] <= 192 else "cheb_strict"
+    return "cheb_slab" if dims[0] <= 32 else "cheb_strict"
+
+
+@pytest.mark.parametrize("family,variant", FAST)
 @pytest.mark.parametrize("dims", CHEB_SHAPES)
-def test_cheb_fast_fitted(gpu_ok, port, dims):
+def test_cheb_fast_fitted(gpu_ok, port, dims, family, variant):
     cf = cases.cheb_fitted(dims)
     x = cases.points(20011, len(dims))
     plan = _lib.Plan.cheb(cf)
-    got, k = eval_plan(plan, x, _lib.KERNEL_AUTO)
-    assert k == ("cheb_slab" if dims[0] <= 32 else "cheb_strict")
+    got, k = eval_plan(plan, x, _lib.KERNEL_AUTO, variant)
+    assert k == expected_kernel(family, dims)
     want = port.evalcheb(cf, x, threads=4)
     scale = np.abs(want).max()
     assert np.abs(got - want).max() <= TOL_REL * scale, (np.abs(got - want).max(), scale)
     plan.close()
 
 
-@pytest.mark.parametrize("dims", [(20, 20), (10,) * 5, (12, 12, 12, 3), (6, 5, 4, 3, 2, 2)])
-def test_cheb_fast_stress_outside_domain(gpu_ok, port, dims):
+@pytest.mark.parametrize("family,variant", FAST)
+@pytest.mark.parametrize("dims", [(20, 20), (10,) * 5, (12, 12, 12, 3), (6, 5, 4, 3, 2, 2), (40, 7), (150,)])
+def test_cheb_fast_stress_outside_domain(gpu_ok, port, dims, family, variant):
     cf = cases.cheb_stress(dims)
     x = cases.points(5003, len(dims), lo=-1.2, hi=1.2)
     plan = _lib.Plan.cheb(cf)
-    got, k = eval_plan(plan, x, _lib.KERNEL_AUTO)
-    assert k == "cheb_slab"
+    got, k = eval_plan(plan, x, _lib.KERNEL_AUTO, variant)
+    assert k == expected_kernel(family, dims)
     want = port.evalcheb(cf, x, threads=4)
     # conditioning bound: sum|c| * prod_d max_k |T_k(x_d)|, |T_k(1.2)| <= cosh(k*acosh(1.2))
     tmax = np.prod([np.cosh((n - 1) * np.arccosh(1.2)) for n in dims])
@@ -139,13 +164,16 @@ def test_cheb_goldens_through_ipol(gpu_ok):
 @pytest.mark.parametrize("dims", [(10,), (7, 9), (11, 11, 11), (16, 16, 16, 16), (5, 4, 3, 6, 4), (3, 4, 3, 2, 5, 3), (3,) * 8])
 def test_mlip_strict(gpu_ok, port, dims, blend):
     grid, values = cases.mlip_case(dims, uniform=False)
-    x = cases.points(4001, len(dims), lo=-1.2, hi=1.2)
+    # blends 1/2 are exp(2 - 1/w): outside the grid (w < 0) they overflow and the result is
+    # numerically meaningless in the reference too, so those two are compared inside the domain
+    ext = 1.0 if blend in (1, 2) else 1.2
+    x = cases.points(4001, len(dims), lo=-ext, hi=ext)
     plan = _lib.Plan.mlip(grid, values, blend)
     got, k = eval_plan(plan, x, _lib.KERNEL_STRICT)
     assert k == "mlip_strict"
     want = port.evalmlip(grid, values, x, blend=blend, threads=4)
     if blend in (1, 2):  # device exp vs glibc exp
-        assert np.abs(got - want).max() <= 1e-14 * np.abs(want).max()
+        assert_close(got, want, 1e-14)
     else:
         assert np.array_equal(bits(got), bits(want))
     plan.close()
@@ -155,14 +183,18 @@ def test_mlip_strict(gpu_ok, port, dims, blend):
 @pytest.mark.parametrize("dims", [(10,), (7, 9), (11, 11, 11), (16, 16, 16, 16), (5, 4, 3, 6, 4), (3, 4, 3, 2, 5, 3)])
 def test_mlip_fast(gpu_ok, port, dims, blend):
     grid, values = cases.mlip_case(dims, uniform=(len(dims) % 2 == 0))
-    x = cases.points(20001, len(dims), lo=-1.2, hi=1.2)
+    # linear blending extrapolates linearly (src/chebpol.c:628-629) and is tested outside the
+    # grid; the other blends are only well conditioned for w in [0,1] (outside, the corner
+    # weights change sign and sum(cw) can cancel to ~0 before the division)
+    ext = 1.2 if blend == 0 else 1.0
+    x = cases.points(20001, len(dims), lo=-ext, hi=ext)
     # points exactly on knots and on the domain edge
     x[:50, 0] = np.resize(grid[0], 50)
     plan = _lib.Plan.mlip(grid, values, blend)
     got, k = eval_plan(plan, x, _lib.KERNEL_AUTO)
     assert k == "mlip_pair"
     want = port.evalmlip(grid, values, x, blend=blend, threads=4)
-    assert np.abs(got - want).max() <= TOL_REL * np.abs(want).max()
+    assert_close(got, want, TOL_REL)
     plan.close()
 
 
@@ -206,6 +238,67 @@ def test_fh_strict_bit_exact(gpu_ok, port, dims, kind, d):
     assert k == "fh_strict"
     want = port.fh(vals, grid, weights, x, threads=4)
     assert np.array_equal(bits(got), bits(want))
+    plan.close()
+
+
+@pytest.mark.parametrize("dims,kind,d", [((10,), "uniform", 4), ((12, 9), "mixed", 3), ((10, 8, 7), "mixed", 3),
+                                         ((50, 30, 20), "mixed", 4), ((5, 4, 3, 4), "uniform", 2), ((40, 40, 40), "uniform", 4),
+                                         ((150, 3), "uniform", 4), ((3, 3, 3, 3, 3), "uniform", 2)])
+def test_fh_fast(gpu_ok, port, dims, kind, d):
+    """DMMA engine with the barycentric basis against the reference's nested num/den recursion.
+
+    Bar: |diff| <= 1e-12*max|f| + 16*eps*Lambda(x)*max|v| pointwise, where
+    Lambda(x) = prod_d sum_i |b_{d,i}(x_d)| is the Lebesgue function of the interpolant.
+    The second term is the "few ULPs accounting for summation order" of the north_star scaled
+    by the conditioning: FH weights alternate in sign, and on irregular grids (cubed, or 5%
+    outside the domain) Lambda reaches 1e4, where the REFERENCE ITSELF is only accurate to
+    ~2e-12 against exact arithmetic (measured with mpmath; DESIGN.md, parity section)."""
+    vals, grid, weights = cases.fh_case(dims, d=d, kind=kind)
+    x = cases.points(6007, len(dims), lo=-1.05, hi=1.05)
+    for j in range(120):  # exact hits, sub-threshold and just-above-threshold distances to knots
+        dd = j % len(dims)
+        x[j, dd] = grid[dd][j % len(grid[dd])] + (0.0, 1e-16, -1e-15, 3e-15, 1e-13, -1e-11)[j % 6]
+    plan = _lib.Plan.fh(vals, grid, weights)
+    got, k = eval_plan(plan, x, _lib.KERNEL_AUTO)
+    assert k == "fh_mma"
+    want = port.fh(vals, grid, weights, x, threads=4)
+    lam = np.ones(x.shape[0])
+    for dd in range(len(dims)):
+        diff = x[:, dd:dd + 1] - grid[dd][None, :]
+        hit = np.abs(diff) < 10 * np.finfo(float).eps
+        with np.errstate(divide="ignore", invalid="ignore"):
+            p = weights[dd][None, :] / diff
+            b = np.abs(p) / np.abs(p.sum(axis=1, keepdims=True))
+        lam *= np.where(hit.any(axis=1), 1.0, b.sum(axis=1))
+    tol = TOL_REL * np.abs(want).max() + 16 * np.finfo(float).eps * lam * np.abs(vals).max()
+    assert np.all(np.abs(got - want) <= tol), (np.abs(got - want).max(), lam.max())
+    # and inside the domain, away from the ill-conditioned fringe, the plain bar holds
+    inside = np.all(np.abs(x) <= 1.0, axis=1) & (lam < 50)
+    assert np.abs(got - want)[inside].max() <= TOL_REL * np.abs(want).max()
+    plan.close()
+
+
+def test_fh_long_grid_falls_back_to_strict(gpu_ok, port):
+    """dims[0] > 192 exceeds the folded K of the DMMA engine: AUTO must serve it with the strict kernel."""
+    vals, grid, weights = cases.fh_case((200, 3), d=4)
+    x = cases.points(3000, 2)
+    plan = _lib.Plan.fh(vals, grid, weights)
+    got, k = eval_plan(plan, x, _lib.KERNEL_AUTO)
+    assert k == "fh_strict"
+    assert np.array_equal(bits(got), bits(port.fh(vals, grid, weights, x, threads=4)))
+    plan.close()
+
+
+def test_fh_fast_far_extrapolation_and_nan(gpu_ok, port):
+    vals, grid, weights = cases.fh_case((30, 20), d=4, kind="uniform")
+    x = np.array([[50.0, 0.3], [-1e6, 2.0], [1e200, 0.0], [0.2, -3e3], [np.nan, 0.1], [0.1, np.nan]])
+    plan = _lib.Plan.fh(vals, grid, weights)
+    got, k = eval_plan(plan, x, _lib.KERNEL_AUTO)
+    want = port.fh(vals, grid, weights, x)
+    assert np.isnan(got[4]) and np.isnan(got[5])
+    fin = np.isfinite(want[:4])
+    assert np.all(np.isfinite(got[:4][fin]))
+    assert np.allclose(got[:4][fin], want[:4][fin], rtol=1e-9)
     plan.close()
 
 
@@ -276,7 +369,7 @@ def test_device_resident_torch(gpu_ok, port):
     torch.cuda.synchronize()
     want = port.evalcheb(cf, x, threads=8)
     assert np.abs(out.cpu().numpy() - want).max() <= TOL_REL * np.abs(want).max()
-    assert plan.kernel_used == "cheb_slab"
+    assert plan.kernel_used == "cheb_mma"
     plan.close()
 
 
