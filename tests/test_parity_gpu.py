@@ -290,15 +290,20 @@ def test_fh_long_grid_falls_back_to_strict(gpu_ok, port):
 
 
 def test_fh_fast_far_extrapolation_and_nan(gpu_ok, port):
+    """Far outside the grid sum_i w_i/(x-k_i) cancels catastrophically (the w_i alternate and
+    nearly sum to zero), so neither the reference nor any reordering of it has correct digits
+    there; the requirement is only: finite where the reference is finite, NaN in -> NaN out,
+    and -- mildly outside (Lambda still moderate) -- agreement within the conditioning bound."""
     vals, grid, weights = cases.fh_case((30, 20), d=4, kind="uniform")
-    x = np.array([[50.0, 0.3], [-1e6, 2.0], [1e200, 0.0], [0.2, -3e3], [np.nan, 0.1], [0.1, np.nan]])
+    x = np.array([[50.0, 0.3], [-1e6, 2.0], [1e200, 0.0], [0.2, -3e3], [np.nan, 0.1], [0.1, np.nan], [1.02, -1.01]])
     plan = _lib.Plan.fh(vals, grid, weights)
     got, k = eval_plan(plan, x, _lib.KERNEL_AUTO)
+    assert k == "fh_mma"
     want = port.fh(vals, grid, weights, x)
     assert np.isnan(got[4]) and np.isnan(got[5])
     fin = np.isfinite(want[:4])
     assert np.all(np.isfinite(got[:4][fin]))
-    assert np.allclose(got[:4][fin], want[:4][fin], rtol=1e-9)
+    assert abs(got[6] - want[6]) <= 1e-9 * max(1.0, abs(want[6]))
     plan.close()
 
 
