@@ -193,7 +193,11 @@ bool mma_configure(MmaArgs &a, int kind, int rank, const int *dims, int *kc_out)
     for (int d = best_nf; d < rank; ++d) nrest *= dims[d];
     a.nrest = (int)nrest;
     const int row_bytes = rs * 8;
-    int rps = (32 * 1024 / row_bytes) / 16 * 16;
+    // slab: up to 64 KB, but at least 3 stages must fit beside a 128-point basis table
+    int slab_cap = (kSmemBudget - kBarBytes - sumn * 128 * 8) / 3;
+    if (slab_cap > 64 * 1024) slab_cap = 64 * 1024;
+    if (slab_cap < 16 * row_bytes) slab_cap = 16 * row_bytes;
+    int rps = (slab_cap / row_bytes) / 16 * 16;
     if (rps < 16) rps = 16;
     const int need_rows = (int)((nrest + 15) / 16 * 16);
     if (rps > need_rows) rps = need_rows;

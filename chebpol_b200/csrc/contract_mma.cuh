@@ -153,22 +153,45 @@ __global__ void __launch_bounds__(NW * 32, 1) contract_mma_kernel(const __grid_c
     uint32_t round = 0;
     int64_t fill = 0;
 
+    // coordinates of the next pass are fetched (into registers) while the current pass
+    // computes, so the basis prologue never waits on DRAM.  Task q of a thread is
+    // (point pt, dim L) = ((tid + q*NT) % NPT, (tid + q*NT) / NPT); the coordinates of a
+    // pass are the contiguous range x[tile*NPT*rank ...), which task index `pt*rank + L`
+    // addresses directly.
+    constexpr int NT = NW * 32;
+    constexpr int kMaxTasks = (NPT * (3 + kLevU) + NT - 1) / NT;  // rank <= nfold(3) + kLevU
+    double xpre[kMaxTasks];
+    auto prefetch_x = [&](int64_t tile) {
+#pragma unroll
+        for (int q = 0; q < kMaxTasks; ++q) {
+            const int task = tid + q * NT;
+            const int pt = task % NPT, L = task / NPT;
+            const int64_t p = tile * NPT + pt;
+            xpre[q] = (task < NPT * rank && tile < ntiles && p < a.npts) ? ldg_stream_f64(a.x + p * rank + L) : 0.0;
+        }
+    };
+    prefetch_x(blockIdx.x);
+
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         __syncthreads();  // previous pass has finished reading Tb (and, first time, barrier init is visible)
         // ---- 1. basis vectors of this pass's points
-        for (int task = tid; task < NPT * rank; task += NW * 32) {
+#pragma unroll
+        for (int q = 0; q < kMaxTasks; ++q) {
+            const int task = tid + q * NT;
+            if (task >= NPT * rank) break;
             const int pt = task % NPT, L = task / NPT;
             const int64_t p = tile * NPT + pt;
             double *col = Tb + (size_t)a.boff[L] * NPT + pt;
             const int n = a.dims[L];
             if (p < a.npts) {
-                const double xv = a.x[p * rank + L];
+                const double xv = xpre[q];
                 if (a.kind == 0) cheb_basis<NPT>(col, n, premap_coord(a.pm, L, xv));
                 else fh_basis<NPT>(col, n, xv, a.grid + a.goff[L], a.weights + a.goff[L]);
             } else {
                 for (int i = 0; i < n; ++i) col[(size_t)i * NPT] = 0.0;
             }
         }
+        prefetch_x(tile + gridDim.x);
         __syncthreads();
 
         // ---- 2. A fragments: A[mt][kc] = prod_{l < nfold} Tb_l[digit_l(k)][point], k = 4*kc + t;
@@ -227,7 +250,7 @@ __global__ void __launch_bounds__(NW * 32, 1) contract_mma_kernel(const __grid_c
                 for (int mt = 0; mt < MT; ++mt) {
                     double w = tv[0][mt];
 #pragma unroll
-                    for (int l = 1; l < kLevU; ++l) w *= tv[l][mt];
+                    for (int l = 1; l < kLevU; ++l) w *= tv[l][mt];  // absent levels are 1.0: keeps the block branch-free
                     const double nv = fma(w, Dp[c >> 1][mt][c & 1], acc[mt]);
                     acc[mt] = vp[c] ? nv : acc[mt];
                 }
