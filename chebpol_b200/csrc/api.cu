@@ -111,6 +111,14 @@ struct chebpol_cuda_plan {
     MmaArgs mma;
     double *d_mma = nullptr;  // [nrest][rs] padded rows
     int *d_ktab = nullptr;    // [kp][3] folded-dim digit rows
+    // multilinear: cell-major expansion of the value table, built on first use
+    double *d_cells = nullptr;
+    int *d_lut = nullptr;     // bucket tables of the cell search
+    int loff[CP_MAXR] = {0}, nbk[CP_MAXR] = {0};
+    double lscale[CP_MAXR] = {0};
+    int64_t cell_bytes = 0;   // 0: shape not supported / disabled
+    int64_t ncells = 0;
+    bool cells_failed = false;
     // statistics
     LaunchInfo last = {0, 0, 0, 0};
     int64_t launches = 0;
@@ -200,6 +208,8 @@ extern "C" void chebpol_cuda_plan_destroy(chebpol_cuda_plan *p)
     cudaFree(p->d_padded);
     cudaFree(p->d_mma);
     cudaFree(p->d_ktab);
+    cudaFree(p->d_cells);
+    cudaFree(p->d_lut);
     cudaFree(p->d_grid);
     cudaFree(p->d_weights);
     delete p;
@@ -401,6 +411,46 @@ extern "C" int chebpol_cuda_plan_mlip(const double *const *grid, const int *dims
     e = cudaMemcpy(p->d_tensor, values, sizeof(double) * nelem, cudaMemcpyHostToDevice);
     if (e != cudaSuccess) return bail(cuda_fail(e, "cudaMemcpy(values)"));
     p->tensor_bytes = sizeof(double) * nelem;
+    // bucket tables for the cell search: 4 buckets per knot interval on average; entry b is
+    // the reference bisection's answer for the bucket's left edge
+    {
+        std::vector<int> lut;
+        for (int d = 0; d < rank; ++d) {
+            const int n = dims[d];
+            const double *g = grid[d];
+            int nb = 1;
+            while (nb < 4 * n && nb < 4096) nb <<= 1;
+            const double span = g[n - 1] - g[0];
+            const double scale = span > 0 ? nb / span : 0.0;
+            p->loff[d] = (int)lut.size();
+            p->nbk[d] = nb;
+            p->lscale[d] = scale;
+            for (int b = 0; b < nb; ++b) {
+                const double edge = g[0] + (scale > 0 ? b / scale : 0.0);
+                int lo = 0, hi = n - 1;  // src/chebpol.c:543-556
+                while (lo + 1 < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (g[mid] >= edge) hi = mid;
+                    else lo = mid;
+                }
+                lut.push_back(hi);
+            }
+        }
+        e = cudaMalloc(&p->d_lut, sizeof(int) * lut.size());
+        if (e != cudaSuccess) return bail(cuda_fail(e, "cudaMalloc(lut)"));
+        e = cudaMemcpy(p->d_lut, lut.data(), sizeof(int) * lut.size(), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) return bail(cuda_fail(e, "cudaMemcpy(lut)"));
+    }
+    // cell-major expansion (mlip_cell.cu) is built lazily, on the first evaluation large
+    // enough to amortise it; capped by CHEBPOL_CUDA_CELL_MAX_GB (default 16) and free memory
+    p->cell_bytes = mlip_cell_bytes(rank, dims);
+    p->ncells = 1;
+    for (int d = 0; d < rank; ++d) p->ncells *= dims[d] - 1;
+    {
+        double cap_gb = 16.0;
+        if (const char *env = getenv("CHEBPOL_CUDA_CELL_MAX_GB")) cap_gb = atof(env);
+        if ((double)p->cell_bytes > cap_gb * 1e9) p->cell_bytes = 0;
+    }
     *plan = p;
     return CHEBPOL_CUDA_OK;
 }
@@ -523,7 +573,31 @@ static int launch_plan(chebpol_cuda_plan *p, const double *d_x, int64_t npts, do
         a.x = d_x;
         a.npts = npts;
         a.out = d_out;
-        if (want_fast && aligned16 && mlip_pair_supported(p->rank, p->blend))
+        a.lut = p->d_lut;
+        for (int i = 0; i < p->rank; ++i) { a.loff[i] = p->loff[i]; a.nb[i] = p->nbk[i]; a.lscale[i] = p->lscale[i]; }
+        // variant: 0 auto, 1 pair-gather kernel, 2 cell-major kernel (always expand),
+        // >= 20 cell-major kernel with layout code warps*10 + stages
+        const bool allow_cell = p->variant == 0 || p->variant >= 2;
+        if (want_fast && allow_cell && p->cell_bytes > 0 && !p->d_cells && !p->cells_failed &&
+            (p->variant >= 2 || npts >= p->ncells / 8)) {
+            size_t free_b = 0, total_b = 0;
+            cudaError_t ce = cudaMemGetInfo(&free_b, &total_b);
+            if (ce == cudaSuccess && (size_t)p->cell_bytes < free_b / 2) ce = cudaMalloc(&p->d_cells, (size_t)p->cell_bytes);
+            else if (ce == cudaSuccess) ce = cudaErrorMemoryAllocation;
+            if (ce == cudaSuccess) ce = mlip_expand(a, p->d_tensor, p->d_cells, s);
+            if (ce != cudaSuccess) {
+                (void)cudaGetLastError();
+                cudaFree(p->d_cells);
+                p->d_cells = nullptr;
+                p->cells_failed = true;  // fall back to the pair kernel for the plan's lifetime
+            } else {
+                p->tensor_bytes += p->cell_bytes;
+                p->launches += 1;
+                g_launches.fetch_add(1);
+            }
+        }
+        if (want_fast && allow_cell && p->d_cells) e = launch_mlip_cell(a, p->d_cells, p->variant, p->num_sms, s, &li);
+        if (e == cudaErrorNotSupported && want_fast && p->variant < 2 && aligned16 && mlip_pair_supported(p->rank, p->blend))
             e = launch_mlip_pair(a, p->variant, p->num_sms, s, &li);
         if (e == cudaErrorNotSupported) {
             if (p->kernel_opt == CHEBPOL_CUDA_KERNEL_FAST)

@@ -35,6 +35,7 @@ enum KernelId {
     K_CHEB_MMA = 12,     // DMMA (FP64 tensor core) contraction, TMA-streamed rows
     K_MLIP_STRICT = 20,  // thread-per-point, reference op order
     K_MLIP_PAIR = 21,    // lane-pair gather kernel
+    K_MLIP_CELL = 22,    // cell-major table: one contiguous 2^D block per point
     K_FH_STRICT = 30,    // thread-per-point nested barycentric, reference op order
     K_FH_MMA = 32,       // barycentric-basis DMMA contraction, TMA-streamed rows
 };
@@ -62,6 +63,12 @@ struct MlipArgs {
     const double *x;
     int64_t npts;
     double *out;
+    // bucket table that accelerates the cell search (mlip_cell.cu): per dim, lut[b] is the
+    // reference bisection's answer for the left edge of bucket b of [g_0, g_{n-1}]
+    const int *lut;
+    int loff[CP_MAXR];     // offset of dim d's table in `lut`
+    int nb[CP_MAXR];       // buckets of dim d
+    double lscale[CP_MAXR];  // buckets per unit length: nb / (g_{n-1} - g_0)
 };
 
 struct FhArgs {
@@ -147,4 +154,7 @@ cudaError_t launch_cheb_slab(const SlabArgs &a, int variant, int num_sms, cudaSt
 bool cheb_slab_supported(int n0, int rank, const int *dims);
 cudaError_t launch_mlip_pair(const MlipArgs &a, int variant, int num_sms, cudaStream_t s, LaunchInfo *li);
 bool mlip_pair_supported(int rank, int blend);
+int64_t mlip_cell_bytes(int rank, const int *dims);
+cudaError_t mlip_expand(const MlipArgs &a, const double *values, double *cells, cudaStream_t s);
+cudaError_t launch_mlip_cell(const MlipArgs &a, const double *cells, int variant, int num_sms, cudaStream_t s, LaunchInfo *li);
 cudaError_t run_fp64_peak(int num_sms, int repeats, cudaStream_t s, double *tflops);

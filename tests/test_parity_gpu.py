@@ -179,9 +179,10 @@ def test_mlip_strict(gpu_ok, port, dims, blend):
     plan.close()
 
 
+@pytest.mark.parametrize("family,variant", [("mlip_pair", _lib.VARIANT_MLIP_PAIR), ("mlip_cell", _lib.VARIANT_MLIP_CELL)])
 @pytest.mark.parametrize("blend", [0, 1, 2, 3, 4, 5])
 @pytest.mark.parametrize("dims", [(10,), (7, 9), (11, 11, 11), (16, 16, 16, 16), (5, 4, 3, 6, 4), (3, 4, 3, 2, 5, 3)])
-def test_mlip_fast(gpu_ok, port, dims, blend):
+def test_mlip_fast(gpu_ok, port, dims, blend, family, variant):
     grid, values = cases.mlip_case(dims, uniform=(len(dims) % 2 == 0))
     # linear blending extrapolates linearly (src/chebpol.c:628-629) and is tested outside the
     # grid; the other blends are only well conditioned for w in [0,1] (outside, the corner
@@ -191,10 +192,27 @@ def test_mlip_fast(gpu_ok, port, dims, blend):
     # points exactly on knots and on the domain edge
     x[:50, 0] = np.resize(grid[0], 50)
     plan = _lib.Plan.mlip(grid, values, blend)
-    got, k = eval_plan(plan, x, _lib.KERNEL_AUTO)
-    assert k == "mlip_pair"
+    got, k = eval_plan(plan, x, _lib.KERNEL_AUTO, variant)
+    assert k == family
     want = port.evalmlip(grid, values, x, blend=blend, threads=4)
     assert_close(got, want, TOL_REL)
+    plan.close()
+
+
+def test_mlip_auto_picks_cell_layout_when_amortised(gpu_ok, port):
+    """AUTO expands the table to the cell-major layout once a batch is large enough (>= cells/8)
+    and keeps using it; small batches before that use the pair-gather kernel."""
+    grid, values = cases.mlip_case((16, 16, 16, 16), uniform=False)
+    plan = _lib.Plan.mlip(grid, values, 0)
+    small = cases.points(1000, 4)
+    _, k = eval_plan(plan, small, _lib.KERNEL_AUTO)
+    assert k == "mlip_pair"
+    big = cases.points(30000, 4, lo=-1.2, hi=1.2)
+    got, k = eval_plan(plan, big, _lib.KERNEL_AUTO)
+    assert k == "mlip_cell"
+    assert_close(got, port.evalmlip(grid, values, big, threads=4), TOL_REL)
+    _, k = eval_plan(plan, small, _lib.KERNEL_AUTO)
+    assert k == "mlip_cell"
     plan.close()
 
 
