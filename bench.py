@@ -59,6 +59,19 @@ def steps_per_eval(dims):
     return s
 
 
+def load_traffic(kernel, cfg_id, npts):
+    """DRAM bytes per launch from the committed ncu capture of this kernel (None if not captured for this config)."""
+    p = os.path.join(ROOT, "profiles", "traffic_r01.json")
+    try:
+        with open(p) as f:
+            t = json.load(f).get(kernel)
+        if t and t.get("cfg") == cfg_id:
+            return t["bytes_per_point"] * npts
+    except (OSError, ValueError):
+        pass
+    return None
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -340,7 +353,8 @@ def run_ours(args, cfg):
             flop = 2.0 * steps_per_eval(cfg["dims"])
             achieved = flop * npts / (kernel_ms * 1e-3) / 1e12
             roofline = {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
-                        "frac": achieved / fp64_peak if fp64_peak else None, "traffic": None,
+                        "frac": achieved / fp64_peak if fp64_peak else None,
+                        "traffic": load_traffic(kernel_used, args.config, npts),
                         "peak_source": "DFMA-only kernel measured in this run (MEASURED_PEAKS.json has no FP64 peak); "
                                        "nominal 148 SM x 64 FMA/clk x 2 x 1.965 GHz = 37.2",
                         "flop_per_eval": flop, "kernel": kernel_used, "kernel_ms": kernel_ms}
@@ -348,7 +362,8 @@ def run_ours(args, cfg):
             byts = 8.0 * (k + 1 + 2 ** k)
             achieved = byts * npts / (kernel_ms * 1e-3) / 1e9
             roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                        "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": f"MEASURED_PEAKS.json ({peak_src})",
+                        "frac": achieved / peaks["hbm_gbs"], "traffic": load_traffic(kernel_used, args.config, npts),
+                        "peak_source": f"MEASURED_PEAKS.json ({peak_src})",
                         "bytes_per_eval": byts, "kernel": kernel_used, "kernel_ms": kernel_ms}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,

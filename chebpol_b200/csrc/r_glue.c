@@ -1,0 +1,178 @@
+/* r_glue.c -- the .Call boundary of chebpol rebound to libchebpol_cuda.
+ *
+ * Drop-in replacements for the three hot-path entry points of the reference,
+ * with the SAME argument lists, the same validation and error messages, and the
+ * same return value (a fresh REALSXP of length P, no dim attribute):
+ *
+ *   R_evalcheb_cuda(coef, inx, Rthreads, spare)            <- R_evalcheb, src/chebpol.c:340-381
+ *   R_evalmlip_cuda(sgrid, values, x, Rthreads, Sblend)    <- R_evalmlip, src/chebpol.c:670-707
+ *   R_FH_cuda(inx, vals, grid, Sweights, Rthreads, spare)  <- R_FH,       src/chebpol.c:220-265
+ *
+ * `spare` (unused in the reference, :347 and :227) carries the per-call pre-map of the
+ * closure so that it runs inside the kernel instead of in R:
+ *   NULL                          no pre-map (chebappx without intervals)
+ *   list(mid=, ispan=)            imap, R/chebyshev.R:223-227
+ *   list(ugm=dims[, mid=, ispan=]) uniform-grid map, R/uniform.R:6,58-77
+ * `Rthreads` keeps its slot; a value <= 0 means "all visible GPUs", otherwise it is the
+ * number of GPUs to spread the point batch over (CHEBPOL_CUDA_GPUS overrides).
+ *
+ * Errors: the C ABI never longjmps.  The glue validates on R's main thread, calls the
+ * library, and only then -- with nothing of its own left to free -- turns a non-zero
+ * return code into error(), exactly where the reference raises its errors.
+ *
+ * This file needs R's headers (R.h, Rdefines.h, R_ext/Rdynload.h).  R is not installed
+ * in the build image; it is compile-checked against the declarations in oracle/shim
+ * (`make -C chebpol_b200/csrc rglue-check`) and is NOT part of libchebpol_cuda.so.
+ * INTEGRATION.md shows the registration-table and closure patches that go with it.
+ */
+#include <R.h>
+#include <Rdefines.h>
+#include <R_ext/Rdynload.h>
+#include <stdlib.h>
+#include "../../include/chebpol_cuda.h"
+
+#define UNUSED(x) (void)(x)
+
+static int gpus_from_threads(SEXP Rthreads)
+{
+    const char *env = getenv("CHEBPOL_CUDA_GPUS");
+    if (env) return atoi(env);
+    (void)INTEGER(AS_INTEGER(Rthreads))[0]; /* same coercion (and same error) as the reference */
+    return 0;                               /* all visible GPUs */
+}
+
+static SEXP list_elt(SEXP list, const char *name)
+{
+    if (isNull(list)) return R_NilValue;
+    SEXP names = getAttrib(list, R_NamesSymbol);
+    for (int i = 0; i < LENGTH(list); i++)
+        if (strcmp(CHAR(STRING_ELT(names, i)), name) == 0) return VECTOR_ELT(list, i);
+    return R_NilValue;
+}
+
+static void raise(int rc)
+{
+    if (rc != CHEBPOL_CUDA_OK)
+        error("chebpol_cuda: %s (%s)", chebpol_cuda_strerror(rc), chebpol_cuda_last_error());
+}
+
+SEXP R_evalcheb_cuda(SEXP coef, SEXP inx, SEXP Rthreads, SEXP spare)
+{
+    int *dims;
+    int siz = 1;
+    double *cf = REAL(coef);
+    SEXP dim;
+    int rank;
+    /* checks and messages of src/chebpol.c:349-365 */
+    dim = getAttrib(coef, R_DimSymbol);
+    dims = INTEGER(dim);
+    rank = LENGTH(dim);
+    if (rank <= 0) error("rank must be positive");
+    if (isMatrix(inx)) {
+        if (rank != nrows(inx))
+            error("coeffcient rank(%d) must match number of rows(%d)", LENGTH(dim), nrows(inx));
+    } else {
+        if (rank != LENGTH(inx))
+            error("coefficient rank(%d) does not match argument length(%d)", LENGTH(dim), LENGTH(inx));
+    }
+    for (int i = 0; i < rank; i++) siz *= dims[i];
+    if (LENGTH(coef) != siz)
+        error("coefficient length(%d) does not match data length(%d)", LENGTH(coef), siz);
+
+    const double *mid = NULL, *ispan = NULL;
+    const int *ugm = NULL;
+    SEXP smid = list_elt(spare, "mid"), sispan = list_elt(spare, "ispan"), sugm = list_elt(spare, "ugm");
+    if (!isNull(smid) && !isNull(sispan)) {
+        if (LENGTH(smid) != rank || LENGTH(sispan) != rank) error("mid/ispan must have one entry per dimension");
+        mid = REAL(smid);
+        ispan = REAL(sispan);
+    }
+    if (!isNull(sugm)) {
+        if (LENGTH(sugm) != rank) error("ugm must have one entry per dimension");
+        ugm = INTEGER(sugm);
+    }
+    const int ngpus = gpus_from_threads(Rthreads);
+    const R_xlen_t numvec = isMatrix(inx) ? ncols(inx) : 1;
+    SEXP resvec = PROTECT(NEW_NUMERIC(numvec));
+    const int rc = chebpol_cuda_evalcheb(cf, dims, rank, REAL(inx), (int64_t)numvec, mid, ispan, ugm, ngpus,
+                                         REAL(resvec));
+    UNPROTECT(1);
+    raise(rc);
+    return resvec;
+}
+
+SEXP R_evalmlip_cuda(SEXP sgrid, SEXP values, SEXP x, SEXP Rthreads, SEXP Sblend)
+{
+    const int rank = LENGTH(sgrid);
+    int gridsize = 1;
+    int blend = 0;
+    /* checks and messages of src/chebpol.c:677-692 */
+    if (!IS_NUMERIC(values)) error("values must be numeric");
+    if (!IS_NUMERIC(x)) error("argument x must be numeric");
+    if (isMatrix(x) ? (nrows(x) != rank) : (LENGTH(x) != rank))
+        error("grid has dimension %d, you supplied a length %d vector", rank, isMatrix(x) ? nrows(x) : LENGTH(x));
+    if (rank <= 0 || rank > CHEBPOL_CUDA_MAXRANK) error("rank must be positive");
+    int dims[CHEBPOL_CUDA_MAXRANK];
+    const double *grid[CHEBPOL_CUDA_MAXRANK];
+    for (int i = 0; i < rank; i++) {
+        dims[i] = LENGTH(VECTOR_ELT(sgrid, i));
+        grid[i] = REAL(VECTOR_ELT(sgrid, i));
+        gridsize *= dims[i];
+    }
+    if (LENGTH(values) != gridsize) error("grid has size %d, you supplied %d values", gridsize, LENGTH(values));
+    if (!isNull(Sblend)) blend = INTEGER(AS_INTEGER(Sblend))[0];
+    const int ngpus = gpus_from_threads(Rthreads);
+    const R_xlen_t numvec = isMatrix(x) ? ncols(x) : 1;
+    SEXP resvec = PROTECT(NEW_NUMERIC(numvec));
+    const int rc = chebpol_cuda_evalmlip(grid, dims, rank, REAL(values), REAL(x), (int64_t)numvec, blend, ngpus,
+                                         REAL(resvec));
+    UNPROTECT(1);
+    raise(rc);
+    return resvec;
+}
+
+SEXP R_FH_cuda(SEXP inx, SEXP vals, SEXP grid, SEXP Sweights, SEXP Rthreads, SEXP spare)
+{
+    int *dims;
+    int siz = 1;
+    SEXP dim;
+    int rank;
+    UNUSED(spare);
+    /* checks and messages of src/chebpol.c:229-248 */
+    dim = getAttrib(vals, R_DimSymbol);
+    dims = INTEGER(dim);
+    rank = LENGTH(dim);
+    if (rank <= 0) error("rank must be positive");
+    if (isMatrix(inx)) {
+        if (rank != nrows(inx))
+            error("coeffcient rank(%d) must match number of rows(%d)", LENGTH(dim), nrows(inx));
+    } else {
+        if (rank != LENGTH(inx))
+            error("coefficient rank(%d) does not match argument length(%d)", LENGTH(dim), LENGTH(inx));
+    }
+    for (int i = 0; i < rank; i++) siz *= dims[i];
+    if (LENGTH(vals) != siz) error("coefficient length(%d) does not match data length(%d)", LENGTH(vals), siz);
+    if (LENGTH(grid) != rank) error("There must be one value for each knot");
+    if (rank > CHEBPOL_CUDA_MAXRANK) error("rank must be positive");
+    const double *knots[CHEBPOL_CUDA_MAXRANK], *weights[CHEBPOL_CUDA_MAXRANK];
+    for (int i = 0; i < rank; i++) {
+        knots[i] = REAL(VECTOR_ELT(grid, i));
+        weights[i] = REAL(VECTOR_ELT(Sweights, i));
+    }
+    const int ngpus = gpus_from_threads(Rthreads);
+    const R_xlen_t numvec = isMatrix(inx) ? ncols(inx) : 1;
+    SEXP resvec = PROTECT(NEW_NUMERIC(numvec));
+    const int rc = chebpol_cuda_fh(REAL(vals), knots, weights, dims, rank, REAL(inx), (int64_t)numvec, ngpus,
+                                   REAL(resvec));
+    UNPROTECT(1);
+    raise(rc);
+    return resvec;
+}
+
+/* rows to append to R_CallMethodDef callMethods[] (src/chebpol.c:943-967), same arities
+ * as "evalcheb", "evalmlip", "FH" */
+const R_CallMethodDef chebpol_cuda_callMethods[] = {
+    {"evalcheb_cuda", (DL_FUNC)&R_evalcheb_cuda, 4},
+    {"evalmlip_cuda", (DL_FUNC)&R_evalmlip_cuda, 5},
+    {"FH_cuda", (DL_FUNC)&R_FH_cuda, 6},
+    {NULL, NULL, 0}};

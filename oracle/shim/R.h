@@ -30,7 +30,7 @@ typedef int Rboolean;
 #define REALSXP 14
 #define VECSXP 19
 
-extern SEXP R_NilValue, R_DimSymbol, R_DimNamesSymbol, R_BaseEnv;
+extern SEXP R_NilValue, R_DimSymbol, R_DimNamesSymbol, R_BaseEnv, R_NamesSymbol;
 extern double R_NaReal;
 #define NA_REAL R_NaReal
 
@@ -54,6 +54,8 @@ void Rf_unprotect(int);
 SEXP Rf_allocVector(unsigned int, R_xlen_t);
 SEXP Rf_allocMatrix(unsigned int, int, int);
 SEXP VECTOR_ELT(SEXP, R_xlen_t);
+SEXP STRING_ELT(SEXP, R_xlen_t);
+const char *CHAR(SEXP);
 SEXP SET_VECTOR_ELT(SEXP, R_xlen_t, SEXP);
 SEXP Rf_coerceVector(SEXP, unsigned int);
 SEXP Rf_eval(SEXP, SEXP);

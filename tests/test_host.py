@@ -35,6 +35,12 @@ def test_library_exports_every_declared_symbol():
     assert "oracle_" not in out and "ref_evalcheb" not in out
 
 
+def test_r_glue_compiles_against_shim():
+    """The .Call wrappers (csrc/r_glue.c) type-check against the R API declarations of oracle/shim."""
+    r = subprocess.run(["make", "-C", os.path.join(ROOT, "chebpol_b200", "csrc"), "rglue-check"], capture_output=True, text=True)
+    assert r.returncode == 0 and "r_glue.c: ok" in r.stdout, r.stdout + r.stderr
+
+
 def test_strerror_and_version():
     L = _lib.lib()
     assert L.chebpol_cuda_version() >= 100
