@@ -6,116 +6,210 @@ namespace {
 constexpr int kMaxStages = 8;
 constexpr int kBarBytes = 128;
 constexpr int kSmemBudget = 220 * 1024;
-constexpr int kLevU = 4;
+constexpr int kLevMax = 4;
 }  // namespace
 
-cudaError_t mma_launch_2_1_4(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
-cudaError_t mma_launch_2_1_8(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
-cudaError_t mma_launch_2_2_8(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
-cudaError_t mma_launch_2_4_8(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
-cudaError_t mma_launch_3_1_4(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
-cudaError_t mma_launch_3_1_8(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
-cudaError_t mma_launch_3_2_8(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
-cudaError_t mma_launch_3_4_8(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
-cudaError_t mma_launch_4_1_4(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
-cudaError_t mma_launch_4_1_8(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
-cudaError_t mma_launch_4_2_8(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
-cudaError_t mma_launch_4_4_8(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
-cudaError_t mma_launch_6_1_4(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
-cudaError_t mma_launch_6_1_8(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
-cudaError_t mma_launch_6_2_8(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
-cudaError_t mma_launch_6_4_8(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
-cudaError_t mma_launch_8_1_4(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
-cudaError_t mma_launch_8_1_8(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
-cudaError_t mma_launch_8_2_8(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
-cudaError_t mma_launch_8_4_8(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
-cudaError_t mma_launch_10_1_4(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
-cudaError_t mma_launch_10_1_8(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
-cudaError_t mma_launch_10_2_8(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
-cudaError_t mma_launch_10_2_16(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
-cudaError_t mma_launch_10_4_8(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
-cudaError_t mma_launch_12_1_4(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
-cudaError_t mma_launch_12_1_8(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
-cudaError_t mma_launch_12_2_8(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
-cudaError_t mma_launch_12_4_8(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
-cudaError_t mma_launch_16_1_4(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
-cudaError_t mma_launch_16_1_8(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
-cudaError_t mma_launch_16_2_8(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
-cudaError_t mma_launch_16_3_8(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
-cudaError_t mma_launch_20_1_4(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
-cudaError_t mma_launch_20_1_8(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
-cudaError_t mma_launch_20_2_8(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
-cudaError_t mma_launch_25_1_4(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
-cudaError_t mma_launch_25_1_8(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
-cudaError_t mma_launch_25_1_16(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
-cudaError_t mma_launch_25_2_8(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
-cudaError_t mma_launch_30_1_4(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
-cudaError_t mma_launch_30_1_8(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
-cudaError_t mma_launch_30_2_8(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
-cudaError_t mma_launch_36_1_4(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
-cudaError_t mma_launch_36_1_8(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
-cudaError_t mma_launch_36_1_16(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
-cudaError_t mma_launch_36_2_8(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
-cudaError_t mma_launch_40_1_4(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
-cudaError_t mma_launch_40_1_8(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
-cudaError_t mma_launch_48_1_4(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
-cudaError_t mma_launch_48_1_8(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_2_1_4_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_2_1_4_4(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_2_1_8_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_2_1_8_4(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_2_2_8_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_2_2_8_4(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_2_4_8_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_2_4_8_4(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_3_1_4_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_3_1_4_4(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_3_1_8_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_3_1_8_4(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_3_2_8_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_3_2_8_4(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_3_4_8_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_3_4_8_4(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_4_1_4_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_4_1_4_4(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_4_1_8_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_4_1_8_4(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_4_2_8_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_4_2_8_4(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_4_4_8_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_4_4_8_4(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_6_1_4_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_6_1_4_4(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_6_1_8_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_6_1_8_4(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_6_2_8_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_6_2_8_4(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_6_4_8_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_6_4_8_4(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_8_1_4_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_8_1_4_4(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_8_1_8_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_8_1_8_4(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_8_2_8_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_8_2_8_4(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_8_4_8_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_8_4_8_4(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_10_1_4_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_10_1_4_4(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_10_1_8_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_10_1_8_4(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_10_2_8_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_10_2_8_4(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_10_4_8_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_10_4_8_4(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_12_1_4_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_12_1_4_4(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_12_1_8_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_12_1_8_4(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_12_2_8_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_12_2_8_4(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_12_4_8_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_12_4_8_4(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_16_1_4_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_16_1_4_4(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_16_1_8_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_16_1_8_4(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_16_2_8_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_16_2_8_4(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_16_3_8_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_16_3_8_4(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_20_1_4_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_20_1_4_4(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_20_1_8_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_20_1_8_4(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_20_2_8_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_20_2_8_4(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_25_1_4_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_25_1_4_4(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_25_1_8_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_25_1_8_4(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_25_1_16_4(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_25_2_8_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_25_2_8_4(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_30_1_4_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_30_1_4_4(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_30_1_8_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_30_1_8_4(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_30_2_8_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_30_2_8_4(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_36_1_4_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_36_1_4_4(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_36_1_8_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_36_1_8_4(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_36_1_16_4(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_36_2_8_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_36_2_8_4(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_40_1_4_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_40_1_4_4(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_40_1_8_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_40_1_8_4(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_48_1_4_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_48_1_4_4(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_48_1_8_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_48_1_8_4(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
 
 namespace {
 typedef cudaError_t (*LaunchFn)(const MmaArgs &, int, cudaStream_t, LaunchInfo *);
-struct Inst { int kc, mt, nw; LaunchFn fn; };
+struct Inst { int kc, mt, nw, lev; LaunchFn fn; };
 const Inst kInsts[] = {
-    {2, 1, 4, mma_launch_2_1_4},
-    {2, 1, 8, mma_launch_2_1_8},
-    {2, 2, 8, mma_launch_2_2_8},
-    {2, 4, 8, mma_launch_2_4_8},
-    {3, 1, 4, mma_launch_3_1_4},
-    {3, 1, 8, mma_launch_3_1_8},
-    {3, 2, 8, mma_launch_3_2_8},
-    {3, 4, 8, mma_launch_3_4_8},
-    {4, 1, 4, mma_launch_4_1_4},
-    {4, 1, 8, mma_launch_4_1_8},
-    {4, 2, 8, mma_launch_4_2_8},
-    {4, 4, 8, mma_launch_4_4_8},
-    {6, 1, 4, mma_launch_6_1_4},
-    {6, 1, 8, mma_launch_6_1_8},
-    {6, 2, 8, mma_launch_6_2_8},
-    {6, 4, 8, mma_launch_6_4_8},
-    {8, 1, 4, mma_launch_8_1_4},
-    {8, 1, 8, mma_launch_8_1_8},
-    {8, 2, 8, mma_launch_8_2_8},
-    {8, 4, 8, mma_launch_8_4_8},
-    {10, 1, 4, mma_launch_10_1_4},
-    {10, 1, 8, mma_launch_10_1_8},
-    {10, 2, 8, mma_launch_10_2_8},
-    {10, 2, 16, mma_launch_10_2_16},
-    {10, 4, 8, mma_launch_10_4_8},
-    {12, 1, 4, mma_launch_12_1_4},
-    {12, 1, 8, mma_launch_12_1_8},
-    {12, 2, 8, mma_launch_12_2_8},
-    {12, 4, 8, mma_launch_12_4_8},
-    {16, 1, 4, mma_launch_16_1_4},
-    {16, 1, 8, mma_launch_16_1_8},
-    {16, 2, 8, mma_launch_16_2_8},
-    {16, 3, 8, mma_launch_16_3_8},
-    {20, 1, 4, mma_launch_20_1_4},
-    {20, 1, 8, mma_launch_20_1_8},
-    {20, 2, 8, mma_launch_20_2_8},
-    {25, 1, 4, mma_launch_25_1_4},
-    {25, 1, 8, mma_launch_25_1_8},
-    {25, 1, 16, mma_launch_25_1_16},
-    {25, 2, 8, mma_launch_25_2_8},
-    {30, 1, 4, mma_launch_30_1_4},
-    {30, 1, 8, mma_launch_30_1_8},
-    {30, 2, 8, mma_launch_30_2_8},
-    {36, 1, 4, mma_launch_36_1_4},
-    {36, 1, 8, mma_launch_36_1_8},
-    {36, 1, 16, mma_launch_36_1_16},
-    {36, 2, 8, mma_launch_36_2_8},
-    {40, 1, 4, mma_launch_40_1_4},
-    {40, 1, 8, mma_launch_40_1_8},
-    {48, 1, 4, mma_launch_48_1_4},
-    {48, 1, 8, mma_launch_48_1_8}
+    {2, 1, 4, 2, mma_launch_2_1_4_2},
+    {2, 1, 4, 4, mma_launch_2_1_4_4},
+    {2, 1, 8, 2, mma_launch_2_1_8_2},
+    {2, 1, 8, 4, mma_launch_2_1_8_4},
+    {2, 2, 8, 2, mma_launch_2_2_8_2},
+    {2, 2, 8, 4, mma_launch_2_2_8_4},
+    {2, 4, 8, 2, mma_launch_2_4_8_2},
+    {2, 4, 8, 4, mma_launch_2_4_8_4},
+    {3, 1, 4, 2, mma_launch_3_1_4_2},
+    {3, 1, 4, 4, mma_launch_3_1_4_4},
+    {3, 1, 8, 2, mma_launch_3_1_8_2},
+    {3, 1, 8, 4, mma_launch_3_1_8_4},
+    {3, 2, 8, 2, mma_launch_3_2_8_2},
+    {3, 2, 8, 4, mma_launch_3_2_8_4},
+    {3, 4, 8, 2, mma_launch_3_4_8_2},
+    {3, 4, 8, 4, mma_launch_3_4_8_4},
+    {4, 1, 4, 2, mma_launch_4_1_4_2},
+    {4, 1, 4, 4, mma_launch_4_1_4_4},
+    {4, 1, 8, 2, mma_launch_4_1_8_2},
+    {4, 1, 8, 4, mma_launch_4_1_8_4},
+    {4, 2, 8, 2, mma_launch_4_2_8_2},
+    {4, 2, 8, 4, mma_launch_4_2_8_4},
+    {4, 4, 8, 2, mma_launch_4_4_8_2},
+    {4, 4, 8, 4, mma_launch_4_4_8_4},
+    {6, 1, 4, 2, mma_launch_6_1_4_2},
+    {6, 1, 4, 4, mma_launch_6_1_4_4},
+    {6, 1, 8, 2, mma_launch_6_1_8_2},
+    {6, 1, 8, 4, mma_launch_6_1_8_4},
+    {6, 2, 8, 2, mma_launch_6_2_8_2},
+    {6, 2, 8, 4, mma_launch_6_2_8_4},
+    {6, 4, 8, 2, mma_launch_6_4_8_2},
+    {6, 4, 8, 4, mma_launch_6_4_8_4},
+    {8, 1, 4, 2, mma_launch_8_1_4_2},
+    {8, 1, 4, 4, mma_launch_8_1_4_4},
+    {8, 1, 8, 2, mma_launch_8_1_8_2},
+    {8, 1, 8, 4, mma_launch_8_1_8_4},
+    {8, 2, 8, 2, mma_launch_8_2_8_2},
+    {8, 2, 8, 4, mma_launch_8_2_8_4},
+    {8, 4, 8, 2, mma_launch_8_4_8_2},
+    {8, 4, 8, 4, mma_launch_8_4_8_4},
+    {10, 1, 4, 2, mma_launch_10_1_4_2},
+    {10, 1, 4, 4, mma_launch_10_1_4_4},
+    {10, 1, 8, 2, mma_launch_10_1_8_2},
+    {10, 1, 8, 4, mma_launch_10_1_8_4},
+    {10, 2, 8, 2, mma_launch_10_2_8_2},
+    {10, 2, 8, 4, mma_launch_10_2_8_4},
+    {10, 4, 8, 2, mma_launch_10_4_8_2},
+    {10, 4, 8, 4, mma_launch_10_4_8_4},
+    {12, 1, 4, 2, mma_launch_12_1_4_2},
+    {12, 1, 4, 4, mma_launch_12_1_4_4},
+    {12, 1, 8, 2, mma_launch_12_1_8_2},
+    {12, 1, 8, 4, mma_launch_12_1_8_4},
+    {12, 2, 8, 2, mma_launch_12_2_8_2},
+    {12, 2, 8, 4, mma_launch_12_2_8_4},
+    {12, 4, 8, 2, mma_launch_12_4_8_2},
+    {12, 4, 8, 4, mma_launch_12_4_8_4},
+    {16, 1, 4, 2, mma_launch_16_1_4_2},
+    {16, 1, 4, 4, mma_launch_16_1_4_4},
+    {16, 1, 8, 2, mma_launch_16_1_8_2},
+    {16, 1, 8, 4, mma_launch_16_1_8_4},
+    {16, 2, 8, 2, mma_launch_16_2_8_2},
+    {16, 2, 8, 4, mma_launch_16_2_8_4},
+    {16, 3, 8, 2, mma_launch_16_3_8_2},
+    {16, 3, 8, 4, mma_launch_16_3_8_4},
+    {20, 1, 4, 2, mma_launch_20_1_4_2},
+    {20, 1, 4, 4, mma_launch_20_1_4_4},
+    {20, 1, 8, 2, mma_launch_20_1_8_2},
+    {20, 1, 8, 4, mma_launch_20_1_8_4},
+    {20, 2, 8, 2, mma_launch_20_2_8_2},
+    {20, 2, 8, 4, mma_launch_20_2_8_4},
+    {25, 1, 4, 2, mma_launch_25_1_4_2},
+    {25, 1, 4, 4, mma_launch_25_1_4_4},
+    {25, 1, 8, 2, mma_launch_25_1_8_2},
+    {25, 1, 8, 4, mma_launch_25_1_8_4},
+    {25, 1, 16, 4, mma_launch_25_1_16_4},
+    {25, 2, 8, 2, mma_launch_25_2_8_2},
+    {25, 2, 8, 4, mma_launch_25_2_8_4},
+    {30, 1, 4, 2, mma_launch_30_1_4_2},
+    {30, 1, 4, 4, mma_launch_30_1_4_4},
+    {30, 1, 8, 2, mma_launch_30_1_8_2},
+    {30, 1, 8, 4, mma_launch_30_1_8_4},
+    {30, 2, 8, 2, mma_launch_30_2_8_2},
+    {30, 2, 8, 4, mma_launch_30_2_8_4},
+    {36, 1, 4, 2, mma_launch_36_1_4_2},
+    {36, 1, 4, 4, mma_launch_36_1_4_4},
+    {36, 1, 8, 2, mma_launch_36_1_8_2},
+    {36, 1, 8, 4, mma_launch_36_1_8_4},
+    {36, 1, 16, 4, mma_launch_36_1_16_4},
+    {36, 2, 8, 2, mma_launch_36_2_8_2},
+    {36, 2, 8, 4, mma_launch_36_2_8_4},
+    {40, 1, 4, 2, mma_launch_40_1_4_2},
+    {40, 1, 4, 4, mma_launch_40_1_4_4},
+    {40, 1, 8, 2, mma_launch_40_1_8_2},
+    {40, 1, 8, 4, mma_launch_40_1_8_4},
+    {48, 1, 4, 2, mma_launch_48_1_4_2},
+    {48, 1, 4, 4, mma_launch_48_1_4_4},
+    {48, 1, 8, 2, mma_launch_48_1_8_2},
+    {48, 1, 8, 4, mma_launch_48_1_8_4}
 };
 
 // smallest instantiated KC with 4*KC >= K (0: none)
@@ -126,31 +220,34 @@ int pick_kc(int K)
         if (4 * i.kc >= K && (best == 0 || i.kc < best)) best = i.kc;
     return best;
 }
-
-const Inst *find_inst(int kc, int mt, int nw)
-{
-    for (const auto &i : kInsts)
-        if (i.kc == kc && i.mt == mt && i.nw == nw) return &i;
-    return nullptr;
-}
 }  // namespace
 
-// ring depth that fits beside the basis table of `npt` points; false if not even the minimum fits
+// Ring geometry for `npt` points per pass (steps of 16 tensor rows): slab size, number of
+// slabs, stages.  False if it does not fit in shared memory.
 bool mma_fit_ring(MmaArgs &a, int npt)
 {
     const int left = kSmemBudget - kBarBytes - a.sumn * npt * 8;
     if (left <= 0) return false;
+    const int row_bytes = a.rs * 8;
+    const int64_t need_rows = ((int64_t)a.nrest + 15) / 16 * 16;
+    int slab_cap = left / 3;
+    if (slab_cap > 64 * 1024) slab_cap = 64 * 1024;
+    int64_t rps = slab_cap / row_bytes / 16 * 16;
+    if (rps < 16) rps = 16;
+    if (rps > need_rows) rps = need_rows;
+    a.rows_per_slab = (int)rps;
+    a.nslabs = (int)((a.nrest + rps - 1) / rps);
+    a.stage_bytes = (int)rps * row_bytes;
     int ns = left / a.stage_bytes;
     if (ns > kMaxStages) ns = kMaxStages;
-    if (ns >= a.nslabs) { a.resident = 1; a.ns = a.nslabs; return true; }
+    if (ns >= a.nslabs && ns >= 1) { a.resident = 1; a.ns = a.nslabs; return true; }
     if (ns < 2) return false;
     a.resident = 0;
     a.ns = ns;
     return true;
 }
 
-
-// Choose the folding, padding and ring geometry for a tensor.  Returns false when the
+// Choose the folding and the padded row layout for a tensor.  Returns false when the
 // shape is outside what the engine supports (the caller then uses another kernel).
 bool mma_configure(MmaArgs &a, int kind, int rank, const int *dims, int *kc_out)
 {
@@ -173,6 +270,7 @@ bool mma_configure(MmaArgs &a, int kind, int rank, const int *dims, int *kc_out)
         if (K > 192) break;
         const int kc = pick_kc((int)K);
         if (!kc) break;
+        if (rank - nf > kLevMax) continue;
         const double score = (double)K / (4.0 * kc + (rank - nf) + 1.0);
         if (score > best) { best = score; best_nf = nf; }
     }
@@ -185,30 +283,20 @@ bool mma_configure(MmaArgs &a, int kind, int rank, const int *dims, int *kc_out)
     *kc_out = kc;
     a.kp = 4 * kc;
     a.nlev = rank - best_nf;
-    if (a.nlev > kLevU) return false;
     int rs = a.kp + (a.nlev + 1) / 2;  // coefficients, then nlev int32 table offsets
     while (rs % 16 != 4 && rs % 16 != 12) ++rs;
     a.rs = rs;
     int64_t nrest = 1;
     for (int d = best_nf; d < rank; ++d) nrest *= dims[d];
     a.nrest = (int)nrest;
-    const int row_bytes = rs * 8;
-    // slab: up to 64 KB, but at least 3 stages must fit beside a 128-point basis table
-    int slab_cap = (kSmemBudget - kBarBytes - sumn * 128 * 8) / 3;
-    if (slab_cap > 64 * 1024) slab_cap = 64 * 1024;
-    if (slab_cap < 16 * row_bytes) slab_cap = 16 * row_bytes;
-    int rps = (slab_cap / row_bytes) / 16 * 16;
-    if (rps < 16) rps = 16;
-    const int need_rows = (int)((nrest + 15) / 16 * 16);
-    if (rps > need_rows) rps = need_rows;
-    a.rows_per_slab = rps;
-    a.nslabs = (int)((nrest + rps - 1) / rps);
-    a.stage_bytes = rps * row_bytes;
-    // some (MT, NW) layout must leave room for a ring beside its basis table
+    // some layout must fit
     for (const auto &i : kInsts) {
-        if (i.kc != kc) continue;
+        if (i.kc != kc || i.lev < a.nlev) continue;
         MmaArgs probe = a;
         if (mma_fit_ring(probe, i.nw * i.mt * 8)) {
+            a.rows_per_slab = probe.rows_per_slab;
+            a.nslabs = probe.nslabs;
+            a.stage_bytes = probe.stage_bytes;
             a.ns = probe.ns;
             a.resident = probe.resident;
             return true;
@@ -217,22 +305,25 @@ bool mma_configure(MmaArgs &a, int kind, int rank, const int *dims, int *kc_out)
     return false;
 }
 
-// variant: 0 = default layout for the shape: 8 warps with the most point tiles per warp
-// (MT) whose basis table still leaves room for the ring, else 4 warps;
-// MT*100 + NW forces a layout (tuning / tests).
+// variant 0: default layout -- the smallest LEVU covering the rest levels; 8 warps with the
+// most point tiles per warp (MT) whose basis table leaves room for the ring, else 4 warps.
+// variant MT*100 + NW forces a layout (tuning / tests).
 cudaError_t launch_contract_mma(const MmaArgs &a, int variant, int num_sms, cudaStream_t s, LaunchInfo *li)
 {
     const int kc = pick_kc(a.K);
     if (!kc) return cudaErrorNotSupported;
+    const int lev = a.nlev <= 2 ? 2 : 4;
     if (variant >= 100) {
-        const Inst *i = find_inst(kc, variant / 100, variant % 100);
-        return i ? i->fn(a, num_sms, s, li) : cudaErrorNotSupported;
+        const int mt = variant / 100, nw = variant % 100;
+        for (const auto &i : kInsts)
+            if (i.kc == kc && i.mt == mt && i.nw == nw && i.lev >= lev) return i.fn(a, num_sms, s, li);
+        return cudaErrorNotSupported;
     }
     const Inst *best = nullptr;
     for (int pass = 0; pass < 2 && !best; ++pass) {
         const int nw = pass == 0 ? 8 : 4;
         for (const auto &i : kInsts) {
-            if (i.kc != kc || i.nw != nw) continue;
+            if (i.kc != kc || i.nw != nw || i.lev != lev) continue;
             MmaArgs probe = a;
             if (!mma_fit_ring(probe, i.nw * i.mt * 8)) continue;
             if (!best || i.mt > best->mt) best = &i;

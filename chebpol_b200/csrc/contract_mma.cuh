@@ -40,7 +40,7 @@ namespace mma_detail {
 constexpr int kMaxStages = 8;
 constexpr int kBarBytes = 128;
 constexpr int kSmemBudget = 220 * 1024;
-constexpr int kLevU = 4;  // rest levels (rank - nfold) the engine supports
+constexpr int kLevMax = 4;  // rest levels (rank - nfold) the engine supports
 
 __device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b)
 {
@@ -112,7 +112,10 @@ __device__ __forceinline__ void fh_basis(double *col, int n, double x, const dou
     }
 }
 
-template <int KC, int MT, int NW>
+// KC: K/4 (padded); MT: 8-point tiles per warp; NW: warps; LEVU: compile-time bound (2 or 4) on
+// the number of unfolded ("rest") dims -- absent levels multiply by 1.0 so the epilogue
+// stays branch-free.
+template <int KC, int MT, int NW, int LEVU>
 __global__ void __launch_bounds__(NW * 32, 1) contract_mma_kernel(const __grid_constant__ MmaArgs a)
 {
     constexpr int NPT = NW * MT * 8;  // points per pass
@@ -159,7 +162,7 @@ __global__ void __launch_bounds__(NW * 32, 1) contract_mma_kernel(const __grid_c
     // pass are the contiguous range x[tile*NPT*rank ...), which task index `pt*rank + L`
     // addresses directly.
     constexpr int NT = NW * 32;
-    constexpr int kMaxTasks = (NPT * (3 + kLevU) + NT - 1) / NT;  // rank <= nfold(3) + kLevU
+    constexpr int kMaxTasks = (NPT * (3 + LEVU) + NT - 1) / NT;  // rank <= nfold(3) + LEVU
     double xpre[kMaxTasks];
     auto prefetch_x = [&](int64_t tile) {
 #pragma unroll
@@ -222,7 +225,7 @@ __global__ void __launch_bounds__(NW * 32, 1) contract_mma_kernel(const __grid_c
         // in flight, the D tiles of step q-1 are weighted into `acc` (branch-free, so ptxas
         // can interleave the two).  A step = 16 tensor rows (two 8-row N-tiles).
         double Dp[2][MT][2];          // D tiles of the previous step
-        int ip[4][kLevU];             // basis-table rows of its 4 columns' rest-level digits
+        int ip[4][LEVU];             // basis-table rows of its 4 columns' rest-level digits
         bool vp[4];                   // column valid (row < nrest)
 #pragma unroll
         for (int j = 0; j < 2; ++j)
@@ -232,7 +235,7 @@ __global__ void __launch_bounds__(NW * 32, 1) contract_mma_kernel(const __grid_c
         for (int c = 0; c < 4; ++c) {
             vp[c] = false;
 #pragma unroll
-            for (int l = 0; l < kLevU; ++l) ip[c][l] = 0;
+            for (int l = 0; l < LEVU; ++l) ip[c][l] = 0;
         }
         const double *tcol = Tb + warp * MT * 8 + g;
 
@@ -240,9 +243,9 @@ __global__ void __launch_bounds__(NW * 32, 1) contract_mma_kernel(const __grid_c
             // per column: its table loads are independent of each other (and of the DMMAs)
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-                double tv[kLevU][MT];
+                double tv[LEVU][MT];
 #pragma unroll
-                for (int l = 0; l < kLevU; ++l)
+                for (int l = 0; l < LEVU; ++l)
 #pragma unroll
                     for (int mt = 0; mt < MT; ++mt)
                         tv[l][mt] = (l < nlev) ? tcol[(size_t)ip[c][l] * NPT + mt * 8] : 1.0;
@@ -250,7 +253,7 @@ __global__ void __launch_bounds__(NW * 32, 1) contract_mma_kernel(const __grid_c
                 for (int mt = 0; mt < MT; ++mt) {
                     double w = tv[0][mt];
 #pragma unroll
-                    for (int l = 1; l < kLevU; ++l) w *= tv[l][mt];  // absent levels are 1.0: keeps the block branch-free
+                    for (int l = 1; l < LEVU; ++l) w *= tv[l][mt];  // absent levels are 1.0: keeps the block branch-free
                     const double nv = fma(w, Dp[c >> 1][mt][c & 1], acc[mt]);
                     acc[mt] = vp[c] ? nv : acc[mt];
                 }
@@ -273,7 +276,7 @@ __global__ void __launch_bounds__(NW * 32, 1) contract_mma_kernel(const __grid_c
                 const double *b1p = b0p + (size_t)8 * a.rs;
                 // this step's row info (column c = 2*j + e -> local row r16 + 8j + 2t + e),
                 // clamped to a valid row so the table index is always in range
-                int ic[4][kLevU];
+                int ic[4][LEVU];
                 bool vc[4];
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
@@ -282,7 +285,7 @@ __global__ void __launch_bounds__(NW * 32, 1) contract_mma_kernel(const __grid_c
                     const int lrc = vc[c] ? lr : rows - 1;
                     const int *info = reinterpret_cast<const int *>(slab + (size_t)lrc * a.rs + a.kp);
 #pragma unroll
-                    for (int l = 0; l < kLevU; ++l) ic[c][l] = (l < nlev) ? info[l] : 0;
+                    for (int l = 0; l < LEVU; ++l) ic[c][l] = (l < nlev) ? info[l] : 0;
                 }
 #pragma unroll
                 for (int kc = 0; kc < KC; ++kc) {
@@ -306,7 +309,7 @@ __global__ void __launch_bounds__(NW * 32, 1) contract_mma_kernel(const __grid_c
                 for (int c = 0; c < 4; ++c) {
                     vp[c] = vc[c];
 #pragma unroll
-                    for (int l = 0; l < kLevU; ++l) ip[c][l] = ic[c][l];
+                    for (int l = 0; l < LEVU; ++l) ip[c][l] = ic[c][l];
                 }
             }
 
@@ -347,13 +350,13 @@ __global__ void __launch_bounds__(NW * 32, 1) contract_mma_kernel(const __grid_c
 bool mma_fit_ring(MmaArgs &a, int npt);
 namespace mma_detail {
 
-template <int KC, int MT, int NW>
+template <int KC, int MT, int NW, int LEVU>
 cudaError_t launch_one(const MmaArgs &a_in, int num_sms, cudaStream_t s, LaunchInfo *li)
 {
-    auto kern = contract_mma_kernel<KC, MT, NW>;
+    auto kern = contract_mma_kernel<KC, MT, NW, LEVU>;
     constexpr int NPT = NW * MT * 8;
     MmaArgs a = a_in;
-    if (!mma_fit_ring(a, NPT)) return cudaErrorNotSupported;
+    if (a.nlev > LEVU || !mma_fit_ring(a, NPT)) return cudaErrorNotSupported;
     const int smem = kBarBytes + a.ns * a.stage_bytes + a.sumn * NPT * 8;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
