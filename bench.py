@@ -138,10 +138,10 @@ def cpu_sample_size(orc, cfg, case, threads, target_s):
     n = 2000
     x = cpu_points(n, k)
     dt = max(time_cpu(orc, cfg, case, x, threads), 1e-4)
-    n2 = int(min(max(n * 0.5 / dt, 2000), 2e6))  # ~0.5 s probe
+    n2 = int(min(max(n * 0.5 / dt, 2000), 4e6))  # ~0.5 s probe (first-touch and thread start-up amortised)
     x = cpu_points(n2, k)
     dt = max(time_cpu(orc, cfg, case, x, threads), 1e-4)
-    return int(min(max(n2 * target_s / dt, 2000), 5e7))
+    return int(min(max(n2 * target_s / dt, 2000), 4e8))
 
 
 # --------------------------------------------------------------- clock sampler
@@ -218,7 +218,7 @@ def run_reference(args, cfg):
     case = build_case(cfg)
     threads = os.cpu_count() or 1
     k = len(cfg["dims"])
-    n = cpu_sample_size(orc, cfg, case, threads, target_s=8.0)
+    n = min(cpu_sample_size(orc, cfg, case, threads, target_s=8.0), 50_000_000)
     x = cpu_points(n, k)
     for _ in range(args.warmup):
         time_cpu(orc, cfg, case, x[: max(1000, n // 8)], threads)
@@ -298,7 +298,7 @@ def run_ours(args, cfg):
         evs[i + 1].record(stream)
     torch.cuda.synchronize(dev)
     shard.barrier()
-    launches = cb.launch_count() - l0
+    launches = int(shard.sum_over_ranks(cb.launch_count() - l0, dev))
     clocks = sampler.stop()
     total_ms = evs[0].elapsed_time(evs[-1])
     step_ms = [evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps)]
@@ -341,8 +341,8 @@ def run_ours(args, cfg):
     if rank == 0 and world == 1 and not args.no_cpu:
         orc, okind = get_oracle()
         threads = os.cpu_count() or 1
-        n = cpu_sample_size(orc, cfg, case, threads, target_s=10.0)
-        xs = hx[:n].numpy() if n <= npts else cpu_points(n, k)
+        n = min(cpu_sample_size(orc, cfg, case, threads, target_s=10.0), npts)
+        xs = hx[:n].numpy()
         dt = time_cpu(orc, cfg, case, np.ascontiguousarray(xs), threads)
         cpu_baseline = {"value": n / dt, "unit": UNIT, "cores": threads, "kind": okind,
                         "sample": f"first {n} points of the rank-0 batch, {dt:.1f} s wall"}

@@ -422,3 +422,87 @@ def test_full_size_properties(gpu_ok, port):
     assert np.abs(whole[idx].cpu().numpy() - want).max() <= TOL_REL * np.abs(want).max()
     plan.close()
     plan2.close()
+
+
+# ------------------------------------------------- full-size shapes, size-independent properties
+def test_full_size_multilinear_properties(gpu_ok, port):
+    """BASELINE config 3 table (64^4, cell-major 2 GB), 4e6 points: (a) partition independence,
+    bitwise; (b) exact reproduction at the knots (interpolation property); (c) affine
+    invariance: scaling the table by 2 and adding nothing doubles the result exactly;
+    (d) a strided sample against the oracle."""
+    import torch
+
+    dims = (64,) * 4
+    grid, values = cases.mlip_case(dims)
+    plan = _lib.Plan.mlip(grid, values, 0)
+    g = torch.Generator(device="cuda").manual_seed(7)
+    xd = torch.rand((4_000_000, 4), generator=g, device="cuda", dtype=torch.float64) * 2 - 1
+    whole = plan.eval_torch(xd)
+    assert plan.kernel_used == "mlip_cell"
+    a = plan.eval_torch(xd[:1_234_567].contiguous())
+    b = plan.eval_torch(xd[1_234_567:].contiguous())
+    torch.cuda.synchronize()
+    assert torch.equal(whole, torch.cat([a, b]))
+    # knots: random grid nodes must return the table value exactly (weights are exactly 0/1)
+    rng = np.random.default_rng(1)
+    idx = rng.integers(0, 64, size=(5000, 4))
+    xk = np.stack([grid[d][idx[:, d]] for d in range(4)], axis=1)
+    got = plan.eval_host(np.ascontiguousarray(xk))
+    assert np.array_equal(got, values[idx[:, 0], idx[:, 1], idx[:, 2], idx[:, 3]])
+    plan2 = _lib.Plan.mlip(grid, 2.0 * values, 0)
+    twice = plan2.eval_torch(xd)
+    torch.cuda.synchronize()
+    assert torch.equal(twice, 2.0 * whole)
+    sel = torch.arange(0, 4_000_000, 2000, device="cuda")
+    want = port.evalmlip(grid, values, xd[sel].cpu().numpy(), threads=8)
+    assert np.abs(whole[sel].cpu().numpy() - want).max() <= TOL_REL * np.abs(want).max()
+    plan.close()
+    plan2.close()
+
+
+def test_full_size_fh_properties(gpu_ok, port):
+    """BASELINE config 4 (40^3, d=4), 1e6 points: partition independence, reproduction of the
+    values at the knots (one-hot basis on a knot hit, src/chebpol.c:195-197), constants are
+    reproduced (barycentric weights sum to one), strided sample against the oracle."""
+    import torch
+
+    vals, grid, weights = cases.fh_case((40, 40, 40), d=4)
+    plan = _lib.Plan.fh(vals, grid, weights)
+    g = torch.Generator(device="cuda").manual_seed(8)
+    xd = torch.rand((1_000_000, 3), generator=g, device="cuda", dtype=torch.float64) * 2 - 1
+    whole = plan.eval_torch(xd)
+    assert plan.kernel_used == "fh_mma"
+    a = plan.eval_torch(xd[:333_333].contiguous())
+    b = plan.eval_torch(xd[333_333:].contiguous())
+    torch.cuda.synchronize()
+    assert torch.equal(whole, torch.cat([a, b]))
+    rng = np.random.default_rng(2)
+    idx = rng.integers(0, 40, size=(3000, 3))
+    xk = np.stack([grid[d][idx[:, d]] for d in range(3)], axis=1)
+    got = plan.eval_host(np.ascontiguousarray(xk))
+    assert np.array_equal(got, vals[idx[:, 0], idx[:, 1], idx[:, 2]])
+    pc = _lib.Plan.fh(np.full((40, 40, 40), 3.25), grid, weights)
+    const = pc.eval_torch(xd[:100_000].contiguous()).cpu().numpy()
+    assert np.abs(const - 3.25).max() <= 1e-13
+    sel = torch.arange(0, 1_000_000, 500, device="cuda")
+    want = port.fh(vals, grid, weights, xd[sel].cpu().numpy(), threads=8)
+    assert np.abs(whole[sel].cpu().numpy() - want).max() <= TOL_REL * np.abs(want).max()
+    plan.close()
+    pc.close()
+
+
+def test_multi_gpu_sharding_matches_single(gpu_ok, port):
+    """The in-process partitioner (csrc/api.cu run_sharded): contiguous ranges over all visible
+    GPUs, replicated tensor; with one GPU visible this degenerates to the single-device path."""
+    ngpu = cb.device_count()
+    cf = cases.cheb_fitted((10, 10, 10))
+    x = cases.points(600_011, 3)
+    one = _lib.evalcheb(cf, x, ngpus=1)
+    allg = _lib.evalcheb(cf, x, ngpus=0)
+    assert np.array_equal(bits(one), bits(allg))
+    if ngpu >= 2:
+        two = _lib.evalcheb(cf, x, ngpus=2)
+        assert np.array_equal(bits(one), bits(two))
+    grid, values = cases.mlip_case((12, 11, 10))
+    # (the kernel chosen per device can differ with the shard size, so this one is tolerance-based)
+    assert np.abs(_lib.evalmlip(grid, values, x, 0, 1) - _lib.evalmlip(grid, values, x, 0, 0)).max() <= 1e-14
