@@ -36,7 +36,7 @@ EXPORTS = [
     "chebpol_cuda_plan_cheb", "chebpol_cuda_plan_mlip", "chebpol_cuda_plan_fh",
     "chebpol_cuda_plan_destroy", "chebpol_cuda_plan_eval_device", "chebpol_cuda_plan_eval_host",
     "chebpol_cuda_plan_set", "chebpol_cuda_plan_get", "chebpol_cuda_fp64_peak",
-    "chebpol_cuda_launch_count",
+    "chebpol_cuda_launch_count", "chebpol_cuda_cache_clear",
 ]
 
 
@@ -79,6 +79,8 @@ def lib() -> C.CDLL:
     L.chebpol_cuda_plan_set.argtypes = [_vp, C.c_int, C.c_int64]
     L.chebpol_cuda_plan_get.argtypes = [_vp, C.c_int, C.POINTER(C.c_int64)]
     L.chebpol_cuda_fp64_peak.argtypes = [C.c_int, C.c_int, _dp]
+    L.chebpol_cuda_cache_clear.restype = None
+    L.chebpol_cuda_cache_clear.argtypes = []
     L.chebpol_cuda_launch_count.restype = C.c_int64
     L.chebpol_cuda_launch_count.argtypes = []
     _lib = L
@@ -97,6 +99,10 @@ def device_count() -> int:
     if rc != 0:
         return 0
     return n.value
+
+
+def cache_clear() -> None:
+    lib().chebpol_cuda_cache_clear()
 
 
 def launch_count() -> int:

@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -362,24 +363,7 @@ extern "C" int chebpol_cuda_plan_cheb(const double *coef, const int *dims, int r
     e = cudaMemcpy(p->d_tensor, coef, sizeof(double) * nelem, cudaMemcpyHostToDevice);
     if (e != cudaSuccess) return bail(cuda_fail(e, "cudaMemcpy(tensor)"));
     p->tensor_bytes = sizeof(double) * nelem;
-    configure_slab(p);
-    if (p->slab_ok) {
-        const int n0 = dims[0], n0p = p->slab.n0p;
-        const int64_t rows = nelem / n0;
-        const double *src = coef;
-        std::vector<double> padded;
-        if (n0p != n0) {
-            padded.assign((size_t)rows * n0p, 0.0);
-            for (int64_t r = 0; r < rows; ++r) memcpy(&padded[(size_t)r * n0p], coef + r * n0, sizeof(double) * n0);
-            src = padded.data();
-        }
-        e = cudaMalloc(&p->d_padded, sizeof(double) * rows * n0p);
-        if (e != cudaSuccess) return bail(cuda_fail(e, "cudaMalloc(padded tensor)"));
-        e = cudaMemcpy(p->d_padded, src, sizeof(double) * rows * n0p, cudaMemcpyHostToDevice);
-        if (e != cudaSuccess) return bail(cuda_fail(e, "cudaMemcpy(padded tensor)"));
-        p->slab.cf = p->d_padded;
-        p->tensor_bytes += sizeof(double) * rows * n0p;
-    }
+    configure_slab(p);  // the padded copy for the DFMA slab kernel is made on first use (ensure_slab_tensor)
     rc = configure_mma(p, 0, coef);
     if (rc) return bail(rc);
     *plan = p;
@@ -522,6 +506,20 @@ extern "C" int chebpol_cuda_plan_get(chebpol_cuda_plan *p, int what, int64_t *va
     return CHEBPOL_CUDA_OK;
 }
 
+// Row-padded copy of the tensor for the DFMA slab kernel, made on the device from the
+// resident R-layout tensor the first time that kernel is asked for.
+static int ensure_slab_tensor(chebpol_cuda_plan *p, cudaStream_t s)
+{
+    if (p->d_padded || !p->slab_ok) return CHEBPOL_CUDA_OK;
+    const size_t n0 = (size_t)p->dims[0], n0p = (size_t)p->slab.n0p, rows = (size_t)(p->nelem / p->dims[0]);
+    CU(cudaMalloc(&p->d_padded, sizeof(double) * rows * n0p));
+    CU(cudaMemsetAsync(p->d_padded, 0, sizeof(double) * rows * n0p, s));
+    CU(cudaMemcpy2DAsync(p->d_padded, n0p * 8, p->d_tensor, n0 * 8, n0 * 8, rows, cudaMemcpyDeviceToDevice, s));
+    p->slab.cf = p->d_padded;
+    p->tensor_bytes += sizeof(double) * rows * n0p;
+    return CHEBPOL_CUDA_OK;
+}
+
 // ------------------------------------------------------------------- launch
 // The current device must be p->device.
 static int launch_plan(chebpol_cuda_plan *p, const double *d_x, int64_t npts, double *d_out, cudaStream_t s)
@@ -544,6 +542,8 @@ static int launch_plan(chebpol_cuda_plan *p, const double *d_x, int64_t npts, do
             e = launch_contract_mma(a, mma_variant, p->num_sms, s, &li);
         }
         if (e == cudaErrorNotSupported && want_fast && p->slab_ok && p->variant < 100000) {
+            const int rcs = ensure_slab_tensor(p, s);
+            if (rcs) return rcs;
             SlabArgs a = p->slab;
             a.x = d_x;
             a.npts = npts;
@@ -650,6 +650,95 @@ extern "C" int chebpol_cuda_plan_eval_device(chebpol_cuda_plan *p, const double 
     return rc;
 }
 
+// ------------------------------------------------------------ pageable staging
+// R hands over pageable memory.  cudaMemcpyAsync from pageable memory is staged by the driver
+// on one thread (measured 12 GB/s against 66 GB/s from pinned memory), so large pageable
+// batches go through our own pinned staging buffers, filled and drained by several host
+// threads (OpenMP) while the GPU works on the neighbouring chunks.
+#include <omp.h>
+
+struct Staging {
+    double *in[2] = {nullptr, nullptr};
+    double *out[2] = {nullptr, nullptr};
+    size_t in_bytes = 0, out_bytes = 0;
+};
+static std::vector<Staging *> g_staging_free;
+static std::mutex g_staging_mu;
+static const size_t kStageInBytes = 32u << 20;  // per input staging buffer
+
+static Staging *staging_get(size_t in_bytes, size_t out_bytes)
+{
+    {
+        std::lock_guard<std::mutex> lk(g_staging_mu);
+        for (size_t i = 0; i < g_staging_free.size(); ++i)
+            if (g_staging_free[i]->in_bytes >= in_bytes && g_staging_free[i]->out_bytes >= out_bytes) {
+                Staging *s = g_staging_free[i];
+                g_staging_free.erase(g_staging_free.begin() + i);
+                return s;
+            }
+    }
+    Staging *s = new Staging();
+    bool ok = true;
+    for (int i = 0; i < 2 && ok; ++i) {
+        ok = cudaHostAlloc(&s->in[i], in_bytes, cudaHostAllocPortable) == cudaSuccess &&
+             cudaHostAlloc(&s->out[i], out_bytes, cudaHostAllocPortable) == cudaSuccess;
+    }
+    if (!ok) {
+        (void)cudaGetLastError();
+        for (int i = 0; i < 2; ++i) { cudaFreeHost(s->in[i]); cudaFreeHost(s->out[i]); }
+        delete s;
+        return nullptr;
+    }
+    s->in_bytes = in_bytes;
+    s->out_bytes = out_bytes;
+    return s;
+}
+
+static void staging_put(Staging *s)
+{
+    std::lock_guard<std::mutex> lk(g_staging_mu);
+    if (g_staging_free.size() < 8) { g_staging_free.push_back(s); return; }
+    for (int i = 0; i < 2; ++i) { cudaFreeHost(s->in[i]); cudaFreeHost(s->out[i]); }
+    delete s;
+}
+
+static int staging_threads()
+{
+    static int n = 0;
+    if (n == 0) {
+        const char *e = getenv("CHEBPOL_CUDA_STAGING_THREADS");
+        n = e ? atoi(e) : 0;
+        if (n <= 0) {
+            n = (int)std::thread::hardware_concurrency() / 2;
+            if (n > 8) n = 8;
+        }
+        if (n < 1) n = 1;
+    }
+    return n;
+}
+
+static void par_memcpy(void *dst, const void *src, size_t bytes)
+{
+    const int T = staging_threads();
+    if (T == 1 || bytes < (4u << 20)) { memcpy(dst, src, bytes); return; }
+    const size_t slice = ((bytes + T - 1) / T + 4095) & ~(size_t)4095;
+#pragma omp parallel for num_threads(T) schedule(static)
+    for (int i = 0; i < T; ++i) {
+        const size_t lo = (size_t)i * slice;
+        if (lo < bytes) memcpy((char *)dst + lo, (const char *)src + lo, (lo + slice <= bytes) ? slice : bytes - lo);
+    }
+}
+
+static bool is_pageable(const void *p)
+{
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return true;
+    }
+    return at.type == cudaMemoryTypeUnregistered;
+}
+
 // ------------------------------------------------------------ host pipeline
 static int ensure_pipeline(chebpol_cuda_plan *p, int64_t chunk)
 {
@@ -690,13 +779,70 @@ extern "C" int chebpol_cuda_plan_eval_host(chebpol_cuda_plan *p, const double *x
     if (cur != p->device) CU(cudaSetDevice(p->device));
 
     int64_t chunk = p->chunk_points;
+    // large pageable batches: our own multi-threaded pinned staging (smaller chunks)
+    Staging *stg = nullptr;
+    if (chunk <= 0 && (size_t)npts * p->rank * 8 >= (16u << 20) && (is_pageable(x) || is_pageable(out))) {
+        const int64_t sc = (int64_t)(kStageInBytes / (8 * (size_t)p->rank));
+        stg = staging_get((size_t)sc * p->rank * 8, (size_t)sc * 8);
+        if (stg) chunk = sc;
+    }
     if (chunk <= 0) {
         chunk = (int64_t(128) << 20) / (8 * p->rank);
         if (chunk < (1 << 20)) chunk = 1 << 20;
     }
     if (chunk > npts) chunk = npts;
     int rc = ensure_pipeline(p, chunk);
-    if (rc) return rc;
+    if (rc) { if (stg) staging_put(stg); return rc; }
+    if (stg) {
+        // chunk c: threads fill in[b]; H2D -> kernel -> D2H into out[b]; chunk c-1 is drained to
+        // the caller's buffer while chunk c runs on the GPU
+        const int64_t nch = (npts + chunk - 1) / chunk;
+        auto bail = [&](int code) {
+            cudaStreamSynchronize(p->st_in);
+            cudaStreamSynchronize(p->st_k);
+            cudaStreamSynchronize(p->st_out);
+            staging_put(stg);
+            if (cur != p->device) cudaSetDevice(cur);
+            return code;
+        };
+        auto drain = [&](int64_t c) -> int {
+            const int b = (int)(c & 1);
+            const int64_t off = c * chunk, n = (off + chunk <= npts) ? chunk : npts - off;
+            cudaError_t e = cudaEventSynchronize(p->ev_out[b]);
+            if (e != cudaSuccess) return cuda_fail(e, "D2H (staged)");
+            par_memcpy(out + off, stg->out[b], sizeof(double) * n);
+            return CHEBPOL_CUDA_OK;
+        };
+        for (int64_t c = 0; c < nch; ++c) {
+            const int b = (int)(c & 1);
+            const int64_t off = c * chunk, n = (off + chunk <= npts) ? chunk : npts - off;
+            if (c >= 2) {
+                cudaError_t e = cudaEventSynchronize(p->ev_in[b]);  // staging buffer b has been read
+                if (e != cudaSuccess) return bail(cuda_fail(e, "H2D (staged)"));
+            }
+            par_memcpy(stg->in[b], x + off * p->rank, sizeof(double) * n * p->rank);
+            cudaError_t e = cudaSuccess;
+            if (c >= 2) e = cudaStreamWaitEvent(p->st_in, p->ev_k[b], 0);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(p->d_x[b], stg->in[b], sizeof(double) * n * p->rank, cudaMemcpyHostToDevice, p->st_in);
+            if (e == cudaSuccess) e = cudaEventRecord(p->ev_in[b], p->st_in);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(p->st_k, p->ev_in[b], 0);
+            if (e == cudaSuccess && c >= 2) e = cudaStreamWaitEvent(p->st_k, p->ev_out[b], 0);
+            if (e != cudaSuccess) return bail(cuda_fail(e, "staged pipeline"));
+            rc = launch_plan(p, p->d_x[b], n, p->d_o[b], p->st_k);
+            if (rc) return bail(rc);
+            e = cudaEventRecord(p->ev_k[b], p->st_k);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(p->st_out, p->ev_k[b], 0);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(stg->out[b], p->d_o[b], sizeof(double) * n, cudaMemcpyDeviceToHost, p->st_out);
+            if (e == cudaSuccess) e = cudaEventRecord(p->ev_out[b], p->st_out);
+            if (e != cudaSuccess) return bail(cuda_fail(e, "staged pipeline"));
+            if (c >= 1) {
+                rc = drain(c - 1);
+                if (rc) return bail(rc);
+            }
+        }
+        rc = drain(nch - 1);
+        return bail(rc);
+    }
     const int64_t nchunks = (npts + chunk - 1) / chunk;
     // chunk c uses buffer c&1:  H2D(c) -> kernel(c) -> D2H(c); D2H(c-1) is
     // enqueued after kernel(c) so that a blocking (pageable) copy-out overlaps
@@ -737,12 +883,121 @@ extern "C" int chebpol_cuda_plan_eval_host(chebpol_cuda_plan *p, const double *x
     return CHEBPOL_CUDA_OK;
 }
 
+// ---------------------------------------------------------------- plan cache
+// The R closures re-pass the tensor on every call (no C-side state in the reference), so a
+// stateless call would rebuild and re-upload its plan each time (~4 ms).  Small interpolants
+// are therefore kept in a process-wide cache keyed by the CONTENT of everything that defines
+// the plan (64-bit hash of tensor, knots, weights, pre-map; plus kind, device, dims), so a
+// closure restored by load() or a tensor re-allocated at another address still hits, and a
+// modified tensor never does.  CHEBPOL_CUDA_PLAN_CACHE=0 disables it.
+static uint64_t hash_bytes(const void *data, size_t n, uint64_t seed)
+{
+    const uint64_t M = 0x9E3779B97F4A7C15ull;
+    uint64_t h[4] = {seed ^ 0x243F6A8885A308D3ull, seed ^ 0x13198A2E03707344ull, seed ^ 0xA4093822299F31D0ull, seed ^ 0x082EFA98EC4E6C89ull};
+    const uint64_t *w = static_cast<const uint64_t *>(data);
+    const size_t nw = n / 8;
+    size_t i = 0;
+    for (; i + 4 <= nw; i += 4)
+        for (int j = 0; j < 4; ++j) {
+            h[j] = (h[j] ^ w[i + j]) * M;
+            h[j] ^= h[j] >> 29;
+        }
+    for (; i < nw; ++i) {
+        h[0] = (h[0] ^ w[i]) * M;
+        h[0] ^= h[0] >> 29;
+    }
+    const unsigned char *tail = static_cast<const unsigned char *>(data) + nw * 8;
+    for (size_t k = 0; k < n % 8; ++k) h[1] = (h[1] ^ tail[k]) * M;
+    uint64_t r = (h[0] * 31 + h[1]) * M ^ (h[2] * 17 + h[3]);
+    r ^= r >> 32;
+    return r * M ^ n;
+}
+
+struct CacheKey {
+    int kind, device, rank;
+    int dims[CP_MAXR];
+    uint64_t hash;
+    bool operator==(const CacheKey &o) const
+    {
+        if (kind != o.kind || device != o.device || rank != o.rank || hash != o.hash) return false;
+        for (int i = 0; i < rank; ++i)
+            if (dims[i] != o.dims[i]) return false;
+        return true;
+    }
+};
+struct CacheEntry { CacheKey key; chebpol_cuda_plan *plan; uint64_t stamp; bool busy; };
+static std::mutex g_cache_mu;
+static std::vector<CacheEntry> g_cache;
+static uint64_t g_cache_clock = 0;
+static const size_t kCacheSlots = 8;
+static const int64_t kCacheMaxBytes = 32ll << 20;  // per tensor; larger ones are cheaper to upload than to hash
+
+static bool cache_enabled()
+{
+    static int on = -1;
+    if (on < 0) {
+        const char *e = getenv("CHEBPOL_CUDA_PLAN_CACHE");
+        on = (e && atoi(e) == 0) ? 0 : 1;
+    }
+    return on == 1;
+}
+
+static chebpol_cuda_plan *cache_take(const CacheKey &k)
+{
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    for (auto &e : g_cache)
+        if (!e.busy && e.key == k) {
+            e.busy = true;
+            e.stamp = ++g_cache_clock;
+            return e.plan;
+        }
+    return nullptr;
+}
+
+// give a plan (back) to the cache; takes ownership
+static void cache_put(const CacheKey &k, chebpol_cuda_plan *p)
+{
+    chebpol_cuda_plan *evict = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(g_cache_mu);
+        for (auto &e : g_cache)
+            if (e.plan == p) {
+                e.busy = false;
+                return;
+            }
+        if (g_cache.size() >= kCacheSlots) {
+            size_t victim = g_cache.size();
+            for (size_t i = 0; i < g_cache.size(); ++i)
+                if (!g_cache[i].busy && (victim == g_cache.size() || g_cache[i].stamp < g_cache[victim].stamp)) victim = i;
+            if (victim == g_cache.size()) {
+                evict = p;  // everything busy: do not cache this one
+            } else {
+                evict = g_cache[victim].plan;
+                g_cache.erase(g_cache.begin() + victim);
+            }
+        }
+        if (evict != p) g_cache.push_back({k, p, ++g_cache_clock, false});
+    }
+    if (evict) chebpol_cuda_plan_destroy(evict);
+}
+
+extern "C" void chebpol_cuda_cache_clear(void)
+{
+    std::vector<CacheEntry> old;
+    {
+        std::lock_guard<std::mutex> lk(g_cache_mu);
+        old.swap(g_cache);
+    }
+    for (auto &e : old) chebpol_cuda_plan_destroy(e.plan);
+}
+
 // -------------------------------------------------- stateless entry points
 // Split [0, npts) into contiguous ranges over `ngpus` devices; one host thread
 // per device builds a plan there (replicating the tensor) and runs the host
 // pipeline on its slice.  No collective: every GPU writes its own slice.
 template <class MakePlan>
-static int run_sharded(int rank, const double *x, int64_t npts, int ngpus, double *out, MakePlan make_plan)
+static int run_sharded(int rank, const double *x, int64_t npts, int ngpus, double *out, CacheKey key,
+                       int64_t tensor_bytes, MakePlan make_plan, int blend = -1)
 {
     if (npts < 0) return fail(CHEBPOL_CUDA_EINVAL, "negative point count");
     if (npts > 0 && (!x || !out)) return fail(CHEBPOL_CUDA_EINVAL, "x or out is NULL");
@@ -754,15 +1009,31 @@ static int run_sharded(int rank, const double *x, int64_t npts, int ngpus, doubl
     // do not spread tiny batches
     const int64_t min_per_gpu = 1 << 16;
     while (ngpus > 1 && npts / ngpus < min_per_gpu) --ngpus;
+    const bool cacheable = cache_enabled() && tensor_bytes <= kCacheMaxBytes;
 
-    if (ngpus == 1) {
-        chebpol_cuda_plan *p = nullptr;
-        rc = make_plan(0, &p);
-        if (rc) return rc;
-        rc = chebpol_cuda_plan_eval_host(p, x, npts, out);
-        chebpol_cuda_plan_destroy(p);
-        return rc;
-    }
+    auto on_device = [&](int dev, const double *xs, int64_t n, double *os) -> int {
+        CacheKey k = key;
+        k.device = dev;
+        chebpol_cuda_plan *p = cacheable ? cache_take(k) : nullptr;
+        int r = CHEBPOL_CUDA_OK;
+        if (!p) r = make_plan(dev, &p);
+        if (!r && blend >= 0) p->blend = blend;  // per-call argument of the multilinear closure, not part of the key
+        if (!r && n > 0) r = chebpol_cuda_plan_eval_host(p, xs, n, os);
+        if (p) {
+            if (cacheable && !r) cache_put(k, p);
+            else {
+                if (cacheable) {  // failed: drop it from the cache if it came from there
+                    std::lock_guard<std::mutex> lk(g_cache_mu);
+                    for (size_t i = 0; i < g_cache.size(); ++i)
+                        if (g_cache[i].plan == p) { g_cache.erase(g_cache.begin() + i); break; }
+                }
+                chebpol_cuda_plan_destroy(p);
+            }
+        }
+        return r;
+    };
+
+    if (ngpus == 1) return on_device(0, x, npts, out);
     std::vector<int> rcs(ngpus, 0);
     std::vector<std::string> msgs(ngpus);
     std::vector<std::thread> th;
@@ -771,12 +1042,8 @@ static int run_sharded(int rank, const double *x, int64_t npts, int ngpus, doubl
         th.emplace_back([&, g]() {
             const int64_t lo = (int64_t)g * per;
             const int64_t n = (lo >= npts) ? 0 : ((lo + per <= npts) ? per : npts - lo);
-            chebpol_cuda_plan *p = nullptr;
-            int r = make_plan(g, &p);
-            if (!r && n > 0) r = chebpol_cuda_plan_eval_host(p, x + lo * rank, n, out + lo);
-            chebpol_cuda_plan_destroy(p);
-            rcs[g] = r;
-            if (r) msgs[g] = g_last_error;
+            rcs[g] = on_device(g, x + lo * rank, n, out + lo);
+            if (rcs[g]) msgs[g] = g_last_error;
         });
     }
     for (auto &t : th) t.join();
@@ -788,11 +1055,32 @@ static int run_sharded(int rank, const double *x, int64_t npts, int ngpus, doubl
     return CHEBPOL_CUDA_OK;
 }
 
+static CacheKey make_key(int kind, const int *dims, int rank)
+{
+    CacheKey k;
+    memset(&k, 0, sizeof k);
+    k.kind = kind;
+    k.rank = rank;
+    for (int i = 0; i < rank && i < CP_MAXR; ++i) k.dims[i] = dims[i];
+    return k;
+}
+
 extern "C" int chebpol_cuda_evalcheb(const double *coef, const int *dims, int rank, const double *x,
                                      int64_t npts, const double *mid, const double *ispan,
                                      const int *ugm_n, int ngpus, double *out)
 {
-    return run_sharded(rank, x, npts, ngpus, out, [&](int dev, chebpol_cuda_plan **p) {
+    int64_t nelem = 0;
+    if (!coef) return fail(CHEBPOL_CUDA_EINVAL, "coef is NULL");
+    int rc = check_dims(dims, rank, &nelem);
+    if (rc) return rc;
+    CacheKey key = make_key(PLAN_CHEB, dims, rank);
+    if (cache_enabled() && nelem * 8 <= kCacheMaxBytes) {
+        uint64_t h = hash_bytes(coef, (size_t)nelem * 8, 1);
+        if (mid && ispan) { h = hash_bytes(mid, rank * 8, h); h = hash_bytes(ispan, rank * 8, h); }
+        if (ugm_n) h = hash_bytes(ugm_n, rank * 4, h ^ 0x55);
+        key.hash = h;
+    }
+    return run_sharded(rank, x, npts, ngpus, out, key, nelem * 8, [&](int dev, chebpol_cuda_plan **p) {
         return chebpol_cuda_plan_cheb(coef, dims, rank, mid, ispan, ugm_n, dev, p);
     });
 }
@@ -801,16 +1089,44 @@ extern "C" int chebpol_cuda_evalmlip(const double *const *grid, const int *dims,
                                      const double *values, const double *x, int64_t npts, int blend,
                                      int ngpus, double *out)
 {
-    return run_sharded(rank, x, npts, ngpus, out, [&](int dev, chebpol_cuda_plan **p) {
+    int64_t nelem = 0;
+    if (!grid || !values) return fail(CHEBPOL_CUDA_EINVAL, "grid or values is NULL");
+    if (blend < 0 || blend > 5) return fail(CHEBPOL_CUDA_EBLEND, "blend %d not in 0..5", blend);
+    int rc = check_dims(dims, rank, &nelem);
+    if (rc) return rc;
+    CacheKey key = make_key(PLAN_MLIP, dims, rank);
+    if (cache_enabled() && nelem * 8 <= kCacheMaxBytes) {
+        uint64_t h = hash_bytes(values, (size_t)nelem * 8, 2);
+        for (int d = 0; d < rank; ++d) {
+            if (!grid[d]) return fail(CHEBPOL_CUDA_EINVAL, "grid[%d] is NULL", d);
+            h = hash_bytes(grid[d], (size_t)dims[d] * 8, h);
+        }
+        key.hash = h;
+    }
+    return run_sharded(rank, x, npts, ngpus, out, key, nelem * 8, [&](int dev, chebpol_cuda_plan **p) {
         return chebpol_cuda_plan_mlip(grid, dims, rank, values, blend, dev, p);
-    });
+    }, blend);
 }
 
 extern "C" int chebpol_cuda_fh(const double *vals, const double *const *grid,
                                const double *const *weights, const int *dims, int rank, const double *x,
                                int64_t npts, int ngpus, double *out)
 {
-    return run_sharded(rank, x, npts, ngpus, out, [&](int dev, chebpol_cuda_plan **p) {
+    int64_t nelem = 0;
+    if (!vals || !grid || !weights) return fail(CHEBPOL_CUDA_EINVAL, "vals, grid or weights is NULL");
+    int rc = check_dims(dims, rank, &nelem);
+    if (rc) return rc;
+    CacheKey key = make_key(PLAN_FH, dims, rank);
+    if (cache_enabled() && nelem * 8 <= kCacheMaxBytes) {
+        uint64_t h = hash_bytes(vals, (size_t)nelem * 8, 3);
+        for (int d = 0; d < rank; ++d) {
+            if (!grid[d] || !weights[d]) return fail(CHEBPOL_CUDA_EINVAL, "grid/weights[%d] is NULL", d);
+            h = hash_bytes(grid[d], (size_t)dims[d] * 8, h);
+            h = hash_bytes(weights[d], (size_t)dims[d] * 8, h);
+        }
+        key.hash = h;
+    }
+    return run_sharded(rank, x, npts, ngpus, out, key, nelem * 8, [&](int dev, chebpol_cuda_plan **p) {
         return chebpol_cuda_plan_fh(vals, grid, weights, dims, rank, dev, p);
     });
 }

@@ -141,6 +141,11 @@ CHEBPOL_CUDA_API int chebpol_cuda_plan_get(chebpol_cuda_plan *plan, int what, in
 /* Register-resident DFMA chain on every SM of `device`: the FP64 roofline
  * denominator (MEASURED_PEAKS.json has none).  Returns TFLOP/s (2 flop/FMA). */
 CHEBPOL_CUDA_API int chebpol_cuda_fp64_peak(int device, int repeats, double *tflops);
+/* The stateless entry points keep up to 8 small (<= 32 MB) interpolants resident between
+ * calls, keyed by a 64-bit hash of their content (tensor, knots, weights, pre-map), so the
+ * closure that re-passes its tensor on every call does not re-upload it.  Clearing is never
+ * required for correctness; CHEBPOL_CUDA_PLAN_CACHE=0 disables the cache. */
+CHEBPOL_CUDA_API void chebpol_cuda_cache_clear(void);
 /* total kernels launched by this library in this process */
 CHEBPOL_CUDA_API int64_t chebpol_cuda_launch_count(void);
 

@@ -168,16 +168,16 @@ mine[lo:hi] = torch.from_numpy(np.polynomial.chebyshev.chebval(x[lo:hi], [1.0, 0
 dist.all_reduce(mine)
 assert np.allclose(mine.numpy(), np.polynomial.chebyshev.chebval(x, [1.0, 0.5, 0.25]))
 dist.destroy_process_group()
-print("rank", rank, "ok")
+open(os.path.join({out!r}, "ok_%d" % rank), "w").write("ok")
 """
 
 
 def test_two_rank_gloo_partition(tmp_path):
     script = tmp_path / "w.py"
-    script.write_text(_WORKER.format(root=ROOT))
+    script.write_text(_WORKER.format(root=ROOT, out=str(tmp_path)))
     env = dict(os.environ, MASTER_ADDR="127.0.0.1")
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
                         "--master-addr", "127.0.0.1", "--master-port", "29611", str(script)],
                        capture_output=True, text=True, env=env, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
-    assert "rank 0 ok" in r.stdout and "rank 1 ok" in r.stdout
+    assert (tmp_path / "ok_0").exists() and (tmp_path / "ok_1").exists(), r.stdout + r.stderr

@@ -506,3 +506,42 @@ def test_multi_gpu_sharding_matches_single(gpu_ok, port):
     grid, values = cases.mlip_case((12, 11, 10))
     # (the kernel chosen per device can differ with the shard size, so this one is tolerance-based)
     assert np.abs(_lib.evalmlip(grid, values, x, 0, 1) - _lib.evalmlip(grid, values, x, 0, 0)).max() <= 1e-14
+
+
+def test_stateless_plan_cache_and_pageable_staging(gpu_ok, port):
+    """(a) The stateless entry points cache small interpolants by CONTENT: a second call with the
+    same tensor (even at another address) must not rebuild; a modified tensor must miss.
+    (b) Large pageable batches take the threaded pinned-staging path and give the same bits as
+    the pinned path."""
+    import torch
+
+    cf = cases.cheb_fitted((10, 10, 10))
+    x = cases.points(5000, 3)
+    _lib.cache_clear()
+    a = _lib.evalcheb(cf, x, ngpus=1)
+    b = _lib.evalcheb(cf.copy(order="F"), x, ngpus=1)  # same content, different address: cache hit
+    assert np.array_equal(bits(a), bits(b))
+    cf2 = cf.copy(order="F")
+    cf2[1, 2, 3] += 0.5
+    c = _lib.evalcheb(cf2, x, ngpus=1)
+    assert np.abs(c - port.evalcheb(cf2, x)).max() <= TOL_REL * np.abs(c).max()
+    assert not np.array_equal(bits(a), bits(c))
+    # blends are a per-call argument on a cached multilinear plan
+    grid, values = cases.mlip_case((9, 8, 7))
+    for blend in (0, 3, 0, 4):
+        got = _lib.evalmlip(grid, values, x, blend, 1)
+        assert np.abs(got - port.evalmlip(grid, values, x, blend=blend)).max() <= 1e-13
+    _lib.cache_clear()
+    # pageable vs pinned, > 16 MB so that staging engages; odd size for a ragged last chunk
+    n = 3_000_017
+    xp = torch.empty((n, 3), dtype=torch.float64, pin_memory=True)
+    xp.uniform_(-1, 1, generator=torch.Generator().manual_seed(5))
+    op = torch.empty(n, dtype=torch.float64, pin_memory=True)
+    plan = _lib.Plan.cheb(cf)
+    plan.eval_host_ptr(xp.data_ptr(), n, op.data_ptr())
+    xg = xp.numpy().copy()
+    og = plan.eval_host(xg)
+    assert np.array_equal(bits(og), bits(op.numpy()))
+    sel = slice(0, n, 3001)
+    assert np.abs(og[sel] - port.evalcheb(cf, xg[sel])).max() <= TOL_REL * np.abs(og).max()
+    plan.close()
