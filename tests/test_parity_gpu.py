@@ -102,6 +102,21 @@ def test_cheb_fast_stress_outside_domain(gpu_ok, port, dims, family, variant):
     plan.close()
 
 
+def test_cheb_auto_kernel_choice(gpu_ok, port):
+    """AUTO picks the DFMA slab kernel for small / poorly folding tensors and the DMMA engine for
+    large well-folded ones (csrc/api.cu launch_plan; crossover measured by tools/crossover.py)."""
+    for dims, want in [((20, 20), "cheb_slab"), ((8, 7, 6), "cheb_slab"), ((16,) * 4, "cheb_slab"),
+                       ((10,) * 5, "cheb_mma"), ((8,) * 5, "cheb_mma"), ((6,) * 6, "cheb_mma"), ((40, 7), "cheb_mma")]:
+        cf = cases.cheb_fitted(dims)
+        x = cases.points(3000, len(dims))
+        plan = _lib.Plan.cheb(cf)
+        got, k = eval_plan(plan, x, _lib.KERNEL_AUTO)
+        assert k == want, (dims, k)
+        ref = port.evalcheb(cf, x, threads=4)
+        assert np.abs(got - ref).max() <= TOL_REL * np.abs(ref).max()
+        plan.close()
+
+
 def test_cheb_intervals_and_uniform_premaps(gpu_ok, port):
     dims = (9, 8, 7)
     iv = [(1.0, 2.0), (1.0, 4.0), (-3.0, 3.0)]
