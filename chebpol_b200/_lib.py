@@ -36,7 +36,7 @@ EXPORTS = [
     "chebpol_cuda_plan_cheb", "chebpol_cuda_plan_mlip", "chebpol_cuda_plan_fh",
     "chebpol_cuda_plan_destroy", "chebpol_cuda_plan_eval_device", "chebpol_cuda_plan_eval_host",
     "chebpol_cuda_plan_set", "chebpol_cuda_plan_get", "chebpol_cuda_fp64_peak",
-    "chebpol_cuda_launch_count", "chebpol_cuda_cache_clear",
+    "chebpol_cuda_launch_count", "chebpol_cuda_cache_clear", "chebpol_cuda_chebcoef", "chebpol_cuda_fhweights",
 ]
 
 
@@ -79,6 +79,8 @@ def lib() -> C.CDLL:
     L.chebpol_cuda_plan_set.argtypes = [_vp, C.c_int, C.c_int64]
     L.chebpol_cuda_plan_get.argtypes = [_vp, C.c_int, C.POINTER(C.c_int64)]
     L.chebpol_cuda_fp64_peak.argtypes = [C.c_int, C.c_int, _dp]
+    L.chebpol_cuda_chebcoef.argtypes = [_vp, _ip, C.c_int, C.c_int, C.c_int, _vp]
+    L.chebpol_cuda_fhweights.argtypes = [_vp, C.c_int, C.c_int, C.c_int, _vp]
     L.chebpol_cuda_cache_clear.restype = None
     L.chebpol_cuda_cache_clear.argtypes = []
     L.chebpol_cuda_launch_count.restype = C.c_int64
@@ -250,6 +252,31 @@ class Plan:
             self.close()
         except Exception:
             pass
+
+
+# ---- fit side ------------------------------------------------------------------
+def chebcoef(val, dct: bool = False, device: int = 0) -> np.ndarray:
+    """Chebyshev coefficients of values on a Chebyshev grid, on the device (chebpol_cuda_chebcoef)."""
+    val = np.asarray(val, dtype=np.float64)
+    if val.ndim == 0:
+        val = val.reshape(1)
+    v = f64(val, order="F")
+    dims = _i32(v.shape)
+    out = np.empty(v.shape, dtype=np.float64, order="F")
+    check(lib().chebpol_cuda_chebcoef(_addr(v), dims.ctypes.data_as(_ip), v.ndim, int(dct), device, _addr(out)))
+    return out
+
+
+def fhweights(grid, d, device: int = 0):
+    """Floater-Hormann weights per dimension, on the device (chebpol_cuda_fhweights)."""
+    dd = np.resize(np.asarray(d, dtype=np.int64), len(grid))
+    out = []
+    for g, deg in zip(grid, dd):
+        g = f64(np.asarray(g, dtype=np.float64).ravel())
+        w = np.empty_like(g)
+        check(lib().chebpol_cuda_fhweights(_addr(g), g.size, int(deg), device, _addr(w)))
+        out.append(w)
+    return out
 
 
 # ---- stateless entry points (what the R .Call glue binds) -------------------------

@@ -1142,6 +1142,50 @@ extern "C" int chebpol_cuda_fh(const double *vals, const double *const *grid,
     });
 }
 
+// ------------------------------------------------------------------ fit side
+extern "C" int chebpol_cuda_chebcoef(const double *val, const int *dims, int rank, int dct, int device, double *coef)
+{
+    if (!val || !coef) return fail(CHEBPOL_CUDA_EINVAL, "val or coef is NULL");
+    int64_t nelem = 0;
+    int rc = check_dims(dims, rank, &nelem);
+    if (rc) return rc;
+    int sms = 0;
+    rc = select_device(device, &sms);
+    if (rc) return rc;
+    double *d_a = nullptr, *d_b = nullptr, *res = nullptr;
+    int launches = 0;
+    cudaError_t e = cudaMalloc(&d_a, sizeof(double) * nelem);
+    if (e == cudaSuccess) e = cudaMalloc(&d_b, sizeof(double) * nelem);
+    if (e == cudaSuccess) e = cudaMemcpy(d_a, val, sizeof(double) * nelem, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = fit_chebcoef_device(d_a, d_b, dims, rank, dct, nullptr, &res, &launches);
+    if (e == cudaSuccess) e = cudaMemcpy(coef, res, sizeof(double) * nelem, cudaMemcpyDeviceToHost);
+    cudaFree(d_a);
+    cudaFree(d_b);
+    g_launches.fetch_add(launches);
+    if (e != cudaSuccess) return cuda_fail(e, "chebcoef");
+    return CHEBPOL_CUDA_OK;
+}
+
+extern "C" int chebpol_cuda_fhweights(const double *grid, int nknots, int d, int device, double *w)
+{
+    if (!grid || !w) return fail(CHEBPOL_CUDA_EINVAL, "grid or w is NULL");
+    if (nknots < 1 || d < 0 || d > nknots - 1) return fail(CHEBPOL_CUDA_ESIZE, "need 0 <= d <= nknots-1 (d=%d, nknots=%d)", d, nknots);
+    int sms = 0;
+    int rc = select_device(device, &sms);
+    if (rc) return rc;
+    double *d_g = nullptr, *d_w = nullptr;
+    cudaError_t e = cudaMalloc(&d_g, sizeof(double) * nknots);
+    if (e == cudaSuccess) e = cudaMalloc(&d_w, sizeof(double) * nknots);
+    if (e == cudaSuccess) e = cudaMemcpy(d_g, grid, sizeof(double) * nknots, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = fit_fhweights_device(d_g, nknots, d, d_w, nullptr);
+    if (e == cudaSuccess) e = cudaMemcpy(w, d_w, sizeof(double) * nknots, cudaMemcpyDeviceToHost);
+    cudaFree(d_g);
+    cudaFree(d_w);
+    g_launches.fetch_add(1);
+    if (e != cudaSuccess) return cuda_fail(e, "fhweights");
+    return CHEBPOL_CUDA_OK;
+}
+
 extern "C" int chebpol_cuda_fp64_peak(int device, int repeats, double *tflops)
 {
     if (!tflops) return fail(CHEBPOL_CUDA_EINVAL, "tflops is NULL");

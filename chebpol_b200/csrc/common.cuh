@@ -157,4 +157,7 @@ bool mlip_pair_supported(int rank, int blend);
 int64_t mlip_cell_bytes(int rank, const int *dims);
 cudaError_t mlip_expand(const MlipArgs &a, const double *values, double *cells, cudaStream_t s);
 cudaError_t launch_mlip_cell(const MlipArgs &a, const double *cells, int variant, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t fit_chebcoef_device(double *d_a, double *d_b, const int *dims, int rank, int dct, cudaStream_t s,
+                                double **result, int *launches);
+cudaError_t fit_fhweights_device(const double *d_grid, int nknots, int d, double *d_w, cudaStream_t s);
 cudaError_t run_fp64_peak(int num_sms, int repeats, cudaStream_t s, double *tflops);

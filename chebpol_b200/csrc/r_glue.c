@@ -169,10 +169,63 @@ SEXP R_FH_cuda(SEXP inx, SEXP vals, SEXP grid, SEXP Sweights, SEXP Rthreads, SEX
     return resvec;
 }
 
+/* fit side: same arguments and return as R_chebcoef (src/chebpol.c:145-180) */
+SEXP R_chebcoef_cuda(SEXP x, SEXP sdct, SEXP Sthreads)
+{
+    SEXP dim;
+    int rank, sdims, *dims, siz = 1;
+    UNUSED(Sthreads);
+    if (!isLogical(sdct) || LENGTH(sdct) < 1) error("dct must be a logical");
+    const int dct = LOGICAL(sdct)[0];
+    dim = getAttrib(x, R_DimSymbol);
+    if (isNull(dim)) {
+        sdims = LENGTH(x);
+        dims = &sdims;
+        rank = 1;
+    } else {
+        rank = LENGTH(dim);
+        if (rank <= 0) error("Rank must be positive");
+        dims = INTEGER(dim);
+    }
+    for (int i = 0; i < rank; i++) siz *= dims[i];
+    if (siz == 0) error("array size must be positive");
+    SEXP resvec = PROTECT(NEW_NUMERIC(siz));
+    const int rc = chebpol_cuda_chebcoef(REAL(x), dims, rank, dct, 0, REAL(resvec));
+    if (rc == CHEBPOL_CUDA_OK) {
+        setAttrib(resvec, R_DimSymbol, dim);
+        setAttrib(resvec, R_DimNamesSymbol, getAttrib(x, R_DimNamesSymbol));
+    }
+    UNPROTECT(1);
+    raise(rc);
+    return resvec;
+}
+
+/* same arguments and return as R_fhweights (src/chebpol.c:285-312) */
+SEXP R_fhweights_cuda(SEXP Sgrid, SEXP Sd, SEXP Sthreads)
+{
+    UNUSED(Sthreads);
+    if (LENGTH(Sgrid) != LENGTH(Sd))
+        error("Length of grid (%d) should equal length of d (%d)", LENGTH(Sgrid), LENGTH(Sd));
+    const int rank = LENGTH(Sgrid);
+    const int *dd = INTEGER(AS_INTEGER(Sd));
+    SEXP ret = PROTECT(NEW_LIST(rank));
+    int rc = CHEBPOL_CUDA_OK;
+    for (int r = 0; r < rank && rc == CHEBPOL_CUDA_OK; r++) {
+        const int n = LENGTH(VECTOR_ELT(Sgrid, r));
+        SET_VECTOR_ELT(ret, r, NEW_NUMERIC(n));
+        rc = chebpol_cuda_fhweights(REAL(VECTOR_ELT(Sgrid, r)), n, dd[r], 0, REAL(VECTOR_ELT(ret, r)));
+    }
+    UNPROTECT(1);
+    raise(rc);
+    return ret;
+}
+
 /* rows to append to R_CallMethodDef callMethods[] (src/chebpol.c:943-967), same arities
  * as "evalcheb", "evalmlip", "FH" */
 const R_CallMethodDef chebpol_cuda_callMethods[] = {
     {"evalcheb_cuda", (DL_FUNC)&R_evalcheb_cuda, 4},
     {"evalmlip_cuda", (DL_FUNC)&R_evalmlip_cuda, 5},
     {"FH_cuda", (DL_FUNC)&R_FH_cuda, 6},
+    {"chebcoef_cuda", (DL_FUNC)&R_chebcoef_cuda, 3},
+    {"FHweights_cuda", (DL_FUNC)&R_fhweights_cuda, 3},
     {NULL, NULL, 0}};

@@ -205,15 +205,16 @@ class Interpolant:
 
 
 # --------------------------------------------------------------- constructors
-def chebappx(val, intervals=None) -> Interpolant:
-    """chebappx.real, R/chebyshev.R:201-233."""
+def chebappx(val, intervals=None, fit: str = "host") -> Interpolant:
+    """chebappx.real, R/chebyshev.R:201-233.  fit="device" computes the coefficients with
+    chebpol_cuda_chebcoef (the GPU counterpart of C_chebcoef) instead of host numpy."""
     val = np.asarray(val, dtype=np.float64)
     if val.ndim == 0:
         val = val.reshape(1)
     K = val.ndim
     if intervals is not None and np.ndim(intervals) == 1 and len(intervals) == 2 and np.isscalar(intervals[0]):
         intervals = [intervals]
-    cf = chebcoef(val)
+    cf = _lib.chebcoef(val) if fit == "device" else chebcoef(val)
     if intervals is None:
         return Interpolant("chebyshev", K, [(-1.0, 1.0)] * K, coef=cf)
     if any(len(iv) != 2 for iv in intervals):
@@ -266,8 +267,8 @@ def mlappx(val, grid) -> Interpolant:
                        values=np.ascontiguousarray(values))
 
 
-def fhappx(val, grid=None, d=1) -> Interpolant:
-    """fhappx.real, R/floater-hormann.R:55-70."""
+def fhappx(val, grid=None, d=1, fit: str = "host") -> Interpolant:
+    """fhappx.real, R/floater-hormann.R:55-70.  fit="device": weights from chebpol_cuda_fhweights."""
     if grid is None:
         raise ValueError("Must specify grid")
     if np.isscalar(grid[0]):
@@ -280,7 +281,7 @@ def fhappx(val, grid=None, d=1) -> Interpolant:
     if val.shape != shape:
         val = val.reshape(shape, order="F")
     dd = np.resize(np.asarray(d, dtype=np.int64), len(grid))
-    weights = fhweights(grid, dd)
+    weights = _lib.fhweights(grid, dd) if fit == "device" else fhweights(grid, dd)
     return Interpolant("fh", len(grid), [(g.min(), g.max()) for g in grid], grid=grid,
                        values=np.asfortranarray(val), weights=weights)
 

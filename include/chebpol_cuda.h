@@ -137,6 +137,16 @@ CHEBPOL_CUDA_API int chebpol_cuda_plan_eval_host(chebpol_cuda_plan *plan, const 
 CHEBPOL_CUDA_API int chebpol_cuda_plan_set(chebpol_cuda_plan *plan, int option, int64_t value);
 CHEBPOL_CUDA_API int chebpol_cuda_plan_get(chebpol_cuda_plan *plan, int what, int64_t *value);
 
+/* ---- fit side (the step before the evaluation path) ----------------------
+ * chebcoef: values on the Chebyshev grid (R array `val`, dims[rank]) -> Chebyshev
+ * coefficients, replacing R_chebcoef / chebcoef (src/chebpol.c:145-180, :8-141); dct != 0
+ * returns the raw DCT-II as chebcoef(val, TRUE) does.  fhweights: Floater-Hormann weights of
+ * one knot vector for degree d, replacing fhweights (src/chebpol.c:267-282; R_fhweights
+ * :285-312 calls it once per dimension).  Host pointers in and out. */
+CHEBPOL_CUDA_API int chebpol_cuda_chebcoef(const double *val, const int *dims, int rank, int dct,
+                                           int device, double *coef);
+CHEBPOL_CUDA_API int chebpol_cuda_fhweights(const double *grid, int nknots, int d, int device, double *w);
+
 /* ---- diagnostics -------------------------------------------------------- */
 /* Register-resident DFMA chain on every SM of `device`: the FP64 roofline
  * denominator (MEASURED_PEAKS.json has none).  Returns TFLOP/s (2 flop/FMA). */

@@ -560,3 +560,47 @@ def test_stateless_plan_cache_and_pageable_staging(gpu_ok, port):
     sel = slice(0, n, 3001)
     assert np.abs(og[sel] - port.evalcheb(cf, xg[sel])).max() <= TOL_REL * np.abs(og).max()
     plan.close()
+
+
+# ----------------------------------------------------------------------------- fit side
+@pytest.mark.parametrize("dims", [(7,), (2, 3, 4), (8, 7, 6), (10,) * 5, (33, 5), (1, 4), (1500,)])
+def test_chebcoef_on_device(gpu_ok, port, dims):
+    """chebpol_cuda_chebcoef against the reference's matrix path (src/chebpol.c:65-140), with and
+    without dct, and the golden table of tests/all.Rout.save:28-48 for the 2x3x4 case."""
+    rng = np.random.default_rng(11)
+    a = np.asfortranarray(rng.standard_normal(dims))
+    for dct in (False, True):
+        got = _lib.chebcoef(a, dct)
+        want = port.chebcoef(a, dct)
+        assert got.shape == want.shape
+        assert np.abs(got - want).max() <= 1e-13 * max(1.0, np.abs(want).max())
+    if dims == (2, 3, 4):
+        from r_rng import RRng
+
+        a = RRng(42).rnorm(24).reshape((2, 3, 4), order="F")
+        cf = _lib.chebcoef(a)
+        assert np.allclose(cf[:, :, 0], [[0.1163838, -0.1845058, -0.05441405], [0.1003040, -0.1881047, -0.34460793]], rtol=0, atol=6e-8)
+
+
+def test_fhweights_on_device_and_fit_on_device_ipol(gpu_ok, port):
+    grid = [np.linspace(-1, 1, 50), np.linspace(-1, 1, 30) ** 3, cb.chebknots([20])[0]]
+    got = _lib.fhweights(grid, [3, 4, 4])
+    want = port.fhweights(grid, [3, 4, 4])
+    for g, w in zip(got, want):
+        assert np.array_equal(bits(g), bits(w))  # same operation order: bit-identical
+    # ipol end to end with the fit on the device: golden values of tests/all.Rout.save:69,71
+    f = lambda x: np.exp(-np.sum(x ** 2))
+    iv = [(1, 2), (1, 4), (1, 3)]
+    val = cb.evalongrid(f, [8, 7, 6], iv)
+    ch = cb.chebappx(val, iv, fit="device")
+    s = np.array([1.4, 2.3, 1.9])
+    assert abs((ch(s)[0] - f(s)) - (-3.115592e-06)) < 5e-13
+    a = np.array([1.01, 1.01, 1.01])
+    assert abs((ch(a)[0] - f(a)) - 0.0001730159) < 5e-11
+    ch.close()
+    fh = cb.fhappx(lambda x: np.sum(np.log(1 + x ** 2)), grid=[g[:12] for g in grid], d=[3, 4, 4], fit="device")
+    x = cases.points(500, 3, lo=0.0, hi=0.9)
+    host = cb.fhappx(lambda x: np.sum(np.log(1 + x ** 2)), grid=[g[:12] for g in grid], d=[3, 4, 4])
+    assert np.array_equal(bits(fh(x.T)), bits(host(x.T)))
+    fh.close()
+    host.close()
