@@ -37,6 +37,7 @@ EXPORTS = [
     "chebpol_cuda_plan_destroy", "chebpol_cuda_plan_eval_device", "chebpol_cuda_plan_eval_host",
     "chebpol_cuda_plan_set", "chebpol_cuda_plan_get", "chebpol_cuda_fp64_peak",
     "chebpol_cuda_launch_count", "chebpol_cuda_cache_clear", "chebpol_cuda_chebcoef", "chebpol_cuda_fhweights",
+    "chebpol_cuda_evalgrid_cheb", "chebpol_cuda_evalgrid_mlip", "chebpol_cuda_evalgrid_fh",
 ]
 
 
@@ -81,6 +82,9 @@ def lib() -> C.CDLL:
     L.chebpol_cuda_fp64_peak.argtypes = [C.c_int, C.c_int, _dp]
     L.chebpol_cuda_chebcoef.argtypes = [_vp, _ip, C.c_int, C.c_int, C.c_int, _vp]
     L.chebpol_cuda_fhweights.argtypes = [_vp, C.c_int, C.c_int, C.c_int, _vp]
+    L.chebpol_cuda_evalgrid_cheb.argtypes = [_vp, _ip, C.c_int, _dpp, _ip, _vp, _vp, _vp, C.c_int, _vp]
+    L.chebpol_cuda_evalgrid_mlip.argtypes = [_dpp, _ip, C.c_int, _vp, _dpp, _ip, C.c_int, C.c_int, _vp]
+    L.chebpol_cuda_evalgrid_fh.argtypes = [_vp, _dpp, _dpp, _ip, C.c_int, _dpp, _ip, C.c_int, _vp]
     L.chebpol_cuda_cache_clear.restype = None
     L.chebpol_cuda_cache_clear.argtypes = []
     L.chebpol_cuda_launch_count.restype = C.c_int64
@@ -276,6 +280,47 @@ def fhweights(grid, d, device: int = 0):
         w = np.empty_like(g)
         check(lib().chebpol_cuda_fhweights(_addr(g), g.size, int(deg), device, _addr(w)))
         out.append(w)
+    return out
+
+
+# ---- evaluation on a tensor grid ---------------------------------------------------
+def evalgrid_cheb(coef, pts, mid=None, ispan=None, ugm_n=None, device: int = 0) -> np.ndarray:
+    coef = np.asarray(coef, dtype=np.float64)
+    cf = f64(coef, order="F")
+    dims = _i32(coef.shape)
+    gdims = _i32([len(p) for p in pts])
+    pl, keep = ptr_list(pts)
+    out = np.empty(tuple(int(g) for g in gdims), dtype=np.float64, order="F")
+    mid_a = f64(mid) if mid is not None else None
+    isp_a = f64(ispan) if ispan is not None else None
+    ugm_a = _i32(ugm_n) if ugm_n is not None else None
+    check(lib().chebpol_cuda_evalgrid_cheb(_addr(cf), dims.ctypes.data_as(_ip), coef.ndim, pl, gdims.ctypes.data_as(_ip),
+                                           _addr(mid_a), _addr(isp_a), _addr(ugm_a), device, _addr(out)))
+    return out
+
+
+def evalgrid_mlip(grid, values, pts, blend: int = 0, device: int = 0) -> np.ndarray:
+    dims = _i32([len(g) for g in grid])
+    vals = f64(np.asarray(values, dtype=np.float64).ravel(order="F"))
+    gdims = _i32([len(p) for p in pts])
+    gl, k1 = ptr_list(grid)
+    pl, k2 = ptr_list(pts)
+    out = np.empty(tuple(int(g) for g in gdims), dtype=np.float64, order="F")
+    check(lib().chebpol_cuda_evalgrid_mlip(gl, dims.ctypes.data_as(_ip), len(grid), _addr(vals), pl,
+                                           gdims.ctypes.data_as(_ip), blend, device, _addr(out)))
+    return out
+
+
+def evalgrid_fh(vals, grid, weights, pts, device: int = 0) -> np.ndarray:
+    dims = _i32([len(g) for g in grid])
+    v = f64(np.asarray(vals, dtype=np.float64).ravel(order="F"))
+    gdims = _i32([len(p) for p in pts])
+    gl, k1 = ptr_list(grid)
+    wl, k2 = ptr_list(weights)
+    pl, k3 = ptr_list(pts)
+    out = np.empty(tuple(int(g) for g in gdims), dtype=np.float64, order="F")
+    check(lib().chebpol_cuda_evalgrid_fh(_addr(v), gl, wl, dims.ctypes.data_as(_ip), len(grid), pl,
+                                         gdims.ctypes.data_as(_ip), device, _addr(out)))
     return out
 
 

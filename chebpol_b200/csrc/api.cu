@@ -1186,6 +1186,95 @@ extern "C" int chebpol_cuda_fhweights(const double *grid, int nknots, int d, int
     return CHEBPOL_CUDA_OK;
 }
 
+// --------------------------------------------------- evaluation on a tensor grid
+// kind 0 Chebyshev (pre-map optional), 1 Floater-Hormann, 2 multilinear
+static int evalgrid_common(int kind, const double *tensor, const int *dims, int rank, const double *const *pts,
+                           const int *gdims, const double *const *knots, const double *const *weights, int blend,
+                           const PreMap *pm, int device, double *out)
+{
+    if (!tensor || !pts || !gdims || !out) return fail(CHEBPOL_CUDA_EINVAL, "NULL argument");
+    int64_t nelem = 0;
+    int rc = check_dims(dims, rank, &nelem);
+    if (rc) return rc;
+    int64_t nout = 1, maxbuf = 1;
+    {
+        // size of the intermediate after each mode product
+        int64_t done = 1, rest = nelem;
+        for (int d = 0; d < rank; ++d) {
+            if (gdims[d] <= 0 || !pts[d]) return fail(CHEBPOL_CUDA_ESIZE, "grid %d is empty", d);
+            if (kind == 2 && dims[d] < 2) return fail(CHEBPOL_CUDA_ESIZE, "multilinear grid %d needs at least 2 knots", d);
+            rest /= dims[d];
+            done *= gdims[d];
+            if (done * rest > maxbuf) maxbuf = done * rest;
+            if (done * rest >= (int64_t(1) << 34)) return fail(CHEBPOL_CUDA_ESIZE, "grid evaluation too large");
+        }
+        nout = done;
+    }
+    int sms = 0;
+    rc = select_device(device, &sms);
+    if (rc) return rc;
+    std::vector<double *> dev;  // everything to free
+    auto up = [&](const double *h, size_t n, double **d) -> cudaError_t {
+        cudaError_t e = cudaMalloc(d, sizeof(double) * n);
+        if (e != cudaSuccess) return e;
+        dev.push_back(*d);
+        return h ? cudaMemcpy(*d, h, sizeof(double) * n, cudaMemcpyHostToDevice) : cudaSuccess;
+    };
+    cudaError_t e = cudaSuccess;
+    double *d_t = nullptr, *d_s0 = nullptr, *d_s1 = nullptr, *res = nullptr;
+    std::vector<double *> d_pts(rank, nullptr), d_kn(rank, nullptr), d_w(rank, nullptr);
+    e = up(tensor, (size_t)nelem, &d_t);
+    if (e == cudaSuccess) e = up(nullptr, (size_t)maxbuf, &d_s0);
+    if (e == cudaSuccess) e = up(nullptr, (size_t)maxbuf, &d_s1);
+    for (int d = 0; d < rank && e == cudaSuccess; ++d) {
+        e = up(pts[d], (size_t)gdims[d], &d_pts[d]);
+        if (e == cudaSuccess && knots) e = up(knots[d], (size_t)dims[d], &d_kn[d]);
+        if (e == cudaSuccess && weights) e = up(weights[d], (size_t)dims[d], &d_w[d]);
+    }
+    int launches = 0;
+    if (e == cudaSuccess)
+        e = fit_evalgrid_device(kind, d_t, dims, rank, d_pts.data(), gdims, knots ? d_kn.data() : nullptr,
+                                weights ? d_w.data() : nullptr, blend, pm, d_s0, d_s1, nullptr, &res, &launches);
+    if (e == cudaSuccess) e = cudaMemcpy(out, res, sizeof(double) * nout, cudaMemcpyDeviceToHost);
+    for (double *d : dev) cudaFree(d);
+    g_launches.fetch_add(launches);
+    if (e != cudaSuccess) return cuda_fail(e, "evalgrid");
+    return CHEBPOL_CUDA_OK;
+}
+
+extern "C" int chebpol_cuda_evalgrid_cheb(const double *coef, const int *dims, int rank, const double *const *pts,
+                                          const int *gdims, const double *mid, const double *ispan, const int *ugm_n,
+                                          int device, double *out)
+{
+    if ((mid == nullptr) != (ispan == nullptr)) return fail(CHEBPOL_CUDA_EINVAL, "mid and ispan must be given together");
+    if (rank <= 0 || rank > CHEBPOL_CUDA_MAXRANK) return fail(CHEBPOL_CUDA_ERANK, "rank must be positive");
+    PreMap pm;
+    memset(&pm, 0, sizeof pm);
+    for (int d = 0; d < rank; ++d) {
+        pm.ispan[d] = 1.0;
+        pm.nd[d] = 1.0;
+        if (mid) { pm.mode |= 1; pm.mid[d] = mid[d]; pm.ispan[d] = ispan[d]; }
+        if (ugm_n) { pm.mode |= 2; pm.nd[d] = (double)ugm_n[d]; }
+    }
+    return evalgrid_common(0, coef, dims, rank, pts, gdims, nullptr, nullptr, 0, &pm, device, out);
+}
+
+extern "C" int chebpol_cuda_evalgrid_mlip(const double *const *grid, const int *dims, int rank, const double *values,
+                                          const double *const *pts, const int *gdims, int blend, int device, double *out)
+{
+    if (!grid) return fail(CHEBPOL_CUDA_EINVAL, "grid is NULL");
+    if (blend < 0 || blend > 5) return fail(CHEBPOL_CUDA_EBLEND, "blend %d not in 0..5", blend);
+    return evalgrid_common(2, values, dims, rank, pts, gdims, grid, nullptr, blend, nullptr, device, out);
+}
+
+extern "C" int chebpol_cuda_evalgrid_fh(const double *vals, const double *const *grid, const double *const *weights,
+                                        const int *dims, int rank, const double *const *pts, const int *gdims, int device,
+                                        double *out)
+{
+    if (!grid || !weights) return fail(CHEBPOL_CUDA_EINVAL, "grid or weights is NULL");
+    return evalgrid_common(1, vals, dims, rank, pts, gdims, grid, weights, 0, nullptr, device, out);
+}
+
 extern "C" int chebpol_cuda_fp64_peak(int device, int repeats, double *tflops)
 {
     if (!tflops) return fail(CHEBPOL_CUDA_EINVAL, "tflops is NULL");

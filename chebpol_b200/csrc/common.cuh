@@ -159,5 +159,8 @@ cudaError_t mlip_expand(const MlipArgs &a, const double *values, double *cells, 
 cudaError_t launch_mlip_cell(const MlipArgs &a, const double *cells, int variant, int num_sms, cudaStream_t s, LaunchInfo *li);
 cudaError_t fit_chebcoef_device(double *d_a, double *d_b, const int *dims, int rank, int dct, cudaStream_t s,
                                 double **result, int *launches);
+cudaError_t fit_evalgrid_device(int kind, const double *d_tensor, const int *dims, int rank, const double *const *d_pts,
+                                const int *gdims, const double *const *d_knots, const double *const *d_weights, int blend,
+                                const PreMap *pm, double *d_s0, double *d_s1, cudaStream_t s, double **result, int *launches);
 cudaError_t fit_fhweights_device(const double *d_grid, int nknots, int d, double *d_w, cudaStream_t s);
 cudaError_t run_fp64_peak(int num_sms, int repeats, cudaStream_t s, double *tflops);

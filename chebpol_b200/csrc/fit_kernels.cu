@@ -13,26 +13,98 @@ namespace {
 
 constexpr int kTileK = 8;
 
-// one thread per (a, k) for fixed b; loops over i.  cosm: [N][N] (k-major) or null -> on the fly
-__global__ void __launch_bounds__(256) dct_mode_kernel(const double *__restrict__ in, double *__restrict__ out,
-                                                       const double *__restrict__ cosm, int64_t inner, int N,
-                                                       int64_t outer, double alpha)
+// Mode product along one dimension of a tensor viewed as (inner, N, outer):
+//   out[a, k, b] = alpha * sum_i Mx[k][i] * in[a, i, b],   k < M
+// One thread per output element.  Mx: [M][N] row-major, or null for the DCT-II cosine
+// matrix generated on the fly (very long 1-D transforms).
+__global__ void __launch_bounds__(256) mode_product_kernel(const double *__restrict__ in, double *__restrict__ out,
+                                                           const double *__restrict__ Mx, int64_t inner, int N, int M,
+                                                           int64_t outer, double alpha)
 {
-    const int64_t total = inner * (int64_t)N * outer;
+    const int64_t total = inner * (int64_t)M * outer;
     for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
          idx += (int64_t)gridDim.x * blockDim.x) {
         const int64_t a = idx % inner;
-        const int k = (int)((idx / inner) % N);
-        const int64_t b = idx / (inner * N);
+        const int k = (int)((idx / inner) % M);
+        const int64_t b = idx / (inner * M);
         const double *src = in + a + b * inner * N;
         double s = 0.0;
-        if (cosm) {
-            const double *c = cosm + (size_t)k * N;
+        if (Mx) {
+            const double *c = Mx + (size_t)k * N;
             for (int i = 0; i < N; ++i) s = fma(__ldg(c + i), __ldg(src + (int64_t)i * inner), s);
         } else {
             for (int i = 0; i < N; ++i) s = fma(cospi((double)k * ((double)i + 0.5) / (double)N), __ldg(src + (int64_t)i * inner), s);
         }
         out[idx] = alpha * s;
+    }
+}
+
+// ---- basis matrices B[m][n] of one dimension at m grid coordinates (evalongridV) -------
+// kind 0: Chebyshev T_i(x) after the pre-map; 1: Floater-Hormann barycentric basis (one-hot on
+// a knot hit, src/chebpol.c:195-197); 2: multilinear hat weights with blending, normalised
+// per dimension (the reference's sum of corner weights factorises over the dimensions).
+__device__ __forceinline__ double grid_blend(double w, int blend)
+{
+    switch (blend) {
+    case 1: return w < 0.5 ? 0.5 * exp(2 - 1 / w) : 1 - 0.5 * exp(2 - 1 / (1 - w));
+    case 2: return w < 0.5 ? 0.5 * exp(4 - 1 / (w * w)) : 1 - 0.5 * exp(4 - 1 / ((1 - w) * (1 - w)));
+    case 3: return (-2 * w + 3) * w * w;
+    case 4: return (w < 0.5) ? 0.0 : 1.0;
+    case 5: return 0.5;
+    default: return w;
+    }
+}
+
+__global__ void basis_matrix_kernel(int kind, double *__restrict__ B, const double *__restrict__ pts, int m, int n,
+                                    const double *__restrict__ knots, const double *__restrict__ weights, int blend,
+                                    int pm_mode, double mid, double ispan, double nd)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= m) return;
+    double *row = B + (size_t)j * n;
+    double x = pts[j];
+    if (kind == 0) {
+        if (pm_mode & 1) x = (x - mid) * ispan;
+        if (pm_mode & 2) x = sin(0.5 * 3.141592653589793 * x * (1.0 - nd) / nd);
+        const double tx = 2.0 * x;
+        double tkm1 = 1.0, tk = x;
+        row[0] = 1.0;
+        if (n > 1) row[1] = x;
+        for (int i = 2; i < n; ++i) {
+            const double t = fma(tx, tk, -tkm1);
+            tkm1 = tk;
+            tk = t;
+            row[i] = t;
+        }
+    } else if (kind == 1) {
+        int hit = -1;
+        for (int i = 0; i < n; ++i)
+            if (fabs(x - knots[i]) < 10.0 * 2.220446049250313e-16) { hit = i; break; }
+        if (hit >= 0 || x != x) {
+            for (int i = 0; i < n; ++i) row[i] = (i == hit) ? 1.0 : ((x != x) ? x : 0.0);
+            return;
+        }
+        double den = 0.0;
+        for (int i = 0; i < n; ++i) {
+            const double p = weights[i] / (x - knots[i]);
+            row[i] = p;
+            den += p;
+        }
+        for (int i = 0; i < n; ++i) row[i] /= den;
+    } else {
+        for (int i = 0; i < n; ++i) row[i] = 0.0;
+        int lo = 0, hi = n - 1;  // src/chebpol.c:543-556, NaN-safe
+        while (lo + 1 < hi) {
+            const int mdl = (lo + hi) >> 1;
+            if (knots[mdl] >= x) hi = mdl;
+            else lo = mdl;
+        }
+        const double w = (x - knots[hi - 1]) / (knots[hi] - knots[hi - 1]);
+        const double bh = grid_blend(w, blend), bl = grid_blend(1 - w, blend);
+        const double sum = bh + bl;
+        row[hi] = bh / sum;
+        row[hi - 1] = bl / sum;
+        if (x != x) row[hi] = row[hi - 1] = x;
     }
 }
 
@@ -99,7 +171,7 @@ cudaError_t fit_chebcoef_device(double *d_a, double *d_b, const int *dims, int r
             cos_matrix_kernel<<<blocks_for((int64_t)N * N), 256, 0, s>>>(cosm, N);
             ++*launches;
         }
-        dct_mode_kernel<<<blocks_for(siz), 256, 0, s>>>(src, dst, cosm, inner, N, outer, dct ? 2.0 : 2.0 / N);
+        mode_product_kernel<<<blocks_for(siz), 256, 0, s>>>(src, dst, cosm, inner, N, N, outer, dct ? 2.0 : 2.0 / N);
         ++*launches;
         if (!dct) {
             halve_plane_kernel<<<blocks_for(inner * outer), 256, 0, s>>>(dst, inner, N, outer);
@@ -120,5 +192,43 @@ cudaError_t fit_chebcoef_device(double *d_a, double *d_b, const int *dims, int r
 cudaError_t fit_fhweights_device(const double *d_grid, int nknots, int d, double *d_w, cudaStream_t s)
 {
     fhweights_kernel<<<(nknots + 127) / 128, 128, 0, s>>>(d_grid, nknots - 1, d, d_w);
+    return cudaGetLastError();
+}
+
+// Evaluate a tensor-product interpolant on the tensor grid pts[0] x ... x pts[rank-1]:
+// out = T x_0 B_0 x_1 B_1 ... with the per-dimension basis matrices above.  d_tensor is the
+// interpolant's tensor (R layout, left untouched); the result (R array of dims gdims) is
+// returned in *result, which is one of the two scratch buffers.
+cudaError_t fit_evalgrid_device(int kind, const double *d_tensor, const int *dims, int rank, const double *const *d_pts,
+                                const int *gdims, const double *const *d_knots, const double *const *d_weights, int blend,
+                                const PreMap *pm, double *d_s0, double *d_s1, cudaStream_t s, double **result, int *launches)
+{
+    *launches = 0;
+    const double *src = d_tensor;
+    double *bufs[2] = {d_s0, d_s1};
+    int which = 0;
+    int64_t inner = 1;  // product of the grid sizes of the dims already done
+    int64_t outer = 1;
+    for (int d = 0; d < rank; ++d) outer *= dims[d];
+    for (int d = 0; d < rank; ++d) {
+        const int N = dims[d], M = gdims[d];
+        outer /= N;
+        double *B = nullptr;
+        cudaError_t e = cudaMalloc(&B, sizeof(double) * (size_t)M * N);
+        if (e != cudaSuccess) return e;
+        basis_matrix_kernel<<<(M + 127) / 128, 128, 0, s>>>(kind, B, d_pts[d], M, N, d_knots ? d_knots[d] : nullptr,
+                                                           d_weights ? d_weights[d] : nullptr, blend, pm ? pm->mode : 0,
+                                                           pm ? pm->mid[d] : 0.0, pm ? pm->ispan[d] : 1.0, pm ? pm->nd[d] : 1.0);
+        double *dst = bufs[which];
+        mode_product_kernel<<<blocks_for(inner * M * outer), 256, 0, s>>>(src, dst, B, inner, N, M, outer, 1.0);
+        *launches += 2;
+        e = cudaStreamSynchronize(s);
+        cudaFree(B);
+        if (e != cudaSuccess) return e;
+        src = dst;
+        which ^= 1;
+        inner *= M;
+    }
+    *result = const_cast<double *>(src);
     return cudaGetLastError();
 }

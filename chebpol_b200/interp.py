@@ -29,7 +29,7 @@ from . import _lib
 
 __all__ = [
     "ipol", "chebappx", "chebappxf", "mlappx", "fhappx", "ucappx", "ucappxf", "chebeval",
-    "chebknots", "chebcoef", "evalongrid", "fhweights", "Interpolant",
+    "chebknots", "chebcoef", "evalongrid", "evalongridV", "fhweights", "Interpolant",
 ]
 
 BLENDS = {"linear": 0, "sigmoid": 1, "parodic": 2, "cubic": 3, "square": 4}  # R/multilinear.R:64-65
@@ -77,6 +77,22 @@ def evalongrid(fun: Callable, dims=None, intervals=None, grid=None) -> np.ndarra
             idx[d] = 0
             arg[d] = grid[d][0]
     return flat.reshape(shape, order="F")
+
+
+def evalongridV(ip, dims=None, intervals=None, grid=None, blend="linear") -> np.ndarray:
+    """evalongridV for an interpolant (R/tools.R:132-137).  The reference evaluates
+    fun(t(expand.grid(grid))) point by point; for the four evaluators of this package the
+    tensor-grid structure is used instead (one mode product per dimension, on the device)."""
+    if grid is None:
+        grid = chebknots(dims, intervals)
+    pts = [np.asarray(g, dtype=np.float64) for g in grid]
+    t = ip.t
+    if ip.kind in ("chebyshev", "uniform"):
+        return _lib.evalgrid_cheb(t["coef"], pts, t.get("mid"), t.get("ispan"), t.get("ugm_n"))
+    if ip.kind == "multilinear":
+        b = BLENDS[blend] if isinstance(blend, str) else int(blend)
+        return _lib.evalgrid_mlip(t["grid"], t["values"], pts, b)
+    return _lib.evalgrid_fh(t["values"], t["grid"], t["weights"], pts)
 
 
 def chebcoef(val, dct: bool = False) -> np.ndarray:

@@ -147,6 +147,23 @@ CHEBPOL_CUDA_API int chebpol_cuda_chebcoef(const double *val, const int *dims, i
                                            int device, double *coef);
 CHEBPOL_CUDA_API int chebpol_cuda_fhweights(const double *grid, int nknots, int d, int device, double *w);
 
+/* ---- evaluation on a tensor grid (evalongridV of an interpolant, R/tools.R:132-137) ----
+ * The reference expands the grid (expand.grid) and evaluates point by point; here the
+ * structure is used: one basis matrix per dimension and one mode product per dimension.
+ * pts[d] holds gdims[d] coordinates of dimension d; out is the R array of dims gdims
+ * (first dimension fastest, the order of expand.grid). */
+CHEBPOL_CUDA_API int chebpol_cuda_evalgrid_cheb(const double *coef, const int *dims, int rank,
+                                                const double *const *pts, const int *gdims,
+                                                const double *mid, const double *ispan, const int *ugm_n,
+                                                int device, double *out);
+CHEBPOL_CUDA_API int chebpol_cuda_evalgrid_mlip(const double *const *grid, const int *dims, int rank,
+                                                const double *values, const double *const *pts,
+                                                const int *gdims, int blend, int device, double *out);
+CHEBPOL_CUDA_API int chebpol_cuda_evalgrid_fh(const double *vals, const double *const *grid,
+                                              const double *const *weights, const int *dims, int rank,
+                                              const double *const *pts, const int *gdims, int device,
+                                              double *out);
+
 /* ---- diagnostics -------------------------------------------------------- */
 /* Register-resident DFMA chain on every SM of `device`: the FP64 roofline
  * denominator (MEASURED_PEAKS.json has none).  Returns TFLOP/s (2 flop/FMA). */

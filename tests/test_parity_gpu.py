@@ -604,3 +604,54 @@ def test_fhweights_on_device_and_fit_on_device_ipol(gpu_ok, port):
     assert np.array_equal(bits(fh(x.T)), bits(host(x.T)))
     fh.close()
     host.close()
+
+
+# --------------------------------------------------------------- evaluation on a tensor grid
+def _expand_grid(pts):
+    mesh = np.meshgrid(*pts, indexing="ij")
+    return np.stack([m.ravel(order="F") for m in mesh], axis=1)  # first factor fastest, as expand.grid
+
+
+def test_evalongridV_matches_pointwise(gpu_ok, port):
+    """evalongridV(interpolant, grid) by mode products against the reference evaluated point by
+    point on expand.grid(grid) (R/tools.R:132-137), for all four evaluators."""
+    rng = np.random.default_rng(4)
+    # Chebyshev with intervals, uniform
+    dims = (7, 6, 5)
+    iv = [(0.0, 1.0), (-2.0, 2.0), (1.0, 3.0)]
+    val = cases.grid_values(cb.chebknots(dims, iv))
+    pts = [np.sort(rng.uniform(a, b, m)) for (a, b), m in zip(iv, (9, 4, 11))]
+    ch = cb.chebappx(val, iv)
+    got = cb.evalongridV(ch, grid=pts)
+    X = _expand_grid(pts)
+    want = port.evalcheb(ch.t["coef"], port.imap(X, ch.t["mid"], ch.t["ispan"])).reshape(got.shape, order="F")
+    assert got.shape == (9, 4, 11)
+    assert np.abs(got - want).max() <= TOL_REL * np.abs(want).max()
+    uc = cb.ucappx(val)
+    ptsu = [np.linspace(-1, 1, m) for m in (5, 6, 7)]
+    gotu = cb.evalongridV(uc, grid=ptsu)
+    wantu = port.evalcheb(uc.t["coef"], port.ugm(_expand_grid(ptsu), dims)).reshape(gotu.shape, order="F")
+    assert np.abs(gotu - wantu).max() <= 1e-13 * np.abs(wantu).max()
+    # the grid of the fit reproduces the values (interpolation property)
+    back = cb.evalongridV(ch, dims=dims, intervals=iv)
+    assert np.abs(back - val).max() <= 1e-13
+    # multilinear, two blends
+    grid, values = cases.mlip_case((8, 7, 6), uniform=False)
+    ml = cb.mlappx(values, grid)
+    ptsm = [np.sort(rng.uniform(-1, 1, m)) for m in (10, 3, 9)]
+    for name, b in (("linear", 0), ("cubic", 3)):
+        gotm = cb.evalongridV(ml, grid=ptsm, blend=name)
+        wantm = port.evalmlip(grid, values, _expand_grid(ptsm), blend=b).reshape(gotm.shape, order="F")
+        assert np.abs(gotm - wantm).max() <= TOL_REL * np.abs(wantm).max()
+    # Floater-Hormann, including grid nodes (knot hits); the example of chebpol-Ex.Rout.save:319-328
+    # evaluates g on its own grid and gets the values back
+    vals, g, w = cases.fh_case((9, 8, 7), d=3, kind="mixed")
+    fh = cb.fhappx(vals, grid=g, d=3)
+    gotf = cb.evalongridV(fh, grid=g)
+    assert np.array_equal(gotf, vals)
+    ptsf = [np.sort(rng.uniform(-0.95, 0.95, m)) for m in (6, 7, 8)]
+    gotf = cb.evalongridV(fh, grid=ptsf)
+    wantf = port.fh(vals, g, fh.t["weights"], _expand_grid(ptsf)).reshape(gotf.shape, order="F")
+    assert np.abs(gotf - wantf).max() <= 1e-11 * np.abs(wantf).max()  # cubed grid: Lebesgue constant ~1e2
+    for ip in (ch, uc, ml, fh):
+        ip.close()
