@@ -14,8 +14,6 @@
 #include <thread>
 #include <vector>
 
-int cheb_slab_pick_n0p(int n0);
-
 // --------------------------------------------------------------- error state
 static thread_local std::string g_last_error;
 static std::atomic<int64_t> g_launches{0};

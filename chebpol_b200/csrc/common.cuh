@@ -151,7 +151,7 @@ cudaError_t launch_mlip_strict(const MlipArgs &a, cudaStream_t s, LaunchInfo *li
 cudaError_t launch_fh_strict(const FhArgs &a, cudaStream_t s, LaunchInfo *li);
 // returns cudaErrorNotSupported when the shape has no fast instantiation
 cudaError_t launch_cheb_slab(const SlabArgs &a, int variant, int num_sms, cudaStream_t s, LaunchInfo *li);
-bool cheb_slab_supported(int n0, int rank, const int *dims);
+int cheb_slab_pick_n0p(int n0);
 cudaError_t launch_mlip_pair(const MlipArgs &a, int variant, int num_sms, cudaStream_t s, LaunchInfo *li);
 bool mlip_pair_supported(int rank, int blend);
 int64_t mlip_cell_bytes(int rank, const int *dims);

@@ -1,0 +1,52 @@
+// peak.cu -- in-run measurement of the FP64 roofline denominator (MEASURED_PEAKS.json
+// carries HBM and bf16 peaks only).
+#include "common.cuh"
+
+// ------------------------------------------------------------------ FP64 peak
+// Register-resident DFMA chains: 8 independent accumulators per thread,
+// 1024 threads per SM-resident CTA pair.  2 flop per FMA.
+__global__ void __launch_bounds__(512) dfma_peak_kernel(double *sink, int iters, double seed)
+{
+    double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3;
+    double a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 0.999999, c = 1e-9;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+            a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+        }
+    }
+    const double r = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+    if (r == 123.456) sink[0] = r;  // never true; keeps the chain alive
+}
+
+cudaError_t run_fp64_peak(int num_sms, int repeats, cudaStream_t s, double *tflops)
+{
+    double *sink = nullptr;
+    cudaError_t e = cudaMalloc(&sink, 8);
+    if (e != cudaSuccess) return e;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    const int iters = 4096, grid = num_sms * 4, block = 512;
+    dfma_peak_kernel<<<grid, block, 0, s>>>(sink, 64, 1.0);  // warm-up
+    double best = 0.0;
+    for (int r = 0; r < (repeats < 1 ? 1 : repeats); ++r) {
+        cudaEventRecord(e0, s);
+        dfma_peak_kernel<<<grid, block, 0, s>>>(sink, iters, 1.0);
+        cudaEventRecord(e1, s);
+        e = cudaEventSynchronize(e1);
+        if (e != cudaSuccess) break;
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double flop = 2.0 * 8 * 16 * (double)iters * (double)grid * block;
+        const double tf = flop / (ms * 1e-3) / 1e12;
+        if (tf > best) best = tf;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(sink);
+    *tflops = best;
+    return e == cudaSuccess ? cudaGetLastError() : e;
+}

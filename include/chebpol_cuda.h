@@ -118,7 +118,7 @@ CHEBPOL_CUDA_API int chebpol_cuda_plan_eval_host(chebpol_cuda_plan *plan, const 
 #define CHEBPOL_CUDA_OPT_KERNEL 1      /* see CHEBPOL_CUDA_KERNEL_*                       */
 #define CHEBPOL_CUDA_OPT_BLEND 2       /* multilinear plans: blend 0..5                   */
 #define CHEBPOL_CUDA_OPT_CHUNK_POINTS 3 /* eval_host chunk size in points (0 = auto)      */
-#define CHEBPOL_CUDA_OPT_VARIANT 4     /* tuning knob of the fast kernels (0 = auto)      */
+#define CHEBPOL_CUDA_OPT_VARIANT 4     /* which fast kernel / layout (0 = auto), see below  */
 #define CHEBPOL_CUDA_GET_KERNEL_USED 101  /* kernel id of the most recent eval            */
 #define CHEBPOL_CUDA_GET_LAUNCHES 102     /* kernels launched by this plan so far         */
 #define CHEBPOL_CUDA_GET_TENSOR_BYTES 103 /* device bytes of the resident tensor          */
@@ -134,6 +134,16 @@ CHEBPOL_CUDA_API int chebpol_cuda_plan_eval_host(chebpol_cuda_plan *plan, const 
 #define CHEBPOL_CUDA_KERNEL_AUTO 0
 #define CHEBPOL_CUDA_KERNEL_STRICT 1
 #define CHEBPOL_CUDA_KERNEL_FAST 2
+/* CHEBPOL_CUDA_OPT_VARIANT (tests, tuning, ncu evidence; 0 lets the library choose):
+ *   Chebyshev plans   1            DFMA slab kernel, default layout
+ *                     2..99999     DFMA slab kernel, layout ROWS*10000 + PT*100 + WARPS (n0 = 10, 12 only)
+ *                     100000       DMMA contraction engine, default layout
+ *                     100000+c     DMMA engine, layout c = MT*100 + WARPS
+ *   multilinear plans 1 pair-gather kernel on the R layout; 2 cell-major kernel;
+ *                     >= 20 cell-major kernel with WARPS*10 + STAGES
+ *   FH plans          100000+c as for Chebyshev
+ * CHEBPOL_CUDA_GET_KERNEL_USED: 10 cheb_strict, 11 cheb_slab (DFMA), 12 cheb_mma (DMMA),
+ *   20 mlip_strict, 21 mlip_pair, 22 mlip_cell, 30 fh_strict, 32 fh_mma. */
 CHEBPOL_CUDA_API int chebpol_cuda_plan_set(chebpol_cuda_plan *plan, int option, int64_t value);
 CHEBPOL_CUDA_API int chebpol_cuda_plan_get(chebpol_cuda_plan *plan, int what, int64_t *value);
 
