@@ -290,19 +290,27 @@ static int configure_mma(chebpol_cuda_plan *p, int kind, const double *host_tens
     if (!mma_configure(p->mma, kind, p->rank, p->dims, &kc)) return CHEBPOL_CUDA_OK;
     MmaArgs &m = p->mma;
     m.pm = p->pm;
-    const size_t rows = (size_t)m.nrest, rs = (size_t)m.rs, K = (size_t)m.K;
+    // rows ordered (r'-tile of 8, level-A index, r' within the tile); zero rows pad level A to an
+    // even count and r' to a multiple of 8; the basis-table rows of r's group-level digits
+    // (int32) follow the coefficients of every row
+    const size_t rows = (size_t)m.nrows, rs = (size_t)m.rs, K = (size_t)m.K;
     std::vector<double> padded(rows * rs, 0.0);
-    for (size_t r = 0; r < rows; ++r) {
-        memcpy(&padded[r * rs], host_tensor + r * K, sizeof(double) * K);
-        // basis-table rows (boff[d] + digit_d) of the rest-level digits of r, as int32
-        int *info = reinterpret_cast<int *>(&padded[r * rs + m.kp]);
-        size_t rem = r;
-        for (int l = 0; l < m.nlev; ++l) {
-            const int d = m.nfold + l;
-            info[l] = m.boff[d] + (int)(rem % (size_t)m.dims[d]);
-            rem /= (size_t)m.dims[d];
-        }
-    }
+    const int ng = m.nrows / (m.nAp * 8);
+    for (int g = 0; g < ng; ++g)
+        for (int ia = 0; ia < m.nAp; ++ia)
+            for (int u = 0; u < 8; ++u) {
+                const size_t dst = ((size_t)g * m.nAp + ia) * 8 + u;
+                const int rp = 8 * g + u;
+                if (rp < m.nrp && ia < m.nA)
+                    memcpy(&padded[dst * rs], host_tensor + ((size_t)ia + (size_t)m.nA * rp) * K, sizeof(double) * K);
+                int *info = reinterpret_cast<int *>(&padded[dst * rs + m.kp]);
+                size_t rem = rp < m.nrp ? (size_t)rp : 0;
+                for (int l = 0; l < m.nlg; ++l) {
+                    const int d = m.nfold + 1 + l;
+                    info[l] = m.boff[d] + (int)(rem % (size_t)m.dims[d]);
+                    rem /= (size_t)m.dims[d];
+                }
+            }
     std::vector<int> ktab((size_t)m.kp * 3, -1);
     for (int k = 0; k < m.K; ++k) {
         int rem = k;

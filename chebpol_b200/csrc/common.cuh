@@ -114,24 +114,30 @@ struct LaunchInfo {
     int grid, block, smem, kernel;
 };
 
-// DMMA contraction engine (contract_mma.cu): f(x) = sum_r W_r(x) * sum_k A_k(x) * C[r][k]
-// where k runs over the first `nfold` dims (folded into the MMA K dimension), r over
-// the remaining dims, A_k / W_r are products of per-dimension basis values
-// (Chebyshev T_i(x_d), or Floater-Hormann barycentric weights).
+// DMMA contraction engine (contract_mma.cuh):
+//   f(x) = sum_{r'} W_{r'}(x) * sum_{iA} b_A[iA](x) * sum_k A_k(x) * C[(iA, r')][k]
+// k runs over the first `nfold` dims (folded into the MMA K dimension, product basis A_k),
+// iA over the next dim ("level A"), r' over the remaining <= 3 dims (weights W_{r'}); b, A, W
+// are (products of) per-dimension basis values: Chebyshev T_i(x_d) or Floater-Hormann
+// barycentric weights.
 struct MmaArgs {
-    const double *tensor;  // [nrest][rs] doubles: row r = the K leading-dim entries of rest index r, zero padded
+    const double *tensor;  // [nrows][rs] doubles, rows ordered (r'-tile of 8, iA, r' within the tile)
     int kind;              // 0 Chebyshev basis, 1 Floater-Hormann basis
     int rank;
     int dims[CP_MAXR];
     int boff[CP_MAXR];     // row offset of dim d in the shared-memory basis table (prefix sum of dims)
-    int sumn;              // sum of dims
+    int sumn;              // sum of dims; table row `sumn` holds ones (used when a level is absent)
     int nfold;             // leading dims folded into K
     int K;                 // prod of folded dims
     int rs;                // row stride in doubles (== 4 or 12 mod 16: conflict-free B loads)
-    int kp;                // 4*KC: padded K; the row's rest-level table offsets (int32) start there
-    int nlev;              // rank - nfold: number of rest levels
+    int kp;                // 4*KC: padded K; the row's group-level table rows (int32) start there
+    int nlev;              // rank - nfold: unfolded dims
+    int nA, nAp;           // size of level A (1 if absent) and its padding to an even count
+    int boffA;             // basis-table row of level A (the ones row if absent)
+    int nrp;               // number of r' values (prod of the dims after level A; 1 if none)
+    int nlg;               // group levels: max(nlev - 1, 0) <= 3
+    int nrows;             // tensor rows: ceil(nrp/8) * nAp * 8 (a multiple of 16)
     const int *ktab;       // [kp][3] basis-table rows of the folded dims for each k (-1: padding)
-    int nrest;             // prod of the remaining dims (1 if none)
     int rows_per_slab;     // multiple of 16
     int nslabs, ns, stage_bytes, resident;
     const double *x;

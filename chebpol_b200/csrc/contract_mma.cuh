@@ -6,8 +6,9 @@
 //   Floater-Hormann  nested barycentric rational, whose value is the same
 //              contraction with b_d[i] = (w_i/(x_d-k_i)) / sum_j w_j/(x_d-k_j)
 //              and a one-hot b_d on a knot hit                      (FH, src/chebpol.c:182-218)
-// Both are  f(x) = sum_r W_r(x) * ( sum_k A_k(x) * C[r][k] )  with k running over the
-// first `nfold` dimensions (folded, product basis A_k) and r over the rest (weights W_r).
+// Both are  f(x) = sum_r' W_r'(x) * sum_iA b_A[iA](x) * ( sum_k A_k(x) * C[(iA,r')][k] )  with k
+// running over the first `nfold` dimensions (folded, product basis A_k), iA over the next
+// one and r' over the rest (weights W_r').
 //
 // Why tensor cores: on B200 the DMMA pipe has the same peak as the DFMA pipe (36.9 vs
 // 36.8 TFLOP/s measured, tools/dmma_peak.cu) but one DMMA.8x8x4 retires 256 FMAs with
@@ -24,10 +25,12 @@
 //  * the tensor, stored as rows C[r][0..K) padded to `rs` doubles, is streamed through a
 //    shared-memory ring by the TMA bulk-copy engine; the last warp to finish a stage
 //    issues its refill (no producer warp);
-//  * per pair of 8-row N-tiles: KC x (2 B-fragment LDS.64 + 2*MT DMMA), then the epilogue
-//    multiplies the 2x2 D elements of each point tile by W_r (product of Tb entries of
-//    the remaining dims) into a per-lane accumulator; the four lanes of a quad are summed
-//    by two shuffles at the end of the pass.
+//  * the rows are ordered so that consecutive 8-row N-tiles walk the first unfolded dim
+//    ("level A") for the same eight columns r'; per pair of N-tiles: KC x (2 B-fragment
+//    LDS.64 + 2*MT DMMA), and the epilogue is one DFMA per D element (acc2 += b_A[iA] * D);
+//    the weights of the other unfolded dims (product of Tb entries) are applied once per
+//    group of nA N-tiles (acc += W_r' * acc2); the four lanes of a quad are summed by two
+//    shuffles at the end of the pass.
 //
 // Rounding: explicit-basis sums (not Clenshaw / not the reference's num/den recursion):
 // differences are O(n*eps*sum|c*basis|), inside 1e-12*max|f| (tests/test_parity_gpu.py).
@@ -112,13 +115,12 @@ __device__ __forceinline__ void fh_basis(double *col, int n, double x, const dou
     }
 }
 
-// KC: K/4 (padded); MT: 8-point tiles per warp; NW: warps; LEVU: compile-time bound (2 or 4) on
-// the number of unfolded ("rest") dims -- absent levels multiply by 1.0 so the epilogue
-// stays branch-free.
-template <int KC, int MT, int NW, int LEVU>
+// KC: K/4 (padded); MT: 8-point tiles per warp; NW: warps.
+template <int KC, int MT, int NW>
 __global__ void __launch_bounds__(NW * 32, 1) contract_mma_kernel(const __grid_constant__ MmaArgs a)
 {
     constexpr int NPT = NW * MT * 8;  // points per pass
+    constexpr int NT = NW * 32;
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem);
     int *done_cnt = reinterpret_cast<int *>(smem + kMaxStages * 8);
@@ -127,14 +129,15 @@ __global__ void __launch_bounds__(NW * 32, 1) contract_mma_kernel(const __grid_c
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
-    const int rank = a.rank, nlev = a.nlev, ns = a.ns;
+    const int rank = a.rank, ns = a.ns;
     const int64_t ntiles = (a.npts + NPT - 1) / NPT;
     const int64_t my_tiles = (ntiles > (int64_t)blockIdx.x) ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     const int64_t total_fills = a.resident ? (int64_t)a.nslabs : my_tiles * a.nslabs;
     const int rps = a.rows_per_slab;
     const uint32_t row_bytes = (uint32_t)a.rs * 8u;
+    const int spg = a.nAp >> 1;  // steps per group (a group = one tile of 8 r' values, all of level A)
 
-    auto slab_rows = [&](int s) { const int left = a.nrest - s * rps; return left < rps ? left : rps; };
+    auto slab_rows = [&](int s) { const int left = a.nrows - s * rps; return left < rps ? left : rps; };
     auto issue_fill = [&](int64_t f, int stage) {
         const int s = (int)(f % a.nslabs);
         const uint32_t bytes = (uint32_t)slab_rows(s) * row_bytes;
@@ -151,18 +154,16 @@ __global__ void __launch_bounds__(NW * 32, 1) contract_mma_kernel(const __grid_c
         if (my_tiles > 0)
             for (int f = 0; f < ns && f < total_fills; ++f) issue_fill(f, f);
     }
+    // the ones row of the basis table (absent levels)
+    for (int i = tid; i < NPT; i += NT) Tb[(size_t)a.sumn * NPT + i] = 1.0;
 
     int stage = 0;
     uint32_t round = 0;
     int64_t fill = 0;
 
     // coordinates of the next pass are fetched (into registers) while the current pass
-    // computes, so the basis prologue never waits on DRAM.  Task q of a thread is
-    // (point pt, dim L) = ((tid + q*NT) % NPT, (tid + q*NT) / NPT); the coordinates of a
-    // pass are the contiguous range x[tile*NPT*rank ...), which task index `pt*rank + L`
-    // addresses directly.
-    constexpr int NT = NW * 32;
-    constexpr int kMaxTasks = (NPT * (3 + LEVU) + NT - 1) / NT;  // rank <= nfold(3) + LEVU
+    // computes, so the basis prologue never waits on DRAM
+    constexpr int kMaxTasks = (NPT * (3 + kLevMax) + NT - 1) / NT;  // rank <= nfold(3) + kLevMax
     double xpre[kMaxTasks];
     auto prefetch_x = [&](int64_t tile) {
 #pragma unroll
@@ -217,49 +218,60 @@ __global__ void __launch_bounds__(NW * 32, 1) contract_mma_kernel(const __grid_c
             }
         }
 
-        double acc[MT];
+        // ---- 3. stream the tensor rows.  A step is 16 rows: two 8-row N-tiles that hold the SAME
+        // eight r' columns at two consecutive level-A indices (iA, iA+1); a group is the nAp/2
+        // steps that walk level A for those columns.  Per step the epilogue is therefore one
+        // basis value per N-tile and point tile and one DFMA per D element (acc2 += b_A * D);
+        // the weights of the remaining levels are applied once per group (acc += W * acc2).
+        // Software pipeline: the D tiles of step q-1 are folded in while the DMMAs of step q are
+        // in flight (the per-step part is branch-free so ptxas interleaves the two).
+        double acc[MT], acc2[2][MT];
 #pragma unroll
-        for (int mt = 0; mt < MT; ++mt) acc[mt] = 0.0;
-
-        // ---- 3. stream the tensor rows.  Software pipeline: while the DMMAs of step q are
-        // in flight, the D tiles of step q-1 are weighted into `acc` (branch-free, so ptxas
-        // can interleave the two).  A step = 16 tensor rows (two 8-row N-tiles).
-        double Dp[2][MT][2];          // D tiles of the previous step
-        int ip[4][LEVU];             // basis-table rows of its 4 columns' rest-level digits
-        bool vp[4];                   // column valid (row < nrest)
+        for (int mt = 0; mt < MT; ++mt) acc[mt] = acc2[0][mt] = acc2[1][mt] = 0.0;
+        double Dp[2][MT][2];
 #pragma unroll
         for (int j = 0; j < 2; ++j)
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt) Dp[j][mt][0] = Dp[j][mt][1] = 0.0;
+        int p_iA = 0;             // level-A index of the pending step's first N-tile
+        bool p_end = false;       // the pending step closes its group
+        int p_info[2][3];         // basis-table rows of the group levels of this lane's two columns
+        bool p_valid[2] = {false, false};
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            vp[c] = false;
+        for (int e = 0; e < 2; ++e)
 #pragma unroll
-            for (int l = 0; l < LEVU; ++l) ip[c][l] = 0;
-        }
+            for (int l = 0; l < 3; ++l) p_info[e][l] = a.sumn;
         const double *tcol = Tb + warp * MT * 8 + g;
+        const int nA1 = a.nA - 1;
 
-        auto weigh_pending = [&]() {
-            // per column: its table loads are independent of each other (and of the DMMAs)
+        auto fold_pending = [&]() {
+            const int ia0 = p_iA < nA1 ? p_iA : nA1, ia1 = p_iA + 1 < nA1 ? p_iA + 1 : nA1;
+            const double *t0 = tcol + (size_t)(a.boffA + ia0) * NPT;
+            const double *t1 = tcol + (size_t)(a.boffA + ia1) * NPT;
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                double tv[LEVU][MT];
+            for (int mt = 0; mt < MT; ++mt) {
+                const double b0 = t0[mt * 8], b1 = t1[mt * 8];
 #pragma unroll
-                for (int l = 0; l < LEVU; ++l)
+                for (int e = 0; e < 2; ++e) {
+                    acc2[e][mt] = fma(b0, Dp[0][mt][e], acc2[e][mt]);
+                    acc2[e][mt] = fma(b1, Dp[1][mt][e], acc2[e][mt]);
+                }
+            }
+        };
+        auto close_group = [&]() {
 #pragma unroll
-                    for (int mt = 0; mt < MT; ++mt)
-                        tv[l][mt] = (l < nlev) ? tcol[(size_t)ip[c][l] * NPT + mt * 8] : 1.0;
+            for (int e = 0; e < 2; ++e) {
 #pragma unroll
                 for (int mt = 0; mt < MT; ++mt) {
-                    double w = tv[0][mt];
-#pragma unroll
-                    for (int l = 1; l < LEVU; ++l) w *= tv[l][mt];  // absent levels are 1.0: keeps the block branch-free
-                    const double nv = fma(w, Dp[c >> 1][mt][c & 1], acc[mt]);
-                    acc[mt] = vp[c] ? nv : acc[mt];
+                    double w = 1.0;
+                    for (int l = 0; l < a.nlg; ++l) w *= tcol[(size_t)p_info[e][l] * NPT + mt * 8];
+                    if (p_valid[e]) acc[mt] = fma(w, acc2[e][mt], acc[mt]);
+                    acc2[e][mt] = 0.0;
                 }
             }
         };
 
+        int sg = 0, g8 = 0;  // step within the group, group index
         for (int s = 0; s < a.nslabs; ++s) {
             const int st = a.resident ? s : stage;
             mbar_wait(&full_bar[st], a.resident ? 0u : (round & 1));
@@ -274,18 +286,15 @@ __global__ void __launch_bounds__(NW * 32, 1) contract_mma_kernel(const __grid_c
                     for (int mt = 0; mt < MT; ++mt) D[j][mt][0] = D[j][mt][1] = 0.0;
                 const double *b0p = slab + (size_t)(r16 + g) * a.rs + t;
                 const double *b1p = b0p + (size_t)8 * a.rs;
-                // this step's row info (column c = 2*j + e -> local row r16 + 8j + 2t + e),
-                // clamped to a valid row so the table index is always in range
-                int ic[4][LEVU];
-                bool vc[4];
+                // this step's bookkeeping; the group-level rows of this lane's columns ride at the
+                // end of the tensor rows of the first N-tile
+                const bool c_end = (sg == spg - 1);
+                int c_info[2][3];
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const int lr = r16 + (c >> 1) * 8 + 2 * t + (c & 1);
-                    vc[c] = lr < rows;
-                    const int lrc = vc[c] ? lr : rows - 1;
-                    const int *info = reinterpret_cast<const int *>(slab + (size_t)lrc * a.rs + a.kp);
+                for (int e = 0; e < 2; ++e) {
+                    const int *info = reinterpret_cast<const int *>(slab + (size_t)(r16 + 2 * t + e) * a.rs + a.kp);
 #pragma unroll
-                    for (int l = 0; l < LEVU; ++l) ic[c][l] = (l < nlev) ? info[l] : 0;
+                    for (int l = 0; l < 3; ++l) c_info[e][l] = (c_end && l < a.nlg) ? info[l] : a.sumn;
                 }
 #pragma unroll
                 for (int kc = 0; kc < KC; ++kc) {
@@ -297,7 +306,8 @@ __global__ void __launch_bounds__(NW * 32, 1) contract_mma_kernel(const __grid_c
                         dmma884(D[1][mt][0], D[1][mt][1], A[mt][kc], b1);
                     }
                 }
-                weigh_pending();
+                fold_pending();
+                if (p_end) close_group();
 #pragma unroll
                 for (int j = 0; j < 2; ++j)
 #pragma unroll
@@ -305,12 +315,15 @@ __global__ void __launch_bounds__(NW * 32, 1) contract_mma_kernel(const __grid_c
                         Dp[j][mt][0] = D[j][mt][0];
                         Dp[j][mt][1] = D[j][mt][1];
                     }
+                p_iA = 2 * sg;
+                p_end = c_end;
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    vp[c] = vc[c];
+                for (int e = 0; e < 2; ++e) {
+                    p_valid[e] = (8 * g8 + 2 * t + e) < a.nrp;
 #pragma unroll
-                    for (int l = 0; l < LEVU; ++l) ip[c][l] = ic[c][l];
+                    for (int l = 0; l < 3; ++l) p_info[e][l] = c_info[e][l];
                 }
+                if (++sg == spg) { sg = 0; ++g8; }
             }
 
             if (!a.resident) {
@@ -332,7 +345,9 @@ __global__ void __launch_bounds__(NW * 32, 1) contract_mma_kernel(const __grid_c
                 if (++stage == ns) { stage = 0; ++round; }
             }
         }
-        weigh_pending();  // drain
+        fold_pending();  // drain: the last step always closes its group
+        close_group();
+        p_end = false;
 
         // ---- 4. sum the four lanes of each quad, store
 #pragma unroll
@@ -350,14 +365,14 @@ __global__ void __launch_bounds__(NW * 32, 1) contract_mma_kernel(const __grid_c
 bool mma_fit_ring(MmaArgs &a, int npt);
 namespace mma_detail {
 
-template <int KC, int MT, int NW, int LEVU>
+template <int KC, int MT, int NW>
 cudaError_t launch_one(const MmaArgs &a_in, int num_sms, cudaStream_t s, LaunchInfo *li)
 {
-    auto kern = contract_mma_kernel<KC, MT, NW, LEVU>;
+    auto kern = contract_mma_kernel<KC, MT, NW>;
     constexpr int NPT = NW * MT * 8;
     MmaArgs a = a_in;
-    if (a.nlev > LEVU || !mma_fit_ring(a, NPT)) return cudaErrorNotSupported;
-    const int smem = kBarBytes + a.ns * a.stage_bytes + a.sumn * NPT * 8;
+    if (!mma_fit_ring(a, NPT)) return cudaErrorNotSupported;
+    const int smem = kBarBytes + a.ns * a.stage_bytes + (a.sumn + 1) * NPT * 8;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     const int64_t ntiles = (a.npts + NPT - 1) / NPT;
