@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libchebpol_cuda.so")
+LIB_PATH = os.environ.get("CHEBPOL_CUDA_LIB") or os.path.join(_HERE, "libchebpol_cuda.so")
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)

@@ -132,13 +132,15 @@ struct MmaArgs {
     int rs;                // row stride in doubles (== 4 or 12 mod 16: conflict-free B loads)
     int kp;                // 4*KC: padded K; the row's group-level table rows (int32) start there
     int nlev;              // rank - nfold: unfolded dims
-    int nA, nAp;           // size of level A (1 if absent) and its padding to an even count
+    int nA, nAp;           // size of level A (1 if absent) and its padding to a multiple of ntb
+    int occ;               // CTAs per SM the ring is sized for (1 or 2)
+    int ntb;               // N-tiles (consecutive level-A indices) per step: 2, or 4 when K is small
     int boffA;             // basis-table row of level A (the ones row if absent)
     int nrp;               // number of r' values (prod of the dims after level A; 1 if none)
     int nlg;               // group levels: max(nlev - 1, 0) <= 3
-    int nrows;             // tensor rows: ceil(nrp/8) * nAp * 8 (a multiple of 16)
+    int nrows;             // tensor rows: ceil(nrp/8) * nAp * 8 (a multiple of 8*ntb)
     const int *ktab;       // [kp][3] basis-table rows of the folded dims for each k (-1: padding)
-    int rows_per_slab;     // multiple of 16
+    int rows_per_slab;     // multiple of 8*ntb
     int nslabs, ns, stage_bytes, resident;
     const double *x;
     int64_t npts;

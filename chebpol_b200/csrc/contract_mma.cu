@@ -6,116 +6,167 @@ namespace {
 constexpr int kMaxStages = 8;
 constexpr int kBarBytes = 128;
 constexpr int kSmemBudget = 220 * 1024;
+constexpr int kSmemBudget2 = 111 * 1024;  // two CTAs per SM (228 KB per SM, 1 KB reserved per CTA)
 constexpr int kLevMax = 4;
 }  // namespace
 
-cudaError_t mma_launch_2_1_4(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
-cudaError_t mma_launch_2_1_8(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
-cudaError_t mma_launch_2_2_8(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
-cudaError_t mma_launch_2_4_8(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
-cudaError_t mma_launch_3_1_4(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
-cudaError_t mma_launch_3_1_8(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
-cudaError_t mma_launch_3_2_8(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
-cudaError_t mma_launch_3_4_8(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
-cudaError_t mma_launch_4_1_4(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
-cudaError_t mma_launch_4_1_8(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
-cudaError_t mma_launch_4_2_8(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
-cudaError_t mma_launch_4_4_8(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
-cudaError_t mma_launch_6_1_4(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
-cudaError_t mma_launch_6_1_8(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
-cudaError_t mma_launch_6_2_8(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
-cudaError_t mma_launch_6_4_8(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
-cudaError_t mma_launch_8_1_4(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
-cudaError_t mma_launch_8_1_8(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
-cudaError_t mma_launch_8_2_8(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
-cudaError_t mma_launch_8_4_8(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
-cudaError_t mma_launch_10_1_4(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
-cudaError_t mma_launch_10_1_8(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
-cudaError_t mma_launch_10_2_8(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
-cudaError_t mma_launch_10_2_16(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
-cudaError_t mma_launch_10_4_8(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
-cudaError_t mma_launch_12_1_4(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
-cudaError_t mma_launch_12_1_8(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
-cudaError_t mma_launch_12_2_8(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
-cudaError_t mma_launch_12_4_8(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
-cudaError_t mma_launch_16_1_4(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
-cudaError_t mma_launch_16_1_8(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
-cudaError_t mma_launch_16_2_8(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
-cudaError_t mma_launch_16_3_8(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
-cudaError_t mma_launch_20_1_4(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
-cudaError_t mma_launch_20_1_8(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
-cudaError_t mma_launch_20_2_8(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
-cudaError_t mma_launch_25_1_4(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
-cudaError_t mma_launch_25_1_8(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
-cudaError_t mma_launch_25_1_16(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
-cudaError_t mma_launch_25_2_8(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
-cudaError_t mma_launch_30_1_4(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
-cudaError_t mma_launch_30_1_8(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
-cudaError_t mma_launch_30_2_8(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
-cudaError_t mma_launch_36_1_4(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
-cudaError_t mma_launch_36_1_8(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
-cudaError_t mma_launch_36_1_16(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
-cudaError_t mma_launch_36_2_8(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
-cudaError_t mma_launch_40_1_4(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
-cudaError_t mma_launch_40_1_8(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
-cudaError_t mma_launch_48_1_4(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
-cudaError_t mma_launch_48_1_8(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_2_1_4_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_2_1_8_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_2_1_16_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_2_2_4_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_2_2_8_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_2_2_12_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_2_4_8_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_3_1_4_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_3_1_8_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_3_1_16_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_3_2_4_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_3_2_8_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_3_2_12_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_3_4_8_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_4_1_4_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_4_1_8_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_4_1_16_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_4_2_4_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_4_2_8_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_4_2_12_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_4_4_8_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_6_1_4_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_6_1_8_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_6_1_16_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_6_2_4_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_6_2_8_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_6_2_12_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_6_4_8_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_8_1_4_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_8_1_8_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_8_1_16_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_8_2_4_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_8_2_8_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_8_2_12_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_8_4_8_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_10_1_4_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_10_1_8_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_10_1_16_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_10_2_4_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_10_2_8_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_10_2_12_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_10_4_8_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_12_1_4_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_12_1_8_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_12_1_16_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_12_2_4_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_12_2_8_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_12_2_12_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_12_4_8_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_16_1_4_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_16_1_8_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_16_2_4_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_16_2_8_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_16_3_8_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_20_1_4_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_20_1_8_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_20_2_4_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_20_2_8_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_25_1_4_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_25_1_8_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_25_1_16_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_25_2_4_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_25_2_8_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_30_1_4_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_30_1_8_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_30_2_4_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_30_2_8_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_36_1_4_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_36_1_8_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_36_1_16_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_36_2_4_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_36_2_8_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_40_1_4_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_40_1_8_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_48_1_4_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_48_1_8_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
 
 namespace {
 typedef cudaError_t (*LaunchFn)(const MmaArgs &, int, cudaStream_t, LaunchInfo *);
-struct Inst { int kc, mt, nw; LaunchFn fn; };
+struct Inst { int kc, mt, nw, ntb; LaunchFn fn; };
 const Inst kInsts[] = {
-    {2, 1, 4, mma_launch_2_1_4},
-    {2, 1, 8, mma_launch_2_1_8},
-    {2, 2, 8, mma_launch_2_2_8},
-    {2, 4, 8, mma_launch_2_4_8},
-    {3, 1, 4, mma_launch_3_1_4},
-    {3, 1, 8, mma_launch_3_1_8},
-    {3, 2, 8, mma_launch_3_2_8},
-    {3, 4, 8, mma_launch_3_4_8},
-    {4, 1, 4, mma_launch_4_1_4},
-    {4, 1, 8, mma_launch_4_1_8},
-    {4, 2, 8, mma_launch_4_2_8},
-    {4, 4, 8, mma_launch_4_4_8},
-    {6, 1, 4, mma_launch_6_1_4},
-    {6, 1, 8, mma_launch_6_1_8},
-    {6, 2, 8, mma_launch_6_2_8},
-    {6, 4, 8, mma_launch_6_4_8},
-    {8, 1, 4, mma_launch_8_1_4},
-    {8, 1, 8, mma_launch_8_1_8},
-    {8, 2, 8, mma_launch_8_2_8},
-    {8, 4, 8, mma_launch_8_4_8},
-    {10, 1, 4, mma_launch_10_1_4},
-    {10, 1, 8, mma_launch_10_1_8},
-    {10, 2, 8, mma_launch_10_2_8},
-    {10, 2, 16, mma_launch_10_2_16},
-    {10, 4, 8, mma_launch_10_4_8},
-    {12, 1, 4, mma_launch_12_1_4},
-    {12, 1, 8, mma_launch_12_1_8},
-    {12, 2, 8, mma_launch_12_2_8},
-    {12, 4, 8, mma_launch_12_4_8},
-    {16, 1, 4, mma_launch_16_1_4},
-    {16, 1, 8, mma_launch_16_1_8},
-    {16, 2, 8, mma_launch_16_2_8},
-    {16, 3, 8, mma_launch_16_3_8},
-    {20, 1, 4, mma_launch_20_1_4},
-    {20, 1, 8, mma_launch_20_1_8},
-    {20, 2, 8, mma_launch_20_2_8},
-    {25, 1, 4, mma_launch_25_1_4},
-    {25, 1, 8, mma_launch_25_1_8},
-    {25, 1, 16, mma_launch_25_1_16},
-    {25, 2, 8, mma_launch_25_2_8},
-    {30, 1, 4, mma_launch_30_1_4},
-    {30, 1, 8, mma_launch_30_1_8},
-    {30, 2, 8, mma_launch_30_2_8},
-    {36, 1, 4, mma_launch_36_1_4},
-    {36, 1, 8, mma_launch_36_1_8},
-    {36, 1, 16, mma_launch_36_1_16},
-    {36, 2, 8, mma_launch_36_2_8},
-    {40, 1, 4, mma_launch_40_1_4},
-    {40, 1, 8, mma_launch_40_1_8},
-    {48, 1, 4, mma_launch_48_1_4},
-    {48, 1, 8, mma_launch_48_1_8}
+    {2, 1, 4, 2, mma_launch_2_1_4_2},
+    {2, 1, 8, 2, mma_launch_2_1_8_2},
+    {2, 1, 16, 2, mma_launch_2_1_16_2},
+    {2, 2, 4, 2, mma_launch_2_2_4_2},
+    {2, 2, 8, 2, mma_launch_2_2_8_2},
+    {2, 2, 12, 2, mma_launch_2_2_12_2},
+    {2, 4, 8, 2, mma_launch_2_4_8_2},
+    {3, 1, 4, 2, mma_launch_3_1_4_2},
+    {3, 1, 8, 2, mma_launch_3_1_8_2},
+    {3, 1, 16, 2, mma_launch_3_1_16_2},
+    {3, 2, 4, 2, mma_launch_3_2_4_2},
+    {3, 2, 8, 2, mma_launch_3_2_8_2},
+    {3, 2, 12, 2, mma_launch_3_2_12_2},
+    {3, 4, 8, 2, mma_launch_3_4_8_2},
+    {4, 1, 4, 2, mma_launch_4_1_4_2},
+    {4, 1, 8, 2, mma_launch_4_1_8_2},
+    {4, 1, 16, 2, mma_launch_4_1_16_2},
+    {4, 2, 4, 2, mma_launch_4_2_4_2},
+    {4, 2, 8, 2, mma_launch_4_2_8_2},
+    {4, 2, 12, 2, mma_launch_4_2_12_2},
+    {4, 4, 8, 2, mma_launch_4_4_8_2},
+    {6, 1, 4, 2, mma_launch_6_1_4_2},
+    {6, 1, 8, 2, mma_launch_6_1_8_2},
+    {6, 1, 16, 2, mma_launch_6_1_16_2},
+    {6, 2, 4, 2, mma_launch_6_2_4_2},
+    {6, 2, 8, 2, mma_launch_6_2_8_2},
+    {6, 2, 12, 2, mma_launch_6_2_12_2},
+    {6, 4, 8, 2, mma_launch_6_4_8_2},
+    {8, 1, 4, 2, mma_launch_8_1_4_2},
+    {8, 1, 8, 2, mma_launch_8_1_8_2},
+    {8, 1, 16, 2, mma_launch_8_1_16_2},
+    {8, 2, 4, 2, mma_launch_8_2_4_2},
+    {8, 2, 8, 2, mma_launch_8_2_8_2},
+    {8, 2, 12, 2, mma_launch_8_2_12_2},
+    {8, 4, 8, 2, mma_launch_8_4_8_2},
+    {10, 1, 4, 2, mma_launch_10_1_4_2},
+    {10, 1, 8, 2, mma_launch_10_1_8_2},
+    {10, 1, 16, 2, mma_launch_10_1_16_2},
+    {10, 2, 4, 2, mma_launch_10_2_4_2},
+    {10, 2, 8, 2, mma_launch_10_2_8_2},
+    {10, 2, 12, 2, mma_launch_10_2_12_2},
+    {10, 4, 8, 2, mma_launch_10_4_8_2},
+    {12, 1, 4, 2, mma_launch_12_1_4_2},
+    {12, 1, 8, 2, mma_launch_12_1_8_2},
+    {12, 1, 16, 2, mma_launch_12_1_16_2},
+    {12, 2, 4, 2, mma_launch_12_2_4_2},
+    {12, 2, 8, 2, mma_launch_12_2_8_2},
+    {12, 2, 12, 2, mma_launch_12_2_12_2},
+    {12, 4, 8, 2, mma_launch_12_4_8_2},
+    {16, 1, 4, 2, mma_launch_16_1_4_2},
+    {16, 1, 8, 2, mma_launch_16_1_8_2},
+    {16, 2, 4, 2, mma_launch_16_2_4_2},
+    {16, 2, 8, 2, mma_launch_16_2_8_2},
+    {16, 3, 8, 2, mma_launch_16_3_8_2},
+    {20, 1, 4, 2, mma_launch_20_1_4_2},
+    {20, 1, 8, 2, mma_launch_20_1_8_2},
+    {20, 2, 4, 2, mma_launch_20_2_4_2},
+    {20, 2, 8, 2, mma_launch_20_2_8_2},
+    {25, 1, 4, 2, mma_launch_25_1_4_2},
+    {25, 1, 8, 2, mma_launch_25_1_8_2},
+    {25, 1, 16, 2, mma_launch_25_1_16_2},
+    {25, 2, 4, 2, mma_launch_25_2_4_2},
+    {25, 2, 8, 2, mma_launch_25_2_8_2},
+    {30, 1, 4, 2, mma_launch_30_1_4_2},
+    {30, 1, 8, 2, mma_launch_30_1_8_2},
+    {30, 2, 4, 2, mma_launch_30_2_4_2},
+    {30, 2, 8, 2, mma_launch_30_2_8_2},
+    {36, 1, 4, 2, mma_launch_36_1_4_2},
+    {36, 1, 8, 2, mma_launch_36_1_8_2},
+    {36, 1, 16, 2, mma_launch_36_1_16_2},
+    {36, 2, 4, 2, mma_launch_36_2_4_2},
+    {36, 2, 8, 2, mma_launch_36_2_8_2},
+    {40, 1, 4, 2, mma_launch_40_1_4_2},
+    {40, 1, 8, 2, mma_launch_40_1_8_2},
+    {48, 1, 4, 2, mma_launch_48_1_4_2},
+    {48, 1, 8, 2, mma_launch_48_1_8_2}
 };
 
 // smallest instantiated KC with 4*KC >= K (0: none)
@@ -132,13 +183,15 @@ int pick_kc(int K)
 // slabs, stages.  False if it does not fit in shared memory.
 bool mma_fit_ring(MmaArgs &a, int npt)
 {
-    const int left = kSmemBudget - kBarBytes - (a.sumn + 1) * npt * 8;
+    const int budget = a.occ == 2 ? kSmemBudget2 : kSmemBudget;
+    const int left = budget - kBarBytes - (a.sumn + 1) * npt * 8;
     if (left <= 0) return false;
     const int row_bytes = a.rs * 8;
     int slab_cap = left / 3;
     if (slab_cap > 64 * 1024) slab_cap = 64 * 1024;
-    int64_t rps = slab_cap / row_bytes / 16 * 16;
-    if (rps < 16) rps = 16;
+    const int step_rows = 8 * a.ntb;
+    int64_t rps = slab_cap / row_bytes / step_rows * step_rows;
+    if (rps < step_rows) rps = step_rows;
     if (rps > a.nrows) rps = a.nrows;
     a.rows_per_slab = (int)rps;
     a.nslabs = (int)((a.nrows + rps - 1) / rps);
@@ -191,7 +244,8 @@ bool mma_configure(MmaArgs &a, int kind, int rank, const int *dims, int *kc_out)
     a.nlg = a.nlev > 1 ? a.nlev - 1 : 0;
     // level A: the first unfolded dim (absent: one entry weighted by the table's ones row)
     a.nA = a.nlev >= 1 ? dims[best_nf] : 1;
-    a.nAp = (a.nA + 1) & ~1;
+    a.ntb = 2;  // 4 N-tiles per step measured no faster for short K (FH 40^3: 0.725 vs 0.72)
+    a.nAp = (a.nA + a.ntb - 1) / a.ntb * a.ntb;
     a.boffA = a.nlev >= 1 ? a.boff[best_nf] : a.sumn;
     int64_t nrp = 1;
     for (int d = best_nf + 1; d < rank; ++d) nrp *= dims[d];
@@ -204,7 +258,7 @@ bool mma_configure(MmaArgs &a, int kind, int rank, const int *dims, int *kc_out)
     a.rs = rs;
     // some layout must fit
     for (const auto &i : kInsts) {
-        if (i.kc != kc) continue;
+        if (i.kc != kc || i.ntb != a.ntb) continue;
         MmaArgs probe = a;
         if (mma_fit_ring(probe, i.nw * i.mt * 8)) {
             a.rows_per_slab = probe.rows_per_slab;
@@ -219,22 +273,25 @@ bool mma_configure(MmaArgs &a, int kind, int rank, const int *dims, int *kc_out)
 }
 
 // variant 0: default layout -- 8 warps with the most point tiles per warp (MT) whose basis
-// table leaves room for the ring, else 4 warps.  variant MT*100 + NW forces a layout.
+// table leaves room for the ring, else 4 warps.  variant OCC*10000 + MT*100 + NW forces a layout
+// (OCC = 2: ring sized for two co-resident CTAs per SM, grid of 2 x SMs).
 cudaError_t launch_contract_mma(const MmaArgs &a, int variant, int num_sms, cudaStream_t s, LaunchInfo *li)
 {
     const int kc = pick_kc(a.K);
     if (!kc) return cudaErrorNotSupported;
     if (variant >= 100) {
-        const int mt = variant / 100, nw = variant % 100;
+        const int occ = variant / 10000, mt = (variant / 100) % 100, nw = variant % 100;
+        MmaArgs b = a;
+        b.occ = occ == 2 ? 2 : 1;
         for (const auto &i : kInsts)
-            if (i.kc == kc && i.mt == mt && i.nw == nw) return i.fn(a, num_sms, s, li);
+            if (i.kc == kc && i.mt == mt && i.nw == nw && i.ntb == a.ntb) return i.fn(b, num_sms, s, li);
         return cudaErrorNotSupported;
     }
     const Inst *best = nullptr;
     for (int pass = 0; pass < 2 && !best; ++pass) {
         const int nw = pass == 0 ? 8 : 4;
         for (const auto &i : kInsts) {
-            if (i.kc != kc || i.nw != nw) continue;
+            if (i.kc != kc || i.nw != nw || i.ntb != a.ntb) continue;
             MmaArgs probe = a;
             if (!mma_fit_ring(probe, i.nw * i.mt * 8)) continue;
             if (!best || i.mt > best->mt) best = &i;

@@ -69,54 +69,72 @@ __device__ __forceinline__ void cheb_basis(double *col, int n, double x)
     }
 }
 
-// Floater-Hormann basis b_i = q_i / sum q, q_i = w_i * prod_{j != i} (x - k_j) * s^(n-1)
-// (prefix/suffix products, one reciprocal), which equals (w_i/(x-k_i)) / sum_j (w_j/(x-k_j)).
-// Knot hit (first i with |x-k_i| < 10*DBL_EPSILON, src/chebpol.c:195-197): one-hot.
+// 1/d to full double precision without the IEEE slow path: the 20-bit hardware seed and two
+// Newton steps.  d is never subnormal here (knot hits are peeled off first).
+__device__ __forceinline__ double fast_rcp(double d)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+    double e = fma(-d, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-d, r, 1.0);
+    r = fma(r, e, r);
+    return r;
+}
+
+// Floater-Hormann basis b_i = (w_i/(x-k_i)) / sum_j (w_j/(x-k_j)), the reference's own form
+// (src/chebpol.c:199-215).  The n reciprocals are independent, so the loop pipelines; the only
+// serial chain is the running sum.  Knot hit (first i with |x-k_i| < 10*DBL_EPSILON,
+// src/chebpol.c:195-197): one-hot.
 template <int NPT>
 __device__ __forceinline__ void fh_basis(double *col, int n, double x, const double *__restrict__ kn,
                                          const double *__restrict__ w)
 {
-    int hit = -1;
-    for (int i = 0; i < n; ++i)
-        if (fabs(x - __ldg(kn + i)) < 10.0 * DBL_EPSILON) { hit = i; break; }
-    if (hit >= 0 || x != x) {
-        for (int i = 0; i < n; ++i) col[(size_t)i * NPT] = (i == hit) ? 1.0 : ((x != x) ? x : 0.0);
+    int hit = n;
+    double den0 = 0.0, den1 = 0.0;
+    int i = 0;
+#pragma unroll 2
+    for (; i + 1 < n; i += 2) {
+        const double d0 = x - __ldg(kn + i), d1 = x - __ldg(kn + i + 1);
+        const double p0 = __ldg(w + i) * fast_rcp(d0), p1 = __ldg(w + i + 1) * fast_rcp(d1);
+        col[(size_t)i * NPT] = p0;
+        col[(size_t)(i + 1) * NPT] = p1;
+        den0 += p0;
+        den1 += p1;
+        hit = (fabs(d1) < 10.0 * DBL_EPSILON && i + 1 < hit) ? i + 1 : hit;
+        hit = (fabs(d0) < 10.0 * DBL_EPSILON && i < hit) ? i : hit;
+    }
+    if (i < n) {
+        const double d0 = x - __ldg(kn + i);
+        const double p0 = __ldg(w + i) * fast_rcp(d0);
+        col[(size_t)i * NPT] = p0;
+        den0 += p0;
+        hit = (fabs(d0) < 10.0 * DBL_EPSILON && i < hit) ? i : hit;
+    }
+    if (hit < n || x != x) {
+        for (int j = 0; j < n; ++j) col[(size_t)j * NPT] = (j == hit) ? 1.0 : ((x != x) ? x : 0.0);
         return;
     }
-    // distances scaled so that the products stay near 1 inside the grid
-    const double k0 = __ldg(kn), k1 = __ldg(kn + n - 1);
-    const double span = fabs(k1 - k0);
-    const double inv_s = (n > 1 && span > 0.0) ? 4.0 / span : 1.0;
-    double pre = 1.0;
-    for (int i = 0; i < n; ++i) {
-        col[(size_t)i * NPT] = pre;
-        pre *= (x - __ldg(kn + i)) * inv_s;
-    }
-    double suf = 1.0, sum = 0.0;
-    for (int i = n - 1; i >= 0; --i) {
-        const double q = __ldg(w + i) * col[(size_t)i * NPT] * suf;
-        col[(size_t)i * NPT] = q;
-        sum += q;
-        suf *= (x - __ldg(kn + i)) * inv_s;
-    }
-    const double r = 1.0 / sum;
-    if (isfinite(r) && isfinite(sum) && r != 0.0) {
-        for (int i = 0; i < n; ++i) col[(size_t)i * NPT] *= r;
+    const double den = den0 + den1;
+    const double r = 1.0 / den;
+    if (isfinite(r)) {
+#pragma unroll 4
+        for (int j = 0; j < n; ++j) col[(size_t)j * NPT] *= r;
     } else {
-        // products over/underflowed (extreme extrapolation or very long grids): the
-        // reference's own form, one division per knot
-        double den = 0.0;
-        for (int i = 0; i < n; ++i) {
-            const double p = __ldg(w + i) / (x - __ldg(kn + i));
-            col[(size_t)i * NPT] = p;
-            den += p;
+        // the sum cancelled to zero or left the range (extreme extrapolation): redo it with IEEE
+        // divisions in the reference's order, so the result is finite exactly when the reference's is
+        double dsum = 0.0;
+        for (int j = 0; j < n; ++j) {
+            const double p = __ldg(w + j) / (x - __ldg(kn + j));
+            col[(size_t)j * NPT] = p;
+            dsum += p;
         }
-        for (int i = 0; i < n; ++i) col[(size_t)i * NPT] /= den;
+        for (int j = 0; j < n; ++j) col[(size_t)j * NPT] /= dsum;
     }
 }
 
-// KC: K/4 (padded); MT: 8-point tiles per warp; NW: warps.
-template <int KC, int MT, int NW>
+// KC: K/4 (padded); MT: 8-point tiles per warp; NW: warps; NTB: N-tiles (level-A indices) per step.
+template <int KC, int MT, int NW, int NTB>
 __global__ void __launch_bounds__(NW * 32, 1) contract_mma_kernel(const __grid_constant__ MmaArgs a)
 {
     constexpr int NPT = NW * MT * 8;  // points per pass
@@ -135,7 +153,8 @@ __global__ void __launch_bounds__(NW * 32, 1) contract_mma_kernel(const __grid_c
     const int64_t total_fills = a.resident ? (int64_t)a.nslabs : my_tiles * a.nslabs;
     const int rps = a.rows_per_slab;
     const uint32_t row_bytes = (uint32_t)a.rs * 8u;
-    const int spg = a.nAp >> 1;  // steps per group (a group = one tile of 8 r' values, all of level A)
+    const int spg = a.nAp / NTB;  // steps per group (a group = one tile of 8 r' values, all of level A)
+    constexpr int ROWS_STEP = 8 * NTB;
 
     auto slab_rows = [&](int s) { const int left = a.nrows - s * rps; return left < rps ? left : rps; };
     auto issue_fill = [&](int64_t f, int stage) {
@@ -187,7 +206,11 @@ __global__ void __launch_bounds__(NW * 32, 1) contract_mma_kernel(const __grid_c
             const int64_t p = tile * NPT + pt;
             double *col = Tb + (size_t)a.boff[L] * NPT + pt;
             const int n = a.dims[L];
+#if defined(MMA_ABL) && (MMA_ABL & 8)
+            if (p < 0) {
+#else
             if (p < a.npts) {
+#endif
                 const double xv = xpre[q];
                 if (a.kind == 0) cheb_basis<NPT>(col, n, premap_coord(a.pm, L, xv));
                 else fh_basis<NPT>(col, n, xv, a.grid + a.goff[L], a.weights + a.goff[L]);
@@ -218,9 +241,9 @@ __global__ void __launch_bounds__(NW * 32, 1) contract_mma_kernel(const __grid_c
             }
         }
 
-        // ---- 3. stream the tensor rows.  A step is 16 rows: two 8-row N-tiles that hold the SAME
-        // eight r' columns at two consecutive level-A indices (iA, iA+1); a group is the nAp/2
-        // steps that walk level A for those columns.  Per step the epilogue is therefore one
+        // ---- 3. stream the tensor rows.  A step is 8*NTB rows: NTB 8-row N-tiles that hold the SAME
+        // eight r' columns at NTB consecutive level-A indices; a group is the nAp/NTB steps that
+        // walk level A for those columns.  Per step the epilogue is therefore one
         // basis value per N-tile and point tile and one DFMA per D element (acc2 += b_A * D);
         // the weights of the remaining levels are applied once per group (acc += W * acc2).
         // Software pipeline: the D tiles of step q-1 are folded in while the DMMAs of step q are
@@ -228,9 +251,9 @@ __global__ void __launch_bounds__(NW * 32, 1) contract_mma_kernel(const __grid_c
         double acc[MT], acc2[2][MT];
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) acc[mt] = acc2[0][mt] = acc2[1][mt] = 0.0;
-        double Dp[2][MT][2];
+        double Dp[NTB][MT][2];
 #pragma unroll
-        for (int j = 0; j < 2; ++j)
+        for (int j = 0; j < NTB; ++j)
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt) Dp[j][mt][0] = Dp[j][mt][1] = 0.0;
         int p_iA = 0;             // level-A index of the pending step's first N-tile
@@ -245,18 +268,20 @@ __global__ void __launch_bounds__(NW * 32, 1) contract_mma_kernel(const __grid_c
         const int nA1 = a.nA - 1;
 
         auto fold_pending = [&]() {
-            const int ia0 = p_iA < nA1 ? p_iA : nA1, ia1 = p_iA + 1 < nA1 ? p_iA + 1 : nA1;
-            const double *t0 = tcol + (size_t)(a.boffA + ia0) * NPT;
-            const double *t1 = tcol + (size_t)(a.boffA + ia1) * NPT;
+            double bA[NTB][MT];
 #pragma unroll
-            for (int mt = 0; mt < MT; ++mt) {
-                const double b0 = t0[mt * 8], b1 = t1[mt * 8];
+            for (int j = 0; j < NTB; ++j) {
+                const int ia = p_iA + j < nA1 ? p_iA + j : nA1;  // padded indices: their tensor rows are zero
+                const double *tj = tcol + (size_t)(a.boffA + ia) * NPT;
 #pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    acc2[e][mt] = fma(b0, Dp[0][mt][e], acc2[e][mt]);
-                    acc2[e][mt] = fma(b1, Dp[1][mt][e], acc2[e][mt]);
-                }
+                for (int mt = 0; mt < MT; ++mt) bA[j][mt] = tj[mt * 8];
             }
+#pragma unroll
+            for (int j = 0; j < NTB; ++j)
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) acc2[e][mt] = fma(bA[j][mt], Dp[j][mt][e], acc2[e][mt]);
         };
         auto close_group = [&]() {
 #pragma unroll
@@ -278,14 +303,13 @@ __global__ void __launch_bounds__(NW * 32, 1) contract_mma_kernel(const __grid_c
             const double *slab = reinterpret_cast<const double *>(ring + (size_t)st * a.stage_bytes);
             const int rows = slab_rows(s);
 
-            for (int r16 = 0; r16 < rows; r16 += 16) {
-                double D[2][MT][2];
+            for (int r16 = 0; r16 < rows; r16 += ROWS_STEP) {
+                double D[NTB][MT][2];
 #pragma unroll
-                for (int j = 0; j < 2; ++j)
+                for (int j = 0; j < NTB; ++j)
 #pragma unroll
                     for (int mt = 0; mt < MT; ++mt) D[j][mt][0] = D[j][mt][1] = 0.0;
-                const double *b0p = slab + (size_t)(r16 + g) * a.rs + t;
-                const double *b1p = b0p + (size_t)8 * a.rs;
+                const double *bp = slab + (size_t)(r16 + g) * a.rs + t;
                 // this step's bookkeeping; the group-level rows of this lane's columns ride at the
                 // end of the tensor rows of the first N-tile
                 const bool c_end = (sg == spg - 1);
@@ -294,28 +318,41 @@ __global__ void __launch_bounds__(NW * 32, 1) contract_mma_kernel(const __grid_c
                 for (int e = 0; e < 2; ++e) {
                     const int *info = reinterpret_cast<const int *>(slab + (size_t)(r16 + 2 * t + e) * a.rs + a.kp);
 #pragma unroll
+#if defined(MMA_ABL) && (MMA_ABL & 2)
+                    for (int l = 0; l < 3; ++l) c_info[e][l] = a.sumn + 0 * (int)(size_t)info;
+#else
                     for (int l = 0; l < 3; ++l) c_info[e][l] = (c_end && l < a.nlg) ? info[l] : a.sumn;
+#endif
                 }
 #pragma unroll
                 for (int kc = 0; kc < KC; ++kc) {
-                    const double b0 = b0p[4 * kc];
-                    const double b1 = b1p[4 * kc];
+                    double b[NTB];
 #pragma unroll
-                    for (int mt = 0; mt < MT; ++mt) {
-                        dmma884(D[0][mt][0], D[0][mt][1], A[mt][kc], b0);
-                        dmma884(D[1][mt][0], D[1][mt][1], A[mt][kc], b1);
-                    }
+#if defined(MMA_ABL) && (MMA_ABL & 4)
+                    for (int j = 0; j < NTB; ++j) b[j] = bp[(size_t)j * 8 * a.rs];
+#else
+                    for (int j = 0; j < NTB; ++j) b[j] = bp[(size_t)j * 8 * a.rs + 4 * kc];
+#endif
+#pragma unroll
+                    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                        for (int j = 0; j < NTB; ++j) dmma884(D[j][mt][0], D[j][mt][1], A[mt][kc], b[j]);
                 }
+#if defined(MMA_ABL) && (MMA_ABL & 1)
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) acc[mt] += Dp[0][mt][0] + Dp[1][mt][1];
+#else
                 fold_pending();
                 if (p_end) close_group();
+#endif
 #pragma unroll
-                for (int j = 0; j < 2; ++j)
+                for (int j = 0; j < NTB; ++j)
 #pragma unroll
                     for (int mt = 0; mt < MT; ++mt) {
                         Dp[j][mt][0] = D[j][mt][0];
                         Dp[j][mt][1] = D[j][mt][1];
                     }
-                p_iA = 2 * sg;
+                p_iA = NTB * sg;
                 p_end = c_end;
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
@@ -365,18 +402,19 @@ __global__ void __launch_bounds__(NW * 32, 1) contract_mma_kernel(const __grid_c
 bool mma_fit_ring(MmaArgs &a, int npt);
 namespace mma_detail {
 
-template <int KC, int MT, int NW>
+template <int KC, int MT, int NW, int NTB>
 cudaError_t launch_one(const MmaArgs &a_in, int num_sms, cudaStream_t s, LaunchInfo *li)
 {
-    auto kern = contract_mma_kernel<KC, MT, NW>;
+    auto kern = contract_mma_kernel<KC, MT, NW, NTB>;
     constexpr int NPT = NW * MT * 8;
     MmaArgs a = a_in;
-    if (!mma_fit_ring(a, NPT)) return cudaErrorNotSupported;
+    if (a.ntb != NTB || !mma_fit_ring(a, NPT)) return cudaErrorNotSupported;
     const int smem = kBarBytes + a.ns * a.stage_bytes + (a.sumn + 1) * NPT * 8;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     const int64_t ntiles = (a.npts + NPT - 1) / NPT;
-    int grid = (int)(ntiles < num_sms ? ntiles : num_sms);
+    const int ctas = num_sms * (a.occ == 2 ? 2 : 1);
+    int grid = (int)(ntiles < ctas ? ntiles : ctas);
     if (grid < 1) grid = 1;
     kern<<<grid, NW * 32, smem, s>>>(a);
     if (li) { li->grid = grid; li->block = NW * 32; li->smem = smem; li->kernel = a.kind == 0 ? K_CHEB_MMA : K_FH_MMA; }
