@@ -61,11 +61,13 @@ cudaError_t mma_launch_12_2_12_2(const MmaArgs &a, int num_sms, cudaStream_t s, 
 cudaError_t mma_launch_12_4_8_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
 cudaError_t mma_launch_16_1_4_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
 cudaError_t mma_launch_16_1_8_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_16_1_16_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
 cudaError_t mma_launch_16_2_4_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
 cudaError_t mma_launch_16_2_8_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
 cudaError_t mma_launch_16_3_8_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
 cudaError_t mma_launch_20_1_4_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
 cudaError_t mma_launch_20_1_8_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t mma_launch_20_1_16_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
 cudaError_t mma_launch_20_2_4_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
 cudaError_t mma_launch_20_2_8_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
 cudaError_t mma_launch_25_1_4_2(const MmaArgs &a, int num_sms, cudaStream_t s, LaunchInfo *li);
@@ -142,11 +144,13 @@ const Inst kInsts[] = {
     {12, 4, 8, 2, mma_launch_12_4_8_2},
     {16, 1, 4, 2, mma_launch_16_1_4_2},
     {16, 1, 8, 2, mma_launch_16_1_8_2},
+    {16, 1, 16, 2, mma_launch_16_1_16_2},
     {16, 2, 4, 2, mma_launch_16_2_4_2},
     {16, 2, 8, 2, mma_launch_16_2_8_2},
     {16, 3, 8, 2, mma_launch_16_3_8_2},
     {20, 1, 4, 2, mma_launch_20_1_4_2},
     {20, 1, 8, 2, mma_launch_20_1_8_2},
+    {20, 1, 16, 2, mma_launch_20_1_16_2},
     {20, 2, 4, 2, mma_launch_20_2_4_2},
     {20, 2, 8, 2, mma_launch_20_2_8_2},
     {25, 1, 4, 2, mma_launch_25_1_4_2},
@@ -287,13 +291,25 @@ cudaError_t launch_contract_mma(const MmaArgs &a, int variant, int num_sms, cuda
             if (i.kc == kc && i.mt == mt && i.nw == nw && i.ntb == a.ntb) return i.fn(b, num_sms, s, li);
         return cudaErrorNotSupported;
     }
+    // Measured preference (tools/layout_sweep.py): up to K = 100 sixteen one-tile warps hide the
+    // per-step epilogue best, then twelve two-tile warps; longer K wants the most point tiles
+    // per warp that still leave room for the ring.
     const Inst *best = nullptr;
+    auto fits = [&](const Inst &i) {
+        MmaArgs probe = a;
+        return mma_fit_ring(probe, i.nw * i.mt * 8);
+    };
+    if (kc <= 25) {
+        static const int pref[2][2] = {{1, 16}, {2, 12}};
+        for (int q = 0; q < 2 && !best; ++q)
+            for (const auto &i : kInsts)
+                if (i.kc == kc && i.ntb == a.ntb && i.mt == pref[q][0] && i.nw == pref[q][1] && fits(i)) { best = &i; break; }
+    }
     for (int pass = 0; pass < 2 && !best; ++pass) {
         const int nw = pass == 0 ? 8 : 4;
         for (const auto &i : kInsts) {
-            if (i.kc != kc || i.nw != nw || i.ntb != a.ntb) continue;
-            MmaArgs probe = a;
-            if (!mma_fit_ring(probe, i.nw * i.mt * 8)) continue;
+            if (i.kc != kc || i.nw != nw || i.ntb != a.ntb || (kc <= 12 && i.mt > 2)) continue;
+            if (!fits(i)) continue;
             if (!best || i.mt > best->mt) best = &i;
         }
     }

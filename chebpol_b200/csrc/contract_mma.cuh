@@ -274,7 +274,11 @@ __global__ void __launch_bounds__(NW * 32, 1) contract_mma_kernel(const __grid_c
                 const int ia = p_iA + j < nA1 ? p_iA + j : nA1;  // padded indices: their tensor rows are zero
                 const double *tj = tcol + (size_t)(a.boffA + ia) * NPT;
 #pragma unroll
+#if defined(MMA_ABL) && (MMA_ABL & 32)
+                for (int mt = 0; mt < MT; ++mt) bA[j][mt] = 1.0 + (double)(ia + (int)(size_t)tj);
+#else
                 for (int mt = 0; mt < MT; ++mt) bA[j][mt] = tj[mt * 8];
+#endif
             }
 #pragma unroll
             for (int j = 0; j < NTB; ++j)
@@ -283,17 +287,25 @@ __global__ void __launch_bounds__(NW * 32, 1) contract_mma_kernel(const __grid_c
 #pragma unroll
                     for (int e = 0; e < 2; ++e) acc2[e][mt] = fma(bA[j][mt], Dp[j][mt][e], acc2[e][mt]);
         };
+        // Runs on group boundaries only (a warp-uniform branch).  Straight-line: the loads of all
+        // weights go out together (absent levels read the ones row), so the exposed latency is one
+        // shared-memory round trip and three dependent multiplies, not a chain per level.
         auto close_group = [&]() {
+            double w[2][MT][3];
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
+            for (int e = 0; e < 2; ++e)
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                    for (int l = 0; l < 3; ++l) w[e][mt][l] = tcol[(size_t)p_info[e][l] * NPT + mt * 8];
+#pragma unroll
+            for (int e = 0; e < 2; ++e)
 #pragma unroll
                 for (int mt = 0; mt < MT; ++mt) {
-                    double w = 1.0;
-                    for (int l = 0; l < a.nlg; ++l) w *= tcol[(size_t)p_info[e][l] * NPT + mt * 8];
-                    if (p_valid[e]) acc[mt] = fma(w, acc2[e][mt], acc[mt]);
+                    const double ww = w[e][mt][0] * w[e][mt][1] * w[e][mt][2];
+                    acc[mt] = fma(p_valid[e] ? ww : 0.0, acc2[e][mt], acc[mt]);
                     acc2[e][mt] = 0.0;
                 }
-            }
         };
 
         int sg = 0, g8 = 0;  // step within the group, group index
@@ -343,7 +355,9 @@ __global__ void __launch_bounds__(NW * 32, 1) contract_mma_kernel(const __grid_c
                 for (int mt = 0; mt < MT; ++mt) acc[mt] += Dp[0][mt][0] + Dp[1][mt][1];
 #else
                 fold_pending();
+#if !(defined(MMA_ABL) && (MMA_ABL & 16))
                 if (p_end) close_group();
+#endif
 #endif
 #pragma unroll
                 for (int j = 0; j < NTB; ++j)
