@@ -251,130 +251,124 @@ __global__ void __launch_bounds__(NW * 32, 1) contract_mma_kernel(const __grid_c
         double acc[MT], acc2[2][MT];
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) acc[mt] = acc2[0][mt] = acc2[1][mt] = 0.0;
-        double Dp[NTB][MT][2];
+        // a step's D tiles and what the epilogue needs to know about them
+        struct Step {
+            double D[NTB][MT][2];
+            int iA;          // level-A index of the first N-tile
+            bool end;        // the step closes its group
+            int info[2][3];  // basis-table rows of the group levels of this lane's two columns
+            bool valid[2];   // the columns exist (r' < nrp)
+        };
+        Step P0, P1;  // the step loop is unrolled by two: the roles (in flight / pending) alternate
 #pragma unroll
         for (int j = 0; j < NTB; ++j)
 #pragma unroll
-            for (int mt = 0; mt < MT; ++mt) Dp[j][mt][0] = Dp[j][mt][1] = 0.0;
-        int p_iA = 0;             // level-A index of the pending step's first N-tile
-        bool p_end = false;       // the pending step closes its group
-        int p_info[2][3];         // basis-table rows of the group levels of this lane's two columns
-        bool p_valid[2] = {false, false};
+            for (int mt = 0; mt < MT; ++mt) P1.D[j][mt][0] = P1.D[j][mt][1] = 0.0;
+        P1.iA = 0;
+        P1.end = false;
+        P1.valid[0] = P1.valid[1] = false;
 #pragma unroll
         for (int e = 0; e < 2; ++e)
 #pragma unroll
-            for (int l = 0; l < 3; ++l) p_info[e][l] = a.sumn;
+            for (int l = 0; l < 3; ++l) P1.info[e][l] = a.sumn;
         const double *tcol = Tb + warp * MT * 8 + g;
         const int nA1 = a.nA - 1;
 
-        auto fold_pending = [&]() {
+        auto fold_pending = [&](const Step &P) {
             double bA[NTB][MT];
 #pragma unroll
             for (int j = 0; j < NTB; ++j) {
-                const int ia = p_iA + j < nA1 ? p_iA + j : nA1;  // padded indices: their tensor rows are zero
+                const int ia = P.iA + j < nA1 ? P.iA + j : nA1;  // padded indices: their tensor rows are zero
                 const double *tj = tcol + (size_t)(a.boffA + ia) * NPT;
 #pragma unroll
-#if defined(MMA_ABL) && (MMA_ABL & 32)
-                for (int mt = 0; mt < MT; ++mt) bA[j][mt] = 1.0 + (double)(ia + (int)(size_t)tj);
-#else
                 for (int mt = 0; mt < MT; ++mt) bA[j][mt] = tj[mt * 8];
-#endif
             }
 #pragma unroll
             for (int j = 0; j < NTB; ++j)
 #pragma unroll
                 for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-                    for (int e = 0; e < 2; ++e) acc2[e][mt] = fma(bA[j][mt], Dp[j][mt][e], acc2[e][mt]);
+                    for (int e = 0; e < 2; ++e) acc2[e][mt] = fma(bA[j][mt], P.D[j][mt][e], acc2[e][mt]);
         };
         // Runs on group boundaries only (a warp-uniform branch).  Straight-line: the loads of all
         // weights go out together (absent levels read the ones row), so the exposed latency is one
         // shared-memory round trip and three dependent multiplies, not a chain per level.
-        auto close_group = [&]() {
+        auto close_group = [&](const Step &P) {
             double w[2][MT][3];
 #pragma unroll
             for (int e = 0; e < 2; ++e)
 #pragma unroll
                 for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-                    for (int l = 0; l < 3; ++l) w[e][mt][l] = tcol[(size_t)p_info[e][l] * NPT + mt * 8];
+                    for (int l = 0; l < 3; ++l) w[e][mt][l] = tcol[(size_t)P.info[e][l] * NPT + mt * 8];
 #pragma unroll
             for (int e = 0; e < 2; ++e)
 #pragma unroll
                 for (int mt = 0; mt < MT; ++mt) {
                     const double ww = w[e][mt][0] * w[e][mt][1] * w[e][mt][2];
-                    acc[mt] = fma(p_valid[e] ? ww : 0.0, acc2[e][mt], acc[mt]);
+                    acc[mt] = fma(P.valid[e] ? ww : 0.0, acc2[e][mt], acc[mt]);
                     acc2[e][mt] = 0.0;
                 }
         };
 
         int sg = 0, g8 = 0;  // step within the group, group index
+        // one step: issue the DMMAs of rows [r16, r16 + ROWS_STEP) into C while P is folded in
+        auto step = [&](Step &C, const Step &P, const double *slab, int r16) {
+#pragma unroll
+            for (int j = 0; j < NTB; ++j)
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) C.D[j][mt][0] = C.D[j][mt][1] = 0.0;
+            const double *bp = slab + (size_t)(r16 + g) * a.rs + t;
+            // bookkeeping: the group-level rows of this lane's columns ride at the end of the
+            // tensor rows of the first N-tile
+            C.end = (sg == spg - 1);
+            C.iA = NTB * sg;
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int *info = reinterpret_cast<const int *>(slab + (size_t)(r16 + 2 * t + e) * a.rs + a.kp);
+                C.valid[e] = (8 * g8 + 2 * t + e) < a.nrp;
+#pragma unroll
+                for (int l = 0; l < 3; ++l) C.info[e][l] = (C.end && l < a.nlg) ? info[l] : a.sumn;
+            }
+#pragma unroll
+            for (int kc = 0; kc < KC; ++kc) {
+                double b[NTB];
+#pragma unroll
+#if defined(MMA_ABL) && (MMA_ABL & 4)
+                for (int j = 0; j < NTB; ++j) b[j] = bp[(size_t)j * 8 * a.rs];
+#else
+                for (int j = 0; j < NTB; ++j) b[j] = bp[(size_t)j * 8 * a.rs + 4 * kc];
+#endif
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                    for (int j = 0; j < NTB; ++j) dmma884(C.D[j][mt][0], C.D[j][mt][1], A[mt][kc], b[j]);
+            }
+#if defined(MMA_ABL) && (MMA_ABL & 1)
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) acc[mt] += P.D[0][mt][0] + P.D[1][mt][1];
+#else
+            fold_pending(P);
+            if (P.end) close_group(P);
+#endif
+            if (++sg == spg) { sg = 0; ++g8; }
+        };
+
         for (int s = 0; s < a.nslabs; ++s) {
             const int st = a.resident ? s : stage;
             mbar_wait(&full_bar[st], a.resident ? 0u : (round & 1));
             const double *slab = reinterpret_cast<const double *>(ring + (size_t)st * a.stage_bytes);
             const int rows = slab_rows(s);
 
-            for (int r16 = 0; r16 < rows; r16 += ROWS_STEP) {
-                double D[NTB][MT][2];
-#pragma unroll
-                for (int j = 0; j < NTB; ++j)
-#pragma unroll
-                    for (int mt = 0; mt < MT; ++mt) D[j][mt][0] = D[j][mt][1] = 0.0;
-                const double *bp = slab + (size_t)(r16 + g) * a.rs + t;
-                // this step's bookkeeping; the group-level rows of this lane's columns ride at the
-                // end of the tensor rows of the first N-tile
-                const bool c_end = (sg == spg - 1);
-                int c_info[2][3];
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const int *info = reinterpret_cast<const int *>(slab + (size_t)(r16 + 2 * t + e) * a.rs + a.kp);
-#pragma unroll
-#if defined(MMA_ABL) && (MMA_ABL & 2)
-                    for (int l = 0; l < 3; ++l) c_info[e][l] = a.sumn + 0 * (int)(size_t)info;
-#else
-                    for (int l = 0; l < 3; ++l) c_info[e][l] = (c_end && l < a.nlg) ? info[l] : a.sumn;
-#endif
-                }
-#pragma unroll
-                for (int kc = 0; kc < KC; ++kc) {
-                    double b[NTB];
-#pragma unroll
-#if defined(MMA_ABL) && (MMA_ABL & 4)
-                    for (int j = 0; j < NTB; ++j) b[j] = bp[(size_t)j * 8 * a.rs];
-#else
-                    for (int j = 0; j < NTB; ++j) b[j] = bp[(size_t)j * 8 * a.rs + 4 * kc];
-#endif
-#pragma unroll
-                    for (int mt = 0; mt < MT; ++mt)
-#pragma unroll
-                        for (int j = 0; j < NTB; ++j) dmma884(D[j][mt][0], D[j][mt][1], A[mt][kc], b[j]);
-                }
-#if defined(MMA_ABL) && (MMA_ABL & 1)
-#pragma unroll
-                for (int mt = 0; mt < MT; ++mt) acc[mt] += Dp[0][mt][0] + Dp[1][mt][1];
-#else
-                fold_pending();
-#if !(defined(MMA_ABL) && (MMA_ABL & 16))
-                if (p_end) close_group();
-#endif
-#endif
-#pragma unroll
-                for (int j = 0; j < NTB; ++j)
-#pragma unroll
-                    for (int mt = 0; mt < MT; ++mt) {
-                        Dp[j][mt][0] = D[j][mt][0];
-                        Dp[j][mt][1] = D[j][mt][1];
-                    }
-                p_iA = NTB * sg;
-                p_end = c_end;
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    p_valid[e] = (8 * g8 + 2 * t + e) < a.nrp;
-#pragma unroll
-                    for (int l = 0; l < 3; ++l) p_info[e][l] = c_info[e][l];
-                }
-                if (++sg == spg) { sg = 0; ++g8; }
+            // pending is P1 on entry and on exit
+            int r16 = 0;
+            for (; r16 + 2 * ROWS_STEP <= rows; r16 += 2 * ROWS_STEP) {
+                step(P0, P1, slab, r16);
+                step(P1, P0, slab, r16 + ROWS_STEP);
+            }
+            if (r16 < rows) {
+                step(P0, P1, slab, r16);
+                P1 = P0;
             }
 
             if (!a.resident) {
@@ -396,9 +390,8 @@ __global__ void __launch_bounds__(NW * 32, 1) contract_mma_kernel(const __grid_c
                 if (++stage == ns) { stage = 0; ++round; }
             }
         }
-        fold_pending();  // drain: the last step always closes its group
-        close_group();
-        p_end = false;
+        fold_pending(P1);  // drain: the last step always closes its group
+        close_group(P1);
 
         // ---- 4. sum the four lanes of each quad, store
 #pragma unroll
