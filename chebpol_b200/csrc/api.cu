@@ -540,18 +540,20 @@ static int launch_plan(chebpol_cuda_plan *p, const double *d_x, int64_t npts, do
     const bool force_slab = p->variant > 0 && p->variant < 100000;
     const int mma_variant = p->variant >= 100000 ? p->variant - 100000 : 0;
     if (p->kind == PLAN_CHEB) {
-        // AUTO between the two fast kernels (measured crossover, tools/crossover.py): the DFMA slab
-        // kernel wins on small tensors (the DMMA engine pays a per-pass basis prologue) and when
-        // the fold leaves the DMMA epilogue-heavy; the DMMA engine wins on large, well-folded ones.
-        bool prefer_slab = false;
-        if (p->variant == 0 && p->slab_ok && p->mma_ok) {
+        // AUTO between the fast kernels (measured crossover, tools/crossover.py; S = Clenshaw
+        // multiply-adds per point): below S ~ 25000 the DMMA engine's per-pass basis prologue
+        // dominates and the DFMA slab kernel wins (up to 6x on 2-D tensors); above it the DMMA
+        // engine wins by 1.1-1.7x.  Small tensors the slab kernel cannot take (first dimension
+        // too long) go to the strict kernel, which beats the DMMA engine there (64x64: 1.5x).
+        bool prefer_slab = false, prefer_strict = false;
+        if (p->variant == 0 && p->mma_ok) {
             double S = 0, prod = 1;
             for (int d = p->rank - 1; d >= 0; --d) { prod *= p->dims[d]; S += prod; }
-            const double score = (double)p->mma.K / (p->mma.kp + p->mma.nlev + 1.0);
-            const bool slab_healthy = p->slab.slab_elems >= 256 || p->slab.nslabs == 1;
-            prefer_slab = slab_healthy && (S < 20000.0 || score < 0.9);
+            const bool slab_healthy = p->slab_ok && (p->slab.slab_elems >= 256 || p->slab.nslabs == 1);
+            prefer_slab = slab_healthy && S < 25000.0;
+            prefer_strict = !slab_healthy && S < 8000.0 && p->kernel_opt == CHEBPOL_CUDA_KERNEL_AUTO;
         }
-        if (want_fast && p->mma_ok && !force_slab && !prefer_slab) {
+        if (want_fast && p->mma_ok && !force_slab && !prefer_slab && !prefer_strict) {
             MmaArgs a = p->mma;
             a.x = d_x;
             a.npts = npts;

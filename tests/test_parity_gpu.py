@@ -103,10 +103,12 @@ def test_cheb_fast_stress_outside_domain(gpu_ok, port, dims, family, variant):
 
 
 def test_cheb_auto_kernel_choice(gpu_ok, port):
-    """AUTO picks the DFMA slab kernel for small / poorly folding tensors and the DMMA engine for
-    large well-folded ones (csrc/api.cu launch_plan; crossover measured by tools/crossover.py)."""
-    for dims, want in [((20, 20), "cheb_slab"), ((8, 7, 6), "cheb_slab"), ((16,) * 4, "cheb_slab"),
-                       ((10,) * 5, "cheb_mma"), ((8,) * 5, "cheb_mma"), ((6,) * 6, "cheb_mma"), ((40, 7), "cheb_mma")]:
+    """AUTO picks the DFMA slab kernel for small tensors, the DMMA engine for large ones, and the
+    strict kernel for small tensors the slab kernel cannot take (csrc/api.cu launch_plan;
+    crossover measured by tools/crossover.py)."""
+    for dims, want in [((20, 20), "cheb_slab"), ((8, 7, 6), "cheb_slab"), ((12,) * 4, "cheb_slab"),
+                       ((16,) * 4, "cheb_mma"), ((10,) * 5, "cheb_mma"), ((8,) * 5, "cheb_mma"), ((6,) * 6, "cheb_mma"),
+                       ((40, 7), "cheb_strict"), ((40, 40, 9), "cheb_mma")]:
         cf = cases.cheb_fitted(dims)
         x = cases.points(3000, len(dims))
         plan = _lib.Plan.cheb(cf)

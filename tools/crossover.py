@@ -1,7 +1,7 @@
 import sys; sys.path.insert(0,"."); sys.path.insert(0,"tests")
 import numpy as np, torch, cases
 from chebpol_b200 import _lib
-shapes=[(10,)*4,(12,)*4,(20,)*3,(8,)*5,(32,32,32),(24,24,24),(10,)*5,(16,)*4,(6,)*6,(30,30),(20,20,20,4)]
+shapes=[(20,20),(30,30),(64,64),(10,10,10),(16,16,16),(8,)*4,(10,)*4,(12,)*4,(20,)*3,(8,)*5,(32,32,32),(24,24,24),(10,)*5,(16,)*4,(6,)*6,(20,)*4,(20,20,20,4),(5,)*7,(12,)*5,(7,)*6]
 for dims in shapes:
     S=0; p_=1
     for n_ in reversed(dims): p_*=n_; S+=p_
