@@ -355,7 +355,7 @@ def run_ours(args, cfg):
             roofline = {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                         "frac": achieved / fp64_peak if fp64_peak else None,
                         "traffic": load_traffic(kernel_used, args.config, npts),
-                        "peak_source": "DFMA-only kernel measured in this run (MEASURED_PEAKS.json has no FP64 peak); "
+                        "peak_source": "best of a DFMA-only and a DMMA-only kernel measured in this run (MEASURED_PEAKS.json has no FP64 peak); "
                                        "nominal 148 SM x 64 FMA/clk x 2 x 1.965 GHz = 37.2",
                         "flop_per_eval": flop, "kernel": kernel_used, "kernel_ms": kernel_ms}
         else:
