@@ -175,8 +175,9 @@ CHEBPOL_CUDA_API int chebpol_cuda_evalgrid_fh(const double *vals, const double *
                                               double *out);
 
 /* ---- diagnostics -------------------------------------------------------- */
-/* Register-resident DFMA chain on every SM of `device`: the FP64 roofline
- * denominator (MEASURED_PEAKS.json has none).  Returns TFLOP/s (2 flop/FMA). */
+/* The FP64 roofline denominator (MEASURED_PEAKS.json has none): the better of a
+ * register-resident DFMA chain and a DMMA-only kernel on every SM of `device`.
+ * Returns TFLOP/s (2 flop/FMA). */
 CHEBPOL_CUDA_API int chebpol_cuda_fp64_peak(int device, int repeats, double *tflops);
 /* The stateless entry points keep up to 8 small (<= 32 MB) interpolants resident between
  * calls, keyed by a 64-bit hash of their content (tensor, knots, weights, pre-map), so the
