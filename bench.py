@@ -46,6 +46,8 @@ CONFIGS = {
     2: dict(kind="cheb", dims=(10,) * 5, points=100_000_000, name="cfg2: 5-D Chebyshev dims=rep(10,5), 1e8 points"),
     3: dict(kind="mlip", dims=(64,) * 4, points=100_000_000, name="cfg3: 4-D multilinear 64^4 grid, 1e8 points"),
     4: dict(kind="fh", dims=(40, 40, 40), points=10_000_000, name="cfg4: 3-D Floater-Hormann dims=c(40,40,40) d=4, 1e7 points"),
+    6: dict(kind="polyh", dims=(6,), rank=6, nknots=1000, k=3, points=20_000_000,
+            name="cfg6 (SURVEY 8f row 4): 6-D polyharmonic spline, 1000 knots, k=3, 2e7 points"),
     5: dict(kind="cheb", dims=(12,) * 6, points=20_000_000, name="cfg5: 6-D Chebyshev dims=rep(12,6), 2e7 points per GPU (1e9 total is ~3 min/step/8 GPUs)"),
 }
 
@@ -91,6 +93,9 @@ def build_case(cfg):
     if kind == "mlip":
         grid, values = cases.mlip_case(dims)
         return dict(grid=grid, values=values)
+    if kind == "polyh":
+        knots, w, lw = cases.polyh_case(cfg["rank"], cfg["nknots"], cfg["k"])
+        return dict(knots=knots, w=w, lw=lw, k=cfg["k"])
     vals, grid, weights = cases.fh_case(dims, d=4)
     return dict(vals=vals, grid=grid, weights=weights)
 
@@ -102,6 +107,8 @@ def make_plan(cfg, case, device):
         return _lib.Plan.cheb(case["coef"], device=device)
     if cfg["kind"] == "mlip":
         return _lib.Plan.mlip(case["grid"], case["values"], 0, device=device)
+    if cfg["kind"] == "polyh":
+        return _lib.Plan.polyh(case["knots"], case["w"], case["lw"], case["k"], device=device)
     return _lib.Plan.fh(case["vals"], case["grid"], case["weights"], device=device)
 
 
@@ -110,6 +117,8 @@ def oracle_eval(orc, cfg, case, x, threads):
         return orc.evalcheb(case["coef"], x, threads=threads)
     if cfg["kind"] == "mlip":
         return orc.evalmlip(case["grid"], case["values"], x, threads=threads)
+    if cfg["kind"] == "polyh":
+        return orc.evalpolyh(case["knots"], case["w"], case["lw"], case["k"], x, threads=threads)
     return orc.fh(case["vals"], case["grid"], case["weights"], x, threads=threads)
 
 
@@ -134,7 +143,7 @@ def time_cpu(orc, cfg, case, x, threads):
 
 def cpu_sample_size(orc, cfg, case, threads, target_s):
     """Calibrate a prefix length that takes about target_s seconds of CPU work."""
-    k = len(cfg["dims"])
+    k = cfg.get("rank", len(cfg["dims"]))
     n = 2000
     x = cpu_points(n, k)
     dt = max(time_cpu(orc, cfg, case, x, threads), 1e-4)
@@ -217,7 +226,7 @@ def run_reference(args, cfg):
     orc, kind = get_oracle()
     case = build_case(cfg)
     threads = os.cpu_count() or 1
-    k = len(cfg["dims"])
+    k = cfg.get("rank", len(cfg["dims"]))
     n = min(cpu_sample_size(orc, cfg, case, threads, target_s=8.0), 50_000_000)
     x = cpu_points(n, k)
     for _ in range(args.warmup):
@@ -257,7 +266,7 @@ def run_ours(args, cfg):
     if world > 1:
         shard.init_process_group("nccl")
     npts = args.points if args.points else cfg["points"]
-    k = len(cfg["dims"])
+    k = cfg.get("rank", len(cfg["dims"]))
     case = build_case(cfg)
     plan = make_plan(cfg, case, local_rank)
     if args.variant:
@@ -349,8 +358,11 @@ def run_ours(args, cfg):
 
     if rank == 0:
         peaks, peak_src = load_peaks()
-        if cfg["kind"] in ("cheb", "fh"):
-            flop = 2.0 * steps_per_eval(cfg["dims"])
+        if cfg["kind"] in ("cheb", "fh", "polyh"):
+            # polyharmonic: per knot one subtract and one FMA per coordinate plus the weight FMA,
+            # counted 2*rank + 2 flop (sqrt / log / exp of the basis not counted)
+            flop = (2.0 * steps_per_eval(cfg["dims"]) if cfg["kind"] != "polyh"
+                    else float(cfg["nknots"]) * (2.0 * cfg["rank"] + 2.0))
             achieved = flop * npts / (kernel_ms * 1e-3) / 1e12
             roofline = {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                         "frac": achieved / fp64_peak if fp64_peak else None,

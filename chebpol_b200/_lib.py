@@ -27,7 +27,7 @@ VARIANT_AUTO, VARIANT_SLAB, VARIANT_MMA = 0, 1, 100000  # OPT_VARIANT families (
 VARIANT_MLIP_PAIR, VARIANT_MLIP_CELL = 1, 2
 KERNEL_NAMES = {
     0: "none", 10: "cheb_strict", 11: "cheb_slab", 12: "cheb_mma", 20: "mlip_strict", 21: "mlip_pair", 22: "mlip_cell",
-    30: "fh_strict", 32: "fh_mma",
+    30: "fh_strict", 32: "fh_mma", 40: "polyh_strict", 41: "polyh_tile",
 }
 
 EXPORTS = [
@@ -38,6 +38,7 @@ EXPORTS = [
     "chebpol_cuda_plan_set", "chebpol_cuda_plan_get", "chebpol_cuda_fp64_peak",
     "chebpol_cuda_launch_count", "chebpol_cuda_cache_clear", "chebpol_cuda_chebcoef", "chebpol_cuda_fhweights",
     "chebpol_cuda_evalgrid_cheb", "chebpol_cuda_evalgrid_mlip", "chebpol_cuda_evalgrid_fh",
+    "chebpol_cuda_evalpolyh", "chebpol_cuda_plan_polyh",
 ]
 
 
@@ -85,6 +86,10 @@ def lib() -> C.CDLL:
     L.chebpol_cuda_evalgrid_cheb.argtypes = [_vp, _ip, C.c_int, _dpp, _ip, _vp, _vp, _vp, C.c_int, _vp]
     L.chebpol_cuda_evalgrid_mlip.argtypes = [_dpp, _ip, C.c_int, _vp, _dpp, _ip, C.c_int, C.c_int, _vp]
     L.chebpol_cuda_evalgrid_fh.argtypes = [_vp, _dpp, _dpp, _ip, C.c_int, _dpp, _ip, C.c_int, _vp]
+    L.chebpol_cuda_evalpolyh.argtypes = [_vp, C.c_int, C.c_int, _vp, _vp, C.c_double, _vp, C.c_int64, _vp, _vp,
+                                         C.c_int, _vp]
+    L.chebpol_cuda_plan_polyh.argtypes = [_vp, C.c_int, C.c_int, _vp, _vp, C.c_double, _vp, _vp, C.c_int,
+                                          C.POINTER(_vp)]
     L.chebpol_cuda_cache_clear.restype = None
     L.chebpol_cuda_cache_clear.argtypes = []
     L.chebpol_cuda_launch_count.restype = C.c_int64
@@ -205,6 +210,24 @@ class Plan:
         check(lib().chebpol_cuda_plan_fh(_addr(v), gl, wl, dims.ctypes.data_as(_ip), len(grid), device, C.byref(h)))
         return Plan(h.value, len(grid), "fh")
 
+    @staticmethod
+    def polyh(knots, weights, lweights, k: float, norm_a=None, norm_b=None, device: int = 0) -> "Plan":
+        """knots: rank x nknots (column i is knot i, as the R matrix)."""
+        kn = np.asarray(knots, dtype=np.float64)
+        rank, nk = kn.shape
+        knf = f64(kn, order="F")
+        w, lw = f64(np.ravel(weights)), f64(np.ravel(lweights))
+        if w.size != nk:
+            raise ValueError(f"number of weights ({w.size}) should equal number of knots ({nk})")
+        if lw.size != rank + 1:
+            raise ValueError(f"linear weights ({lw.size}) should be one longer than rank({rank})")
+        na = f64(np.ravel(norm_a)) if norm_a is not None else None
+        nb = f64(np.ravel(norm_b)) if norm_b is not None else None
+        h = _vp()
+        check(lib().chebpol_cuda_plan_polyh(_addr(knf), rank, nk, _addr(w), _addr(lw), float(k), _addr(na), _addr(nb),
+                                            device, C.byref(h)))
+        return Plan(h.value, rank, "polyh")
+
     # -- evaluation --------------------------------------------------------------
     def eval_host(self, x_pk: np.ndarray, out: np.ndarray | None = None) -> np.ndarray:
         """x_pk: (P, K) C-contiguous float64 host array (pinned or pageable)."""
@@ -280,6 +303,21 @@ def fhweights(grid, d, device: int = 0):
         w = np.empty_like(g)
         check(lib().chebpol_cuda_fhweights(_addr(g), g.size, int(deg), device, _addr(w)))
         out.append(w)
+    return out
+
+
+def evalpolyh(knots, weights, lweights, k: float, x_pk, norm_a=None, norm_b=None, ngpus: int = 0) -> np.ndarray:
+    """chebpol_cuda_evalpolyh: knots rank x nknots (column i is knot i), x_pk (P, rank)."""
+    kn = np.asarray(knots, dtype=np.float64)
+    rank, nk = kn.shape
+    knf = f64(kn, order="F")
+    w, lw = f64(np.ravel(weights)), f64(np.ravel(lweights))
+    na = f64(np.ravel(norm_a)) if norm_a is not None else None
+    nb = f64(np.ravel(norm_b)) if norm_b is not None else None
+    x_pk = f64(x_pk)
+    out = np.empty(x_pk.shape[0], dtype=np.float64)
+    check(lib().chebpol_cuda_evalpolyh(_addr(knf), rank, nk, _addr(w), _addr(lw), float(k), _addr(x_pk),
+                                       x_pk.shape[0], _addr(na), _addr(nb), ngpus, _addr(out)))
     return out
 
 

@@ -80,7 +80,7 @@ extern "C" int chebpol_cuda_device_count(int *count)
 }
 
 // ---------------------------------------------------------------------- plan
-enum PlanKind { PLAN_CHEB = 1, PLAN_MLIP = 2, PLAN_FH = 3 };
+enum PlanKind { PLAN_CHEB = 1, PLAN_MLIP = 2, PLAN_FH = 3, PLAN_POLYH = 4 };
 
 struct chebpol_cuda_plan {
     int kind = 0;
@@ -118,6 +118,10 @@ struct chebpol_cuda_plan {
     int64_t cell_bytes = 0;   // 0: shape not supported / disabled
     int64_t ncells = 0;
     bool cells_failed = false;
+    // polyharmonic spline: knots in d_tensor, weights in d_weights, affine part in d_grid,
+    // packed [w, knot, pad] rows in d_padded
+    int nknots = 0;
+    double polyh_k = 0.0;
     // statistics
     LaunchInfo last = {0, 0, 0, 0};
     int64_t launches = 0;
@@ -473,6 +477,64 @@ extern "C" int chebpol_cuda_plan_fh(const double *vals, const double *const *gri
     return CHEBPOL_CUDA_OK;
 }
 
+extern "C" int chebpol_cuda_plan_polyh(const double *knots, int rank, int nknots, const double *weights,
+                                       const double *lweights, double k, const double *norm_a,
+                                       const double *norm_b, int device, chebpol_cuda_plan **plan)
+{
+    if (!plan) return fail(CHEBPOL_CUDA_EINVAL, "plan is NULL");
+    *plan = nullptr;
+    if (rank <= 0) return fail(CHEBPOL_CUDA_ERANK, "rank must be positive");
+    if (rank > CHEBPOL_CUDA_MAXRANK) return fail(CHEBPOL_CUDA_ERANK, "rank %d exceeds %d", rank, CHEBPOL_CUDA_MAXRANK);
+    if (nknots < 0) return fail(CHEBPOL_CUDA_ESIZE, "negative number of knots");
+    if ((int64_t)nknots * rank >= (int64_t(1) << 31)) return fail(CHEBPOL_CUDA_ESIZE, "knot matrix has 2^31 or more elements");
+    if (!lweights || (nknots > 0 && (!knots || !weights))) return fail(CHEBPOL_CUDA_EINVAL, "knots, weights or lweights is NULL");
+    if ((norm_a == nullptr) != (norm_b == nullptr)) return fail(CHEBPOL_CUDA_EINVAL, "norm_a and norm_b go together");
+    if (k != k) return fail(CHEBPOL_CUDA_EINVAL, "k is NaN");
+    int sms = 0;
+    int rc = select_device(device, &sms);
+    if (rc) return rc;
+    int dims[CP_MAXR];
+    for (int i = 0; i < rank; ++i) dims[i] = nknots > 0 ? nknots : 1;
+    chebpol_cuda_plan *p = new_plan(PLAN_POLYH, device, sms, dims, rank, (int64_t)nknots * rank);
+    auto bail = [&](int code) { chebpol_cuda_plan_destroy(p); return code; };
+    p->nknots = nknots;
+    p->polyh_k = k;
+    if (norm_a) {
+        p->pm.mode = 1;
+        for (int i = 0; i < rank; ++i) { p->pm.mid[i] = norm_b[i]; p->pm.ispan[i] = norm_a[i]; }
+    }
+    cudaError_t e = cudaMalloc(&p->d_grid, sizeof(double) * (rank + 1));
+    if (e != cudaSuccess) return bail(cuda_fail(e, "cudaMalloc(lweights)"));
+    e = cudaMemcpy(p->d_grid, lweights, sizeof(double) * (rank + 1), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return bail(cuda_fail(e, "cudaMemcpy(lweights)"));
+    if (nknots > 0) {
+        const size_t nk = (size_t)nknots;
+        e = cudaMalloc(&p->d_tensor, sizeof(double) * nk * rank);
+        if (e != cudaSuccess) return bail(cuda_fail(e, "cudaMalloc(knots)"));
+        e = cudaMemcpy(p->d_tensor, knots, sizeof(double) * nk * rank, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) return bail(cuda_fail(e, "cudaMemcpy(knots)"));
+        e = cudaMalloc(&p->d_weights, sizeof(double) * nk);
+        if (e != cudaSuccess) return bail(cuda_fail(e, "cudaMalloc(weights)"));
+        e = cudaMemcpy(p->d_weights, weights, sizeof(double) * nk, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) return bail(cuda_fail(e, "cudaMemcpy(weights)"));
+        const int rs = polyh_row_stride(rank);
+        if (rs > 0) {
+            std::vector<double> rows(nk * rs, 0.0);
+            for (size_t i = 0; i < nk; ++i) {
+                rows[i * rs] = weights[i];
+                for (int j = 0; j < rank; ++j) rows[i * rs + 1 + j] = knots[i * rank + j];
+            }
+            e = cudaMalloc(&p->d_padded, sizeof(double) * rows.size());
+            if (e != cudaSuccess) return bail(cuda_fail(e, "cudaMalloc(packed knots)"));
+            e = cudaMemcpy(p->d_padded, rows.data(), sizeof(double) * rows.size(), cudaMemcpyHostToDevice);
+            if (e != cudaSuccess) return bail(cuda_fail(e, "cudaMemcpy(packed knots)"));
+        }
+    }
+    p->tensor_bytes = sizeof(double) * ((int64_t)nknots * (rank + 1) + rank + 1);
+    *plan = p;
+    return CHEBPOL_CUDA_OK;
+}
+
 extern "C" int chebpol_cuda_plan_set(chebpol_cuda_plan *p, int option, int64_t value)
 {
     if (!p) return fail(CHEBPOL_CUDA_EINVAL, "plan is NULL");
@@ -644,6 +706,25 @@ static int launch_plan(chebpol_cuda_plan *p, const double *d_x, int64_t npts, do
             if (p->kernel_opt == CHEBPOL_CUDA_KERNEL_FAST)
                 return fail(CHEBPOL_CUDA_EINVAL, "no fast Floater-Hormann kernel for this shape");
             e = launch_fh_strict(a, s, &li);
+        }
+    } else if (p->kind == PLAN_POLYH) {
+        PolyhArgs a;
+        a.knots = p->d_tensor;
+        a.weights = p->d_weights;
+        a.lweights = p->d_grid;
+        a.packed = p->d_padded;
+        a.rank = p->rank;
+        a.nknots = p->nknots;
+        a.k = p->polyh_k;
+        a.x = d_x;
+        a.npts = npts;
+        a.out = d_out;
+        a.pm = p->pm;
+        if (want_fast) e = launch_polyh_tile(a, p->variant, p->num_sms, s, &li);
+        if (e == cudaErrorNotSupported) {
+            if (p->kernel_opt == CHEBPOL_CUDA_KERNEL_FAST)
+                return fail(CHEBPOL_CUDA_EINVAL, "no fast polyharmonic kernel for rank %d with %d knots", p->rank, p->nknots);
+            e = launch_polyh_strict(a, s, &li);
         }
     } else {
         return fail(CHEBPOL_CUDA_EINVAL, "corrupt plan");
@@ -1147,6 +1228,35 @@ extern "C" int chebpol_cuda_fh(const double *vals, const double *const *grid,
     }
     return run_sharded(rank, x, npts, ngpus, out, key, nelem * 8, [&](int dev, chebpol_cuda_plan **p) {
         return chebpol_cuda_plan_fh(vals, grid, weights, dims, rank, dev, p);
+    });
+}
+
+extern "C" int chebpol_cuda_evalpolyh(const double *knots, int rank, int nknots, const double *weights,
+                                      const double *lweights, double k, const double *x, int64_t npts,
+                                      const double *norm_a, const double *norm_b, int ngpus, double *out)
+{
+    if (rank <= 0 || rank > CHEBPOL_CUDA_MAXRANK) return fail(CHEBPOL_CUDA_ERANK, "rank %d not in 1..%d", rank, CHEBPOL_CUDA_MAXRANK);
+    if (nknots < 0) return fail(CHEBPOL_CUDA_ESIZE, "negative number of knots");
+    if (!lweights || (nknots > 0 && (!knots || !weights))) return fail(CHEBPOL_CUDA_EINVAL, "knots, weights or lweights is NULL");
+    int dims[CP_MAXR];
+    for (int i = 0; i < rank; ++i) dims[i] = nknots;
+    CacheKey key = make_key(PLAN_POLYH, dims, rank);
+    const int64_t bytes = 8ll * ((int64_t)nknots * (rank + 1) + rank + 1);
+    if (cache_enabled() && bytes <= kCacheMaxBytes) {
+        uint64_t h = hash_bytes(&k, sizeof k, 4);
+        if (nknots > 0) {
+            h = hash_bytes(knots, (size_t)nknots * rank * 8, h);
+            h = hash_bytes(weights, (size_t)nknots * 8, h);
+        }
+        h = hash_bytes(lweights, (size_t)(rank + 1) * 8, h);
+        if (norm_a && norm_b) {
+            h = hash_bytes(norm_a, (size_t)rank * 8, h);
+            h = hash_bytes(norm_b, (size_t)rank * 8, h);
+        }
+        key.hash = h;
+    }
+    return run_sharded(rank, x, npts, ngpus, out, key, bytes, [&](int dev, chebpol_cuda_plan **p) {
+        return chebpol_cuda_plan_polyh(knots, rank, nknots, weights, lweights, k, norm_a, norm_b, dev, p);
     });
 }
 

@@ -38,6 +38,8 @@ enum KernelId {
     K_MLIP_CELL = 22,    // cell-major table: one contiguous 2^D block per point
     K_FH_STRICT = 30,    // thread-per-point nested barycentric, reference op order
     K_FH_MMA = 32,       // barycentric-basis DMMA contraction, TMA-streamed rows
+    K_POLYH_STRICT = 40, // thread-per-point radial sum, reference op order
+    K_POLYH_TILE = 41,   // points in registers, knot rows broadcast from a TMA-filled ring
 };
 
 // ---- launch descriptors filled by api.cu, consumed by the kernel TUs -------
@@ -69,6 +71,20 @@ struct MlipArgs {
     int loff[CP_MAXR];     // offset of dim d's table in `lut`
     int nb[CP_MAXR];       // buckets of dim d
     double lscale[CP_MAXR];  // buckets per unit length: nb / (g_{n-1} - g_0)
+};
+
+// Polyharmonic spline evaluation (C_evalpolyh, src/chebpol.c:383-415)
+struct PolyhArgs {
+    const double *knots;    // rank x nknots, knot i at knots + i*rank (R matrix)
+    const double *weights;  // nknots
+    const double *lweights; // rank + 1: constant, then one per coordinate
+    const double *packed;   // nknots rows of polyh_row_stride(rank) doubles: w, coordinates, zero pad
+    int rank, nknots;
+    double k;               // < 0: exp(k r^2); odd (int)k: r^k; even: log(r) r^k
+    const double *x;
+    int64_t npts;
+    double *out;
+    PreMap pm;              // bit 0: x <- (x - b)*a, the closure's normfun (R/polyharmonic.R:77,82)
 };
 
 struct FhArgs {
@@ -157,6 +173,11 @@ cudaError_t launch_contract_mma(const MmaArgs &a, int variant, int num_sms, cuda
 cudaError_t launch_cheb_strict(const ChebStrictArgs &a, cudaStream_t s, LaunchInfo *li);
 cudaError_t launch_mlip_strict(const MlipArgs &a, cudaStream_t s, LaunchInfo *li);
 cudaError_t launch_fh_strict(const FhArgs &a, cudaStream_t s, LaunchInfo *li);
+cudaError_t launch_polyh_strict(const PolyhArgs &a, cudaStream_t s, LaunchInfo *li);
+// fast polyharmonic kernel (polyh.cu); cudaErrorNotSupported for rank > 32
+cudaError_t launch_polyh_tile(const PolyhArgs &a, int variant, int num_sms, cudaStream_t s, LaunchInfo *li);
+// row stride (doubles) of the packed knot table the tile kernel reads: [w, k_0..k_{rank-1}, 0...]
+int polyh_row_stride(int rank);
 // returns cudaErrorNotSupported when the shape has no fast instantiation
 cudaError_t launch_cheb_slab(const SlabArgs &a, int variant, int num_sms, cudaStream_t s, LaunchInfo *li);
 int cheb_slab_pick_n0p(int n0);

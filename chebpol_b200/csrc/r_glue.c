@@ -169,6 +169,44 @@ SEXP R_FH_cuda(SEXP inx, SEXP vals, SEXP grid, SEXP Sweights, SEXP Rthreads, SEX
     return resvec;
 }
 
+/* Polyharmonic splines: same arguments and return as R_evalpolyh (src/chebpol.c:416-451).
+ * `spare` (unused in the reference, :424) may carry the closure's normalisation
+ * list(a=, b=) so that normfun(x) = a*(x-b) (R/polyharmonic.R:77,82,129) runs inside the kernel. */
+SEXP R_evalpolyh_cuda(SEXP inx, SEXP Sknots, SEXP weights, SEXP lweights, SEXP Sk, SEXP Sthreads, SEXP spare)
+{
+    const double k = REAL(AS_NUMERIC(Sk))[0];
+    const int rank = nrows(Sknots);
+    R_xlen_t numvec;
+    /* checks and messages of src/chebpol.c:425-441 */
+    if (LENGTH(lweights) != rank + 1)
+        error("linear weights (%d) should be one longer than rank(%d)", LENGTH(lweights), rank);
+    if (LENGTH(weights) != ncols(Sknots))
+        error("number of weights (%d) should equal number of knots (%d)", LENGTH(weights), ncols(Sknots));
+    if (isMatrix(inx)) {
+        if (nrows(inx) != nrows(Sknots))
+            error("Dimension of input (%d) must match dimension of interpolant (%d)", nrows(inx), nrows(Sknots));
+        numvec = ncols(inx);
+    } else {
+        if (length(inx) != nrows(Sknots))
+            error("Dimension of input (%d) must match dimension of interpolant (%d)", length(inx), nrows(Sknots));
+        numvec = 1;
+    }
+    const double *na = NULL, *nb = NULL;
+    SEXP sa = list_elt(spare, "a"), sb = list_elt(spare, "b");
+    if (!isNull(sa) && !isNull(sb)) {
+        if (LENGTH(sa) != rank || LENGTH(sb) != rank) error("normalisation must have one entry per dimension");
+        na = REAL(sa);
+        nb = REAL(sb);
+    }
+    const int ngpus = gpus_from_threads(Sthreads);
+    SEXP res = PROTECT(NEW_NUMERIC(numvec));
+    const int rc = chebpol_cuda_evalpolyh(REAL(Sknots), rank, ncols(Sknots), REAL(weights), REAL(lweights), k,
+                                          REAL(inx), (int64_t)numvec, na, nb, ngpus, REAL(res));
+    UNPROTECT(1);
+    raise(rc);
+    return res;
+}
+
 /* fit side: same arguments and return as R_chebcoef (src/chebpol.c:145-180) */
 SEXP R_chebcoef_cuda(SEXP x, SEXP sdct, SEXP Sthreads)
 {
@@ -228,4 +266,5 @@ const R_CallMethodDef chebpol_cuda_callMethods[] = {
     {"FH_cuda", (DL_FUNC)&R_FH_cuda, 6},
     {"chebcoef_cuda", (DL_FUNC)&R_chebcoef_cuda, 3},
     {"FHweights_cuda", (DL_FUNC)&R_fhweights_cuda, 3},
+    {"evalpolyh_cuda", (DL_FUNC)&R_evalpolyh_cuda, 7},
     {NULL, NULL, 0}};

@@ -235,3 +235,70 @@ cudaError_t launch_fh_strict(const FhArgs &a, cudaStream_t s, LaunchInfo *li)
     if (li) { li->grid = (int)nb; li->block = block; li->smem = 0; li->kernel = K_FH_STRICT; }
     return cudaGetLastError();
 }
+
+// ---------------------------------------------------------- polyharmonic spline
+// C_evalpolyh, src/chebpol.c:383-415, operation for operation (this TU is compiled without
+// FMA contraction): squared distance summed over the coordinates in order, knots in order,
+// knots at distance zero skipped for k >= 0, then the affine part.  r^k is R's R_pow_di
+// (repeated squaring).  sqrt is IEEE; exp and log are CUDA's (<= 1 ulp), so k odd is
+// bit-identical to the reference and k even / k < 0 agree to ~1e-15 relative per term.
+__device__ __forceinline__ double pow_di_strict(double x, int n)
+{
+    double xn = 1.0;
+    if (x != x) return x;
+    if (n != 0) {
+        if (isinf(x)) return pow(x, (double)n);
+        const bool neg = n < 0;
+        if (neg) n = -n;
+        for (;;) {
+            if (n & 1) xn *= x;
+            n >>= 1;
+            if (!n) break;
+            x *= x;
+        }
+        if (neg) xn = 1.0 / xn;
+    }
+    return xn;
+}
+
+__global__ void __launch_bounds__(256) polyh_strict_kernel(const __grid_constant__ PolyhArgs a)
+{
+    const int rank = a.rank;
+    const int ki = (int)a.k;
+    const int mode = (a.k < 0) ? 0 : ((ki % 2 == 1) ? 1 : 2);
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < a.npts;
+         p += (int64_t)gridDim.x * blockDim.x) {
+        double x[CP_MAXR];
+        for (int d = 0; d < rank; ++d) x[d] = premap_coord(a.pm, d, a.x[p * rank + d]);
+        double wsum = 0.0;
+        for (int i = 0; i < a.nknots; ++i) {
+            const double *kn = a.knots + (size_t)i * rank;
+            double sqdist = 0.0;
+            for (int j = 0; j < rank; ++j) {
+                const double t = x[j] - __ldg(kn + j);
+                sqdist += t * t;
+            }
+            if (mode == 0) {
+                wsum += __ldg(a.weights + i) * exp(a.k * sqdist);
+            } else if (sqdist != 0) {
+                const double r = sqrt(sqdist);
+                if (mode == 1) wsum += __ldg(a.weights + i) * pow_di_strict(r, ki);
+                else wsum += __ldg(a.weights + i) * log(r) * pow_di_strict(r, ki);
+            }
+        }
+        wsum += __ldg(a.lweights);
+        for (int j = 0; j < rank; ++j) wsum += __ldg(a.lweights + j + 1) * x[j];
+        a.out[p] = wsum;
+    }
+}
+
+cudaError_t launch_polyh_strict(const PolyhArgs &a, cudaStream_t s, LaunchInfo *li)
+{
+    const int block = 256;
+    int64_t nb = (a.npts + block - 1) / block;
+    if (nb > 148 * 64) nb = 148 * 64;
+    if (nb < 1) nb = 1;
+    polyh_strict_kernel<<<(int)nb, block, 0, s>>>(a);
+    if (li) { li->grid = (int)nb; li->block = block; li->smem = 0; li->kernel = K_POLYH_STRICT; }
+    return cudaGetLastError();
+}

@@ -172,6 +172,9 @@ class Interpolant:
                 p = _lib.Plan.mlip(t["grid"], t["values"], 0, device)
             elif self.kind == "fh":
                 p = _lib.Plan.fh(t["values"], t["grid"], t["weights"], device)
+            elif self.kind == "polyharmonic":
+                p = _lib.Plan.polyh(t["knots"], t["weights"], t["lweights"], t["k"], t.get("norm_a"), t.get("norm_b"),
+                                    device)
             else:
                 raise ValueError(self.kind)
             self._plans[device] = p
@@ -208,6 +211,9 @@ class Interpolant:
                 return _lib.evalcheb(t["coef"], xp, t.get("mid"), t.get("ispan"), t.get("ugm_n"), ngpus)
             if self.kind == "multilinear":
                 return _lib.evalmlip(t["grid"], t["values"], xp, b, ngpus)
+            if self.kind == "polyharmonic":
+                return _lib.evalpolyh(t["knots"], t["weights"], t["lweights"], t["k"], xp, t.get("norm_a"),
+                                      t.get("norm_b"), ngpus)
             return _lib.fh(t["values"], t["grid"], t["weights"], xp, ngpus)
         p = self.plan(device)
         if self.kind == "multilinear":
@@ -302,6 +308,78 @@ def fhappx(val, grid=None, d=1, fit: str = "host") -> Interpolant:
                        values=np.asfortranarray(val), weights=weights)
 
 
+def _phifunc(d2: np.ndarray, k) -> np.ndarray:
+    """R_phifunc, src/chebpol.c:886-921, on squared distances."""
+    d2 = np.asarray(d2, dtype=np.float64)
+    if k < 0:
+        return np.exp(k * d2)
+    ki = int(k)
+    out = np.zeros_like(d2)
+    pos = d2 > 0.0
+    r = np.sqrt(d2[pos])
+    out[pos] = r ** ki if ki % 2 == 1 else 0.5 * np.log(d2[pos]) * r ** ki
+    return out
+
+
+def polyh(val, knots, k=2, normalize=None, nowarn: bool = False) -> Interpolant:
+    """polyh.real, R/polyharmonic.R:48-131: polyharmonic spline on scattered knots (columns of
+    ``knots``).  The fit (a dense (N+M+1)-square solve, R's solve()/lm.fit) runs on the host with
+    LAPACK as in R; the evaluator is chebpol_cuda_evalpolyh with the closure's normalisation
+    x -> a*(x-b) applied inside the kernel."""
+    knots = np.asarray(knots, dtype=np.float64)
+    if knots.ndim == 1:
+        knots = knots.reshape(1, -1)
+    if callable(val):
+        val = np.array([float(val(knots[:, i])) for i in range(knots.shape[1])])
+    val = np.asarray(val, dtype=np.float64).ravel()
+    M, N = knots.shape
+    if k > 0:
+        if abs(round(k) - k) > np.sqrt(np.finfo(float).eps):
+            raise ValueError(f"k is positive, but not an integer: {k:.17f}")
+        k = int(round(k))
+    norm_a = norm_b = None
+    if normalize is None:
+        normalize = bool(knots.min() < 0 or knots.max() > 1)
+    if not isinstance(normalize, (bool, np.bool_)):
+        nm = np.asarray(normalize, dtype=np.float64)
+        if nm.size == 2 and nm.ndim == 1:
+            nm = nm.reshape(1, 2)
+        if nm.ndim != 2 or nm.shape[1] != 2 or M % nm.shape[0] != 0:
+            raise ValueError(f"normalize must but be a n x 2 matrix with {M} divisible by n({nm.shape[0]})")
+        norm_a = np.resize(nm[:, 0], M)
+        norm_b = np.resize(nm[:, 1], M)
+        kn = knots  # as in R: with an explicit matrix the knots are NOT transformed (R/polyharmonic.R:72-78)
+        normalize = True
+    elif normalize:
+        norm_a = 1.0 / (knots.max(axis=1) - knots.min(axis=1))
+        norm_b = knots.min(axis=1)
+        kn = norm_a[:, None] * (knots - norm_b[:, None])
+    else:
+        kn = knots
+    diff = kn[:, :, None] - kn[:, None, :]
+    A = _phifunc(np.einsum("kij,kij->ij", diff, diff), k)
+    B = np.vstack([np.ones((1, N)), kn])
+    mat = np.zeros((N + M + 1, N + M + 1))
+    mat[:N, :N] = A
+    mat[N:, :N] = B
+    mat[:N, N:] = B.T
+    rhs = np.concatenate([val, np.zeros(M + 1)])
+    try:
+        with warnings.catch_warnings():
+            warnings.simplefilter("error")
+            wv = np.linalg.solve(mat, rhs)
+        if not np.all(np.isfinite(wv)) or 1.0 / np.linalg.cond(mat, 1) < np.finfo(float).eps:
+            raise np.linalg.LinAlgError("computationally singular")
+    except (np.linalg.LinAlgError, Warning):
+        if not nowarn:
+            warnings.warn("Failed to fit exactly, fallback to least squares fit."
+                          + ("" if normalize else " You could try normalize=TRUE."))
+        wv = np.linalg.lstsq(mat, rhs, rcond=None)[0]
+        wv[~np.isfinite(wv)] = 0.0
+    return Interpolant("polyharmonic", M, [(r.min(), r.max()) for r in kn], knots=np.asfortranarray(kn),
+                       weights=wv[:N].copy(), lweights=wv[N:].copy(), k=float(k), norm_a=norm_a, norm_b=norm_b)
+
+
 def ucappx(val, intervals=None) -> Interpolant:
     """ucappx.real, R/uniform.R:58-77: Chebyshev series of the values with the
     per-coordinate map x -> sin(0.5*pi*x*(1-n)/n) (ugm, R/uniform.R:6) applied,
@@ -335,7 +413,7 @@ def ucappxf(fun, dims, intervals=None) -> Interpolant:
 
 _METHODS = ["chebyshev", "multilinear", "fh", "uniform", "general", "polyharmonic", "simplexlinear",
             "hstalker", "stalker", "crbf", "oldstalker"]
-_ON_PATH = {"chebyshev", "multilinear", "fh", "uniform"}
+_ON_PATH = {"chebyshev", "multilinear", "fh", "uniform", "polyharmonic"}
 
 
 def ipol(val, dims=None, intervals=None, grid=None, knots=None, k=None, method="chebyshev", **kw) -> Interpolant:
@@ -349,6 +427,14 @@ def ipol(val, dims=None, intervals=None, grid=None, knots=None, k=None, method="
     if method not in _ON_PATH:
         raise NotImplementedError(
             f"method '{method}' is outside the GPU evaluation path (SURVEY.md section 2); use the R package")
+    if method == "polyharmonic":  # R/ipol.R:169-186
+        if knots is None:
+            if grid is None:
+                raise ValueError("Must specify knots for polyharmonic splines.")
+            gl = [np.asarray(g, dtype=np.float64) for g in ([grid] if np.isscalar(grid[0]) else grid)]
+            mesh = np.meshgrid(*gl, indexing="ij")
+            knots = np.stack([m.ravel(order="F") for m in mesh])  # t(expand.grid(grid))
+        return polyh(val, knots, 3 if k is None else k, kw.get("normalize"), kw.get("nowarn", False))
     if method == "chebyshev":
         if callable(val):
             if dims is None:

@@ -157,6 +157,22 @@ CHEBPOL_CUDA_API int chebpol_cuda_chebcoef(const double *val, const int *dims, i
                                            int device, double *coef);
 CHEBPOL_CUDA_API int chebpol_cuda_fhweights(const double *grid, int nknots, int d, int device, double *w);
 
+/* ---- polyharmonic splines on scattered knots ------------
+ * Replaces R_evalpolyh / C_evalpolyh, src/chebpol.c:383-451, as called by the closure of
+ * polyh.real (R/polyharmonic.R:129): f(x) = sum_i w_i phi(|x - k_i|) + v_0 + sum_j v_{j+1} x_j,
+ * phi(r) = exp(k r^2) for k < 0, r^k for odd (int)k, log(r) r^k for even (int)k.
+ * knots: rank x nknots R matrix (knot i at knots + i*rank); weights: nknots; lweights: rank+1.
+ * norm_a/norm_b (both or neither, `rank` entries): the closure's normfun x <- a*(x - b)
+ * (R/polyharmonic.R:77,82) applied inside the kernel instead of in R.
+ * Kernel ids: 40 polyh_strict, 41 polyh_tile.  rank <= CHEBPOL_CUDA_MAXRANK. */
+CHEBPOL_CUDA_API int chebpol_cuda_evalpolyh(const double *knots, int rank, int nknots, const double *weights,
+                                            const double *lweights, double k, const double *x,
+                                            int64_t npts, const double *norm_a, const double *norm_b,
+                                            int ngpus, double *out);
+CHEBPOL_CUDA_API int chebpol_cuda_plan_polyh(const double *knots, int rank, int nknots, const double *weights,
+                                             const double *lweights, double k, const double *norm_a,
+                                             const double *norm_b, int device, chebpol_cuda_plan **plan);
+
 /* ---- evaluation on a tensor grid (evalongridV of an interpolant, R/tools.R:132-137) ----
  * The reference expands the grid (expand.grid) and evaluates point by point; here the
  * structure is used: one basis matrix per dimension and one mode product per dimension.

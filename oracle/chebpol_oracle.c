@@ -292,6 +292,67 @@ API int oracle_fh(const double *vals, const double *x, const double *const *knot
 }
 
 /* ------------------------------------------------------------------------
+ * Polyharmonic spline evaluation.
+ * Follows C_evalpolyh, src/chebpol.c:383-415, and the loop of R_evalpolyh, :443-446:
+ *   f(x) = sum_i w_i phi(|x - k_i|) + v_0 + sum_j v_{j+1} x_j
+ *   phi(r) = exp(k r^2)        k < 0            (:388-394)
+ *            r^k               k odd  (int)k    (:395-402, knots at distance 0 skipped)
+ *            log(r) r^k        k even           (:403-411, likewise)
+ * knots is rank x nknots column-major (knot i at knots + i*rank); the sum runs over the knots
+ * in order; r^k is R's R_pow_di (repeated squaring, R src/main/arithmetic.c).
+ * ------------------------------------------------------------------------ */
+static double oracle_pow_di(double x, int n)
+{
+    double xn = 1.0;
+    if (isnan(x)) return x;
+    if (n != 0) {
+        if (!isfinite(x)) return pow(x, (double)n);
+        const int neg = n < 0;
+        if (neg) n = -n;
+        for (;;) {
+            if (n & 1) xn *= x;
+            n >>= 1;
+            if (!n) break;
+            x *= x;
+        }
+        if (neg) xn = 1.0 / xn;
+    }
+    return xn;
+}
+
+static double polyh_point(const double *x, const double *knots, const double *w, const double *lw,
+                          int rank, int nknots, double k)
+{
+    const int ki = (int)k;
+    const int mode = (k < 0) ? 0 : ((ki % 2 == 1) ? 1 : 2);
+    double sum = 0.0;
+    for (int i = 0; i < nknots; ++i) {
+        const double *kn = knots + (size_t)i * rank;
+        double d2 = 0.0;
+        for (int j = 0; j < rank; ++j) d2 += (x[j] - kn[j]) * (x[j] - kn[j]);
+        if (mode == 0) {
+            sum += w[i] * exp(k * d2);
+        } else if (d2 != 0) {
+            if (mode == 1) sum += w[i] * oracle_pow_di(sqrt(d2), ki);
+            else sum += w[i] * log(sqrt(d2)) * oracle_pow_di(sqrt(d2), ki);
+        }
+    }
+    sum += lw[0];
+    for (int j = 0; j < rank; ++j) sum += lw[j + 1] * x[j];
+    return sum;
+}
+
+API int oracle_evalpolyh(const double *x, int64_t npts, const double *knots, const double *weights,
+                         const double *lweights, int rank, int nknots, double k, int threads, double *out)
+{
+    if (rank <= 0 || nknots < 0) return 1;
+#pragma omp parallel for num_threads(threads) schedule(static) if (npts > 1 && threads > 1)
+    for (int64_t p = 0; p < npts; ++p)
+        out[p] = polyh_point(x + p * rank, knots, weights, lweights, rank, nknots, k);
+    return 0;
+}
+
+/* ------------------------------------------------------------------------
  * Fit-side helpers (fixtures only; not on the timed path).
  * ------------------------------------------------------------------------ */
 /* Floater-Hormann weights, eq. (18) of the FH paper, as fhweights at

@@ -168,6 +168,21 @@ class Oracle:
         f(vals.ctypes.data_as(_dp), _ptr(x), gl, dims.ctypes.data_as(_ip), rank, wl, x.shape[0], threads, _ptr(out))
         return out
 
+    def evalpolyh(self, knots, weights, lweights, k: float, x, threads: int = 1):
+        """knots: rank x nknots (R matrix; any array whose [:, i] is knot i); x: P x rank."""
+        knots = np.asfortranarray(knots, dtype=np.float64)
+        rank, nk = knots.shape
+        w = np.ascontiguousarray(weights, dtype=np.float64)
+        lw = np.ascontiguousarray(lweights, dtype=np.float64)
+        assert w.size == nk and lw.size == rank + 1
+        x = _as_pts(x, rank)
+        out = np.empty(x.shape[0], dtype=np.float64)
+        f = getattr(self.lib, self.pfx + "evalpolyh")
+        f.restype = None if self.kind == "reference" else C.c_int
+        f.argtypes = [_dp, C.c_int64, _dp, _dp, _dp, C.c_int, C.c_int, C.c_double, C.c_int, _dp]
+        f(_ptr(x), x.shape[0], knots.ctypes.data_as(_dp), _ptr(w), _ptr(lw), rank, nk, float(k), threads, _ptr(out))
+        return out
+
     # -- fit side (fixtures) -------------------------------------------------
     def fhweights(self, grid, d):
         d = np.broadcast_to(np.asarray(d, dtype=np.int64), (len(grid),))

@@ -96,7 +96,24 @@ double cospi(double x) {
   if (x == 0.0) return 1.0;
   return cos(M_PI * x);
 }
-double R_pow_di(double x, int n) { return pow(x, (double)n); }
+/* R's R_pow_di (R >= 3.x, src/main/arithmetic.c): x^n by repeated squaring -- a dependency of the
+ * reference that is not vendored under /root/reference; restated from the published R source so the
+ * polyharmonic basis r^k (src/chebpol.c:402,410) rounds as it does inside R. */
+double R_pow_di(double x, int n) {
+  double xn = 1.0;
+  if (isnan(x)) return x;
+  if (n != 0) {
+    if (!isfinite(x)) return pow(x, (double)n);
+    int is_neg = (n < 0);
+    if (is_neg) n = -n;
+    for (;;) {
+      if (n & 01) xn *= x;
+      if (n >>= 1) x *= x; else break;
+    }
+    if (is_neg) xn = 1. / xn;
+  }
+  return xn;
+}
 /* dgemm, only the ("T","T") case reached from src/chebpol.c:119:
  * C(MxN) = alpha * A^T * B^T + beta*C, column-major, A is KxM (lda), B is NxK (ldb) */
 void dgemm_(const char *ta, const char *tb, const int *M, const int *N, const int *K,
@@ -133,6 +150,14 @@ EXPORT void ref_fh(const double *vals, const double *x, const double *const *kno
 #pragma omp parallel for num_threads(threads) schedule(static) if (npts > 1 && threads > 1)
   for (int64_t i = 0; i < npts; i++)
     out[i] = FH((double *)vals, (double *)x + i * rank, (double **)knots, (int *)dims, rank, (double **)weights);
+}
+
+/* the loop of R_evalpolyh (src/chebpol.c:443-446) over the reference's C_evalpolyh (:383-415) */
+EXPORT void ref_evalpolyh(const double *x, int64_t npts, const double *knots, const double *weights,
+                          const double *lweights, int rank, int nknots, double k, int threads, double *out) {
+#pragma omp parallel for num_threads(threads) schedule(static) if (npts > 1 && threads > 1)
+  for (int64_t i = 0; i < npts; i++)
+    out[i] = C_evalpolyh(x + i * rank, knots, weights, lweights, rank, nknots, k);
 }
 
 EXPORT void ref_chebcoef(const double *val, const int *dims, int rank, double *F, int dct) {

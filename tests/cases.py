@@ -63,3 +63,15 @@ def fh_case(dims, d=4, kind="uniform"):
     dd = [min(d, n - 1) for n in dims]
     weights = interp.fhweights(grid, dd)
     return vals, grid, weights
+
+
+def polyh_case(rank, nknots, k=3, seed=45):
+    """Polyharmonic spline of gfun on `nknots` seeded random knots of [-1,1]^rank, fitted as
+    polyh.real does (R/polyharmonic.R:48-131) with normalize=FALSE: (knots rank x nknots,
+    weights, lweights)."""
+    from chebpol_b200 import interp
+
+    rng = np.random.default_rng(seed)
+    knots = rng.uniform(-1.0, 1.0, (rank, nknots))
+    ip = interp.polyh(lambda x: float(gfun(np.asarray(x).reshape(1, -1))[0]), knots, k=k, normalize=False)
+    return ip.t["knots"], ip.t["weights"], ip.t["lweights"]

@@ -122,7 +122,9 @@ def test_ipol_front_end_checks():
     with pytest.raises(ValueError):
         cb.ipol(np.zeros(3), grid=[np.array([0.0, 2.0, 1.0])], method="fh")  # unsorted
     with pytest.raises(NotImplementedError):
-        cb.ipol(np.zeros(4), knots=np.zeros((2, 2)), method="polyharmonic")
+        cb.ipol(np.zeros(4), grid=[np.linspace(0, 1, 4)], method="stalker")  # outside the GPU path
+    with pytest.raises(ValueError):
+        cb.ipol(np.zeros(4), method="polyharmonic")  # Must specify knots
     ip = cb.ipol(np.zeros(9), grid=[np.linspace(0, 1, 3)] * 2, method="multi")  # partial match
     assert ip.kind == "multilinear" and ip.arity == 2
     ip = cb.ipol(np.arange(24.0), dims=[2, 3, 4], method="cheb")
@@ -131,6 +133,27 @@ def test_ipol_front_end_checks():
     assert [len(w) for w in ip.t["weights"]] == [5, 5]  # decreasing grids are legal (R/ipol.R:241-243)
     ip = cb.ipol(np.zeros(15), method="uniform")
     assert ip.kind == "uniform" and list(ip.t["ugm_n"]) == [15]
+
+
+def test_polyh_fit_mirrors_the_reference_system(port):
+    """polyh.real (R/polyharmonic.R:48-131): the fitted weights solve the saddle system, so the
+    spline (evaluated by the CPU oracle here; no GPU in this test) reproduces the values on the
+    knots, and the side conditions sum w = 0, knots @ w = 0 hold."""
+    rng = np.random.default_rng(5)
+    knots = rng.uniform(0, 1, (3, 60))
+    f = lambda x: 10.0 / (1.0 + 25.0 * np.mean(x ** 2))
+    for k in (1, 2, 3, -2.0):
+        ip = cb.polyh(f, knots, k=k)
+        t = ip.t
+        assert ip.kind == "polyharmonic" and ip.arity == 3 and t["norm_a"] is None
+        got = port.evalpolyh(t["knots"], t["weights"], t["lweights"], t["k"], knots.T)
+        want = np.array([f(knots[:, i]) for i in range(60)])
+        assert np.abs(got - want).max() < 1e-8
+        assert abs(t["weights"].sum()) < 1e-8 and np.abs(t["knots"] @ t["weights"]).max() < 1e-8
+    # knots outside [0,1]: normalised to the unit cube, the map is carried for the kernel
+    ip = cb.polyh(f, 20 * knots - 3, k=3)
+    assert np.allclose(ip.t["norm_b"], (20 * knots - 3).min(axis=1)) and ip.t["knots"].min() == 0.0
+    assert ip.t["knots"].max() == 1.0
 
 
 def test_shard_range_tiles_the_batch():

@@ -657,3 +657,135 @@ def test_evalongridV_matches_pointwise(gpu_ok, port):
     assert np.abs(gotf - wantf).max() <= 1e-11 * np.abs(wantf).max()  # cubed grid: Lebesgue constant ~1e2
     for ip in (ch, uc, ml, fh):
         ip.close()
+
+
+# --------------------------------------------------------------- polyharmonic splines
+def _polyh_case(rank, nk, seed=0):
+    rng = np.random.default_rng(seed)
+    return rng.uniform(0, 1, (rank, nk)), rng.standard_normal(nk), rng.standard_normal(rank + 1)
+
+
+def _polyh_scale(kn, w, lw, k, x):
+    """sum_i |w_i phi_i(x)| + |affine terms|: the conditioning bound of the radial sum."""
+    d2 = np.maximum((x ** 2).sum(axis=1)[:, None] + (kn ** 2).sum(axis=0)[None, :] - 2.0 * x @ kn, 0.0)
+    from chebpol_b200.interp import _phifunc
+    return (np.abs(w)[None, :] * np.abs(_phifunc(d2, k))).sum(axis=1) + np.abs(lw[0]) + np.abs(x * lw[1:]).sum(axis=1)
+
+
+POLYH_SHAPES = [(1, 17), (2, 40), (3, 1000), (4, 33), (5, 64), (6, 1000), (7, 9), (8, 100), (11, 50), (16, 300), (20, 1000),
+                (31, 20), (3, 1), (24, 3000)]
+
+
+@pytest.mark.parametrize("rank,nk", POLYH_SHAPES)
+@pytest.mark.parametrize("k", [1, 2, 3, 4, 5, 0, -1.0, -0.37])
+def test_polyh_strict_and_tile(gpu_ok, port, rank, nk, k):
+    """Both kernels against the oracle; points inside and outside the knots' hull plus exact knot
+    hits (distance zero is skipped for k >= 0, src/chebpol.c:400,408).
+    strict, odd k (sqrt and multiplies only): BIT-IDENTICAL.  strict, even k / k < 0 (device
+    log/exp within 1 ulp of libm) and the tile kernel (FMA, phi reformulated):
+    |diff| <= 1e-12*max|f| + 8*eps*sum_i|w_i phi_i| pointwise."""
+    kn, w, lw = _polyh_case(rank, nk, seed=rank * 100 + nk)
+    rng = np.random.default_rng(9)
+    x = np.ascontiguousarray(np.vstack([rng.uniform(-0.3, 1.3, (2500, rank)), kn.T[: min(nk, 11)]]))
+    want = port.evalpolyh(kn, w, lw, k, x, threads=4)
+    scale = _polyh_scale(kn, w, lw, k, x)
+    tol = TOL_REL * np.abs(want).max() + 8 * np.finfo(float).eps * scale
+    plan = _lib.Plan.polyh(kn, w, lw, k)
+    got, kern = eval_plan(plan, x, _lib.KERNEL_STRICT)
+    assert kern == "polyh_strict"
+    if k > 0 and int(k) % 2 == 1:
+        assert np.array_equal(bits(got), bits(want))
+    else:
+        assert np.all(np.abs(got - want) <= tol)
+    got, kern = eval_plan(plan, x, _lib.KERNEL_AUTO)
+    assert kern == "polyh_tile"
+    assert np.all(np.abs(got - want) <= tol), (np.abs(got - want).max(), tol.min())
+    plan.close()
+
+
+def test_polyh_normalisation_nan_and_empty(gpu_ok, port):
+    kn, w, lw = _polyh_case(4, 50, seed=3)
+    a = np.array([0.05, 2.0, 1.0, 0.5])
+    b = np.array([-3.0, 0.25, 0.0, 1.0])
+    rng = np.random.default_rng(2)
+    x = np.ascontiguousarray(rng.uniform(-3, 17, (3000, 4)))
+    xn = a * (x - b)  # normfun, R/polyharmonic.R:77
+    for kern, exact in ((_lib.KERNEL_STRICT, True), (_lib.KERNEL_AUTO, False)):
+        plan = _lib.Plan.polyh(kn, w, lw, 3, norm_a=a, norm_b=b)
+        got, _ = eval_plan(plan, x, kern)
+        want = port.evalpolyh(kn, w, lw, 3, xn, threads=2)
+        if exact:
+            assert np.array_equal(bits(got), bits(want))
+        else:
+            assert np.all(np.abs(got - want) <= TOL_REL * np.abs(want).max() + 8e-16 * _polyh_scale(kn, w, lw, 3, xn))
+        xx = x[:5].copy()
+        xx[1, 2] = np.nan
+        got, _ = eval_plan(plan, xx, kern)
+        assert np.isnan(got[1]) and np.all(np.isfinite(got[[0, 2, 3, 4]]))
+        plan.close()
+    # no knots: the affine part alone
+    plan = _lib.Plan.polyh(np.zeros((2, 0)), np.zeros(0), np.array([1.0, 2.0, -3.0]), 3)
+    got, kern = eval_plan(plan, np.array([[0.5, 0.25], [1.0, 1.0]]), _lib.KERNEL_AUTO)
+    assert kern == "polyh_strict" and np.array_equal(got, [1.25, 0.0])
+    plan.close()
+
+
+def test_polyh_goldens_through_ipol(gpu_ok):
+    """all.R:82-95 -> all.Rout.save:195,203,207,208 through fit + GPU evaluation (ipol front end)."""
+    from r_rng import RRng
+
+    r = RRng(42)
+    r.rnorm(24); r.runif(3, -1, 1); r.runif(1); r.runif(3); r.runif(3); r.rnorm(24); r.runif(10); r.runif(1, -1, 1)
+    f = lambda x: 10.0 / (10.0 + np.sum(np.sqrt(x)))
+    knots = r.runif(6000, 0, 20).reshape((6, 1000), order="F")
+    a = r.runif(6, 0, 20)
+    assert abs(f(a) - 0.3536114) < 5e-8
+    phs = cb.ipol(f, knots=knots, k=3, method="poly")
+    assert abs(phs(a)[0] - 0.3539679) < 5e-7
+    assert np.abs(phs(knots) - np.array([f(knots[:, i]) for i in range(1000)])).max() < 5e-7
+    assert abs(cb.ipol(f, knots=knots, k=5, method="poly", normalize=True)(a)[0] - 0.3539086) < 5e-7
+    assert abs(cb.ipol(f, knots=knots, k=-1, method="poly", normalize=False)(a)[0] - 0.3561987) < 5e-7
+    nphs = cb.ipol(f, knots=knots, k=-1, method="poly", normalize=True)
+    assert abs(nphs(a)[0] - 0.3523617) < 5e-7
+    for kern in (_lib.KERNEL_STRICT, _lib.KERNEL_AUTO):
+        nphs.kernel = kern
+        assert abs(nphs(a, threads=2)[0] - 0.3523617) < 5e-7
+
+
+def test_polyh_stateless_and_sharded(gpu_ok, port):
+    kn, w, lw = _polyh_case(6, 1000, seed=8)
+    rng = np.random.default_rng(1)
+    x = np.ascontiguousarray(rng.uniform(0, 1, (300_000, 6)))
+    want = port.evalpolyh(kn, w, lw, 3, x[:4000], threads=8)
+    tol = TOL_REL * np.abs(want).max() + 8e-16 * _polyh_scale(kn, w, lw, 3, x[:4000])
+    got1 = _lib.evalpolyh(kn, w, lw, 3, x, ngpus=1)
+    assert np.all(np.abs(got1[:4000] - want) <= tol)
+    got2 = _lib.evalpolyh(kn, w, lw, 3, x, ngpus=0)  # all visible GPUs; second call hits the plan cache
+    assert np.array_equal(got1, got2)
+    a = np.full(6, 0.5)
+    b = np.full(6, -0.25)
+    gotn = _lib.evalpolyh(kn, w, lw, 2, x[:5000], norm_a=a, norm_b=b)
+    wantn = port.evalpolyh(kn, w, lw, 2, a * (x[:5000] - b), threads=8)
+    assert np.all(np.abs(gotn - wantn) <= TOL_REL * np.abs(wantn).max() + 8e-16 * _polyh_scale(kn, w, lw, 2, a * (x[:5000] - b)))
+
+
+def test_polyh_fitted_spline_error_against_extended_precision(gpu_ok, port):
+    """A fitted spline sums 1000 terms w_i phi_i of mixed sign that are ~1e3 times larger than f,
+    so |GPU - reference| (3e-13 on max|f| = 0.15) is above 1e-12*max|f| -- but so is the
+    reference's own distance from the exactly rounded sum.  Measured against an 80-bit evaluation:
+    the tile kernel is as close to the exact value as the reference C is."""
+    kn, w, lw = cases.polyh_case(6, 1000, 3)
+    x = cases.points(400, 6)
+    ld = np.longdouble
+    d2 = ((x[:, :, None].astype(ld) - kn[None, :, :].astype(ld)) ** 2).sum(axis=1)
+    exact = (w.astype(ld)[None, :] * d2 * np.sqrt(d2)).sum(axis=1) + ld(lw[0]) + (x.astype(ld) * lw[1:].astype(ld)).sum(axis=1)
+    ref = port.evalpolyh(kn, w, lw, 3, x, threads=4)
+    plan = _lib.Plan.polyh(kn, w, lw, 3)
+    got, kern = eval_plan(plan, x, _lib.KERNEL_AUTO)
+    assert kern == "polyh_tile"
+    err_ref = np.abs(ref.astype(ld) - exact).max()
+    err_gpu = np.abs(got.astype(ld) - exact).max()
+    scale = _polyh_scale(kn, w, lw, 3, x).max()
+    assert err_ref > 1e-13 * np.abs(ref).max()          # the reference is not within 1e-13*max|f| of exact either
+    assert err_gpu <= 2.0 * err_ref + 2e-16 * scale, (float(err_gpu), float(err_ref), scale)
+    plan.close()
