@@ -27,7 +27,7 @@ VARIANT_AUTO, VARIANT_SLAB, VARIANT_MMA = 0, 1, 100000  # OPT_VARIANT families (
 VARIANT_MLIP_PAIR, VARIANT_MLIP_CELL = 1, 2
 KERNEL_NAMES = {
     0: "none", 10: "cheb_strict", 11: "cheb_slab", 12: "cheb_mma", 20: "mlip_strict", 21: "mlip_pair", 22: "mlip_cell",
-    30: "fh_strict", 32: "fh_mma", 40: "polyh_strict", 41: "polyh_tile",
+    30: "fh_strict", 32: "fh_mma", 40: "polyh_strict", 41: "polyh_tile", 50: "stalk_strict", 51: "stalk_cell",
 }
 
 EXPORTS = [
@@ -39,6 +39,7 @@ EXPORTS = [
     "chebpol_cuda_launch_count", "chebpol_cuda_cache_clear", "chebpol_cuda_chebcoef", "chebpol_cuda_fhweights",
     "chebpol_cuda_evalgrid_cheb", "chebpol_cuda_evalgrid_mlip", "chebpol_cuda_evalgrid_fh",
     "chebpol_cuda_evalpolyh", "chebpol_cuda_plan_polyh",
+    "chebpol_cuda_evalstalk", "chebpol_cuda_evalhyp", "chebpol_cuda_plan_stalk",
 ]
 
 
@@ -89,6 +90,11 @@ def lib() -> C.CDLL:
     L.chebpol_cuda_evalpolyh.argtypes = [_vp, C.c_int, C.c_int, _vp, _vp, C.c_double, _vp, C.c_int64, _vp, _vp,
                                          C.c_int, _vp]
     L.chebpol_cuda_plan_polyh.argtypes = [_vp, C.c_int, C.c_int, _vp, _vp, C.c_double, _vp, _vp, C.c_int,
+                                          C.POINTER(_vp)]
+    L.chebpol_cuda_evalstalk.argtypes = [_vp, _dpp, _ip, C.c_int, _vp, _vp, _vp, C.c_int, _vp, C.c_int64, C.c_int, _vp]
+    L.chebpol_cuda_evalhyp.argtypes = [_vp, _dpp, _ip, C.c_int, _vp, _vp, _vp, _vp, C.c_int, _vp, C.c_int64, C.c_int,
+                                       _vp]
+    L.chebpol_cuda_plan_stalk.argtypes = [C.c_int, _vp, _dpp, _ip, C.c_int, _vp, _vp, _vp, _vp, C.c_int, C.c_int,
                                           C.POINTER(_vp)]
     L.chebpol_cuda_cache_clear.restype = None
     L.chebpol_cuda_cache_clear.argtypes = []
@@ -228,6 +234,26 @@ class Plan:
                                             device, C.byref(h)))
         return Plan(h.value, rank, "polyh")
 
+    @staticmethod
+    def stalk(kind: int, val, grid, tables, blend: int = 3, device: int = 0) -> "Plan":
+        """kind 0: stalker, tables (b, c, r); kind 1: hstalker, tables (a, b, c, d).  b, c, r/d are
+        rank x prod(dims) (column i belongs to grid point i in R order), a has prod(dims) entries."""
+        dims = _i32([len(g) for g in grid])
+        n = int(np.prod(dims.astype(np.int64)))
+        v = f64(np.asarray(val, dtype=np.float64).ravel(order="F"))
+        if v.size != n:
+            raise ValueError(f"number of values ({v.size}) does not match grid size ({n})")
+        a = f64(np.ravel(tables[0])) if kind == 1 else None
+        b, t1, t2 = (f64(np.asarray(t, dtype=np.float64), order="F") for t in tables[-3:])
+        for t in (b, t1, t2):
+            if t.shape != (len(grid), n):
+                raise ValueError(f"parameter table has shape {t.shape}, expected {(len(grid), n)}")
+        gl, keep = ptr_list(grid)
+        h = _vp()
+        check(lib().chebpol_cuda_plan_stalk(kind, _addr(v), gl, dims.ctypes.data_as(_ip), len(grid), _addr(a), _addr(b),
+                                            _addr(t1), _addr(t2), blend, device, C.byref(h)))
+        return Plan(h.value, len(grid), "stalk")
+
     # -- evaluation --------------------------------------------------------------
     def eval_host(self, x_pk: np.ndarray, out: np.ndarray | None = None) -> np.ndarray:
         """x_pk: (P, K) C-contiguous float64 host array (pinned or pageable)."""
@@ -318,6 +344,31 @@ def evalpolyh(knots, weights, lweights, k: float, x_pk, norm_a=None, norm_b=None
     out = np.empty(x_pk.shape[0], dtype=np.float64)
     check(lib().chebpol_cuda_evalpolyh(_addr(knf), rank, nk, _addr(w), _addr(lw), float(k), _addr(x_pk),
                                        x_pk.shape[0], _addr(na), _addr(nb), ngpus, _addr(out)))
+    return out
+
+
+def evalstalk(val, grid, b, c, r, x_pk, blend: int = 3, ngpus: int = 0) -> np.ndarray:
+    dims = _i32([len(g) for g in grid])
+    v = f64(np.asarray(val, dtype=np.float64).ravel(order="F"))
+    b, c, r = (f64(np.asarray(t, dtype=np.float64), order="F") for t in (b, c, r))
+    x_pk = f64(x_pk)
+    out = np.empty(x_pk.shape[0], dtype=np.float64)
+    gl, keep = ptr_list(grid)
+    check(lib().chebpol_cuda_evalstalk(_addr(v), gl, dims.ctypes.data_as(_ip), len(grid), _addr(b), _addr(c), _addr(r),
+                                       blend, _addr(x_pk), x_pk.shape[0], ngpus, _addr(out)))
+    return out
+
+
+def evalhyp(val, grid, a, b, c, d, x_pk, blend: int = 3, ngpus: int = 0) -> np.ndarray:
+    dims = _i32([len(g) for g in grid])
+    v = f64(np.asarray(val, dtype=np.float64).ravel(order="F"))
+    a = f64(np.ravel(a))
+    b, c, d = (f64(np.asarray(t, dtype=np.float64), order="F") for t in (b, c, d))
+    x_pk = f64(x_pk)
+    out = np.empty(x_pk.shape[0], dtype=np.float64)
+    gl, keep = ptr_list(grid)
+    check(lib().chebpol_cuda_evalhyp(_addr(v), gl, dims.ctypes.data_as(_ip), len(grid), _addr(a), _addr(b), _addr(c),
+                                     _addr(d), blend, _addr(x_pk), x_pk.shape[0], ngpus, _addr(out)))
     return out
 
 

@@ -80,7 +80,10 @@ extern "C" int chebpol_cuda_device_count(int *count)
 }
 
 // ---------------------------------------------------------------------- plan
-enum PlanKind { PLAN_CHEB = 1, PLAN_MLIP = 2, PLAN_FH = 3, PLAN_POLYH = 4 };
+enum PlanKind { PLAN_CHEB = 1, PLAN_MLIP = 2, PLAN_FH = 3, PLAN_POLYH = 4, PLAN_STALK = 5 };
+
+cudaError_t stalk_pack_records(const double *val, const double *aa, const double *b, const double *t1,
+                               const double *t2, int rank, int64_t n, double *rec, cudaStream_t s);
 
 struct chebpol_cuda_plan {
     int kind = 0;
@@ -122,6 +125,9 @@ struct chebpol_cuda_plan {
     // packed [w, knot, pad] rows in d_padded
     int nknots = 0;
     double polyh_k = 0.0;
+    // stalker splines: values in d_tensor, knots in d_grid, packed records in d_padded
+    int stalk_kind = 0;  // 0 stalker, 1 hstalker
+    double *d_stalk[4] = {nullptr, nullptr, nullptr, nullptr};  // a, b, t1, t2
     // statistics
     LaunchInfo last = {0, 0, 0, 0};
     int64_t launches = 0;
@@ -215,6 +221,7 @@ extern "C" void chebpol_cuda_plan_destroy(chebpol_cuda_plan *p)
     cudaFree(p->d_lut);
     cudaFree(p->d_grid);
     cudaFree(p->d_weights);
+    for (int i = 0; i < 4; ++i) cudaFree(p->d_stalk[i]);
     delete p;
     if (prev >= 0) cudaSetDevice(prev);
 }
@@ -535,6 +542,61 @@ extern "C" int chebpol_cuda_plan_polyh(const double *knots, int rank, int nknots
     return CHEBPOL_CUDA_OK;
 }
 
+extern "C" int chebpol_cuda_plan_stalk(int kind, const double *val, const double *const *grid, const int *dims,
+                                       int rank, const double *a, const double *b, const double *t1,
+                                       const double *t2, int blend, int device, chebpol_cuda_plan **plan)
+{
+    if (!plan) return fail(CHEBPOL_CUDA_EINVAL, "plan is NULL");
+    *plan = nullptr;
+    if (kind != 0 && kind != 1) return fail(CHEBPOL_CUDA_EINVAL, "kind %d: 0 stalker, 1 hstalker", kind);
+    if (!val || !grid || !b || !t1 || !t2 || (kind == 1 && !a)) return fail(CHEBPOL_CUDA_EINVAL, "a table pointer is NULL");
+    if (blend < 0 || blend > 5) return fail(CHEBPOL_CUDA_EBLEND, "blend %d not in 0..5", blend);
+    int64_t nelem = 0;
+    int rc = check_dims(dims, rank, &nelem);
+    if (rc) return rc;
+    if (rank > 24) return fail(CHEBPOL_CUDA_ERANK, "rank %d: the corner loop supports at most 24 dimensions", rank);
+    for (int d = 0; d < rank; ++d)
+        if (dims[d] < 2) return fail(CHEBPOL_CUDA_ESIZE, "dims[%d] = %d: a stalker grid needs two knots per dimension", d, dims[d]);
+    if (nelem * rank >= (int64_t(1) << 31)) return fail(CHEBPOL_CUDA_ESIZE, "parameter tables have 2^31 or more elements");
+    int sms = 0;
+    rc = select_device(device, &sms);
+    if (rc) return rc;
+    chebpol_cuda_plan *p = new_plan(PLAN_STALK, device, sms, dims, rank, nelem);
+    auto bail = [&](int code) { chebpol_cuda_plan_destroy(p); return code; };
+    p->stalk_kind = kind;
+    p->blend = blend;
+    rc = upload_lists(p, grid, nullptr);
+    if (rc) return bail(rc);
+    auto up = [&](double **dst, const double *src, size_t n, const char *what) -> int {
+        cudaError_t e = cudaMalloc(dst, sizeof(double) * n);
+        if (e != cudaSuccess) return cuda_fail(e, what);
+        e = cudaMemcpy(*dst, src, sizeof(double) * n, cudaMemcpyHostToDevice);
+        return e == cudaSuccess ? CHEBPOL_CUDA_OK : cuda_fail(e, what);
+    };
+    const size_t n = (size_t)nelem, nr = n * rank;
+    if ((rc = up(&p->d_tensor, val, n, "upload(val)"))) return bail(rc);
+    if (kind == 1 && (rc = up(&p->d_stalk[0], a, n, "upload(a)"))) return bail(rc);
+    if ((rc = up(&p->d_stalk[1], b, nr, "upload(b)"))) return bail(rc);
+    if ((rc = up(&p->d_stalk[2], t1, nr, "upload(c)"))) return bail(rc);
+    if ((rc = up(&p->d_stalk[3], t2, nr, "upload(r/d)"))) return bail(rc);
+    p->tensor_bytes = sizeof(double) * (n * (kind == 1 ? 2 : 1) + 3 * nr);
+    const int rs = stalk_record_stride(rank, kind);
+    if (rs > 0) {
+        cudaError_t e = cudaMalloc(&p->d_padded, sizeof(double) * n * rs);
+        if (e == cudaSuccess) {
+            e = stalk_pack_records(p->d_tensor, p->d_stalk[0], p->d_stalk[1], p->d_stalk[2], p->d_stalk[3], rank,
+                                   nelem, p->d_padded, 0);
+            if (e == cudaSuccess) e = cudaDeviceSynchronize();
+            if (e != cudaSuccess) return bail(cuda_fail(e, "pack stalker records"));
+        } else {
+            (void)cudaGetLastError();  // no room for the packed copy: the strict kernel serves the plan
+            p->d_padded = nullptr;
+        }
+    }
+    *plan = p;
+    return CHEBPOL_CUDA_OK;
+}
+
 extern "C" int chebpol_cuda_plan_set(chebpol_cuda_plan *p, int option, int64_t value)
 {
     if (!p) return fail(CHEBPOL_CUDA_EINVAL, "plan is NULL");
@@ -544,7 +606,8 @@ extern "C" int chebpol_cuda_plan_set(chebpol_cuda_plan *p, int option, int64_t v
         p->kernel_opt = (int)value;
         return CHEBPOL_CUDA_OK;
     case CHEBPOL_CUDA_OPT_BLEND:
-        if (p->kind != PLAN_MLIP) return fail(CHEBPOL_CUDA_EINVAL, "blend applies to multilinear plans");
+        if (p->kind != PLAN_MLIP && p->kind != PLAN_STALK)
+            return fail(CHEBPOL_CUDA_EINVAL, "blend applies to multilinear and stalker plans");
         if (value < 0 || value > 5) return fail(CHEBPOL_CUDA_EBLEND, "blend %lld not in 0..5", (long long)value);
         p->blend = (int)value;
         return CHEBPOL_CUDA_OK;
@@ -725,6 +788,28 @@ static int launch_plan(chebpol_cuda_plan *p, const double *d_x, int64_t npts, do
             if (p->kernel_opt == CHEBPOL_CUDA_KERNEL_FAST)
                 return fail(CHEBPOL_CUDA_EINVAL, "no fast polyharmonic kernel for rank %d with %d knots", p->rank, p->nknots);
             e = launch_polyh_strict(a, s, &li);
+        }
+    } else if (p->kind == PLAN_STALK) {
+        StalkArgs a;
+        a.kind = p->stalk_kind;
+        a.val = p->d_tensor;
+        a.a = p->d_stalk[0];
+        a.b = p->d_stalk[1];
+        a.t1 = p->d_stalk[2];
+        a.t2 = p->d_stalk[3];
+        a.records = p->d_padded;
+        a.grid = p->d_grid;
+        a.rank = p->rank;
+        for (int i = 0; i < p->rank; ++i) { a.dims[i] = p->dims[i]; a.stride[i] = p->stride[i]; a.goff[i] = p->goff[i]; }
+        a.blend = p->blend;
+        a.x = d_x;
+        a.npts = npts;
+        a.out = d_out;
+        if (want_fast) e = launch_stalk_cell(a, p->variant, p->num_sms, s, &li);
+        if (e == cudaErrorNotSupported) {
+            if (p->kernel_opt == CHEBPOL_CUDA_KERNEL_FAST)
+                return fail(CHEBPOL_CUDA_EINVAL, "no fast stalker kernel for rank %d", p->rank);
+            e = launch_stalk_strict(a, s, &li);
         }
     } else {
         return fail(CHEBPOL_CUDA_EINVAL, "corrupt plan");
@@ -1258,6 +1343,48 @@ extern "C" int chebpol_cuda_evalpolyh(const double *knots, int rank, int nknots,
     return run_sharded(rank, x, npts, ngpus, out, key, bytes, [&](int dev, chebpol_cuda_plan **p) {
         return chebpol_cuda_plan_polyh(knots, rank, nknots, weights, lweights, k, norm_a, norm_b, dev, p);
     });
+}
+
+static int stalk_stateless(int kind, const double *val, const double *const *grid, const int *dims, int rank,
+                           const double *a, const double *b, const double *t1, const double *t2, int blend,
+                           const double *x, int64_t npts, int ngpus, double *out)
+{
+    int64_t nelem = 0;
+    if (!val || !grid || !b || !t1 || !t2 || (kind == 1 && !a)) return fail(CHEBPOL_CUDA_EINVAL, "a table pointer is NULL");
+    int rc = check_dims(dims, rank, &nelem);
+    if (rc) return rc;
+    if (blend < 0 || blend > 5) return fail(CHEBPOL_CUDA_EBLEND, "blend %d not in 0..5", blend);
+    CacheKey key = make_key(PLAN_STALK, dims, rank);
+    const int64_t bytes = 8 * (nelem * (kind == 1 ? 2 : 1) + 3 * nelem * rank);
+    if (cache_enabled() && bytes <= kCacheMaxBytes) {
+        uint64_t h = hash_bytes(val, (size_t)nelem * 8, 5 + kind);
+        if (kind == 1) h = hash_bytes(a, (size_t)nelem * 8, h);
+        h = hash_bytes(b, (size_t)nelem * rank * 8, h);
+        h = hash_bytes(t1, (size_t)nelem * rank * 8, h);
+        h = hash_bytes(t2, (size_t)nelem * rank * 8, h);
+        for (int d = 0; d < rank; ++d) {
+            if (!grid[d]) return fail(CHEBPOL_CUDA_EINVAL, "grid[%d] is NULL", d);
+            h = hash_bytes(grid[d], (size_t)dims[d] * 8, h);
+        }
+        key.hash = h;
+    }
+    return run_sharded(rank, x, npts, ngpus, out, key, bytes, [&](int dev, chebpol_cuda_plan **p) {
+        return chebpol_cuda_plan_stalk(kind, val, grid, dims, rank, a, b, t1, t2, blend, dev, p);
+    }, blend);
+}
+
+extern "C" int chebpol_cuda_evalstalk(const double *val, const double *const *grid, const int *dims, int rank,
+                                      const double *b, const double *c, const double *r, int blend,
+                                      const double *x, int64_t npts, int ngpus, double *out)
+{
+    return stalk_stateless(0, val, grid, dims, rank, nullptr, b, c, r, blend, x, npts, ngpus, out);
+}
+
+extern "C" int chebpol_cuda_evalhyp(const double *val, const double *const *grid, const int *dims, int rank,
+                                    const double *a, const double *b, const double *c, const double *d, int blend,
+                                    const double *x, int64_t npts, int ngpus, double *out)
+{
+    return stalk_stateless(1, val, grid, dims, rank, a, b, c, d, blend, x, npts, ngpus, out);
 }
 
 // ------------------------------------------------------------------ fit side

@@ -38,6 +38,8 @@ enum KernelId {
     K_MLIP_CELL = 22,    // cell-major table: one contiguous 2^D block per point
     K_FH_STRICT = 30,    // thread-per-point nested barycentric, reference op order
     K_FH_MMA = 32,       // barycentric-basis DMMA contraction, TMA-streamed rows
+    K_STALK_STRICT = 50, // stalker / hstalker, thread per point, reference op order
+    K_STALK_CELL = 51,   // packed per-grid-point records, blend weights hoisted, fast reciprocal
     K_POLYH_STRICT = 40, // thread-per-point radial sum, reference op order
     K_POLYH_TILE = 41,   // points in registers, knot rows broadcast from a TMA-filled ring
 };
@@ -71,6 +73,25 @@ struct MlipArgs {
     int loff[CP_MAXR];     // offset of dim d's table in `lut`
     int nb[CP_MAXR];       // buckets of dim d
     double lscale[CP_MAXR];  // buckets per unit length: nb / (g_{n-1} - g_0)
+};
+
+// Stalker splines (evalstalk src/stalker.c:366-442, evalhyp :537-613): cell lookup, 2^rank corners,
+// per corner and dimension a one-dimensional basis with tabulated parameters.
+struct StalkArgs {
+    int kind;               // 0 stalker: b z + c |z|^r;  1 hstalker: b z + d/(1 + c z), NaN c: b z^2
+    const double *val;      // prod(dims), R layout
+    const double *a;        // hstalker only: prod(dims)
+    const double *b, *t1, *t2;  // rank x prod(dims) each (entry j of grid point i at [rank*i + j]); t1 = c, t2 = r or d
+    const double *records;  // packed per grid point: [val (+a), b_0.., t1_0.., t2_0.., pad], see stalker.cu
+    const double *grid;     // all knot vectors, concatenated
+    int goff[CP_MAXR];
+    int rank;
+    int dims[CP_MAXR];
+    int64_t stride[CP_MAXR];
+    int blend;
+    const double *x;
+    int64_t npts;
+    double *out;
 };
 
 // Polyharmonic spline evaluation (C_evalpolyh, src/chebpol.c:383-415)
@@ -174,6 +195,10 @@ cudaError_t launch_cheb_strict(const ChebStrictArgs &a, cudaStream_t s, LaunchIn
 cudaError_t launch_mlip_strict(const MlipArgs &a, cudaStream_t s, LaunchInfo *li);
 cudaError_t launch_fh_strict(const FhArgs &a, cudaStream_t s, LaunchInfo *li);
 cudaError_t launch_polyh_strict(const PolyhArgs &a, cudaStream_t s, LaunchInfo *li);
+cudaError_t launch_stalk_strict(const StalkArgs &a, cudaStream_t s, LaunchInfo *li);
+// fast stalker kernel (stalker.cu): rank <= 6; record stride in doubles for a rank and kind
+cudaError_t launch_stalk_cell(const StalkArgs &a, int variant, int num_sms, cudaStream_t s, LaunchInfo *li);
+int stalk_record_stride(int rank, int kind);
 // fast polyharmonic kernel (polyh.cu); cudaErrorNotSupported for rank > 32
 cudaError_t launch_polyh_tile(const PolyhArgs &a, int variant, int num_sms, cudaStream_t s, LaunchInfo *li);
 // row stride (doubles) of the packed knot table the tile kernel reads: [w, k_0..k_{rank-1}, 0...]

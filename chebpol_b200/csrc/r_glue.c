@@ -207,6 +207,50 @@ SEXP R_evalpolyh_cuda(SEXP inx, SEXP Sknots, SEXP weights, SEXP lweights, SEXP S
     return res;
 }
 
+/* Stalker splines: same arguments and return as R_evalstalk / R_evalhyp (src/stalker.c:765-832);
+ * `stalker` is the list R_makestalk (b, c, r, val, grid) / R_makehyp (a, b, c, d, val, grid) returned. */
+static SEXP stalk_common(int kind, SEXP Sx, SEXP stalker, SEXP Sblend, SEXP Sthreads)
+{
+    const int off = kind ? 1 : 0;
+    SEXP Sgrid = VECTOR_ELT(stalker, 4 + off);
+    const int rank = LENGTH(Sgrid);
+    if (rank <= 0 || rank > CHEBPOL_CUDA_MAXRANK) error("rank must be positive");
+    if (isMatrix(Sx) ? (nrows(Sx) != rank) : (LENGTH(Sx) != rank))
+        error("Rank of input(%d) does not match rank of spline", isMatrix(Sx) ? nrows(Sx) : LENGTH(Sx));
+    int dims[CHEBPOL_CUDA_MAXRANK];
+    const double *grid[CHEBPOL_CUDA_MAXRANK];
+    for (int i = 0; i < rank; i++) {
+        dims[i] = LENGTH(VECTOR_ELT(Sgrid, i));
+        grid[i] = REAL(VECTOR_ELT(Sgrid, i));
+    }
+    const int blend = INTEGER(Sblend)[0];
+    const int ngpus = gpus_from_threads(Sthreads);
+    const R_xlen_t N = isMatrix(Sx) ? ncols(Sx) : 1;
+    SEXP ret = PROTECT(NEW_NUMERIC(N));
+    int rc;
+    if (kind == 0)
+        rc = chebpol_cuda_evalstalk(REAL(VECTOR_ELT(stalker, 3)), grid, dims, rank, REAL(VECTOR_ELT(stalker, 0)),
+                                    REAL(VECTOR_ELT(stalker, 1)), REAL(VECTOR_ELT(stalker, 2)), blend, REAL(Sx),
+                                    (int64_t)N, ngpus, REAL(ret));
+    else
+        rc = chebpol_cuda_evalhyp(REAL(VECTOR_ELT(stalker, 4)), grid, dims, rank, REAL(VECTOR_ELT(stalker, 0)),
+                                  REAL(VECTOR_ELT(stalker, 1)), REAL(VECTOR_ELT(stalker, 2)),
+                                  REAL(VECTOR_ELT(stalker, 3)), blend, REAL(Sx), (int64_t)N, ngpus, REAL(ret));
+    UNPROTECT(1);
+    raise(rc);
+    return ret;
+}
+
+SEXP R_evalstalk_cuda(SEXP Sx, SEXP stalker, SEXP Sblend, SEXP Sthreads)
+{
+    return stalk_common(0, Sx, stalker, Sblend, Sthreads);
+}
+
+SEXP R_evalhyp_cuda(SEXP Sx, SEXP stalker, SEXP Sblend, SEXP Sthreads)
+{
+    return stalk_common(1, Sx, stalker, Sblend, Sthreads);
+}
+
 /* fit side: same arguments and return as R_chebcoef (src/chebpol.c:145-180) */
 SEXP R_chebcoef_cuda(SEXP x, SEXP sdct, SEXP Sthreads)
 {
@@ -267,4 +311,6 @@ const R_CallMethodDef chebpol_cuda_callMethods[] = {
     {"chebcoef_cuda", (DL_FUNC)&R_chebcoef_cuda, 3},
     {"FHweights_cuda", (DL_FUNC)&R_fhweights_cuda, 3},
     {"evalpolyh_cuda", (DL_FUNC)&R_evalpolyh_cuda, 7},
+    {"evalstalk_cuda", (DL_FUNC)&R_evalstalk_cuda, 4},
+    {"evalhyp_cuda", (DL_FUNC)&R_evalhyp_cuda, 4},
     {NULL, NULL, 0}};

@@ -302,3 +302,93 @@ cudaError_t launch_polyh_strict(const PolyhArgs &a, cudaStream_t s, LaunchInfo *
     if (li) { li->grid = (int)nb; li->block = block; li->smem = 0; li->kernel = K_POLYH_STRICT; }
     return cudaGetLastError();
 }
+
+// ---------------------------------------------------------- stalker splines
+// evalstalk (src/stalker.c:366-442) and evalhyp (:537-613), operation for operation.  The cell
+// is R's findInterval(rightmost_closed = all_inside = TRUE): knots <= x counted by bisection,
+// clamped, so g[gp] <= x < g[gp+1] inside the grid.  evalhyp uses only + - * /: bit-identical
+// to the reference; evalstalk calls pow (device pow within 2 ulp of libm).
+__device__ __forceinline__ int strict_find_interval0(const double *__restrict__ g, int n, double x)
+{
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        const int mid = (lo + hi) / 2;
+        if (__ldg(g + mid) <= x) lo = mid + 1; else hi = mid;
+    }
+    if (lo < 1) lo = 1;
+    if (lo > n - 1) lo = n - 1;
+    return lo - 1;
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(256) stalk_strict_kernel(const __grid_constant__ StalkArgs a)
+{
+    const int rank = a.rank;
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < a.npts;
+         p += (int64_t)gridDim.x * blockDim.x) {
+        double weight[CP_MAXR], x[CP_MAXR], zx[CP_MAXR];
+        int gbase[CP_MAXR];
+        int64_t llcorner = 0;
+        for (int g = 0; g < rank; ++g) {
+            x[g] = a.x[p * rank + g];
+            const double *gr = a.grid + a.goff[g];
+            const int gp = strict_find_interval0(gr, a.dims[g], x[g]);
+            gbase[g] = gp;
+            double w = 1 - (x[g] - __ldg(gr + gp)) / (__ldg(gr + gp + 1) - __ldg(gr + gp));
+            if (w < 0) w = 0;
+            if (w > 1) w = 1;
+            weight[g] = w;
+            llcorner += a.stride[g] * gp;
+        }
+        double V = 0.0, sumw = 0.0;
+        const unsigned long ncorner = 1ul << rank;
+        for (unsigned long i = 0; i < ncorner; ++i) {
+            int64_t corner = llcorner;
+            double cw = 1.0;
+            for (int g = 0; g < rank; ++g) {
+                const double *gr = a.grid + a.goff[g];
+                if (i & (1ul << g)) {
+                    cw *= strict_blend(1 - weight[g], a.blend);
+                    corner += a.stride[g];
+                    zx[g] = x[g] - __ldg(gr + gbase[g] + 1);
+                } else {
+                    zx[g] = x[g] - __ldg(gr + gbase[g]);
+                    cw *= strict_blend(weight[g], a.blend);
+                }
+            }
+            if (cw == 0.0) continue;
+            const double *bb = a.b + rank * corner, *p1 = a.t1 + rank * corner, *p2 = a.t2 + rank * corner;
+            double fval;
+            if (KIND == 0) {
+                fval = __ldg(a.val + corner);
+                for (int j = 0; j < rank; ++j) {
+                    const double cj = __ldg(p1 + j);
+                    if (cj == 0) fval += __ldg(bb + j) * zx[j];
+                    else fval += __ldg(bb + j) * zx[j] + cj * pow(fabs(zx[j]), __ldg(p2 + j));
+                }
+            } else {
+                fval = __ldg(a.val + corner) + __ldg(a.a + corner);
+                for (int j = 0; j < rank; ++j) {
+                    const double cj = __ldg(p1 + j);
+                    if (cj == cj) fval += __ldg(bb + j) * zx[j] + __ldg(p2 + j) / (1.0 + cj * zx[j]);
+                    else fval += __ldg(bb + j) * zx[j] * zx[j];
+                }
+            }
+            sumw += cw;
+            V += cw * fval;
+        }
+        a.out[p] = V / sumw;
+    }
+}
+
+cudaError_t launch_stalk_strict(const StalkArgs &a, cudaStream_t s, LaunchInfo *li)
+{
+    const int block = 256;
+    int64_t nb = (a.npts + block - 1) / block;
+    if (nb > 148 * 64) nb = 148 * 64;
+    if (nb < 1) nb = 1;
+    if (a.kind == 0) stalk_strict_kernel<0><<<(int)nb, block, 0, s>>>(a);
+    else stalk_strict_kernel<1><<<(int)nb, block, 0, s>>>(a);
+    if (li) { li->grid = (int)nb; li->block = block; li->smem = 0; li->kernel = K_STALK_STRICT; }
+    return cudaGetLastError();
+}

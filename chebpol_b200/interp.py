@@ -172,6 +172,8 @@ class Interpolant:
                 p = _lib.Plan.mlip(t["grid"], t["values"], 0, device)
             elif self.kind == "fh":
                 p = _lib.Plan.fh(t["values"], t["grid"], t["weights"], device)
+            elif self.kind in ("stalker", "hstalker"):
+                p = _lib.Plan.stalk(1 if self.kind == "hstalker" else 0, t["values"], t["grid"], t["tables"], 3, device)
             elif self.kind == "polyharmonic":
                 p = _lib.Plan.polyh(t["knots"], t["weights"], t["lweights"], t["k"], t.get("norm_a"), t.get("norm_b"),
                                     device)
@@ -201,9 +203,12 @@ class Interpolant:
             return _lib.f64(x.reshape(numvec, K)), False
         raise ValueError(f"Function should take {K} arguments, you supplied a vector of length {x.size}")
 
-    def __call__(self, x, threads=None, blend: str | int = "linear", ngpus: int = 1, device: int = 0):
+    def __call__(self, x, threads=None, blend: str | int | None = None, ngpus: int = 1, device: int = 0):
         xp, _single = self._coerce(x)
-        if self.kind == "multilinear":
+        blended = self.kind in ("multilinear", "stalker", "hstalker")
+        if blended:
+            if blend is None:  # closure defaults: 'linear' (R/multilinear.R:63), 'cubic' (R/stalker.R:62,80)
+                blend = "linear" if self.kind == "multilinear" else "cubic"
             b = BLENDS[blend] if isinstance(blend, str) else int(blend)
         if ngpus != 1:
             t = self.t
@@ -211,12 +216,16 @@ class Interpolant:
                 return _lib.evalcheb(t["coef"], xp, t.get("mid"), t.get("ispan"), t.get("ugm_n"), ngpus)
             if self.kind == "multilinear":
                 return _lib.evalmlip(t["grid"], t["values"], xp, b, ngpus)
+            if self.kind == "stalker":
+                return _lib.evalstalk(t["values"], t["grid"], *t["tables"], xp, b, ngpus)
+            if self.kind == "hstalker":
+                return _lib.evalhyp(t["values"], t["grid"], *t["tables"], xp, b, ngpus)
             if self.kind == "polyharmonic":
                 return _lib.evalpolyh(t["knots"], t["weights"], t["lweights"], t["k"], xp, t.get("norm_a"),
                                       t.get("norm_b"), ngpus)
             return _lib.fh(t["values"], t["grid"], t["weights"], xp, ngpus)
         p = self.plan(device)
-        if self.kind == "multilinear":
+        if blended:
             p.set(_lib.OPT_BLEND, b)
         return p.eval_host(xp)
 
@@ -306,6 +315,141 @@ def fhappx(val, grid=None, d=1, fit: str = "host") -> Interpolant:
     weights = _lib.fhweights(grid, dd) if fit == "device" else fhweights(grid, dd)
     return Interpolant("fh", len(grid), [(g.min(), g.max()) for g in grid], grid=grid,
                        values=np.asfortranarray(val), weights=weights)
+
+
+_MYEPS = 1e3 * np.sqrt(np.finfo(float).eps)  # MYEPS, src/stalker.c:8
+
+
+def _stalk_neighbours(val, grid, i):
+    """Interior slices of dimension i: v0, vplus, vmin, kplus, kmin broadcast over the array."""
+    D = val.ndim
+    sl = lambda a, b: tuple(slice(a, b) if d == i else slice(None) for d in range(D))
+    v0 = val[sl(1, -1)]
+    g = np.asarray(grid[i], dtype=np.float64)
+    shp = [1] * D
+    shp[i] = g.size - 2
+    kplus = (g[2:] - g[1:-1]).reshape(shp)
+    kmin = (g[:-2] - g[1:-1]).reshape(shp)
+    return sl, v0, val[sl(2, None)] - v0, val[sl(0, -2)] - v0, kplus, kmin
+
+
+def _stalk_borders(out_b, val, grid, i):
+    """Linear one-sided slopes on the two border hyperplanes (src/stalker.c:305-313, 481-490)."""
+    D = val.ndim
+    at = lambda k: tuple(k if d == i else slice(None) for d in range(D))
+    g = grid[i]
+    out_b[at(0)] = (val[at(1)] - val[at(0)]) / (g[1] - g[0])
+    out_b[at(-1)] = (val[at(-2)] - val[at(-1)]) / (g[-2] - g[-1])
+
+
+def makehyp(val, grid):
+    """makehyp, src/stalker.c:446-535: tables a (prod(dims)) and b, c, d (rank x prod(dims)) of the
+    hyperbolic stalker; c = NaN marks a parabola.  Host fit (runs once per interpolant)."""
+    val = np.asarray(val, dtype=np.float64)
+    D = val.ndim
+    b = np.zeros((D,) + val.shape)
+    c = np.zeros_like(b)
+    d = np.zeros_like(b)
+    with np.errstate(all="ignore"):
+        for i in range(D):
+            _stalk_borders(b[i], val, grid, i)
+            if val.shape[i] < 3:
+                continue
+            sl, v0, vp, vm, kp, km = _stalk_neighbours(val, grid, i)
+            Dd = km * vp - kp * vm
+            D2 = km * km * vp - kp * kp * vm
+            mono = (np.sign(vp * vm) <= 0) | (np.abs(vp) <= _MYEPS) | (np.abs(vm) <= _MYEPS)
+            const = mono & (np.abs(vp - vm) <= _MYEPS * kp)
+            lin = mono & ~const & (np.abs(Dd) <= _MYEPS * kp)
+            gen = mono & ~const & ~lin
+            par = ~mono & (np.abs(D2) <= _MYEPS * kp)
+            hyp = ~mono & ~par
+            bi = np.zeros(v0.shape)
+            ci = np.zeros(v0.shape)
+            di = np.zeros(v0.shape)
+            kpb, kmb = np.broadcast_to(kp, v0.shape), np.broadcast_to(km, v0.shape)
+            bi[lin] = (vp / kpb)[lin]
+            ci[gen] = (-Dd / (kmb * kpb * (vp - vm)))[gen]
+            di[gen] = (-vp * vm * (kmb - kpb) / Dd)[gen]
+            bi[par] = (vp / (kpb * kpb))[par]
+            ci[par] = np.nan
+            bi[hyp] = (vp * vm * (kmb - kpb) / D2)[hyp]
+            ci[hyp] = (-D2 / (kmb * kpb * Dd))[hyp]
+            di[hyp] = (-kmb * vp * kpb * vm * (kmb - kpb) * Dd / (D2 * D2))[hyp]
+            b[i][sl(1, -1)], c[i][sl(1, -1)], d[i][sl(1, -1)] = bi, ci, di
+    a = np.zeros(val.shape)
+    for i in range(D):
+        a = a - d[i]
+    flat = lambda t: np.asfortranarray(np.stack([t[i].ravel(order="F") for i in range(D)]))
+    return a.ravel(order="F").copy(), flat(b), flat(c), flat(d)
+
+
+def makestalk(val, grid):
+    """makestalk, src/stalker.c:271-364, as built WITHOUT GSL: tables b, c, r (rank x prod(dims)).
+    Without GSL the reference uses degree 2 on non-uniform grids and warns (R_makestalk :711-718)."""
+    val = np.asarray(val, dtype=np.float64)
+    D = val.ndim
+    for g in grid:
+        if np.any(np.abs(np.diff(g)[1:] - (g[1] - g[0])) > _MYEPS):
+            warnings.warn("Non-uniform grid requires linking chebpol with GSL")
+            break
+    b = np.zeros((D,) + val.shape)
+    c = np.zeros_like(b)
+    r = np.zeros_like(b)
+    with np.errstate(all="ignore"):
+        for i in range(D):
+            _stalk_borders(b[i], val, grid, i)
+            if val.shape[i] < 3:
+                continue
+            sl, v0, vp, vm, kp, km = _stalk_neighbours(val, grid, i)
+            kpb, kmb = np.broadcast_to(kp, v0.shape), np.broadcast_to(km, v0.shape)
+            uniform = np.abs(kpb + kmb) < _MYEPS * kpb
+            mono = np.sign(vp * vm) <= 0
+            const = mono & (np.abs(vp - vm) <= _MYEPS * kpb)
+            lin = mono & ~const & (np.abs(kmb * vp - kpb * vm) <= _MYEPS * kpb)
+            ru = np.abs((vp - vm) / (vp + vm))
+            ru = np.where(ru < 1, 1.0, ru)
+            ru = np.where(np.isnan(ru) | (ru > 2.0), 2.0, ru)
+            ri = np.where(mono & ~const & ~lin & uniform, ru, 2.0)
+            q = np.power(-kpb / kmb, ri)
+            b[i][sl(1, -1)] = (vp - vm * q) / (kpb - kmb * q)
+            c[i][sl(1, -1)] = (kpb * vm - kmb * vp) / (kpb * np.power(-kmb, ri) - kmb * np.power(kpb, ri))
+            r[i][sl(1, -1)] = ri
+    flat = lambda t: np.asfortranarray(np.stack([t[i].ravel(order="F") for i in range(D)]))
+    return flat(b), flat(c), flat(r)
+
+
+def _stalk_front(val, grid):
+    if np.isscalar(grid[0]):
+        grid = [grid]
+    grid = [np.asarray(g, dtype=np.float64) for g in grid]
+    if any(np.any(np.diff(g) <= 0) for g in grid):
+        if not callable(val):
+            raise ValueError("Grid points must be ordered in increasing order")
+        grid = [np.sort(g) for g in grid]
+    if callable(val):
+        val = evalongrid(val, grid=grid)
+    val = np.asarray(val, dtype=np.float64)
+    shape = tuple(len(g) for g in grid)
+    if val.size != int(np.prod(shape)):
+        raise ValueError(f"number of values ({val.size}) does not match grid size ({int(np.prod(shape))})")
+    if val.shape != shape:
+        val = val.reshape(shape, order="F")
+    return val, grid
+
+
+def hstalkerappx(val, grid) -> Interpolant:
+    """hstalkerappx, R/stalker.R:53-69: hyperbolic stalker spline; evaluator chebpol_cuda_evalhyp."""
+    val, grid = _stalk_front(val, grid)
+    return Interpolant("hstalker", len(grid), [(g.min(), g.max()) for g in grid], grid=grid,
+                       values=np.asfortranarray(val), tables=makehyp(val, grid))
+
+
+def stalkerappx(val, grid) -> Interpolant:
+    """stalkerappx, R/stalker.R:71-87: stalker spline; evaluator chebpol_cuda_evalstalk."""
+    val, grid = _stalk_front(val, grid)
+    return Interpolant("stalker", len(grid), [(g.min(), g.max()) for g in grid], grid=grid,
+                       values=np.asfortranarray(val), tables=makestalk(val, grid))
 
 
 def _phifunc(d2: np.ndarray, k) -> np.ndarray:
@@ -413,7 +557,7 @@ def ucappxf(fun, dims, intervals=None) -> Interpolant:
 
 _METHODS = ["chebyshev", "multilinear", "fh", "uniform", "general", "polyharmonic", "simplexlinear",
             "hstalker", "stalker", "crbf", "oldstalker"]
-_ON_PATH = {"chebyshev", "multilinear", "fh", "uniform", "polyharmonic"}
+_ON_PATH = {"chebyshev", "multilinear", "fh", "uniform", "polyharmonic", "stalker", "hstalker"}
 
 
 def ipol(val, dims=None, intervals=None, grid=None, knots=None, k=None, method="chebyshev", **kw) -> Interpolant:
@@ -427,6 +571,14 @@ def ipol(val, dims=None, intervals=None, grid=None, knots=None, k=None, method="
     if method not in _ON_PATH:
         raise NotImplementedError(
             f"method '{method}' is outside the GPU evaluation path (SURVEY.md section 2); use the R package")
+    if method in ("stalker", "hstalker"):  # R/ipol.R:198-218
+        if grid is None:
+            raise ValueError("grid must be specified for stalker interpolation")
+        if np.isscalar(grid[0]):
+            grid = [grid]
+        if any(_unsorted(np.asarray(g, dtype=np.float64)) for g in grid):
+            raise ValueError("grid must be distinct ordered values")
+        return (hstalkerappx if method == "hstalker" else stalkerappx)(val, grid)
     if method == "polyharmonic":  # R/ipol.R:169-186
         if knots is None:
             if grid is None:

@@ -173,6 +173,26 @@ CHEBPOL_CUDA_API int chebpol_cuda_plan_polyh(const double *knots, int rank, int 
                                              const double *lweights, double k, const double *norm_a,
                                              const double *norm_b, int device, chebpol_cuda_plan **plan);
 
+/* ---- stalker splines ------------------------------------
+ * Replace R_evalstalk / R_evalhyp, src/stalker.c:765-832 (evalstalk :366-442, evalhyp :537-613),
+ * as called by the closures of stalkerappx / hstalkerappx (R/stalker.R:80-85,62-67).  The tables
+ * are what R_makestalk (b, c, r) / R_makehyp (a, b, c, d) return: a has prod(dims) entries, the
+ * others are rank x prod(dims) R matrices (entry j of grid point i at [rank*i + j]); val is the
+ * R array of values, grid[d] the dims[d] increasing knots of dimension d.  blend as for
+ * chebpol_cuda_evalmlip (0 linear .. 5 mean; the closures default to 3, cubic).
+ * Kernel ids: 50 stalk_strict, 51 stalk_cell (rank <= 6).
+ * chebpol_cuda_plan_stalk: kind 0 stalker (a ignored, t1 = c, t2 = r), kind 1 hstalker (t1 = c, t2 = d). */
+CHEBPOL_CUDA_API int chebpol_cuda_evalstalk(const double *val, const double *const *grid, const int *dims, int rank,
+                                            const double *b, const double *c, const double *r, int blend,
+                                            const double *x, int64_t npts, int ngpus, double *out);
+CHEBPOL_CUDA_API int chebpol_cuda_evalhyp(const double *val, const double *const *grid, const int *dims, int rank,
+                                          const double *a, const double *b, const double *c, const double *d,
+                                          int blend, const double *x, int64_t npts, int ngpus, double *out);
+CHEBPOL_CUDA_API int chebpol_cuda_plan_stalk(int kind, const double *val, const double *const *grid,
+                                             const int *dims, int rank, const double *a, const double *b,
+                                             const double *t1, const double *t2, int blend, int device,
+                                             chebpol_cuda_plan **plan);
+
 /* ---- evaluation on a tensor grid (evalongridV of an interpolant, R/tools.R:132-137) ----
  * The reference expands the grid (expand.grid) and evaluates point by point; here the
  * structure is used: one basis matrix per dimension and one mode product per dimension.

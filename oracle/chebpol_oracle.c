@@ -353,6 +353,223 @@ API int oracle_evalpolyh(const double *x, int64_t npts, const double *knots, con
 }
 
 /* ------------------------------------------------------------------------
+ * Stalker splines: src/stalker.c built WITHOUT GSL (HAVE_GSL
+ * undefined, what configure produces when GSL is absent -- as in this image): non-uniform
+ * grids then use degree r = 2 in makestalk (:340-347,355-359).
+ *   makestalk :271-364, evalstalk :366-442   ("stalker":  f_corner = v + sum_j b_j z_j + c_j |z_j|^r_j)
+ *   makehyp   :446-535, evalhyp   :537-613   ("hstalker": f_corner = v + a + sum_j b_j z_j + d_j/(1 + c_j z_j),
+ *                                             c_j = NA marks the parabola b_j z_j^2)
+ * Tables are rank x prod(dims), column-major (entry j of grid point `index` at [rank*index + j]).
+ * The cell is R's findInterval(rightmost_closed = all_inside = TRUE): gp with g[gp] <= x < g[gp+1],
+ * clamped to 0..n-2; weights clamped to [0,1] (linear extrapolation); corners weighted by
+ * blendfun (src/chebpol.h:24-45), corners of weight zero skipped.
+ * ------------------------------------------------------------------------ */
+#define ORACLE_MYEPS (1e3 * sqrt(DBL_EPSILON))
+static double oracle_sign(double x) { return isnan(x) ? x : ((x > 0) ? 1.0 : ((x == 0) ? 0.0 : -1.0)); }
+static double oracle_na_real(void)
+{
+    union { double d; unsigned long long u; } v;
+    v.u = 0x7FF00000000007A2ULL; /* R's NA_real_ */
+    return v.d;
+}
+
+static int find_interval0(const double *g, int n, double x)
+{
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        const int mid = (lo + hi) / 2;
+        if (g[mid] <= x) lo = mid + 1; else hi = mid;
+    }
+    if (lo < 1) lo = 1;
+    if (lo > n - 1) lo = n - 1;
+    return lo - 1;
+}
+
+API int oracle_makestalk(int rank, const int *dims, const double *const *grid, const double *val,
+                         double *b, double *c, double *r)
+{
+    if (rank <= 0 || rank > ORACLE_MAXRANK) return 1;
+    int64_t len = 1;
+    for (int i = 0; i < rank; ++i) len *= dims[i];
+    for (int64_t index = 0; index < len; ++index) {
+        double *bb = b + rank * index, *cc = c + rank * index, *rr = r + rank * index;
+        int64_t stride = 1, rem = index;
+        for (int i = 0; i < rank; ++i) {
+            const double *gr = grid[i];
+            const int idx = (int)(rem % dims[i]);
+            rem /= dims[i];
+            if (idx == 0) {
+                bb[i] = (val[index + stride] - val[index]) / (gr[idx + 1] - gr[idx]);
+                cc[i] = rr[i] = 0.0;
+            } else if (idx == dims[i] - 1) {
+                bb[i] = (val[index - stride] - val[index]) / (gr[idx - 1] - gr[idx]);
+                cc[i] = rr[i] = 0.0;
+            } else {
+                const double v0 = val[index];
+                const double vplus = val[index + stride] - v0, vmin = val[index - stride] - v0;
+                const double kplus = gr[idx + 1] - gr[idx], kmin = gr[idx - 1] - gr[idx];
+                const int uniform = fabs(kplus + kmin) < ORACLE_MYEPS * kplus;
+                double rv;
+                if (oracle_sign(vplus * vmin) <= 0) {
+                    if (fabs(vplus - vmin) <= ORACLE_MYEPS * kplus) {
+                        rv = 2.0;
+                        bb[i] = cc[i] = 0.0;
+                    } else if (fabs(kmin * vplus - kplus * vmin) <= ORACLE_MYEPS * kplus) {
+                        rv = 2.0;
+                    } else if (uniform) {
+                        rv = fabs((vplus - vmin) / (vplus + vmin));
+                        if (rv < 1) rv = 1;
+                        if (isnan(rv) || rv > 2.0) rv = 2.0;
+                    } else {
+                        rv = 2.0; /* no GSL */
+                    }
+                } else {
+                    rv = 2.0; /* no GSL */
+                }
+                rr[i] = rv;
+                bb[i] = (vplus - vmin * pow(-kplus / kmin, rv)) / (kplus - kmin * pow(-kplus / kmin, rv));
+                cc[i] = (kplus * vmin - kmin * vplus) / (kplus * pow(-kmin, rv) - kmin * pow(kplus, rv));
+            }
+            stride *= dims[i];
+        }
+    }
+    return 0;
+}
+
+API int oracle_makehyp(int rank, const int *dims, const double *const *grid, const double *val,
+                       double *a, double *b, double *c, double *d)
+{
+    if (rank <= 0 || rank > ORACLE_MAXRANK) return 1;
+    int64_t len = 1;
+    for (int i = 0; i < rank; ++i) len *= dims[i];
+    for (int64_t index = 0; index < len; ++index) {
+        double *bb = b + rank * index, *cc = c + rank * index, *dd = d + rank * index;
+        a[index] = 0.0;
+        int64_t stride = 1, rem = index;
+        for (int i = 0; i < rank; ++i) {
+            const double *gr = grid[i];
+            const int idx = (int)(rem % dims[i]);
+            rem /= dims[i];
+            if (idx == 0) {
+                bb[i] = (val[index + stride] - val[index]) / (gr[idx + 1] - gr[idx]);
+                cc[i] = dd[i] = 0.0;
+            } else if (idx == dims[i] - 1) {
+                bb[i] = (val[index - stride] - val[index]) / (gr[idx - 1] - gr[idx]);
+                cc[i] = dd[i] = 0.0;
+            } else {
+                const double v0 = val[index];
+                const double vplus = val[index + stride] - v0, vmin = val[index - stride] - v0;
+                const double kplus = gr[idx + 1] - gr[idx], kmin = gr[idx - 1] - gr[idx];
+                const double D = kmin * vplus - kplus * vmin;
+                const double D2 = kmin * kmin * vplus - kplus * kplus * vmin;
+                if (oracle_sign(vplus * vmin) <= 0 || fabs(vplus) <= ORACLE_MYEPS || fabs(vmin) <= ORACLE_MYEPS) {
+                    if (fabs(vplus - vmin) <= ORACLE_MYEPS * kplus) {
+                        bb[i] = cc[i] = dd[i] = 0.0;
+                    } else if (fabs(D) <= ORACLE_MYEPS * kplus) {
+                        bb[i] = vplus / kplus;
+                        cc[i] = dd[i] = 0.0;
+                    } else {
+                        bb[i] = 0.0;
+                        cc[i] = -D / (kmin * kplus * (vplus - vmin));
+                        dd[i] = -vplus * vmin * (kmin - kplus) / D;
+                    }
+                } else if (fabs(D2) <= ORACLE_MYEPS * kplus) {
+                    bb[i] = vplus / (kplus * kplus);
+                    dd[i] = 0.0;
+                    cc[i] = oracle_na_real();
+                } else {
+                    bb[i] = vplus * vmin * (kmin - kplus) / D2;
+                    cc[i] = -D2 / (kmin * kplus * D);
+                    dd[i] = -kmin * vplus * kplus * vmin * (kmin - kplus) * D / (D2 * D2);
+                }
+            }
+            a[index] -= dd[i];
+            stride *= dims[i];
+        }
+    }
+    return 0;
+}
+
+/* kind 0: stalker (t1 = c, t2 = r, a unused); kind 1: hstalker (t1 = c, t2 = d) */
+static double stalk_point(int kind, const double *x, int rank, const int *dims, const double *const *grid,
+                          const double *val, int blend, const double *a, const double *b, const double *t1,
+                          const double *t2)
+{
+    double weight[ORACLE_MAXRANK], zx[ORACLE_MAXRANK];
+    int gbase[ORACLE_MAXRANK];
+    int64_t llcorner = 0, stride = 1;
+    for (int g = 0; g < rank; ++g) {
+        const double *gr = grid[g];
+        const int gp = find_interval0(gr, dims[g], x[g]);
+        gbase[g] = gp;
+        weight[g] = 1 - (x[g] - gr[gp]) / (gr[gp + 1] - gr[gp]);
+        if (weight[g] < 0) weight[g] = 0;
+        if (weight[g] > 1) weight[g] = 1;
+        llcorner += stride * gp;
+        stride *= dims[g];
+    }
+    double V = 0.0, sumw = 0.0;
+    for (int i = 0; i < (1 << rank); ++i) {
+        int64_t corner = llcorner;
+        double cw = 1.0;
+        stride = 1;
+        for (int g = 0; g < rank; ++g) {
+            const double *gr = grid[g];
+            if (i & (1 << g)) {
+                cw *= oracle_blendfun(1 - weight[g], blend);
+                corner += stride;
+                zx[g] = x[g] - gr[gbase[g] + 1];
+            } else {
+                zx[g] = x[g] - gr[gbase[g]];
+                cw *= oracle_blendfun(weight[g], blend);
+            }
+            stride *= dims[g];
+        }
+        if (cw == 0.0) continue;
+        const double *bb = b + rank * corner, *p1 = t1 + rank * corner, *p2 = t2 + rank * corner;
+        double fval;
+        if (kind == 0) {
+            fval = val[corner];
+            for (int j = 0; j < rank; ++j) {
+                if (p1[j] == 0) fval += bb[j] * zx[j];
+                else fval += bb[j] * zx[j] + p1[j] * pow(fabs(zx[j]), p2[j]);
+            }
+        } else {
+            fval = val[corner] + a[corner];
+            for (int j = 0; j < rank; ++j) {
+                if (!isnan(p1[j])) fval += bb[j] * zx[j] + p2[j] / (1.0 + p1[j] * zx[j]);
+                else fval += bb[j] * zx[j] * zx[j];
+            }
+        }
+        sumw += cw;
+        V += cw * fval;
+    }
+    return V / sumw;
+}
+
+API int oracle_evalstalk(const double *x, int64_t npts, int rank, const int *dims, const double *const *grid,
+                         const double *val, int blend, const double *b, const double *c, const double *r,
+                         int threads, double *out)
+{
+    if (rank <= 0 || rank > 30) return 1;
+#pragma omp parallel for num_threads(threads) schedule(guided) if (npts > 1 && threads > 1)
+    for (int64_t p = 0; p < npts; ++p)
+        out[p] = stalk_point(0, x + p * rank, rank, dims, grid, val, blend, NULL, b, c, r);
+    return 0;
+}
+
+API int oracle_evalhyp(const double *x, int64_t npts, int rank, const int *dims, const double *const *grid,
+                       const double *val, int blend, const double *a, const double *b, const double *c,
+                       const double *d, int threads, double *out)
+{
+    if (rank <= 0 || rank > 30) return 1;
+#pragma omp parallel for num_threads(threads) schedule(guided) if (npts > 1 && threads > 1)
+    for (int64_t p = 0; p < npts; ++p)
+        out[p] = stalk_point(1, x + p * rank, rank, dims, grid, val, blend, a, b, c, d);
+    return 0;
+}
+
+/* ------------------------------------------------------------------------
  * Fit-side helpers (fixtures only; not on the timed path).
  * ------------------------------------------------------------------------ */
 /* Floater-Hormann weights, eq. (18) of the FH paper, as fhweights at

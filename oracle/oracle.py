@@ -183,6 +183,68 @@ class Oracle:
         f(_ptr(x), x.shape[0], knots.ctypes.data_as(_dp), _ptr(w), _ptr(lw), rank, nk, float(k), threads, _ptr(out))
         return out
 
+    # -- stalker splines (fit + evaluation) ------------------------------------
+    def _grid_args(self, grid):
+        dims = np.array([len(g) for g in grid], dtype=np.int32)
+        gl, keep = _ptr_list(grid)
+        return dims, gl, keep
+
+    def makestalk(self, val, grid):
+        """makestalk (no GSL): tables b, c, r, each rank x prod(dims) (Fortran order)."""
+        dims, gl, keep = self._grid_args(grid)
+        rank, n = len(grid), int(np.prod(dims.astype(np.int64)))
+        v = np.ascontiguousarray(np.asarray(val, dtype=np.float64).ravel(order="F"))
+        assert v.size == n
+        b, c, r = (np.zeros((rank, n), order="F") for _ in range(3))
+        f = getattr(self.lib, self.pfx + "makestalk")
+        f.restype = None if self.kind == "reference" else C.c_int
+        f.argtypes = [C.c_int, _ip, _dpp, _dp, _dp, _dp, _dp]
+        f(rank, dims.ctypes.data_as(_ip), gl, _ptr(v), b.ctypes.data_as(_dp), c.ctypes.data_as(_dp), r.ctypes.data_as(_dp))
+        return b, c, r
+
+    def makehyp(self, val, grid):
+        dims, gl, keep = self._grid_args(grid)
+        rank, n = len(grid), int(np.prod(dims.astype(np.int64)))
+        v = np.ascontiguousarray(np.asarray(val, dtype=np.float64).ravel(order="F"))
+        assert v.size == n
+        a = np.zeros(n)
+        b, c, d = (np.zeros((rank, n), order="F") for _ in range(3))
+        f = getattr(self.lib, self.pfx + "makehyp")
+        f.restype = None if self.kind == "reference" else C.c_int
+        f.argtypes = [C.c_int, _ip, _dpp, _dp, _dp, _dp, _dp, _dp]
+        f(rank, dims.ctypes.data_as(_ip), gl, _ptr(v), _ptr(a), b.ctypes.data_as(_dp), c.ctypes.data_as(_dp),
+          d.ctypes.data_as(_dp))
+        return a, b, c, d
+
+    def evalstalk(self, val, grid, b, c, r, x, blend: int = 3, threads: int = 1):
+        dims, gl, keep = self._grid_args(grid)
+        rank = len(grid)
+        v = np.ascontiguousarray(np.asarray(val, dtype=np.float64).ravel(order="F"))
+        b, c, r = (np.asfortranarray(t, dtype=np.float64) for t in (b, c, r))
+        x = _as_pts(x, rank)
+        out = np.empty(x.shape[0], dtype=np.float64)
+        f = getattr(self.lib, self.pfx + "evalstalk")
+        f.restype = None if self.kind == "reference" else C.c_int
+        f.argtypes = [_dp, C.c_int64, C.c_int, _ip, _dpp, _dp, C.c_int, _dp, _dp, _dp, C.c_int, _dp]
+        f(_ptr(x), x.shape[0], rank, dims.ctypes.data_as(_ip), gl, _ptr(v), blend, b.ctypes.data_as(_dp),
+          c.ctypes.data_as(_dp), r.ctypes.data_as(_dp), threads, _ptr(out))
+        return out
+
+    def evalhyp(self, val, grid, a, b, c, d, x, blend: int = 3, threads: int = 1):
+        dims, gl, keep = self._grid_args(grid)
+        rank = len(grid)
+        v = np.ascontiguousarray(np.asarray(val, dtype=np.float64).ravel(order="F"))
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        b, c, d = (np.asfortranarray(t, dtype=np.float64) for t in (b, c, d))
+        x = _as_pts(x, rank)
+        out = np.empty(x.shape[0], dtype=np.float64)
+        f = getattr(self.lib, self.pfx + "evalhyp")
+        f.restype = None if self.kind == "reference" else C.c_int
+        f.argtypes = [_dp, C.c_int64, C.c_int, _ip, _dpp, _dp, C.c_int, _dp, _dp, _dp, _dp, C.c_int, _dp]
+        f(_ptr(x), x.shape[0], rank, dims.ctypes.data_as(_ip), gl, _ptr(v), blend, _ptr(a), b.ctypes.data_as(_dp),
+          c.ctypes.data_as(_dp), d.ctypes.data_as(_dp), threads, _ptr(out))
+        return out
+
     # -- fit side (fixtures) -------------------------------------------------
     def fhweights(self, grid, d):
         d = np.broadcast_to(np.asarray(d, dtype=np.int64), (len(grid),))

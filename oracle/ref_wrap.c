@@ -18,6 +18,7 @@
 #include <stdarg.h>
 #include <stdint.h>
 #include "chebpol.c" /* resolved through -I/root/reference/src at build time */
+#include "stalker.c" /* the reference's second TU: makehyp/evalhyp, makestalk/evalstalk (no GSL here) */
 
 /* ---- R API link-time stubs (never executed on the paths we call) ---- */
 #undef error
@@ -26,6 +27,10 @@
 #define SHIM_DIE(name) do { fprintf(stderr, "oracle shim: R API '%s' called\n", name); abort(); } while (0)
 SEXP R_NilValue, R_DimSymbol, R_DimNamesSymbol, R_BaseEnv;
 double R_NaReal;
+/* R's NA_real_: a quiet NaN whose low word is 1954 (R src/main/arithmetic.c, R_NaReal) */
+__attribute__((constructor)) static void shim_init_na(void) {
+  union { double d; unsigned long long u; } v; v.u = 0x7FF00000000007A2ULL; R_NaReal = v.d;
+}
 double *REAL(SEXP s) { (void)s; SHIM_DIE("REAL"); }
 int *INTEGER(SEXP s) { (void)s; SHIM_DIE("INTEGER"); }
 int *LOGICAL(SEXP s) { (void)s; SHIM_DIE("LOGICAL"); }
@@ -66,14 +71,24 @@ void Rf_warning(const char *fmt, ...) {
   va_list ap; va_start(ap, fmt); fprintf(stderr, "oracle shim: warning(): "); vfprintf(stderr, fmt, ap);
   fprintf(stderr, "\n"); va_end(ap);
 }
-/* entry points of the reference's other TU (src/stalker.c), named by the
- * registration table only */
-SEXP R_evalstalker(SEXP a, SEXP b, SEXP c, SEXP d, SEXP e) { (void)a;(void)b;(void)c;(void)d;(void)e; SHIM_DIE("R_evalstalker"); }
-SEXP R_makehyp(SEXP a, SEXP b) { (void)a;(void)b; SHIM_DIE("R_makehyp"); }
-SEXP R_evalhyp(SEXP a, SEXP b, SEXP c, SEXP d) { (void)a;(void)b;(void)c;(void)d; SHIM_DIE("R_evalhyp"); }
-SEXP R_makestalk(SEXP a, SEXP b) { (void)a;(void)b; SHIM_DIE("R_makestalk"); }
-SEXP R_evalstalk(SEXP a, SEXP b, SEXP c, SEXP d) { (void)a;(void)b;(void)c;(void)d; SHIM_DIE("R_evalstalk"); }
-SEXP havegsl(void) { SHIM_DIE("havegsl"); }
+void SET_STRING_ELT(SEXP s, R_xlen_t i, SEXP v) { (void)s; (void)i; (void)v; SHIM_DIE("SET_STRING_ELT"); }
+SEXP Rf_mkChar(const char *c) { (void)c; SHIM_DIE("mkChar"); }
+SEXP R_NamesSymbol;
+/* R's sign() (nmath/sign.c) and findInterval() (appl/interv.c) are not vendored under
+ * /root/reference; restated from their documented semantics.  findInterval is only called with
+ * rightmost_closed = all_inside = TRUE (src/stalker.c:382,553,633): the 1-based index i with
+ * xt[i-1] <= x < xt[i], clamped to 1..n-1. */
+double Rf_sign(double x) { if (isnan(x)) return x; return (x > 0) ? 1.0 : ((x == 0) ? 0.0 : -1.0); }
+int findInterval(double *xt, int n, double x, Rboolean rightmost_closed, Rboolean all_inside, int ilo, int *mflag)
+{
+  (void)rightmost_closed; (void)all_inside; (void)ilo;
+  int lo = 0, hi = n; /* count of knots <= x by bisection */
+  while (lo < hi) { int mid = (lo + hi) / 2; if (xt[mid] <= x) lo = mid + 1; else hi = mid; }
+  *mflag = (lo == 0) ? -1 : ((lo == n) ? 1 : 0);
+  if (lo < 1) lo = 1;
+  if (lo > n - 1) lo = n - 1;
+  return lo;
+}
 void dgetrf_(const int *a, const int *b, double *c, const int *d, int *e, int *f)
 { (void)a;(void)b;(void)c;(void)d;(void)e;(void)f; SHIM_DIE("dgetrf"); }
 void dgetrs_(const char *t, const int *a, const int *b, const double *c, const int *d, const int *e, double *f, const int *g, int *h)
@@ -158,6 +173,35 @@ EXPORT void ref_evalpolyh(const double *x, int64_t npts, const double *knots, co
 #pragma omp parallel for num_threads(threads) schedule(static) if (npts > 1 && threads > 1)
   for (int64_t i = 0; i < npts; i++)
     out[i] = C_evalpolyh(x + i * rank, knots, weights, lweights, rank, nknots, k);
+}
+
+/* stalker splines: the fit (makestalk :271-364, makehyp :446-535) and the point loops of
+ * R_evalstalk (:789-792) and R_evalhyp (:824-827) over evalstalk (:366-442) / evalhyp (:537-613).
+ * Tables are rank x prod(dims) column-major, as R_makestalk / R_makehyp allocate them. */
+EXPORT void ref_makestalk(int rank, const int *dims, const double *const *grid, const double *val,
+                          double *b, double *c, double *r) {
+  int point[rank > 0 ? rank : 1];
+  makestalk(rank, dims, (double **)grid, val, b, c, r, 0, point);
+}
+EXPORT void ref_makehyp(int rank, const int *dims, const double *const *grid, const double *val,
+                        double *a, double *b, double *c, double *d) {
+  int point[rank > 0 ? rank : 1];
+  makehyp(rank, dims, (double **)grid, val, a, b, c, d, 0, point);
+}
+EXPORT void ref_evalstalk(const double *x, int64_t npts, int rank, const int *dims, const double *const *grid,
+                          const double *val, int blend, const double *b, const double *c, const double *r,
+                          int threads, double *out) {
+#pragma omp parallel for num_threads(threads) schedule(guided) if (npts > 1 && threads > 1)
+  for (int64_t i = 0; i < npts; i++)
+    out[i] = evalstalk(x + i * rank, rank, dims, (double **)grid, val, blend, (double *)b, (double *)c, (double *)r);
+}
+EXPORT void ref_evalhyp(const double *x, int64_t npts, int rank, const int *dims, const double *const *grid,
+                        const double *val, int blend, const double *a, const double *b, const double *c,
+                        const double *d, int threads, double *out) {
+#pragma omp parallel for num_threads(threads) schedule(guided) if (npts > 1 && threads > 1)
+  for (int64_t i = 0; i < npts; i++)
+    out[i] = evalhyp(x + i * rank, rank, dims, (double **)grid, val, blend, (double *)a, (double *)b, (double *)c,
+                     (double *)d);
 }
 
 EXPORT void ref_chebcoef(const double *val, const int *dims, int rank, double *F, int dct) {

@@ -29,6 +29,7 @@ typedef int Rboolean;
 #define INTSXP 13
 #define REALSXP 14
 #define VECSXP 19
+#define STRSXP 16
 
 extern SEXP R_NilValue, R_DimSymbol, R_DimNamesSymbol, R_BaseEnv, R_NamesSymbol;
 extern double R_NaReal;
@@ -57,6 +58,9 @@ SEXP VECTOR_ELT(SEXP, R_xlen_t);
 SEXP STRING_ELT(SEXP, R_xlen_t);
 const char *CHAR(SEXP);
 SEXP SET_VECTOR_ELT(SEXP, R_xlen_t, SEXP);
+void SET_STRING_ELT(SEXP, R_xlen_t, SEXP);
+SEXP Rf_mkChar(const char *);
+#define mkChar Rf_mkChar
 SEXP Rf_coerceVector(SEXP, unsigned int);
 SEXP Rf_eval(SEXP, SEXP);
 SEXP Rf_lang2(SEXP, SEXP);

@@ -9,4 +9,5 @@
 #define AS_LOGICAL(x) Rf_coerceVector(x, LGLSXP)
 #define AS_NUMERIC(x) Rf_coerceVector(x, REALSXP)
 #define IS_NUMERIC(x) Rf_isReal(x)
+#define SET_NAMES(x, n) Rf_setAttrib(x, R_NamesSymbol, n)
 #endif

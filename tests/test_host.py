@@ -122,7 +122,11 @@ def test_ipol_front_end_checks():
     with pytest.raises(ValueError):
         cb.ipol(np.zeros(3), grid=[np.array([0.0, 2.0, 1.0])], method="fh")  # unsorted
     with pytest.raises(NotImplementedError):
-        cb.ipol(np.zeros(4), grid=[np.linspace(0, 1, 4)], method="stalker")  # outside the GPU path
+        cb.ipol(np.zeros(4), grid=[np.linspace(0, 1, 4)], method="simplexlinear")  # outside the GPU path
+    with pytest.raises(ValueError):
+        cb.ipol(np.zeros(4), method="hstalker")  # grid must be specified
+    hs = cb.ipol(lambda x: float(np.sum(x ** 2)), grid=[np.linspace(0, 1, 5)] * 2, method="hstalker")
+    assert hs.kind == "hstalker" and hs.t["tables"][1].shape == (2, 25) and hs.t["tables"][0].shape == (25,)
     with pytest.raises(ValueError):
         cb.ipol(np.zeros(4), method="polyharmonic")  # Must specify knots
     ip = cb.ipol(np.zeros(9), grid=[np.linspace(0, 1, 3)] * 2, method="multi")  # partial match
@@ -154,6 +158,33 @@ def test_polyh_fit_mirrors_the_reference_system(port):
     ip = cb.polyh(f, 20 * knots - 3, k=3)
     assert np.allclose(ip.t["norm_b"], (20 * knots - 3).min(axis=1)) and ip.t["knots"].min() == 0.0
     assert ip.t["knots"].max() == 1.0
+
+
+def test_stalker_fits_mirror_the_reference(ref):
+    """makehyp / makestalk (src/stalker.c:446-535, 271-364, no GSL) in numpy against the reference C:
+    hyperbolic tables identical, stalker tables to an ulp of pow; NaN (parabola) pattern equal."""
+    import warnings
+
+    rng = np.random.default_rng(0)
+    for dims, uniform in [((9,), True), ((8, 7), False), ((6, 5, 7), True), ((5, 6, 4, 5), False), ((2, 3), True)]:
+        grid = [np.linspace(-1, 1, n) if uniform else np.sort(rng.uniform(-1, 1, n)) for n in dims]
+        val = rng.standard_normal(dims)
+        if len(dims) == 1:
+            val[3:6] = 1.0       # constant triple
+            val[6:9] = [0, 1, 2]  # linear triple
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            ts = cb.interp.makestalk(val, grid)
+        th = cb.interp.makehyp(val, grid)
+        for mine, theirs in zip(th, ref.makehyp(val, grid)):
+            assert np.array_equal(np.isnan(mine), np.isnan(theirs))
+            assert np.array_equal(np.nan_to_num(mine), np.nan_to_num(theirs))
+        for mine, theirs in zip(ts, ref.makestalk(val, grid)):
+            assert np.allclose(mine, theirs, rtol=1e-14, atol=1e-15)
+    # the parabola marker: symmetric values around an interior extremum on a non-uniform grid
+    g = [np.array([0.0, 1.0, 3.0])]
+    th = cb.interp.makehyp(np.array([1.0, 0.0, 4.0]), g)
+    assert np.isnan(th[2][0, 1]) and np.isnan(ref.makehyp(np.array([1.0, 0.0, 4.0]), g)[2][0, 1])
 
 
 def test_shard_range_tiles_the_batch():

@@ -789,3 +789,151 @@ def test_polyh_fitted_spline_error_against_extended_precision(gpu_ok, port):
     assert err_ref > 1e-13 * np.abs(ref).max()          # the reference is not within 1e-13*max|f| of exact either
     assert err_gpu <= 2.0 * err_ref + 2e-16 * scale, (float(err_gpu), float(err_ref), scale)
     plan.close()
+
+
+# --------------------------------------------------------------- stalker splines
+def _stalk_case(dims, uniform, smooth, seed=0):
+    rng = np.random.default_rng(seed)
+    grid = [np.linspace(-1, 1, n) if uniform else np.sort(rng.uniform(-1, 1, n)) for n in dims]
+    val = cases.grid_values(grid) if smooth else np.asfortranarray(rng.standard_normal(dims))
+    x = np.ascontiguousarray(rng.uniform(-1.15, 1.15, (4000, len(dims))))
+    x[:3] = np.array([g[min(1, len(g) - 1)] for g in grid])  # knot hits
+    x[3] = [g[-1] for g in grid]
+    x[4] = [g[0] for g in grid]
+    return grid, val, x
+
+
+def _close(got, want, tol):
+    """Same non-finite pattern (the hyperbola's pole 1 + c*z == 0 is reached by exact knot hits under
+    the blends that keep every corner: 0/0 in the reference too), finite values within tol."""
+    fin = np.isfinite(want)
+    return (np.array_equal(fin, np.isfinite(got)) and np.array_equal(np.isnan(want), np.isnan(got))
+            and (not fin.any() or np.abs(got[fin] - want[fin]).max() <= tol))
+
+
+def _stalk_scale(kind, val, grid, tables, x):
+    """Magnitude of the terms a corner sums (the cancellation the evaluator is exposed to)."""
+    rank = len(grid)
+    H = max(float(np.max(np.diff(g))) for g in grid) + 0.2
+    if kind == 1:
+        a, b, c, d = tables
+        return np.abs(val).max() + np.abs(a).max() + rank * (np.abs(b).max() * H * max(H, 1.0) + np.abs(d).max())
+    b, c, r = tables
+    return np.abs(val).max() + rank * (np.abs(b).max() * H + np.abs(c).max() * max(H, H ** 2))
+
+
+STALK_SHAPES = [((9,), True), ((12, 7), False), ((8, 9, 7), True), ((6, 5, 7), False), ((5, 6, 4, 5), True),
+                ((4, 3, 5, 3, 4), False), ((3, 4, 3, 3, 2, 3), True), ((2, 2), True)]
+
+
+@pytest.mark.parametrize("dims,uniform", STALK_SHAPES)
+@pytest.mark.parametrize("smooth", [True, False])
+def test_hstalker_strict_bit_exact_and_cell(gpu_ok, port, dims, uniform, smooth):
+    """evalhyp uses only + - * /: the strict kernel is BIT-IDENTICAL to the reference for the
+    blends without exp (0, 3, 4, 5) and within 1e-14 for 1, 2; the packed-record kernel within
+    1e-12*max|f| plus 32*eps times the size of the terms that cancel in a corner."""
+    grid, val, x = _stalk_case(dims, uniform, smooth, seed=len(dims))
+    th = port.makehyp(val, grid)
+    plan = _lib.Plan.stalk(1, val, grid, th)
+    for blend in range(6):
+        want = port.evalhyp(val, grid, *th, x, blend, threads=4)
+        plan.set(_lib.OPT_BLEND, blend)
+        got, k = eval_plan(plan, x, _lib.KERNEL_STRICT)
+        assert k == "stalk_strict"
+        if blend in (0, 3, 4, 5):
+            assert np.array_equal(bits(got), bits(want)), blend
+        else:
+            assert _close(got, want, 1e-13 * _stalk_scale(1, val, grid, th, x))
+        got, k = eval_plan(plan, x, _lib.KERNEL_AUTO)
+        assert k == "stalk_cell"
+        tol = TOL_REL * np.nanmax(np.abs(want)) + 32 * np.finfo(float).eps * _stalk_scale(1, val, grid, th, x)
+        assert _close(got, want, tol), (blend, np.nanmax(np.abs(got - want)), tol)
+    plan.close()
+
+
+@pytest.mark.parametrize("dims,uniform", STALK_SHAPES)
+@pytest.mark.parametrize("degrees", ["fit", "random"])
+def test_stalker_strict_and_cell(gpu_ok, port, dims, uniform, degrees):
+    """evalstalk: fitted tables (degrees 2, or |dv/sv| in [1,2] on uniform grids) and random
+    degrees in (1,2) on every grid point (the pow branch).  Device pow is within 2 ulp of libm."""
+    import warnings
+
+    grid, val, x = _stalk_case(dims, uniform, True, seed=10 + len(dims))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        b, c, r = port.makestalk(val, grid)
+    if degrees == "random":
+        rng = np.random.default_rng(4)
+        r = np.asfortranarray(np.where(c != 0, rng.uniform(1.0, 2.0, r.shape), r))
+    ts = (b, c, r)
+    plan = _lib.Plan.stalk(0, val, grid, ts)
+    scale = _stalk_scale(0, val, grid, ts, x)
+    for blend in (3, 0, 1, 4):
+        want = port.evalstalk(val, grid, *ts, x, blend, threads=4)
+        plan.set(_lib.OPT_BLEND, blend)
+        for kern, name in ((_lib.KERNEL_STRICT, "stalk_strict"), (_lib.KERNEL_AUTO, "stalk_cell")):
+            got, k = eval_plan(plan, x, kern)
+            assert k == name
+            tol = TOL_REL * np.nanmax(np.abs(want)) + 32 * np.finfo(float).eps * scale
+            assert _close(got, want, tol), (blend, name, np.nanmax(np.abs(got - want)), tol)
+    plan.close()
+
+
+def test_stalker_high_rank_nan_and_golden(gpu_ok, port):
+    # rank 7: outside the packed kernel, served by the strict one
+    dims = (3, 2, 3, 2, 3, 2, 3)
+    grid, val, x = _stalk_case(dims, True, True, seed=2)
+    th = port.makehyp(val, grid)
+    plan = _lib.Plan.stalk(1, val, grid, th)
+    got, k = eval_plan(plan, x[:500], _lib.KERNEL_AUTO)
+    assert k == "stalk_strict"
+    assert np.array_equal(bits(got), bits(port.evalhyp(val, grid, *th, x[:500], 3)))
+    plan.close()
+    # NaN coordinates give NaN, the other points are unaffected
+    grid, val, x = _stalk_case((8, 9, 7), False, True, seed=5)
+    th = port.makehyp(val, grid)
+    plan = _lib.Plan.stalk(1, val, grid, th)
+    xx = x[:6].copy()
+    xx[2, 1] = np.nan
+    for kern in (_lib.KERNEL_STRICT, _lib.KERNEL_AUTO):
+        got, _ = eval_plan(plan, xx, kern)
+        assert np.isnan(got[2]) and np.all(np.isfinite(np.delete(got, 2)))
+    plan.close()
+    # chebpol-Ex.Rout.save:465,486: hst <- ipol(f, grid=grid, method='hstalker'); hst(m)
+    import math
+    from r_rng import RRng
+
+    su = np.array([i * (1.0 / 9.0) for i in range(10)])
+    su[-1] = 1.0
+    s = np.array([math.pow(v, 3.0) for v in su])
+    f = lambda x: 10.0 / (1.0 + 25.0 * np.mean(np.asarray(x) ** 2))
+    r = RRng(1)
+    r.runif(3000)
+    m = r.runif(21).reshape((3, 7), order="F")
+    hst = cb.ipol(f, grid=[s, su, np.sort(1.0 - s)], method="hstalker")
+    assert np.allclose(hst(m), [1.166729, 0.6569404, 1.552856, 0.9696696, 0.5326136, 1.416647, 0.7832519], rtol=6e-7)
+    assert not np.allclose(hst(m, blend="linear"), hst(m), rtol=1e-6)  # the blend argument reaches the kernel
+    st = cb.ipol(f, grid=[su, su, su], method="stalker")
+    want = port.evalstalk(st.t["values"], st.t["grid"], *st.t["tables"], m.T, 3)
+    assert np.abs(st(m) - want).max() <= 1e-12 * np.abs(want).max()
+
+
+def test_stalker_stateless_and_sharded(gpu_ok, port):
+    grid, val, _ = _stalk_case((20, 18, 16), False, True, seed=6)
+    x = cases.points(300_000, 3)
+    th = port.makehyp(val, grid)
+    want = port.evalhyp(val, grid, *th, x[:5000], 3, threads=8)
+    tol = TOL_REL * np.abs(want).max() + 32 * np.finfo(float).eps * _stalk_scale(1, val, grid, th, x)
+    g1 = _lib.evalhyp(val, grid, *th, x, blend=3, ngpus=1)
+    assert np.abs(g1[:5000] - want).max() <= tol
+    g2 = _lib.evalhyp(val, grid, *th, x, blend=3, ngpus=0)  # all GPUs; plan cache hit on device 0
+    assert np.array_equal(g1, g2)
+    g0 = _lib.evalhyp(val, grid, *th, x[:5000], blend=0)  # blend is per call, not part of the cached plan
+    assert np.abs(g0 - port.evalhyp(val, grid, *th, x[:5000], 0, threads=8)).max() <= tol
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ts = port.makestalk(val, grid)
+    gs = _lib.evalstalk(val, grid, *ts, x[:5000], blend=3)
+    ws = port.evalstalk(val, grid, *ts, x[:5000], 3, threads=8)
+    assert np.abs(gs - ws).max() <= TOL_REL * np.abs(ws).max() + 32 * np.finfo(float).eps * _stalk_scale(0, val, grid, ts, x)
