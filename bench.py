@@ -48,6 +48,8 @@ CONFIGS = {
     4: dict(kind="fh", dims=(40, 40, 40), points=10_000_000, name="cfg4: 3-D Floater-Hormann dims=c(40,40,40) d=4, 1e7 points"),
     6: dict(kind="polyh", dims=(6,), rank=6, nknots=1000, k=3, points=20_000_000,
             name="cfg6 (SURVEY 8f row 4): 6-D polyharmonic spline, 1000 knots, k=3, 2e7 points"),
+    7: dict(kind="hstalk", dims=(64, 64, 64), points=50_000_000,
+            name="cfg7 (SURVEY 8f row 3): 3-D hyperbolic stalker spline on a 64^3 grid, cubic blend, 5e7 points"),
     5: dict(kind="cheb", dims=(12,) * 6, points=20_000_000, name="cfg5: 6-D Chebyshev dims=rep(12,6), 2e7 points per GPU (1e9 total is ~3 min/step/8 GPUs)"),
 }
 
@@ -93,6 +95,12 @@ def build_case(cfg):
     if kind == "mlip":
         grid, values = cases.mlip_case(dims)
         return dict(grid=grid, values=values)
+    if kind == "hstalk":
+        from chebpol_b200 import interp
+
+        grid = [np.linspace(-1.0, 1.0, n) for n in dims]
+        val = cases.grid_values(grid)
+        return dict(grid=grid, val=val, tables=interp.makehyp(val, grid))
     if kind == "polyh":
         knots, w, lw = cases.polyh_case(cfg["rank"], cfg["nknots"], cfg["k"])
         return dict(knots=knots, w=w, lw=lw, k=cfg["k"])
@@ -107,6 +115,8 @@ def make_plan(cfg, case, device):
         return _lib.Plan.cheb(case["coef"], device=device)
     if cfg["kind"] == "mlip":
         return _lib.Plan.mlip(case["grid"], case["values"], 0, device=device)
+    if cfg["kind"] == "hstalk":
+        return _lib.Plan.stalk(1, case["val"], case["grid"], case["tables"], 3, device=device)
     if cfg["kind"] == "polyh":
         return _lib.Plan.polyh(case["knots"], case["w"], case["lw"], case["k"], device=device)
     return _lib.Plan.fh(case["vals"], case["grid"], case["weights"], device=device)
@@ -117,6 +127,8 @@ def oracle_eval(orc, cfg, case, x, threads):
         return orc.evalcheb(case["coef"], x, threads=threads)
     if cfg["kind"] == "mlip":
         return orc.evalmlip(case["grid"], case["values"], x, threads=threads)
+    if cfg["kind"] == "hstalk":
+        return orc.evalhyp(case["val"], case["grid"], *case["tables"], x, blend=3, threads=threads)
     if cfg["kind"] == "polyh":
         return orc.evalpolyh(case["knots"], case["w"], case["lw"], case["k"], x, threads=threads)
     return orc.fh(case["vals"], case["grid"], case["weights"], x, threads=threads)
@@ -358,7 +370,17 @@ def run_ours(args, cfg):
 
     if rank == 0:
         peaks, peak_src = load_peaks()
-        if cfg["kind"] in ("cheb", "fh", "polyh"):
+        if cfg["kind"] == "hstalk":
+            # 2^D corners, each one packed record of 3D+1 doubles, plus the point and the result.  The
+            # 21 MB record table is L2-resident, so this is the L2-side byte count set against the HBM
+            # peak: a reference line for the gather rate, not a bound.
+            byts = 8.0 * (k + 1 + 2 ** k * (3 * k + 1))
+            achieved = byts * npts / (kernel_ms * 1e-3) / 1e9
+            roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                        "frac": achieved / peaks["hbm_gbs"], "traffic": load_traffic(kernel_used, args.config, npts),
+                        "peak_source": f"MEASURED_PEAKS.json ({peak_src}); bytes are gathered from L2, not HBM",
+                        "bytes_per_eval": byts, "kernel": kernel_used, "kernel_ms": kernel_ms}
+        elif cfg["kind"] in ("cheb", "fh", "polyh"):
             # polyharmonic: per knot a subtract and a multiply-add per coordinate plus the weight
             # multiply-add, 3*rank + 2 flop as the reference executes them; the basis function
             # (sqrt / log / exp) is not counted.  Half of those instruction slots are not FMAs, so
