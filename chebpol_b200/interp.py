@@ -79,7 +79,7 @@ def evalongrid(fun: Callable, dims=None, intervals=None, grid=None) -> np.ndarra
     return flat.reshape(shape, order="F")
 
 
-def evalongridV(ip, dims=None, intervals=None, grid=None, blend="linear") -> np.ndarray:
+def evalongridV(ip, dims=None, intervals=None, grid=None, blend=None) -> np.ndarray:
     """evalongridV for an interpolant (R/tools.R:132-137).  The reference evaluates
     fun(t(expand.grid(grid))) point by point; for the four evaluators of this package the
     tensor-grid structure is used instead (one mode product per dimension, on the device)."""
@@ -90,9 +90,16 @@ def evalongridV(ip, dims=None, intervals=None, grid=None, blend="linear") -> np.
     if ip.kind in ("chebyshev", "uniform"):
         return _lib.evalgrid_cheb(t["coef"], pts, t.get("mid"), t.get("ispan"), t.get("ugm_n"))
     if ip.kind == "multilinear":
-        b = BLENDS[blend] if isinstance(blend, str) else int(blend)
+        b = BLENDS[blend or "linear"] if isinstance(blend or "linear", str) else int(blend)
         return _lib.evalgrid_mlip(t["grid"], t["values"], pts, b)
-    return _lib.evalgrid_fh(t["values"], t["grid"], t["weights"], pts)
+    if ip.kind == "fh":
+        return _lib.evalgrid_fh(t["values"], t["grid"], t["weights"], pts)
+    # any other interpolant: the reference's own route, fun(t(expand.grid(grid))), evaluated on the GPU
+    mesh = np.meshgrid(*pts, indexing="ij")
+    x = np.stack([m.ravel(order="F") for m in mesh])
+    out = ip(x, blend=blend) if ip.kind in ("stalker", "hstalker") else ip(x)
+    shape = tuple(len(p) for p in pts)
+    return out.reshape(shape, order="F") if len(shape) > 1 else out
 
 
 def chebcoef(val, dct: bool = False) -> np.ndarray:

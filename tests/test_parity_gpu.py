@@ -655,7 +655,13 @@ def test_evalongridV_matches_pointwise(gpu_ok, port):
     gotf = cb.evalongridV(fh, grid=ptsf)
     wantf = port.fh(vals, g, fh.t["weights"], _expand_grid(ptsf)).reshape(gotf.shape, order="F")
     assert np.abs(gotf - wantf).max() <= 1e-11 * np.abs(wantf).max()  # cubed grid: Lebesgue constant ~1e2
-    for ip in (ch, uc, ml, fh):
+    # interpolants without a tensor-grid kernel take the reference's route (expand.grid, pointwise)
+    hs = cb.ipol(cases.grid_values([np.linspace(-1, 1, 7)] * 2), grid=[np.linspace(-1, 1, 7)] * 2, method="hstalker")
+    ptsh = [np.linspace(-0.9, 0.9, 5), np.linspace(-1, 1, 4)]
+    goth = cb.evalongridV(hs, grid=ptsh)
+    wanth = port.evalhyp(hs.t["values"], hs.t["grid"], *hs.t["tables"], _expand_grid(ptsh), 3).reshape((5, 4), order="F")
+    assert goth.shape == (5, 4) and np.abs(goth - wanth).max() <= TOL_REL * np.abs(wanth).max()
+    for ip in (ch, uc, ml, fh, hs):
         ip.close()
 
 
@@ -937,3 +943,34 @@ def test_stalker_stateless_and_sharded(gpu_ok, port):
     gs = _lib.evalstalk(val, grid, *ts, x[:5000], blend=3)
     ws = port.evalstalk(val, grid, *ts, x[:5000], 3, threads=8)
     assert np.abs(gs - ws).max() <= TOL_REL * np.abs(ws).max() + 32 * np.finfo(float).eps * _stalk_scale(0, val, grid, ts, x)
+
+
+def test_empty_and_single_point_batches_every_evaluator(gpu_ok, port):
+    """P = 0 returns an empty vector and P = 1 (a length-K vector in R, src/chebpol.c:368) one value,
+    through plans and through the stateless entry points, for every evaluator."""
+    import warnings
+
+    cf = cases.cheb_fitted((6, 5, 4))
+    grid, values = cases.mlip_case((6, 5, 4))
+    vals, g, w = cases.fh_case((6, 5, 4))
+    kn, wk, lw = _polyh_case(3, 30)
+    sgrid, sval, _ = _stalk_case((6, 5, 4), True, True)
+    th = port.makehyp(sval, sgrid)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ts = port.makestalk(sval, sgrid)
+    x1 = np.array([[0.3, -0.2, 0.5]])
+    x0 = np.empty((0, 3))
+    todo = [
+        (_lib.Plan.cheb(cf), lambda x: _lib.evalcheb(cf, x), port.evalcheb(cf, x1)),
+        (_lib.Plan.mlip(grid, values, 0), lambda x: _lib.evalmlip(grid, values, x, 0), port.evalmlip(grid, values, x1)),
+        (_lib.Plan.fh(vals, g, w), lambda x: _lib.fh(vals, g, w, x), port.fh(vals, g, w, x1)),
+        (_lib.Plan.polyh(kn, wk, lw, 3), lambda x: _lib.evalpolyh(kn, wk, lw, 3, x), port.evalpolyh(kn, wk, lw, 3, x1)),
+        (_lib.Plan.stalk(1, sval, sgrid, th), lambda x: _lib.evalhyp(sval, sgrid, *th, x), port.evalhyp(sval, sgrid, *th, x1, 3)),
+        (_lib.Plan.stalk(0, sval, sgrid, ts), lambda x: _lib.evalstalk(sval, sgrid, *ts, x), port.evalstalk(sval, sgrid, *ts, x1, 3)),
+    ]
+    for plan, stateless, want in todo:
+        assert plan.eval_host(x0).shape == (0,) and stateless(x0).shape == (0,)
+        for got in (plan.eval_host(x1), stateless(x1)):
+            assert got.shape == (1,) and abs(got[0] - want[0]) <= 1e-12 * max(1.0, abs(want[0]))
+        plan.close()
