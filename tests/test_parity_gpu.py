@@ -974,3 +974,48 @@ def test_empty_and_single_point_batches_every_evaluator(gpu_ok, port):
         for got in (plan.eval_host(x1), stateless(x1)):
             assert got.shape == (1,) and abs(got[0] - want[0]) <= 1e-12 * max(1.0, abs(want[0]))
         plan.close()
+
+
+def test_cheb_and_fh_random_shapes_sweep(gpu_ok, port):
+    """Sixty seeded random shapes (rank 1-7, dims 1-14) through both fast Chebyshev kernels and
+    the DMMA Floater-Hormann path: odd step counts, partial slabs, padded level-A / column tiles,
+    rank-deficient foldings -- whatever the layout logic does with them must agree with the oracle."""
+    rng = np.random.default_rng(2024)
+    n_mma = n_slab = n_fh = 0
+    for _ in range(60):
+        rank = int(rng.integers(1, 8))
+        dims = tuple(int(v) for v in rng.integers(1, 15, rank))
+        while np.prod(dims) > 300_000:
+            dims = tuple(max(1, d - 2) for d in dims)
+        cf = cases.cheb_stress(dims, seed=int(rng.integers(1 << 30)))
+        x = cases.points(int(rng.integers(1, 3000)), rank, seed=int(rng.integers(1 << 30)))
+        want = port.evalcheb(cf, x, threads=4)
+        scale = np.abs(cf).sum()
+        plan = _lib.Plan.cheb(cf)
+        for variant in (_lib.VARIANT_MMA, _lib.VARIANT_SLAB, 0):
+            got, k = eval_plan(plan, x, _lib.KERNEL_AUTO, variant)
+            assert np.abs(got - want).max() <= TOL_REL * scale, (dims, k, np.abs(got - want).max(), scale)
+            n_mma += k == "cheb_mma"
+            n_slab += k == "cheb_slab"
+        plan.close()
+        if rank <= 4 and min(dims) >= 2:
+            g = [np.sort(rng.uniform(-1, 1, n)) for n in dims]
+            w = port.fhweights(g, [min(3, n - 1) for n in dims])
+            vals = np.asfortranarray(rng.standard_normal(dims))
+            xin = np.ascontiguousarray(np.stack([rng.uniform(gg[0], gg[-1], x.shape[0]) for gg in g], axis=1))
+            wantf = port.fh(vals, g, w, xin, threads=4)
+            # Lebesgue-function bound of the product basis (see test_fh_fast_irregular_grids)
+            lam = np.ones(xin.shape[0])
+            for d in range(rank):
+                p = w[d][None, :] / (xin[:, d, None] - g[d][None, :])
+                lam *= np.abs(p).sum(axis=1) / np.abs(p.sum(axis=1))
+            planf = _lib.Plan.fh(vals, g, w)
+            gotf, k = eval_plan(planf, xin, _lib.KERNEL_AUTO)
+            n_fh += k == "fh_mma"
+            # random knots come arbitrarily close, Lambda reaches 1e4 and |f| ~ Lambda*max|v|: a relative
+            # perturbation of the poles moves the numerator by Lambda*max|v| and, through the cancelling
+            # denominator, f by Lambda*|f| -- for the reference's roundings as much as for ours
+            tol = TOL_REL * np.abs(wantf).max() + 16 * np.finfo(float).eps * lam * (np.abs(vals).max() + np.abs(wantf))
+            assert np.all(np.abs(gotf - wantf) <= tol), (dims, k, np.abs(gotf - wantf).max())
+            planf.close()
+    assert n_mma >= 40 and n_slab >= 40 and n_fh >= 15, (n_mma, n_slab, n_fh)
