@@ -38,7 +38,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-METRIC = "interpolant evaluations/sec (FP64)"
+METRIC = "interpolant evaluations/sec (FP64) at 1/2/4/8 B200 vs FP64/HBM roofline"  # BASELINE.json "metric", verbatim
 UNIT = "evals/s"
 
 CONFIGS = {
@@ -388,7 +388,10 @@ def run_ours(args, cfg):
             flop = (2.0 * steps_per_eval(cfg["dims"]) if cfg["kind"] != "polyh"
                     else float(cfg["nknots"]) * (3.0 * cfg["rank"] + 2.0))
             achieved = flop * npts / (kernel_ms * 1e-3) / 1e12
-            roofline = {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
+            # "tensor": the kernel's multiply-adds run as DMMA (FP64 tensor-core instructions); the DFMA
+            # kernels are bounded by the same FP64 peak (B200's DMMA and DFMA rates are equal)
+            bound = "tensor" if kernel_used in ("cheb_mma", "fh_mma") else "fp64"
+            roofline = {"bound": bound, "precision": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                         "frac": achieved / fp64_peak if fp64_peak else None,
                         "traffic": load_traffic(kernel_used, args.config, npts),
                         "peak_source": "best of a DFMA-only and a DMMA-only kernel measured in this run (MEASURED_PEAKS.json has no FP64 peak); "
