@@ -40,6 +40,7 @@ EXPORTS = [
     "chebpol_cuda_evalgrid_cheb", "chebpol_cuda_evalgrid_mlip", "chebpol_cuda_evalgrid_fh",
     "chebpol_cuda_evalpolyh", "chebpol_cuda_plan_polyh",
     "chebpol_cuda_evalstalk", "chebpol_cuda_evalhyp", "chebpol_cuda_plan_stalk",
+    "chebpol_cuda_evalchebg", "chebpol_cuda_plan_chebg",
 ]
 
 
@@ -96,6 +97,8 @@ def lib() -> C.CDLL:
                                        _vp]
     L.chebpol_cuda_plan_stalk.argtypes = [C.c_int, _vp, _dpp, _ip, C.c_int, _vp, _vp, _vp, _vp, C.c_int, C.c_int,
                                           C.POINTER(_vp)]
+    L.chebpol_cuda_evalchebg.argtypes = [_vp, _ip, C.c_int, _vp, C.c_int64, _ip, _dpp, _dpp, _dpp, _dpp, _dpp, C.c_int, _vp]
+    L.chebpol_cuda_plan_chebg.argtypes = [_vp, _ip, C.c_int, _ip, _dpp, _dpp, _dpp, _dpp, _dpp, C.c_int, C.POINTER(_vp)]
     L.chebpol_cuda_cache_clear.restype = None
     L.chebpol_cuda_cache_clear.argtypes = []
     L.chebpol_cuda_launch_count.restype = C.c_int64
@@ -190,6 +193,21 @@ class Plan:
         h = _vp()
         check(lib().chebpol_cuda_plan_cheb(_addr(cf), dims.ctypes.data_as(_ip), coef.ndim, _addr(mid_a),
                                            _addr(isp_a), _addr(ugm_a), device, C.byref(h)))
+        return Plan(h.value, coef.ndim, "cheb")
+
+    @staticmethod
+    def chebg(coef, splines, device: int = 0) -> "Plan":
+        """Chebyshev plan behind the 'general' grid maps; splines: per dimension (x, y, b, c, d)."""
+        coef = np.asarray(coef, dtype=np.float64)
+        dims = _i32(coef.shape)
+        cf = f64(coef, order="F")
+        if len(splines) != coef.ndim:
+            raise ValueError(f"{len(splines)} grid maps for a rank-{coef.ndim} coefficient array")
+        sn = _i32([len(t[0]) for t in splines])
+        lists = [ptr_list([t[j] for t in splines]) for j in range(5)]
+        h = _vp()
+        check(lib().chebpol_cuda_plan_chebg(_addr(cf), dims.ctypes.data_as(_ip), coef.ndim, sn.ctypes.data_as(_ip),
+                                            *[l[0] for l in lists], device, C.byref(h)))
         return Plan(h.value, coef.ndim, "cheb")
 
     @staticmethod
@@ -425,6 +443,20 @@ def evalcheb(coef, x_pk, mid=None, ispan=None, ugm_n=None, ngpus: int = 0) -> np
     ugm_a = _i32(ugm_n) if ugm_n is not None else None
     check(lib().chebpol_cuda_evalcheb(_addr(cf), dims.ctypes.data_as(_ip), coef.ndim, _addr(x_pk), x_pk.shape[0],
                                       _addr(mid_a), _addr(isp_a), _addr(ugm_a), ngpus, _addr(out)))
+    return out
+
+
+def evalchebg(coef, splines, x_pk, ngpus: int = 0) -> np.ndarray:
+    """Stateless 'general' method evaluation (chebpol_cuda_evalchebg); splines: per dimension (x, y, b, c, d)."""
+    coef = np.asarray(coef, dtype=np.float64)
+    dims = _i32(coef.shape)
+    cf = f64(coef, order="F")
+    x = f64(x_pk)
+    sn = _i32([len(t[0]) for t in splines])
+    lists = [ptr_list([t[j] for t in splines]) for j in range(5)]
+    out = np.empty(x.shape[0], dtype=np.float64)
+    check(lib().chebpol_cuda_evalchebg(_addr(cf), dims.ctypes.data_as(_ip), coef.ndim, _addr(x), x.shape[0],
+                                       sn.ctypes.data_as(_ip), *[l[0] for l in lists], ngpus, _addr(out)))
     return out
 
 

@@ -100,6 +100,7 @@ struct chebpol_cuda_plan {
     int goff[CP_MAXR] = {0};
     int grid_elems = 0;
     PreMap pm;
+    double *d_spline = nullptr;  // 'general' grid maps: per dimension knots + [y, b, c, d] records (PreMap bit 2)
     int blend = 0;
     // options
     int kernel_opt = CHEBPOL_CUDA_KERNEL_AUTO;
@@ -221,6 +222,7 @@ extern "C" void chebpol_cuda_plan_destroy(chebpol_cuda_plan *p)
     cudaFree(p->d_lut);
     cudaFree(p->d_grid);
     cudaFree(p->d_weights);
+    cudaFree(p->d_spline);
     for (int i = 0; i < 4; ++i) cudaFree(p->d_stalk[i]);
     delete p;
     if (prev >= 0) cudaSetDevice(prev);
@@ -348,9 +350,72 @@ static int configure_mma(chebpol_cuda_plan *p, int kind, const double *host_tens
     return CHEBPOL_CUDA_OK;
 }
 
+// spline tables of the 'general' grid maps as the caller holds them (one pointer per dimension)
+struct SplineTabs {
+    const int *sn;
+    const double *const *x, *const *y, *const *b, *const *c, *const *d;
+};
+
+static int check_spline_tabs(const SplineTabs &t, int rank)
+{
+    if (!t.sn || !t.x || !t.y || !t.b || !t.c || !t.d) return fail(CHEBPOL_CUDA_EINVAL, "spline table list is NULL");
+    for (int k = 0; k < rank; ++k) {
+        if (t.sn[k] < 2) return fail(CHEBPOL_CUDA_ESIZE, "grid map %d needs at least 2 knots", k);
+        if (!t.x[k] || !t.y[k] || !t.b[k] || !t.c[k] || !t.d[k])
+            return fail(CHEBPOL_CUDA_EINVAL, "spline table of dimension %d is NULL", k);
+        for (int i = 1; i < t.sn[k]; ++i)
+            if (!(t.x[k][i] > t.x[k][i - 1]))
+                return fail(CHEBPOL_CUDA_EINVAL, "grid map %d: knots must be strictly increasing (as splinefun stores them)", k);
+    }
+    return CHEBPOL_CUDA_OK;
+}
+
+// device layout read by premap_spline (common.cuh): per dimension the knots, padded to a multiple
+// of 4 doubles, then one 32-byte record [y, b, c, d] per knot
+static int upload_spline_tabs(chebpol_cuda_plan *p, const SplineTabs &t)
+{
+    std::vector<double> h;
+    for (int k = 0; k < p->rank; ++k) {
+        const int n = t.sn[k], npad = (n + 3) & ~3;
+        p->pm.soff[k] = (int)h.size();
+        p->pm.sn[k] = n;
+        h.insert(h.end(), t.x[k], t.x[k] + n);
+        h.resize(h.size() + (npad - n), 0.0);
+        for (int i = 0; i < n; ++i) {
+            h.push_back(t.y[k][i]);
+            h.push_back(t.b[k][i]);
+            h.push_back(t.c[k][i]);
+            h.push_back(t.d[k][i]);
+        }
+    }
+    CU(cudaMalloc(&p->d_spline, sizeof(double) * h.size()));
+    CU(cudaMemcpy(p->d_spline, h.data(), sizeof(double) * h.size(), cudaMemcpyHostToDevice));
+    p->pm.spl = p->d_spline;
+    p->pm.mode |= 4;
+    return CHEBPOL_CUDA_OK;
+}
+
+static int plan_cheb_impl(const double *coef, const int *dims, int rank, const double *mid, const double *ispan,
+                          const int *ugm_n, const SplineTabs *spl, int device, chebpol_cuda_plan **plan);
+
 extern "C" int chebpol_cuda_plan_cheb(const double *coef, const int *dims, int rank, const double *mid,
                                       const double *ispan, const int *ugm_n, int device,
                                       chebpol_cuda_plan **plan)
+{
+    return plan_cheb_impl(coef, dims, rank, mid, ispan, ugm_n, nullptr, device, plan);
+}
+
+extern "C" int chebpol_cuda_plan_chebg(const double *coef, const int *dims, int rank, const int *sn,
+                                       const double *const *sx, const double *const *sy, const double *const *sb,
+                                       const double *const *sc, const double *const *sd, int device,
+                                       chebpol_cuda_plan **plan)
+{
+    SplineTabs t = {sn, sx, sy, sb, sc, sd};
+    return plan_cheb_impl(coef, dims, rank, nullptr, nullptr, nullptr, &t, device, plan);
+}
+
+static int plan_cheb_impl(const double *coef, const int *dims, int rank, const double *mid, const double *ispan,
+                          const int *ugm_n, const SplineTabs *spl, int device, chebpol_cuda_plan **plan)
 {
     if (!plan) return fail(CHEBPOL_CUDA_EINVAL, "plan is NULL");
     *plan = nullptr;
@@ -359,6 +424,7 @@ extern "C" int chebpol_cuda_plan_cheb(const double *coef, const int *dims, int r
     int64_t nelem = 0;
     int rc = check_dims(dims, rank, &nelem);
     if (rc) return rc;
+    if (spl && (rc = check_spline_tabs(*spl, rank))) return rc;
     int sms = 0;
     rc = select_device(device, &sms);
     if (rc) return rc;
@@ -375,6 +441,7 @@ extern "C" int chebpol_cuda_plan_cheb(const double *coef, const int *dims, int r
         }
     }
     auto bail = [&](int code) { chebpol_cuda_plan_destroy(p); return code; };
+    if (spl && (rc = upload_spline_tabs(p, *spl))) return bail(rc);
     cudaError_t e = cudaMalloc(&p->d_tensor, sizeof(double) * nelem);
     if (e != cudaSuccess) return bail(cuda_fail(e, "cudaMalloc(tensor)"));
     e = cudaMemcpy(p->d_tensor, coef, sizeof(double) * nelem, cudaMemcpyHostToDevice);
@@ -1267,6 +1334,30 @@ extern "C" int chebpol_cuda_evalcheb(const double *coef, const int *dims, int ra
     }
     return run_sharded(rank, x, npts, ngpus, out, key, nelem * 8, [&](int dev, chebpol_cuda_plan **p) {
         return chebpol_cuda_plan_cheb(coef, dims, rank, mid, ispan, ugm_n, dev, p);
+    });
+}
+
+extern "C" int chebpol_cuda_evalchebg(const double *coef, const int *dims, int rank, const double *x,
+                                      int64_t npts, const int *sn, const double *const *sx,
+                                      const double *const *sy, const double *const *sb, const double *const *sc,
+                                      const double *const *sd, int ngpus, double *out)
+{
+    int64_t nelem = 0;
+    if (!coef) return fail(CHEBPOL_CUDA_EINVAL, "coef is NULL");
+    int rc = check_dims(dims, rank, &nelem);
+    if (rc) return rc;
+    SplineTabs t = {sn, sx, sy, sb, sc, sd};
+    if ((rc = check_spline_tabs(t, rank))) return rc;
+    CacheKey key = make_key(PLAN_CHEB, dims, rank);
+    if (cache_enabled() && nelem * 8 <= kCacheMaxBytes) {
+        uint64_t h = hash_bytes(coef, (size_t)nelem * 8, 7);
+        const double *const *tabs[5] = {sx, sy, sb, sc, sd};
+        for (int k = 0; k < rank; ++k)
+            for (int j = 0; j < 5; ++j) h = hash_bytes(tabs[j][k], (size_t)sn[k] * 8, h + j);
+        key.hash = h;
+    }
+    return run_sharded(rank, x, npts, ngpus, out, key, nelem * 8, [&](int dev, chebpol_cuda_plan **p) {
+        return plan_cheb_impl(coef, dims, rank, nullptr, nullptr, nullptr, &t, dev, p);
     });
 }
 

@@ -9,12 +9,42 @@
 // Pre-map applied to every coordinate before evaluation (Chebyshev plans):
 //   bit 0: x <- (x - mid)*ispan                 R/chebyshev.R:223-227 (imap)
 //   bit 1: x <- sin(0.5*pi*x*(1-n)/n)           R/uniform.R:6 (ugm)
+//   bit 2: x <- gridmaps[[d]](x)                R/chebyshev.R:349-354 (chebappxg.real): the monotone
+//          cubic spline stats::splinefun(grid, chebknots, method='hyman') of dimension d, evaluated
+//          as R's spline_eval does for a scalar call.  Table of dimension d at spl + soff[d]:
+//          sn knots (padded to a multiple of 4 doubles), then sn records [y, b, c, d].
 struct PreMap {
     int mode;
     double mid[CP_MAXR];
     double ispan[CP_MAXR];
     double nd[CP_MAXR];
+    const double *spl;
+    int soff[CP_MAXR];
+    int sn[CP_MAXR];
 };
+
+__device__ __forceinline__ double premap_spline(const PreMap &pm, int d, double u)
+{
+    const double *__restrict__ sx = pm.spl + pm.soff[d];
+    const int n = pm.sn[d];
+    // a scalar call of the closure starts its search at i = 0 and keeps it when x[0] <= u <= x[1]
+    // (NaN keeps it too, and propagates through dx); else bisection for the last knot <= u
+    int i = 0;
+    if (u < __ldg(sx) || __ldg(sx + 1) < u) {
+        int j = n;
+        do {
+            const int k = (i + j) >> 1;
+            if (u < __ldg(sx + k)) j = k; else i = k;
+        } while (j > i + 1);
+    }
+    const double2 *rec = reinterpret_cast<const double2 *>(sx + ((n + 3) & ~3) + 4 * i);
+    const double2 yb = __ldg(rec), cd = __ldg(rec + 1);
+    const double dx = __dsub_rn(u, __ldg(sx + i));
+    // Horner in R's order, no fused multiply-add: the mapped coordinate is bit-identical in every kernel
+    double t = __dadd_rn(cd.x, __dmul_rn(dx, cd.y));
+    t = __dadd_rn(yb.y, __dmul_rn(dx, t));
+    return __dadd_rn(yb.x, __dmul_rn(dx, t));
+}
 
 __device__ __forceinline__ double premap_coord(const PreMap &pm, int d, double v)
 {
@@ -24,6 +54,7 @@ __device__ __forceinline__ double premap_coord(const PreMap &pm, int d, double v
         const double n = pm.nd[d];
         v = sin(0.5 * 3.141592653589793 * v * (1.0 - n) / n);
     }
+    if (pm.mode & 4) v = premap_spline(pm, d, v);
     return v;
 }
 

@@ -13,6 +13,9 @@
  *   NULL                          no pre-map (chebappx without intervals)
  *   list(mid=, ispan=)            imap, R/chebyshev.R:223-227
  *   list(ugm=dims[, mid=, ispan=]) uniform-grid map, R/uniform.R:6,58-77
+ *   list(splines=lapply(gridmaps, function(gm) environment(gm)$z))
+ *                                 the 'general' grid maps, R/chebyshev.R:349-354: the x, y, b, c, d
+ *                                 tables each stats::splinefun(method='hyman') closure holds
  * `Rthreads` keeps its slot; a value <= 0 means "all visible GPUs", otherwise it is the
  * number of GPUs to spread the point batch over (CHEBPOL_CUDA_GPUS overrides).
  *
@@ -93,6 +96,30 @@ SEXP R_evalcheb_cuda(SEXP coef, SEXP inx, SEXP Rthreads, SEXP spare)
     }
     const int ngpus = gpus_from_threads(Rthreads);
     const R_xlen_t numvec = isMatrix(inx) ? ncols(inx) : 1;
+    SEXP ssp = list_elt(spare, "splines");
+    if (!isNull(ssp)) {
+        /* chebappxg.real: ch(gridmap(x), threads) with the grid maps evaluated in the kernel */
+        static const char *nm[5] = {"x", "y", "b", "c", "d"};
+        const double *tab[5][CHEBPOL_CUDA_MAXRANK];
+        int sn[CHEBPOL_CUDA_MAXRANK];
+        if (rank > CHEBPOL_CUDA_MAXRANK) error("rank must be positive");
+        if (LENGTH(ssp) != rank) error("splines must have one entry per dimension");
+        for (int k = 0; k < rank; k++) {
+            SEXP z = VECTOR_ELT(ssp, k);
+            sn[k] = LENGTH(list_elt(z, "x"));
+            for (int j = 0; j < 5; j++) {
+                SEXP v = list_elt(z, nm[j]);
+                if (isNull(v) || !IS_NUMERIC(v) || LENGTH(v) != sn[k]) error("spline table %s of dimension %d is malformed", nm[j], k + 1);
+                tab[j][k] = REAL(v);
+            }
+        }
+        SEXP res = PROTECT(NEW_NUMERIC(numvec));
+        const int rcg = chebpol_cuda_evalchebg(cf, dims, rank, REAL(inx), (int64_t)numvec, sn, tab[0], tab[1], tab[2],
+                                               tab[3], tab[4], ngpus, REAL(res));
+        UNPROTECT(1);
+        raise(rcg);
+        return res;
+    }
     SEXP resvec = PROTECT(NEW_NUMERIC(numvec));
     const int rc = chebpol_cuda_evalcheb(cf, dims, rank, REAL(inx), (int64_t)numvec, mid, ispan, ugm, ngpus,
                                          REAL(resvec));

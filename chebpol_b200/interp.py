@@ -28,7 +28,8 @@ import numpy as np
 from . import _lib
 
 __all__ = [
-    "ipol", "chebappx", "chebappxf", "mlappx", "fhappx", "ucappx", "ucappxf", "chebeval",
+    "ipol", "chebappx", "chebappxf", "chebappxg", "chebappxgf", "hyman_spline", "mlappx", "fhappx", "ucappx", "ucappxf",
+    "chebeval",
     "chebknots", "chebcoef", "evalongrid", "evalongridV", "fhweights", "Interpolant",
 ]
 
@@ -175,6 +176,8 @@ class Interpolant:
             t = self.t
             if self.kind in ("chebyshev", "uniform"):
                 p = _lib.Plan.cheb(t["coef"], t.get("mid"), t.get("ispan"), t.get("ugm_n"), device)
+            elif self.kind == "general":
+                p = _lib.Plan.chebg(t["coef"], t["splines"], device)
             elif self.kind == "multilinear":
                 p = _lib.Plan.mlip(t["grid"], t["values"], 0, device)
             elif self.kind == "fh":
@@ -221,6 +224,8 @@ class Interpolant:
             t = self.t
             if self.kind in ("chebyshev", "uniform"):
                 return _lib.evalcheb(t["coef"], xp, t.get("mid"), t.get("ispan"), t.get("ugm_n"), ngpus)
+            if self.kind == "general":
+                return _lib.evalchebg(t["coef"], t["splines"], xp, ngpus)
             if self.kind == "multilinear":
                 return _lib.evalmlip(t["grid"], t["values"], xp, b, ngpus)
             if self.kind == "stalker":
@@ -270,6 +275,97 @@ def chebappxf(fun, dims, intervals=None) -> Interpolant:
     if intervals is not None and np.ndim(intervals) == 1 and len(intervals) == 2 and np.isscalar(intervals[0]):
         intervals = [intervals]
     return chebappx(evalongrid(fun, dims, intervals), intervals)
+
+
+def hyman_spline(x, y):
+    """Tables (x, y, b, c, d) of R's stats::splinefun(x, y, method='hyman') -- the fit behind the
+    grid maps of chebappxg.real (R/chebyshev.R:349).  Fit side, host numpy: the "fmm" cubic spline
+    (Forsythe, Malcolm & Moler; end conditions from the third divided differences of the first and
+    last four points), Hyman's monotonicity filter on the slopes, and the c, d coefficients
+    recomputed from the filtered slopes (R's spline_coef / hyman_filter / spl_coef_conv).  As
+    splinefun does (regularize.values), the knots are sorted increasingly first."""
+    x = np.asarray(x, dtype=np.float64).ravel()
+    y = np.asarray(y, dtype=np.float64).ravel()
+    if x.size != y.size or x.size < 2:
+        raise ValueError("hyman_spline needs two vectors of the same length >= 2")
+    o = np.argsort(x, kind="stable")
+    x, y = x[o].copy(), y[o].copy()
+    if np.any(np.diff(x) <= 0):
+        raise ValueError("grid must be distinct ordered values")
+    dy = np.diff(y)
+    if not (np.all(dy >= 0) or np.all(dy <= 0)):
+        raise ValueError("'y' must be increasing or decreasing")
+    n = x.size
+    b, c, d = np.zeros(n), np.zeros(n), np.zeros(n)
+    if n < 3:
+        b[:] = (y[1] - y[0]) / (x[1] - x[0])
+    else:
+        m = n - 1
+        d[0] = x[1] - x[0]
+        c[1] = (y[1] - y[0]) / d[0]
+        for i in range(1, m):
+            d[i] = x[i + 1] - x[i]
+            b[i] = 2.0 * (d[i - 1] + d[i])
+            c[i + 1] = (y[i + 1] - y[i]) / d[i]
+            c[i] = c[i + 1] - c[i]
+        b[0], b[m] = -d[0], -d[m - 1]
+        c[0] = c[m] = 0.0
+        if n > 3:
+            c[0] = c[2] / (x[3] - x[1]) - c[1] / (x[2] - x[0])
+            c[m] = c[m - 1] / (x[m] - x[m - 2]) - c[m - 2] / (x[m - 1] - x[m - 3])
+            c[0] = c[0] * d[0] * d[0] / (x[3] - x[0])
+            c[m] = -c[m] * d[m - 1] * d[m - 1] / (x[m] - x[m - 3])
+        for i in range(1, m + 1):
+            t = d[i - 1] / b[i - 1]
+            b[i] = b[i] - t * d[i - 1]
+            c[i] = c[i] - t * c[i - 1]
+        c[m] = c[m] / b[m]
+        for i in range(m - 1, -1, -1):
+            c[i] = (c[i] - d[i] * c[i + 1]) / b[i]
+        b[m] = (y[m] - y[m - 1]) / d[m - 1] + d[m - 1] * (c[m - 1] + 2.0 * c[m])
+        for i in range(m):
+            b[i] = (y[i + 1] - y[i]) / d[i] - d[i] * (c[i + 1] + 2.0 * c[i])
+    # hyman_filter
+    ss = np.diff(y) / np.diff(x)
+    s0, s1 = np.concatenate([ss[:1], ss]), np.concatenate([ss, ss[-1:]])
+    t1 = np.minimum(np.abs(s0), np.abs(s1))
+    sig = np.where(s0 * s1 > 0, s1, b)
+    pos = sig >= 0
+    b = np.where(pos, np.minimum(np.maximum(0.0, b), 3.0 * t1), np.maximum(np.minimum(0.0, b), -3.0 * t1))
+    # spl_coef_conv
+    h, yy = np.diff(x), -np.diff(y)
+    b0, b1 = b[:-1], b[1:]
+    cc = -(3.0 * yy + (2.0 * b0 + b1) * h) / (h * h)
+    c1 = (3.0 * yy[-1] + (b0[-1] + 2.0 * b1[-1]) * h[-1]) / (h[-1] * h[-1])
+    dd = (2.0 * yy / h + b0 + b1) / (h * h)
+    return x, y, b, np.concatenate([cc, [c1]]), np.concatenate([dd, dd[-1:]])
+
+
+def chebappxg(val, grid=None) -> Interpolant:
+    """chebappxg.real, R/chebyshev.R:333-359: Chebyshev interpolation of values given on an
+    arbitrary tensor grid; every coordinate is first mapped to the Chebyshev grid by a monotone
+    (Hyman) cubic spline.  The reference applies the maps in R on every call (mapply per point
+    column); here they run in the kernel prologue."""
+    if grid is None:
+        return chebappx(val)
+    val = np.asarray(val, dtype=np.float64)
+    if np.isscalar(grid[0]):
+        grid = [grid]
+    grid = [np.asarray(g, dtype=np.float64) for g in grid]
+    shape = tuple(len(g) for g in grid)
+    if int(np.prod(shape)) != val.size:
+        raise ValueError("grid size must match data length")
+    if val.shape != shape:
+        val = val.reshape(shape, order="F")
+    splines = [hyman_spline(g, kn) for g, kn in zip(grid, chebknots(shape))]
+    return Interpolant("general", len(grid), [(g.min(), g.max()) for g in grid], coef=chebcoef(val), splines=splines)
+
+
+def chebappxgf(fun, grid) -> Interpolant:
+    """chebappxgf.real, R/chebyshev.R:367-371."""
+    if np.isscalar(grid[0]):
+        grid = [grid]
+    return chebappxg(evalongrid(fun, grid=grid), grid)
 
 
 def chebeval(x, coef, intervals=None, threads=None):
@@ -564,7 +660,7 @@ def ucappxf(fun, dims, intervals=None) -> Interpolant:
 
 _METHODS = ["chebyshev", "multilinear", "fh", "uniform", "general", "polyharmonic", "simplexlinear",
             "hstalker", "stalker", "crbf", "oldstalker"]
-_ON_PATH = {"chebyshev", "multilinear", "fh", "uniform", "polyharmonic", "stalker", "hstalker"}
+_ON_PATH = {"chebyshev", "multilinear", "fh", "uniform", "general", "polyharmonic", "stalker", "hstalker"}
 
 
 def ipol(val, dims=None, intervals=None, grid=None, knots=None, k=None, method="chebyshev", **kw) -> Interpolant:
@@ -586,6 +682,15 @@ def ipol(val, dims=None, intervals=None, grid=None, knots=None, k=None, method="
         if any(_unsorted(np.asarray(g, dtype=np.float64)) for g in grid):
             raise ValueError("grid must be distinct ordered values")
         return (hstalkerappx if method == "hstalker" else stalkerappx)(val, grid)
+    if method == "general":  # R/ipol.R:161-168
+        if grid is None:
+            raise ValueError("grid must be specified for general interpolation")
+        if np.isscalar(grid[0]):
+            grid = [grid]
+        grid = [np.asarray(g, dtype=np.float64) for g in grid]
+        if any(_unsorted(g) for g in grid):
+            raise ValueError("grid must be distinct ordered values")
+        return chebappxgf(val, grid) if callable(val) else chebappxg(val, grid)
     if method == "polyharmonic":  # R/ipol.R:169-186
         if knots is None:
             if grid is None:

@@ -71,6 +71,20 @@ CHEBPOL_CUDA_API int chebpol_cuda_evalcheb(const double *coef, const int *dims, 
                           const double *mid, const double *ispan, const int *ugm_n,
                           int ngpus, double *out);
 
+/* The 'general' grid method: replaces the closure of chebappxg.real (R/chebyshev.R:333-359),
+ *   function(x, threads) ch(gridmap(x), threads)
+ * i.e. R_evalcheb preceded by the R-level grid map that runs on every call: coordinate d goes
+ * through gridmaps[[d]] = stats::splinefun(grid[[d]], chebknots(dims)[[d]], method='hyman'),
+ * applied per point column with mapply (:351-354, interpreter-bound like ugm).  The tables are
+ * the ones the splinefun closure already holds -- environment(gridmaps[[d]])$z: x (sn[d] strictly
+ * increasing knots), y, b, c, d -- and the map is evaluated as R's spline_eval does for a scalar
+ * call: piece i = 0 if x[0] <= u <= x[1], else the last knot <= u; y + dx*(b + dx*(c + dx*d));
+ * the first / last piece extrapolates. */
+CHEBPOL_CUDA_API int chebpol_cuda_evalchebg(const double *coef, const int *dims, int rank,
+                           const double *x, int64_t npts, const int *sn,
+                           const double *const *sx, const double *const *sy, const double *const *sb,
+                           const double *const *sc, const double *const *sd, int ngpus, double *out);
+
 /* Replaces R_evalmlip (src/chebpol.c:670-707) + C_evalmlip (:617-667),
  * binsearch (:543-556) and blendfun (src/chebpol.h:24-45).
  * grid[d] has dims[d] strictly increasing knots; blend: 0 linear, 1 sigmoid,
@@ -96,6 +110,11 @@ typedef struct chebpol_cuda_plan chebpol_cuda_plan;
 CHEBPOL_CUDA_API int chebpol_cuda_plan_cheb(const double *coef, const int *dims, int rank,
                            const double *mid, const double *ispan, const int *ugm_n,
                            int device, chebpol_cuda_plan **plan);
+/* Chebyshev plan with the 'general' grid maps (see chebpol_cuda_evalchebg) */
+CHEBPOL_CUDA_API int chebpol_cuda_plan_chebg(const double *coef, const int *dims, int rank, const int *sn,
+                            const double *const *sx, const double *const *sy, const double *const *sb,
+                            const double *const *sc, const double *const *sd, int device,
+                            chebpol_cuda_plan **plan);
 CHEBPOL_CUDA_API int chebpol_cuda_plan_mlip(const double *const *grid, const int *dims, int rank,
                            const double *values, int blend, int device,
                            chebpol_cuda_plan **plan);

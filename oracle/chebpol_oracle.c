@@ -128,6 +128,127 @@ API void oracle_ugm(const double *x, int rank, int64_t npts, const int *n, const
 }
 
 /* ------------------------------------------------------------------------
+ * The 'general' grid method's pre-map (chebappxg.real, R/chebyshev.R:333-359):
+ *   gridmaps <- mapply(stats::splinefun, grid, chebknots(dim(val)), method='hyman')
+ *   ch(gridmap(x), threads)   with gridmap applying gridmaps[[d]] to coordinate d,
+ *                             one scalar call per coordinate (:351-354).
+ * splinefun is R's stats package -- a dependency of the reference that is NOT
+ * under /root/reference (the reference's saved test output was produced with
+ * R-devel r77544, i.e. the code base of R 4.0.0).  Its published algorithm is
+ * restated here:
+ *   - spline_coef, method "fmm" (R src/library/stats/src/splines.c, fmm_spline:
+ *     the cubic spline of Forsythe, Malcolm & Moler with end conditions from
+ *     the third divided differences of the first / last four points);
+ *   - hyman_filter (R src/library/stats/R/splinefun.R): the slopes b are
+ *     clamped into [0, 3 min(|S_{i-1}|,|S_i|)] (or the mirrored interval),
+ *     Hyman (1983) as simplified by Dougherty, Edelman & Hyman (1989);
+ *   - spl_coef_conv (same file): c, d recomputed from the filtered slopes;
+ *   - spline_eval, method 3 (splines.c): i = 0 is kept when x[0] <= u <= x[1]
+ *     (every call of the closure above is a scalar call, so the search always
+ *     starts at i = 0), else bisection for the last knot <= u; Horner
+ *     y + dx*(b + dx*(c + dx*d)); outside the knots the first / last cubic
+ *     piece extrapolates.
+ * Parity anchor: the three 'general' values of tests/all.Rout.save:109,121,126
+ * (7 digits); tests/test_oracle.py.  Knots must be strictly increasing (R's
+ * regularize.values sorts them; the Python mirror does the same before the fit).
+ * ------------------------------------------------------------------------ */
+API int oracle_hyman_fit(int n, const double *x, const double *y, double *b, double *c, double *d)
+{
+    if (n < 2) return 1;
+    if (n < 3) {
+        const double t = y[1] - y[0];
+        b[0] = t / (x[1] - x[0]);
+        b[1] = b[0];
+        c[0] = c[1] = d[0] = d[1] = 0.0;
+    } else {
+        /* tridiagonal system: b diagonal, d off-diagonal, c right-hand side */
+        const int m = n - 1;
+        d[0] = x[1] - x[0];
+        c[1] = (y[1] - y[0]) / d[0];
+        for (int i = 1; i < m; ++i) {
+            d[i] = x[i + 1] - x[i];
+            b[i] = 2.0 * (d[i - 1] + d[i]);
+            c[i + 1] = (y[i + 1] - y[i]) / d[i];
+            c[i] = c[i + 1] - c[i];
+        }
+        b[0] = -d[0];
+        b[m] = -d[m - 1];
+        c[0] = c[m] = 0.0;
+        if (n > 3) {
+            c[0] = c[2] / (x[3] - x[1]) - c[1] / (x[2] - x[0]);
+            c[m] = c[m - 1] / (x[m] - x[m - 2]) - c[m - 2] / (x[m - 1] - x[m - 3]);
+            c[0] = c[0] * d[0] * d[0] / (x[3] - x[0]);
+            c[m] = -c[m] * d[m - 1] * d[m - 1] / (x[m] - x[m - 3]);
+        }
+        for (int i = 1; i <= m; ++i) { /* forward elimination */
+            const double t = d[i - 1] / b[i - 1];
+            b[i] = b[i] - t * d[i - 1];
+            c[i] = c[i] - t * c[i - 1];
+        }
+        c[m] = c[m] / b[m]; /* back substitution */
+        for (int i = m - 1; i >= 0; --i) c[i] = (c[i] - d[i] * c[i + 1]) / b[i];
+        b[m] = (y[m] - y[m - 1]) / d[m - 1] + d[m - 1] * (c[m - 1] + 2.0 * c[m]);
+        for (int i = 0; i < m; ++i) {
+            b[i] = (y[i + 1] - y[i]) / d[i] - d[i] * (c[i + 1] + 2.0 * c[i]);
+            d[i] = (c[i + 1] - c[i]) / d[i];
+            c[i] = 3.0 * c[i];
+        }
+        c[m] = 3.0 * c[m];
+        d[m] = d[m - 1];
+    }
+    /* hyman_filter: S0 = c(ss[1], ss), S1 = c(ss, ss[n-1]) with ss the secant slopes */
+    for (int i = 0; i < n; ++i) {
+        const int il = (i == 0) ? 0 : i - 1, ir = (i == n - 1) ? n - 2 : i;
+        const double s0 = (y[il + 1] - y[il]) / (x[il + 1] - x[il]);
+        const double s1 = (y[ir + 1] - y[ir]) / (x[ir + 1] - x[ir]);
+        const double t1 = fmin(fabs(s0), fabs(s1));
+        double sig = b[i];
+        if (s0 * s1 > 0) sig = s1;
+        if (sig >= 0) b[i] = fmin(fmax(0.0, b[i]), 3.0 * t1);
+        else b[i] = fmax(fmin(0.0, b[i]), -3.0 * t1);
+    }
+    /* spl_coef_conv */
+    for (int i = 0; i < n - 1; ++i) {
+        const double h = x[i + 1] - x[i], yy = -(y[i + 1] - y[i]);
+        c[i] = -(3.0 * yy + (2.0 * b[i] + b[i + 1]) * h) / (h * h);
+        d[i] = (2.0 * yy / h + b[i] + b[i + 1]) / (h * h);
+    }
+    {
+        const int i = n - 2;
+        const double h = x[i + 1] - x[i], yy = -(y[i + 1] - y[i]);
+        c[n - 1] = (3.0 * yy + (b[i] + 2.0 * b[i + 1]) * h) / (h * h);
+        d[n - 1] = d[n - 2];
+    }
+    return 0;
+}
+
+static inline double spline_point(int n, const double *x, const double *y, const double *b,
+                                  const double *c, const double *d, double u)
+{
+    int i = 0;
+    if (u < x[0] || (n > 1 && x[1] < u)) {
+        int j = n;
+        do {
+            const int k = (i + j) / 2;
+            if (u < x[k]) j = k; else i = k;
+        } while (j > i + 1);
+    }
+    const double dx = u - x[i];
+    return y[i] + dx * (b[i] + dx * (c[i] + dx * d[i]));
+}
+
+/* out[i*rank + k] = gridmaps[[k]](x[i*rank + k]); table pointers per dimension */
+API void oracle_splinemap(const double *x, int rank, int64_t npts, const int *sn, const double *const *sx,
+                          const double *const *sy, const double *const *sb, const double *const *sc,
+                          const double *const *sd, int threads, double *out)
+{
+#pragma omp parallel for num_threads(threads) schedule(static) if (npts > 1 && threads > 1)
+    for (int64_t i = 0; i < npts; ++i)
+        for (int k = 0; k < rank; ++k)
+            out[i * rank + k] = spline_point(sn[k], sx[k], sy[k], sb[k], sc[k], sd[k], x[i * rank + k]);
+}
+
+/* ------------------------------------------------------------------------
  * Multilinear interpolation with blending.
  * Follows binsearch (src/chebpol.c:543-556), blendfun (src/chebpol.h:24-45)
  * and C_evalmlip (src/chebpol.c:617-667).

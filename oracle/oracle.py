@@ -124,6 +124,34 @@ class Oracle:
             f(_ptr(x), rank, x.shape[0], n.ctypes.data_as(_ip), _ptr(mid), _ptr(ispan), threads, _ptr(out))
         return out
 
+    # -- 'general' grid map: R's splinefun(method='hyman'), port only (not in the C reference) ----
+    def hyman_fit(self, x, y):
+        """Tables (x, y, b, c, d) of stats::splinefun(x, y, method='hyman'); x strictly increasing."""
+        lib = Oracle("port").lib if self.kind == "reference" else self.lib
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        y = np.ascontiguousarray(y, dtype=np.float64)
+        b, c, d = np.empty_like(x), np.empty_like(x), np.empty_like(x)
+        f = lib.oracle_hyman_fit
+        f.restype = C.c_int
+        f.argtypes = [C.c_int, _dp, _dp, _dp, _dp, _dp]
+        if f(x.size, _ptr(x), _ptr(y), _ptr(b), _ptr(c), _ptr(d)):
+            raise ValueError("hyman_fit needs at least 2 knots")
+        return x, y, b, c, d
+
+    def splinemap(self, x, tabs, threads: int = 1):
+        """tabs: per dimension a tuple (x, y, b, c, d).  Returns the mapped P x K points."""
+        lib = Oracle("port").lib if self.kind == "reference" else self.lib
+        rank = len(tabs)
+        x = _as_pts(x, rank)
+        out = np.empty_like(x)
+        sn = np.array([len(t[0]) for t in tabs], dtype=np.int32)
+        lists = [_ptr_list([t[j] for t in tabs]) for j in range(5)]
+        f = lib.oracle_splinemap
+        f.restype = None
+        f.argtypes = [_dp, C.c_int, C.c_int64, _ip, _dpp, _dpp, _dpp, _dpp, _dpp, C.c_int, _dp]
+        f(_ptr(x), rank, x.shape[0], sn.ctypes.data_as(_ip), *[l[0] for l in lists], threads, _ptr(out))
+        return out
+
     # -- multilinear -------------------------------------------------------
     def evalmlip(self, grid, values, x, blend: int = 0, threads: int = 1):
         rank = len(grid)

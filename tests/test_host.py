@@ -133,6 +133,11 @@ def test_ipol_front_end_checks():
     assert ip.kind == "multilinear" and ip.arity == 2
     ip = cb.ipol(np.arange(24.0), dims=[2, 3, 4], method="cheb")
     assert ip.t["coef"].shape == (2, 3, 4)
+    with pytest.raises(ValueError):
+        cb.ipol(np.zeros(4), method="general")  # grid must be specified
+    g = cb.ipol(lambda x: float(np.sum(x)), grid=[np.linspace(0, 1, 5) ** 2, np.linspace(0, 2, 4)], method="general")
+    assert g.kind == "general" and g.arity == 2 and g.t["coef"].shape == (5, 4) and len(g.t["splines"]) == 2
+    assert all(len(t) == 5 for t in g.t["splines"])
     ip = cb.ipol(np.zeros((5, 5)), grid=[np.linspace(0, 1, 5)[::-1], np.linspace(0, 1, 5)], method="fh")
     assert [len(w) for w in ip.t["weights"]] == [5, 5]  # decreasing grids are legal (R/ipol.R:241-243)
     ip = cb.ipol(np.zeros(15), method="uniform")

@@ -1019,3 +1019,82 @@ def test_cheb_and_fh_random_shapes_sweep(gpu_ok, port):
             assert np.all(np.abs(gotf - wantf) <= tol), (dims, k, np.abs(gotf - wantf).max())
             planf.close()
     assert n_mma >= 40 and n_slab >= 40 and n_fh >= 15, (n_mma, n_slab, n_fh)
+
+
+# ------------------------------------------------- 'general' grid method (chebappxg)
+def general_case(dims, seed=5):
+    """Values of g on an irregular tensor grid (mixed increasing / decreasing, clustered knots)."""
+    rng = np.random.default_rng(seed)
+    grid = []
+    for i, n in enumerate(dims):
+        g = np.sort(np.concatenate([[-1.0, 1.0], rng.uniform(-1, 1, n - 2)])) if i % 2 == 0 else np.linspace(-1, 1, n) ** 3
+        grid.append(g[::-1].copy() if i % 3 == 2 else g)
+    return grid, cases.grid_values(grid)
+
+
+@pytest.mark.parametrize("dims", [(10,), (12, 9), (8, 7, 6), (10,) * 5, (40, 7)])
+def test_general_method_all_kernels(gpu_ok, port, dims):
+    """chebappxg.real (R/chebyshev.R:333-359): hyman-spline grid map fused into the Chebyshev kernels.
+    Strict kernel bit-identical to oracle map + oracle Clenshaw; fast kernels within 1e-12 max|f|.
+    Points reach 5 % outside the grid (the first / last cubic piece extrapolates) and hit knots."""
+    grid, val = general_case(dims)
+    ip = cb.ipol(val, grid=grid, method="general")
+    K = len(dims)
+    x = cases.points(20011, K, lo=-1.05, hi=1.05)
+    for k in range(K):
+        x[: dims[k], k] = grid[k]
+    want = port.evalcheb(ip.t["coef"], port.splinemap(x, ip.t["splines"], threads=4), threads=4)
+    ip.kernel = _lib.KERNEL_STRICT
+    got = ip(x.T)
+    assert ip.plan().kernel_used == "cheb_strict"
+    assert np.array_equal(bits(got), bits(want))
+    plan = ip.plan()
+    for variant in (_lib.VARIANT_MMA, _lib.VARIANT_SLAB, 0):
+        got, k = eval_plan(plan, x, _lib.KERNEL_AUTO, variant)
+        assert np.abs(got - want).max() <= TOL_REL * np.abs(want).max(), (k, np.abs(got - want).max())
+    # the interpolant reproduces the data on its grid
+    mesh = np.meshgrid(*grid, indexing="ij")
+    gx = np.stack([m.ravel(order="F") for m in mesh])
+    ip.kernel = _lib.KERNEL_AUTO
+    assert np.abs(ip(gx) - val.ravel(order="F")).max() <= 1e-12
+    # stateless entry point, spread over all GPUs, equals the plan path; NaN in, NaN out
+    xs = cases.points(200000, K, seed=3)
+    assert np.array_equal(bits(_lib.evalchebg(ip.t["coef"], ip.t["splines"], xs, 0)), bits(ip(xs.T)))
+    xn = x[:4].copy()
+    xn[1, 0] = np.nan
+    out = ip(xn.T)
+    assert np.isnan(out[1]) and np.isfinite(out[[0, 2, 3]]).all()
+    ip.close()
+
+
+def test_general_goldens_through_ipol(gpu_ok):
+    """tests/all.R:36-59 -> all.Rout.save:109,121,126 through ipol(method='general') on the GPU."""
+    from r_rng import RRng
+
+    f = lambda x: np.exp(-np.sum(np.asarray(x) ** 2))
+    r = RRng(42)
+    r.rnorm(24)
+    r.runif(3, -1, 1)
+    s = (np.arange(10) * (1.0 / 9)) ** 3
+    ch = cb.ipol(np.exp(s), grid=[s], method="general")
+    rr = r.runif(1)
+    assert abs(ch(rr)[0] - 1.418184) < 5e-7
+    ch.close()
+    su = np.linspace(0, 1, 11)
+    grid = [su, su ** 2, su ** 3]
+    ch = cb.ipol(f, grid=grid, method="general")
+    for kern in (_lib.KERNEL_AUTO, _lib.KERNEL_STRICT):
+        ch.kernel = kern
+        rs = RRng(42)
+        rs.rnorm(24); rs.runif(3, -1, 1); rs.runif(1)
+        assert abs(ch(rs.runif(3))[0] - 0.460965) < 5e-7
+        assert abs(ch(rs.runif(3))[0] - 0.3501301) < 5e-7
+    # evalongridV falls to the expand-grid route for this method
+    pts = [np.linspace(0.1, 0.9, 4), np.linspace(0.2, 0.8, 3), np.linspace(0.0, 1.0, 5)]
+    G = cb.evalongridV(ch, grid=pts)
+    assert G.shape == (4, 3, 5) and abs(G[1, 2, 3] - ch(np.array([pts[0][1], pts[1][2], pts[2][3]]))[0]) == 0.0
+    ch.close()
+    with pytest.raises(cb.ChebpolCudaError):
+        t = ch.t["splines"]
+        bad = [(t[0][0][::-1].copy(),) + tuple(t[0][1:])] + list(t[1:])
+        _lib.Plan.chebg(ch.t["coef"], bad)
