@@ -21,6 +21,7 @@ _vp = C.c_void_p
 
 # option / query keys (include/chebpol_cuda.h)
 OPT_KERNEL, OPT_BLEND, OPT_CHUNK_POINTS, OPT_VARIANT = 1, 2, 3, 4
+OPT_EPOL = 5
 GET_KERNEL_USED, GET_LAUNCHES, GET_TENSOR_BYTES, GET_DEVICE, GET_SMEM_BYTES, GET_GRID = 101, 102, 103, 104, 105, 106
 KERNEL_AUTO, KERNEL_STRICT, KERNEL_FAST = 0, 1, 2
 VARIANT_AUTO, VARIANT_SLAB, VARIANT_MMA = 0, 1, 100000  # OPT_VARIANT families (csrc/api.cu: launch_plan)
@@ -28,6 +29,7 @@ VARIANT_MLIP_PAIR, VARIANT_MLIP_CELL = 1, 2
 KERNEL_NAMES = {
     0: "none", 10: "cheb_strict", 11: "cheb_slab", 12: "cheb_mma", 20: "mlip_strict", 21: "mlip_pair", 22: "mlip_cell",
     30: "fh_strict", 32: "fh_mma", 40: "polyh_strict", 41: "polyh_tile", 50: "stalk_strict", 51: "stalk_cell",
+    60: "sl_strict", 61: "sl_cell",
 }
 
 EXPORTS = [
@@ -41,6 +43,7 @@ EXPORTS = [
     "chebpol_cuda_evalpolyh", "chebpol_cuda_plan_polyh",
     "chebpol_cuda_evalstalk", "chebpol_cuda_evalhyp", "chebpol_cuda_plan_stalk",
     "chebpol_cuda_evalchebg", "chebpol_cuda_plan_chebg",
+    "chebpol_cuda_evalsl", "chebpol_cuda_plan_sl", "chebpol_cuda_analyzesimplex",
 ]
 
 
@@ -99,6 +102,10 @@ def lib() -> C.CDLL:
                                           C.POINTER(_vp)]
     L.chebpol_cuda_evalchebg.argtypes = [_vp, _ip, C.c_int, _vp, C.c_int64, _ip, _dpp, _dpp, _dpp, _dpp, _dpp, C.c_int, _vp]
     L.chebpol_cuda_plan_chebg.argtypes = [_vp, _ip, C.c_int, _ip, _dpp, _dpp, _dpp, _dpp, _dpp, C.c_int, C.POINTER(_vp)]
+    L.chebpol_cuda_evalsl.argtypes = [_vp, C.c_int64, _vp, C.c_int, C.c_int, _vp, C.c_int, _vp, _vp, _vp, _vp, C.c_int,
+                                      C.c_int, C.c_int, _vp]
+    L.chebpol_cuda_plan_sl.argtypes = [_vp, C.c_int, C.c_int, _vp, C.c_int, _vp, _vp, _vp, _vp, C.c_int, C.POINTER(_vp)]
+    L.chebpol_cuda_analyzesimplex.argtypes = [_vp, C.c_int, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp]
     L.chebpol_cuda_cache_clear.restype = None
     L.chebpol_cuda_cache_clear.argtypes = []
     L.chebpol_cuda_launch_count.restype = C.c_int64
@@ -272,6 +279,17 @@ class Plan:
                                             _addr(t1), _addr(t2), blend, device, C.byref(h)))
         return Plan(h.value, len(grid), "stalk")
 
+    @staticmethod
+    def sl(knots, dtri, adata, val, device: int = 0) -> "Plan":
+        """Simplex-linear plan.  knots: dim x nknots; dtri: (dim+1) x numsimplex, 1-based;
+        adata = (lumats, pivots, bbox) as analyzesimplex returns them."""
+        kn, tri, (lu, piv, bb), v = _sl_args(knots, dtri, adata, val)
+        dim, nk = kn.shape
+        h = _vp()
+        check(lib().chebpol_cuda_plan_sl(_addr(kn), dim, nk, _addr(tri), tri.shape[1], _addr(lu), _addr(piv), _addr(bb),
+                                         _addr(v), device, C.byref(h)))
+        return Plan(h.value, dim, "sl")
+
     # -- evaluation --------------------------------------------------------------
     def eval_host(self, x_pk: np.ndarray, out: np.ndarray | None = None) -> np.ndarray:
         """x_pk: (P, K) C-contiguous float64 host array (pinned or pageable)."""
@@ -323,6 +341,50 @@ class Plan:
             self.close()
         except Exception:
             pass
+
+
+# ---- simplex-linear ------------------------------------------------------------
+def _sl_args(knots, dtri, adata, val):
+    kn = f64(np.asarray(knots, dtype=np.float64), order="F")
+    tri = np.require(dtri, dtype=np.int32, requirements=["F", "A"])
+    dim, nk = kn.shape
+    if tri.ndim != 2 or tri.shape[0] != dim + 1:
+        raise ValueError(f"dtri must be a {dim + 1} x numsimplex matrix, got shape {tri.shape}")
+    ns = tri.shape[1]
+    lu, piv, bb = adata
+    lu, bb = f64(np.ravel(lu, order="F")), f64(np.ravel(bb, order="F"))
+    piv = np.ascontiguousarray(np.ravel(piv, order="F"), dtype=np.int32)
+    v = f64(np.ravel(val))
+    if lu.size != ns * (dim + 1) ** 2 or piv.size != ns * (dim + 1) or bb.size != ns * 2 * dim:
+        raise ValueError("adata does not match the triangulation")
+    if v.size != nk:
+        raise ValueError(f"number of values ({v.size}) should equal number of knots ({nk})")
+    return kn, tri, (lu, piv, bb), v
+
+
+def analyzesimplex(dtri, knots, device: int = 0):
+    """R_analyzesimplex on the device: (lumats, pivots, bbox)."""
+    kn = f64(np.asarray(knots, dtype=np.float64), order="F")
+    tri = np.require(dtri, dtype=np.int32, requirements=["F", "A"])
+    dim, nk = kn.shape
+    N, ns = tri.shape
+    if N != dim + 1:
+        raise ValueError(f"dtri must be a {dim + 1} x numsimplex matrix, got shape {tri.shape}")
+    lu = np.empty(ns * N * N)
+    piv = np.empty(ns * N, dtype=np.int32)
+    bb = np.empty(ns * 2 * dim)
+    check(lib().chebpol_cuda_analyzesimplex(_addr(tri), ns, _addr(kn), dim, nk, device, _addr(lu), _addr(piv), _addr(bb)))
+    return lu, piv, bb
+
+
+def evalsl(x_pk, knots, dtri, adata, val, epol: bool = False, blend: int = 3, ngpus: int = 0) -> np.ndarray:
+    kn, tri, (lu, piv, bb), v = _sl_args(knots, dtri, adata, val)
+    dim, nk = kn.shape
+    x = f64(x_pk)
+    out = np.empty(x.shape[0], dtype=np.float64)
+    check(lib().chebpol_cuda_evalsl(_addr(x), x.shape[0], _addr(kn), dim, nk, _addr(tri), tri.shape[1], _addr(lu),
+                                    _addr(piv), _addr(bb), _addr(v), int(bool(epol)), blend, ngpus, _addr(out)))
+    return out
 
 
 # ---- fit side ------------------------------------------------------------------

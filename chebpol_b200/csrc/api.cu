@@ -80,7 +80,7 @@ extern "C" int chebpol_cuda_device_count(int *count)
 }
 
 // ---------------------------------------------------------------------- plan
-enum PlanKind { PLAN_CHEB = 1, PLAN_MLIP = 2, PLAN_FH = 3, PLAN_POLYH = 4, PLAN_STALK = 5 };
+enum PlanKind { PLAN_CHEB = 1, PLAN_MLIP = 2, PLAN_FH = 3, PLAN_POLYH = 4, PLAN_STALK = 5, PLAN_SL = 6 };
 
 cudaError_t stalk_pack_records(const double *val, const double *aa, const double *b, const double *t1,
                                const double *t2, int rank, int64_t n, double *rec, cudaStream_t s);
@@ -129,6 +129,9 @@ struct chebpol_cuda_plan {
     // stalker splines: values in d_tensor, knots in d_grid, packed records in d_padded
     int stalk_kind = 0;  // 0 stalker, 1 hstalker
     double *d_stalk[4] = {nullptr, nullptr, nullptr, nullptr};  // a, b, t1, t2
+    // simplex-linear: every device table of the triangulation (simplex.cu)
+    SlDevice *sl = nullptr;
+    int epol = 0;
     // statistics
     LaunchInfo last = {0, 0, 0, 0};
     int64_t launches = 0;
@@ -223,6 +226,7 @@ extern "C" void chebpol_cuda_plan_destroy(chebpol_cuda_plan *p)
     cudaFree(p->d_grid);
     cudaFree(p->d_weights);
     cudaFree(p->d_spline);
+    sl_destroy(p->sl);
     for (int i = 0; i < 4; ++i) cudaFree(p->d_stalk[i]);
     delete p;
     if (prev >= 0) cudaSetDevice(prev);
@@ -664,6 +668,83 @@ extern "C" int chebpol_cuda_plan_stalk(int kind, const double *val, const double
     return CHEBPOL_CUDA_OK;
 }
 
+static int check_sl(const double *knots, int dim, int nknots, const int *dtri, int ns, const double *lumats,
+                    const int *pivots, const double *bbox, const double *val)
+{
+    if (dim <= 0) return fail(CHEBPOL_CUDA_ERANK, "rank must be positive");
+    if (dim > CHEBPOL_CUDA_MAXRANK - 1) return fail(CHEBPOL_CUDA_ERANK, "dimension %d exceeds %d", dim, CHEBPOL_CUDA_MAXRANK - 1);
+    if (nknots < 0 || ns < 0) return fail(CHEBPOL_CUDA_ESIZE, "negative number of knots or simplices");
+    if ((int64_t)ns * (dim + 1) * (dim + 1) >= (int64_t(1) << 31) || (int64_t)nknots * dim >= (int64_t(1) << 31))
+        return fail(CHEBPOL_CUDA_ESIZE, "a simplex table has 2^31 or more elements");
+    if ((nknots > 0 && (!knots || !val)) || (ns > 0 && (!dtri || !lumats || !pivots || !bbox)))
+        return fail(CHEBPOL_CUDA_EINVAL, "a simplex table pointer is NULL");
+    for (int64_t i = 0; i < (int64_t)ns * (dim + 1); ++i)
+        if (dtri[i] < 1 || dtri[i] > nknots)
+            return fail(CHEBPOL_CUDA_EINVAL, "dtri[%lld] = %d is not a knot index in 1..%d", (long long)i, dtri[i], nknots);
+    return CHEBPOL_CUDA_OK;
+}
+
+extern "C" int chebpol_cuda_plan_sl(const double *knots, int dim, int nknots, const int *dtri, int numsimplex,
+                                    const double *lumats, const int *pivots, const double *bbox, const double *val,
+                                    int device, chebpol_cuda_plan **plan)
+{
+    if (!plan) return fail(CHEBPOL_CUDA_EINVAL, "plan is NULL");
+    *plan = nullptr;
+    int rc = check_sl(knots, dim, nknots, dtri, numsimplex, lumats, pivots, bbox, val);
+    if (rc) return rc;
+    int sms = 0;
+    rc = select_device(device, &sms);
+    if (rc) return rc;
+    int dims[CP_MAXR];
+    for (int i = 0; i < dim; ++i) dims[i] = nknots > 0 ? nknots : 1;
+    chebpol_cuda_plan *p = new_plan(PLAN_SL, device, sms, dims, dim, (int64_t)nknots * dim);
+    p->blend = 3;  // the closure's default, 'cubic' (R/simplexlinear.R:36)
+    p->nknots = nknots;
+    const char *env = getenv("CHEBPOL_CUDA_SL_CELLS");
+    cudaError_t e = sl_create(knots, dim, nknots, dtri, numsimplex, lumats, pivots, bbox, val, env ? atoi(env) : 0, &p->sl);
+    if (e != cudaSuccess) {
+        chebpol_cuda_plan_destroy(p);
+        return cuda_fail(e, "simplex tables");
+    }
+    p->tensor_bytes = sl_bytes(p->sl);
+    *plan = p;
+    return CHEBPOL_CUDA_OK;
+}
+
+extern "C" int chebpol_cuda_analyzesimplex(const int *dtri, int numsimplex, const double *knots, int dim, int nknots,
+                                           int device, double *lumats, int *pivots, double *bbox)
+{
+    if (dim <= 0 || dim > CHEBPOL_CUDA_MAXRANK - 1) return fail(CHEBPOL_CUDA_ERANK, "dimension %d not in 1..%d", dim, CHEBPOL_CUDA_MAXRANK - 1);
+    if (numsimplex < 0 || nknots < 0) return fail(CHEBPOL_CUDA_ESIZE, "negative number of knots or simplices");
+    if (numsimplex == 0) return CHEBPOL_CUDA_OK;
+    if (!dtri || !knots || !lumats || !pivots || !bbox) return fail(CHEBPOL_CUDA_EINVAL, "a pointer is NULL");
+    const int N = dim + 1;
+    if ((int64_t)numsimplex * N * N >= (int64_t(1) << 31)) return fail(CHEBPOL_CUDA_ESIZE, "too many simplices");
+    for (int64_t i = 0; i < (int64_t)numsimplex * N; ++i)
+        if (dtri[i] < 1 || dtri[i] > nknots)
+            return fail(CHEBPOL_CUDA_EINVAL, "dtri[%lld] = %d is not a knot index in 1..%d", (long long)i, dtri[i], nknots);
+    int sms = 0;
+    int rc = select_device(device, &sms);
+    if (rc) return rc;
+    int *d_tri = nullptr, *d_piv = nullptr;
+    double *d_kn = nullptr, *d_lu = nullptr, *d_bb = nullptr;
+    const size_t ns = (size_t)numsimplex;
+    cudaError_t e = cudaMalloc(&d_tri, sizeof(int) * ns * N);
+    if (e == cudaSuccess) e = cudaMalloc(&d_piv, sizeof(int) * ns * N);
+    if (e == cudaSuccess) e = cudaMalloc(&d_kn, sizeof(double) * (size_t)nknots * dim);
+    if (e == cudaSuccess) e = cudaMalloc(&d_lu, sizeof(double) * ns * N * N);
+    if (e == cudaSuccess) e = cudaMalloc(&d_bb, sizeof(double) * ns * 2 * dim);
+    if (e == cudaSuccess) e = cudaMemcpy(d_tri, dtri, sizeof(int) * ns * N, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d_kn, knots, sizeof(double) * (size_t)nknots * dim, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = sl_analyze_device(d_tri, numsimplex, d_kn, dim, d_lu, d_piv, d_bb, 0);
+    if (e == cudaSuccess) { g_launches.fetch_add(1); e = cudaMemcpy(lumats, d_lu, sizeof(double) * ns * N * N, cudaMemcpyDeviceToHost); }
+    if (e == cudaSuccess) e = cudaMemcpy(pivots, d_piv, sizeof(int) * ns * N, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(bbox, d_bb, sizeof(double) * ns * 2 * dim, cudaMemcpyDeviceToHost);
+    cudaFree(d_tri); cudaFree(d_piv); cudaFree(d_kn); cudaFree(d_lu); cudaFree(d_bb);
+    if (e != cudaSuccess) return cuda_fail(e, "analyzesimplex");
+    return CHEBPOL_CUDA_OK;
+}
+
 extern "C" int chebpol_cuda_plan_set(chebpol_cuda_plan *p, int option, int64_t value)
 {
     if (!p) return fail(CHEBPOL_CUDA_EINVAL, "plan is NULL");
@@ -673,8 +754,8 @@ extern "C" int chebpol_cuda_plan_set(chebpol_cuda_plan *p, int option, int64_t v
         p->kernel_opt = (int)value;
         return CHEBPOL_CUDA_OK;
     case CHEBPOL_CUDA_OPT_BLEND:
-        if (p->kind != PLAN_MLIP && p->kind != PLAN_STALK)
-            return fail(CHEBPOL_CUDA_EINVAL, "blend applies to multilinear and stalker plans");
+        if (p->kind != PLAN_MLIP && p->kind != PLAN_STALK && p->kind != PLAN_SL)
+            return fail(CHEBPOL_CUDA_EINVAL, "blend applies to multilinear, stalker and simplex-linear plans");
         if (value < 0 || value > 5) return fail(CHEBPOL_CUDA_EBLEND, "blend %lld not in 0..5", (long long)value);
         p->blend = (int)value;
         return CHEBPOL_CUDA_OK;
@@ -684,6 +765,10 @@ extern "C" int chebpol_cuda_plan_set(chebpol_cuda_plan *p, int option, int64_t v
         return CHEBPOL_CUDA_OK;
     case CHEBPOL_CUDA_OPT_VARIANT:
         p->variant = (int)value;
+        return CHEBPOL_CUDA_OK;
+    case CHEBPOL_CUDA_OPT_EPOL:
+        if (p->kind != PLAN_SL) return fail(CHEBPOL_CUDA_EINVAL, "epol applies to simplex-linear plans");
+        p->epol = value != 0;
         return CHEBPOL_CUDA_OK;
     default: return fail(CHEBPOL_CUDA_EINVAL, "unknown option %d", option);
     }
@@ -878,6 +963,10 @@ static int launch_plan(chebpol_cuda_plan *p, const double *d_x, int64_t npts, do
                 return fail(CHEBPOL_CUDA_EINVAL, "no fast stalker kernel for rank %d", p->rank);
             e = launch_stalk_strict(a, s, &li);
         }
+    } else if (p->kind == PLAN_SL) {
+        e = launch_sl(p->sl, p->kernel_opt, p->epol, p->blend, d_x, npts, d_out, p->num_sms, s, &li);
+        if (e == cudaErrorNotSupported)
+            return fail(CHEBPOL_CUDA_EINVAL, "no cell-list kernel for %d-dimensional simplices", p->rank);
     } else {
         return fail(CHEBPOL_CUDA_EINVAL, "corrupt plan");
     }
@@ -1249,7 +1338,7 @@ extern "C" void chebpol_cuda_cache_clear(void)
 // pipeline on its slice.  No collective: every GPU writes its own slice.
 template <class MakePlan>
 static int run_sharded(int rank, const double *x, int64_t npts, int ngpus, double *out, CacheKey key,
-                       int64_t tensor_bytes, MakePlan make_plan, int blend = -1)
+                       int64_t tensor_bytes, MakePlan make_plan, int blend = -1, int epol = -1)
 {
     if (npts < 0) return fail(CHEBPOL_CUDA_EINVAL, "negative point count");
     if (npts > 0 && (!x || !out)) return fail(CHEBPOL_CUDA_EINVAL, "x or out is NULL");
@@ -1270,6 +1359,7 @@ static int run_sharded(int rank, const double *x, int64_t npts, int ngpus, doubl
         int r = CHEBPOL_CUDA_OK;
         if (!p) r = make_plan(dev, &p);
         if (!r && blend >= 0) p->blend = blend;  // per-call argument of the multilinear closure, not part of the key
+        if (!r && epol >= 0) p->epol = epol;
         if (!r && n > 0) r = chebpol_cuda_plan_eval_host(p, xs, n, os);
         if (p) {
             if (cacheable && !r) cache_put(k, p);
@@ -1479,6 +1569,33 @@ extern "C" int chebpol_cuda_evalhyp(const double *val, const double *const *grid
 }
 
 // ------------------------------------------------------------------ fit side
+extern "C" int chebpol_cuda_evalsl(const double *x, int64_t npts, const double *knots, int dim, int nknots,
+                                   const int *dtri, int numsimplex, const double *lumats, const int *pivots,
+                                   const double *bbox, const double *val, int epol, int blend, int ngpus, double *out)
+{
+    int rc = check_sl(knots, dim, nknots, dtri, numsimplex, lumats, pivots, bbox, val);
+    if (rc) return rc;
+    if (blend < 0 || blend > 5) return fail(CHEBPOL_CUDA_EBLEND, "blend %d not in 0..5", blend);
+    int dims[CP_MAXR];
+    for (int i = 0; i < dim; ++i) dims[i] = nknots > 0 ? nknots : 1;
+    CacheKey key = make_key(PLAN_SL, dims, dim);
+    const int N = dim + 1;
+    const int64_t bytes = (int64_t)numsimplex * (N * N * 8 + N * 8 + 2 * dim * 8) + (int64_t)nknots * (dim + 1) * 8;
+    if (cache_enabled() && bytes <= kCacheMaxBytes) {
+        uint64_t h = hash_bytes(knots, (size_t)nknots * dim * 8, 11);
+        h = hash_bytes(val, (size_t)nknots * 8, h);
+        h = hash_bytes(dtri, (size_t)numsimplex * N * 4, h);
+        h = hash_bytes(lumats, (size_t)numsimplex * N * N * 8, h);
+        h = hash_bytes(pivots, (size_t)numsimplex * N * 4, h);
+        h = hash_bytes(bbox, (size_t)numsimplex * 2 * dim * 8, h);
+        key.hash = h ^ (uint64_t)numsimplex;
+    }
+    // blend and epol are per-call arguments of the closure (R/simplexlinear.R:34-38), not part of the key
+    return run_sharded(dim, x, npts, ngpus, out, key, bytes, [&](int dev, chebpol_cuda_plan **p) {
+        return chebpol_cuda_plan_sl(knots, dim, nknots, dtri, numsimplex, lumats, pivots, bbox, val, dev, p);
+    }, blend, epol);
+}
+
 extern "C" int chebpol_cuda_chebcoef(const double *val, const int *dims, int rank, int dct, int device, double *coef)
 {
     if (!val || !coef) return fail(CHEBPOL_CUDA_EINVAL, "val or coef is NULL");

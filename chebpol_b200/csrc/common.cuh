@@ -73,6 +73,8 @@ enum KernelId {
     K_STALK_CELL = 51,   // packed per-grid-point records, blend weights hoisted, fast reciprocal
     K_POLYH_STRICT = 40, // thread-per-point radial sum, reference op order
     K_POLYH_TILE = 41,   // points in registers, knot rows broadcast from a TMA-filled ring
+    K_SL_STRICT = 60,    // simplex-linear: the reference's linear scan over all simplices
+    K_SL_CELL = 61,      // simplex-linear: candidates from a uniform cell grid, same acceptance test
 };
 
 // ---- launch descriptors filled by api.cu, consumed by the kernel TUs -------
@@ -249,3 +251,13 @@ cudaError_t fit_evalgrid_device(int kind, const double *d_tensor, const int *dim
                                 const PreMap *pm, double *d_s0, double *d_s1, cudaStream_t s, double **result, int *launches);
 cudaError_t fit_fhweights_device(const double *d_grid, int nknots, int d, double *d_w, cudaStream_t s);
 cudaError_t run_fp64_peak(int num_sms, int repeats, cudaStream_t s, double *tflops);
+// simplex-linear interpolation (simplex.cu): device tables of one triangulation
+struct SlDevice;
+cudaError_t sl_create(const double *knots, int dim, int nknots, const int *dtri, int ns, const double *lumats,
+                      const int *pivots, const double *bbox, const double *val, int cells_per_dim, SlDevice **out);
+void sl_destroy(SlDevice *d);
+int64_t sl_bytes(const SlDevice *d);
+cudaError_t launch_sl(const SlDevice *d, int kernel, int epol, int blend, const double *x, int64_t npts, double *out,
+                      int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t sl_analyze_device(const int *d_dtri, int ns, const double *d_knots, int dim, double *d_lumats,
+                              int *d_pivots, double *d_bbox, cudaStream_t s);

@@ -329,6 +329,50 @@ SEXP R_fhweights_cuda(SEXP Sgrid, SEXP Sd, SEXP Sthreads)
     return ret;
 }
 
+/* same arguments and return as R_evalsl (src/chebpol.c:803-828), called by the closure of
+ * slappx.real (R/simplexlinear.R:38) */
+SEXP R_evalsl_cuda(SEXP Sx, SEXP Sknots, SEXP Sdtri, SEXP adata, SEXP Sval, SEXP extrapolate, SEXP Sthreads,
+                   SEXP Sblend)
+{
+    const int dim = nrows(Sknots);
+    const int nknots = ncols(Sknots);
+    const int numsimplex = ncols(Sdtri);
+    if (nrows(Sdtri) != dim + 1) error("triangulation has %d rows, knots have dimension %d", nrows(Sdtri), dim);
+    if (isMatrix(Sx) ? (nrows(Sx) != dim) : (LENGTH(Sx) != dim)) error("argument x must have %d rows", dim);
+    if (LENGTH(Sval) != nknots) error("number of values (%d) should equal number of knots (%d)", LENGTH(Sval), nknots);
+    const int epol = LOGICAL(AS_LOGICAL(extrapolate))[0];
+    int blend = 0;
+    if (!isNull(Sblend)) blend = INTEGER(AS_INTEGER(Sblend))[0];
+    const int ngpus = gpus_from_threads(Sthreads);
+    const R_xlen_t numvec = isMatrix(Sx) ? ncols(Sx) : 1;
+    SEXP ret = PROTECT(NEW_NUMERIC(numvec));
+    const int rc = chebpol_cuda_evalsl(REAL(Sx), (int64_t)numvec, REAL(Sknots), dim, nknots, INTEGER(Sdtri), numsimplex,
+                                       REAL(VECTOR_ELT(adata, 0)), INTEGER(VECTOR_ELT(adata, 1)),
+                                       REAL(VECTOR_ELT(adata, 2)), REAL(Sval), epol, blend, ngpus, REAL(ret));
+    UNPROTECT(1);
+    raise(rc);
+    return ret;
+}
+
+/* fit side: same arguments and return as R_analyzesimplex (src/chebpol.c:830-875) */
+SEXP R_analyzesimplex_cuda(SEXP Sdtri, SEXP Sknots, SEXP Sthreads)
+{
+    UNUSED(Sthreads);
+    const int dim = nrows(Sknots);
+    const int numsimplex = ncols(Sdtri);
+    const int N = dim + 1;
+    SEXP retlist = PROTECT(NEW_LIST(3));
+    SET_VECTOR_ELT(retlist, 0, NEW_NUMERIC(numsimplex * N * N));
+    SET_VECTOR_ELT(retlist, 1, NEW_INTEGER(numsimplex * N));
+    SET_VECTOR_ELT(retlist, 2, allocMatrix(REALSXP, 2 * dim, numsimplex));
+    const int rc = chebpol_cuda_analyzesimplex(INTEGER(Sdtri), numsimplex, REAL(Sknots), dim, ncols(Sknots), 0,
+                                               REAL(VECTOR_ELT(retlist, 0)), INTEGER(VECTOR_ELT(retlist, 1)),
+                                               REAL(VECTOR_ELT(retlist, 2)));
+    UNPROTECT(1);
+    raise(rc);
+    return retlist;
+}
+
 /* rows to append to R_CallMethodDef callMethods[] (src/chebpol.c:943-967), same arities
  * as "evalcheb", "evalmlip", "FH" */
 const R_CallMethodDef chebpol_cuda_callMethods[] = {
@@ -340,4 +384,6 @@ const R_CallMethodDef chebpol_cuda_callMethods[] = {
     {"evalpolyh_cuda", (DL_FUNC)&R_evalpolyh_cuda, 7},
     {"evalstalk_cuda", (DL_FUNC)&R_evalstalk_cuda, 4},
     {"evalhyp_cuda", (DL_FUNC)&R_evalhyp_cuda, 4},
+    {"evalsl_cuda", (DL_FUNC)&R_evalsl_cuda, 8},
+    {"analyzesimplex_cuda", (DL_FUNC)&R_analyzesimplex_cuda, 3},
     {NULL, NULL, 0}};

@@ -28,12 +28,12 @@ import numpy as np
 from . import _lib
 
 __all__ = [
-    "ipol", "chebappx", "chebappxf", "chebappxg", "chebappxgf", "hyman_spline", "mlappx", "fhappx", "ucappx", "ucappxf",
+    "ipol", "chebappx", "chebappxf", "chebappxg", "chebappxgf", "hyman_spline", "slappx", "mlappx", "fhappx", "ucappx", "ucappxf",
     "chebeval",
     "chebknots", "chebcoef", "evalongrid", "evalongridV", "fhweights", "Interpolant",
 ]
 
-BLENDS = {"linear": 0, "sigmoid": 1, "parodic": 2, "cubic": 3, "square": 4}  # R/multilinear.R:64-65
+BLENDS = {"linear": 0, "sigmoid": 1, "parodic": 2, "cubic": 3, "square": 4, "mean": 5}  # R/multilinear.R:64-65, R/simplexlinear.R:37
 
 
 # ------------------------------------------------------------------ fit side
@@ -184,6 +184,8 @@ class Interpolant:
                 p = _lib.Plan.fh(t["values"], t["grid"], t["weights"], device)
             elif self.kind in ("stalker", "hstalker"):
                 p = _lib.Plan.stalk(1 if self.kind == "hstalker" else 0, t["values"], t["grid"], t["tables"], 3, device)
+            elif self.kind == "simplexlinear":
+                p = _lib.Plan.sl(t["knots"], t["dtri"], t["adata"], t["values"], device)
             elif self.kind == "polyharmonic":
                 p = _lib.Plan.polyh(t["knots"], t["weights"], t["lweights"], t["k"], t.get("norm_a"), t.get("norm_b"),
                                     device)
@@ -213,13 +215,22 @@ class Interpolant:
             return _lib.f64(x.reshape(numvec, K)), False
         raise ValueError(f"Function should take {K} arguments, you supplied a vector of length {x.size}")
 
-    def __call__(self, x, threads=None, blend: str | int | None = None, ngpus: int = 1, device: int = 0):
+    def __call__(self, x, threads=None, blend: str | int | None = None, ngpus: int = 1, device: int = 0,
+                 epol: bool = False):
         xp, _single = self._coerce(x)
-        blended = self.kind in ("multilinear", "stalker", "hstalker")
+        blended = self.kind in ("multilinear", "stalker", "hstalker", "simplexlinear")
         if blended:
-            if blend is None:  # closure defaults: 'linear' (R/multilinear.R:63), 'cubic' (R/stalker.R:62,80)
+            if blend is None:  # closure defaults: 'linear' (R/multilinear.R:63), 'cubic' (R/stalker.R:62,80; R/simplexlinear.R:36)
                 blend = "linear" if self.kind == "multilinear" else "cubic"
             b = BLENDS[blend] if isinstance(blend, str) else int(blend)
+        if self.kind == "simplexlinear":
+            t = self.t
+            if ngpus != 1:
+                return _lib.evalsl(xp, t["knots"], t["dtri"], t["adata"], t["values"], epol, b, ngpus)
+            p = self.plan(device)
+            p.set(_lib.OPT_BLEND, b)
+            p.set(_lib.OPT_EPOL, int(bool(epol)))
+            return p.eval_host(xp)
         if ngpus != 1:
             t = self.t
             if self.kind in ("chebyshev", "uniform"):
@@ -555,6 +566,63 @@ def stalkerappx(val, grid) -> Interpolant:
                        values=np.asfortranarray(val), tables=makestalk(val, grid))
 
 
+def analyzesimplex(dtri, knots):
+    """Host (numpy) counterpart of C_analyzesimplex, src/chebpol.c:830-875, vectorised over the
+    simplices: the matrix [vertices; 1 ... 1] of every simplex LU-factorised with partial pivoting
+    (first largest pivot, multipliers scaled by the pivot's reciprocal, as LAPACK dgetrf does) and
+    the bounding boxes.  Returns (lumats, pivots, bbox) in the reference's layout."""
+    knots = np.asarray(knots, dtype=np.float64)
+    dtri = np.asarray(dtri)
+    dim, N, ns = knots.shape[0], knots.shape[0] + 1, dtri.shape[1]
+    V = knots[:, dtri - 1]  # dim x N x ns
+    M = np.ones((ns, N, N))
+    M[:, :dim, :] = V.transpose(2, 0, 1)  # row j, column v: coordinate j of vertex v; last row ones
+    bbox = np.empty((ns, 2 * dim))
+    bbox[:, 0::2] = V.min(axis=1).T
+    bbox[:, 1::2] = V.max(axis=1).T
+    piv = np.empty((ns, N), dtype=np.int32)
+    idx = np.arange(ns)
+    for j in range(N):
+        jp = np.argmax(np.abs(M[:, j:, j]), axis=1) + j
+        piv[:, j] = jp + 1
+        rj, rp = M[idx, j, :].copy(), M[idx, jp, :].copy()
+        M[idx, j, :], M[idx, jp, :] = rp, rj
+        if j < N - 1:
+            with np.errstate(divide="ignore", invalid="ignore"):
+                r = 1.0 / M[:, j, j]
+                M[:, j + 1:, j] *= r[:, None]
+                M[:, j + 1:, j + 1:] += M[:, j + 1:, j][:, :, None] * (-M[:, j, j + 1:])[:, None, :]
+    return np.ascontiguousarray(M.transpose(0, 2, 1)).reshape(-1), piv.reshape(-1), bbox.reshape(-1)
+
+
+def slappx(val, knots, fit: str = "device") -> Interpolant:
+    """slappx.real, R/simplexlinear.R:27-40: piecewise linear interpolation on the Delaunay
+    triangulation of scattered knots (dim x nknots matrix, one knot per column).  The
+    triangulation is qhull's, as in the reference (geometry::delaunayn(..., "Qt Pp") there,
+    scipy.spatial.Delaunay here); the per-simplex LU factors and bounding boxes
+    (C_analyzesimplex) are computed on the device."""
+    from scipy.spatial import Delaunay
+
+    knots = np.asarray(knots, dtype=np.float64)
+    if knots.ndim == 1:
+        knots = knots.reshape(1, -1)
+    dim, nk = knots.shape
+    if callable(val):
+        val = np.array([val(knots[:, i].copy()) for i in range(nk)], dtype=np.float64)
+    val = np.asarray(val, dtype=np.float64).ravel()
+    if val.size != nk:
+        raise ValueError(f"number of values ({val.size}) should equal number of knots ({nk})")
+    if dim == 1:  # qhull needs >= 2 dimensions: consecutive sorted knots are the 1-simplices
+        o = np.argsort(knots[0], kind="stable")
+        simplices = np.stack([o[:-1], o[1:]], axis=1)
+    else:
+        simplices = Delaunay(knots.T, qhull_options="Qt Pp").simplices
+    dtri = np.asfortranarray((simplices.T + 1).astype(np.int32))
+    adata = _lib.analyzesimplex(dtri, knots) if fit == "device" else analyzesimplex(dtri, knots)
+    return Interpolant("simplexlinear", dim, [(knots[d].min(), knots[d].max()) for d in range(dim)],
+                       knots=np.asfortranarray(knots), dtri=dtri, adata=adata, values=val)
+
+
 def _phifunc(d2: np.ndarray, k) -> np.ndarray:
     """R_phifunc, src/chebpol.c:886-921, on squared distances."""
     d2 = np.asarray(d2, dtype=np.float64)
@@ -660,7 +728,7 @@ def ucappxf(fun, dims, intervals=None) -> Interpolant:
 
 _METHODS = ["chebyshev", "multilinear", "fh", "uniform", "general", "polyharmonic", "simplexlinear",
             "hstalker", "stalker", "crbf", "oldstalker"]
-_ON_PATH = {"chebyshev", "multilinear", "fh", "uniform", "general", "polyharmonic", "stalker", "hstalker"}
+_ON_PATH = {"chebyshev", "multilinear", "fh", "uniform", "general", "polyharmonic", "simplexlinear", "stalker", "hstalker"}
 
 
 def ipol(val, dims=None, intervals=None, grid=None, knots=None, k=None, method="chebyshev", **kw) -> Interpolant:
@@ -682,6 +750,14 @@ def ipol(val, dims=None, intervals=None, grid=None, knots=None, k=None, method="
         if any(_unsorted(np.asarray(g, dtype=np.float64)) for g in grid):
             raise ValueError("grid must be distinct ordered values")
         return (hstalkerappx if method == "hstalker" else stalkerappx)(val, grid)
+    if method == "simplexlinear":  # R/ipol.R:131-142
+        if knots is None:
+            if grid is None:
+                raise ValueError("knots must be specified for simplex linear interpolation")
+            gl = [np.asarray(g, dtype=np.float64) for g in ([grid] if np.isscalar(grid[0]) else grid)]
+            mesh = np.meshgrid(*gl, indexing="ij")
+            knots = np.stack([m.ravel(order="F") for m in mesh])  # t(expand.grid(grid))
+        return slappx(val, knots, fit=kw.get("fit", "device"))
     if method == "general":  # R/ipol.R:161-168
         if grid is None:
             raise ValueError("grid must be specified for general interpolation")

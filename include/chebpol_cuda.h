@@ -138,6 +138,7 @@ CHEBPOL_CUDA_API int chebpol_cuda_plan_eval_host(chebpol_cuda_plan *plan, const 
 #define CHEBPOL_CUDA_OPT_BLEND 2       /* multilinear plans: blend 0..5                   */
 #define CHEBPOL_CUDA_OPT_CHUNK_POINTS 3 /* eval_host chunk size in points (0 = auto)      */
 #define CHEBPOL_CUDA_OPT_VARIANT 4     /* which fast kernel / layout (0 = auto), see below  */
+#define CHEBPOL_CUDA_OPT_EPOL 5        /* simplex-linear plans: extrapolate outside the hull */
 #define CHEBPOL_CUDA_GET_KERNEL_USED 101  /* kernel id of the most recent eval            */
 #define CHEBPOL_CUDA_GET_LAUNCHES 102     /* kernels launched by this plan so far         */
 #define CHEBPOL_CUDA_GET_TENSOR_BYTES 103 /* device bytes of the resident tensor          */
@@ -162,7 +163,8 @@ CHEBPOL_CUDA_API int chebpol_cuda_plan_eval_host(chebpol_cuda_plan *plan, const 
  *                     >= 20 cell-major kernel with WARPS*10 + STAGES
  *   FH plans          100000+c as for Chebyshev
  * CHEBPOL_CUDA_GET_KERNEL_USED: 10 cheb_strict, 11 cheb_slab (DFMA), 12 cheb_mma (DMMA),
- *   20 mlip_strict, 21 mlip_pair, 22 mlip_cell, 30 fh_strict, 32 fh_mma. */
+ *   20 mlip_strict, 21 mlip_pair, 22 mlip_cell, 30 fh_strict, 32 fh_mma, 40/41 polyh, 50/51 stalk,
+ *   60 sl_strict, 61 sl_cell. */
 CHEBPOL_CUDA_API int chebpol_cuda_plan_set(chebpol_cuda_plan *plan, int option, int64_t value);
 CHEBPOL_CUDA_API int chebpol_cuda_plan_get(chebpol_cuda_plan *plan, int what, int64_t *value);
 
@@ -211,6 +213,31 @@ CHEBPOL_CUDA_API int chebpol_cuda_plan_stalk(int kind, const double *val, const 
                                              const int *dims, int rank, const double *a, const double *b,
                                              const double *t1, const double *t2, int blend, int device,
                                              chebpol_cuda_plan **plan);
+
+/* ---- simplex-linear interpolation on a Delaunay triangulation -------------
+ * Replaces R_evalsl / findsimplex (src/chebpol.c:738-828), as called by the closure of
+ * slappx.real (R/simplexlinear.R:34-39), and the fit step R_analyzesimplex (:830-875).
+ * knots: dim x nknots R matrix (knot i at knots + i*dim); dtri: (dim+1) x numsimplex matrix of
+ * 1-based knot indices (t(geometry::delaunayn(...))); lumats (numsimplex x (dim+1)^2), pivots
+ * (numsimplex x (dim+1)) and bbox (2*dim x numsimplex) are the three elements of the list
+ * R_analyzesimplex returns; val: nknots values.  The result for a point is that of the FIRST
+ * simplex (index order) whose bounding box holds it and whose barycentric coordinates are all
+ * >= -1e-10, blended (0 linear .. 5 mean; the closure defaults to 3, cubic); outside the hull
+ * NA_real_, or with epol != 0 the barycentric extrapolation from the first simplex holding the
+ * nearest knot.  Both kernels (60 sl_strict: the reference's linear scan; 61 sl_cell: candidates
+ * from a uniform cell grid, dim <= 6) issue the reference's floating-point operations in the
+ * reference's order and are bit-identical to it.
+ * chebpol_cuda_analyzesimplex: LAPACK dgetrf semantics (first largest pivot, reciprocal-scaled
+ * multipliers), one GPU thread per simplex. */
+CHEBPOL_CUDA_API int chebpol_cuda_evalsl(const double *x, int64_t npts, const double *knots, int dim, int nknots,
+                                         const int *dtri, int numsimplex, const double *lumats, const int *pivots,
+                                         const double *bbox, const double *val, int epol, int blend, int ngpus,
+                                         double *out);
+CHEBPOL_CUDA_API int chebpol_cuda_plan_sl(const double *knots, int dim, int nknots, const int *dtri, int numsimplex,
+                                          const double *lumats, const int *pivots, const double *bbox,
+                                          const double *val, int device, chebpol_cuda_plan **plan);
+CHEBPOL_CUDA_API int chebpol_cuda_analyzesimplex(const int *dtri, int numsimplex, const double *knots, int dim,
+                                                 int nknots, int device, double *lumats, int *pivots, double *bbox);
 
 /* ---- evaluation on a tensor grid (evalongridV of an interpolant, R/tools.R:132-137) ----
  * The reference expands the grid (expand.grid) and evaluates point by point; here the

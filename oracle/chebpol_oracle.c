@@ -768,3 +768,153 @@ API void oracle_chebcoef(const double *val, const int *dims, int rank, double *F
         }
     }
 }
+
+/* ------------------------------------------------------------------------
+ * Simplex-linear interpolation on a Delaunay triangulation (slappx.real,
+ * R/simplexlinear.R:27-40).
+ *   analyzesimplex  R_analyzesimplex, src/chebpol.c:830-875: per simplex the matrix
+ *                   [vertices; 1 ... 1] (column v = vertex v, last row ones),
+ *                   LU-factorised by LAPACK dgetrf, and the bounding box;
+ *   evalsl          R_evalsl :803-828 over findsimplex :738-801: the FIRST simplex
+ *                   (index order) whose bounding box holds x and whose barycentric
+ *                   coordinates (dgetrs) are all >= -1e-10; blended weights
+ *                   (blendfun, src/chebpol.h:24-45) normalised by their sum; outside
+ *                   the hull NA, or with epol: the first simplex containing the
+ *                   nearest knot, plain barycentric combination.
+ * dgetrf/dgetrs are LAPACK (not under /root/reference); the published reference
+ * algorithm -- first-largest pivot, reciprocal-scaled multipliers, row-swapped
+ * right-hand side, unit-lower then upper substitution skipping zero entries -- is
+ * what lu_factor / lu_solve below issue, operation for operation.
+ * dtri: (dim+1) x numsimplex, 1-based knot indices; knots: dim x nknots.
+ * ------------------------------------------------------------------------ */
+static void lu_factor(int n, double *a, int *ipiv)
+{
+    for (int j = 0; j < n; ++j) {
+        int jp = j;
+        double mx = fabs(a[j + j * n]);
+        for (int i = j + 1; i < n; ++i)
+            if (fabs(a[i + j * n]) > mx) { mx = fabs(a[i + j * n]); jp = i; }
+        ipiv[j] = jp + 1;
+        if (a[jp + j * n] != 0.0) {
+            if (jp != j)
+                for (int c = 0; c < n; ++c) { const double t = a[j + c * n]; a[j + c * n] = a[jp + c * n]; a[jp + c * n] = t; }
+            if (j < n - 1) {
+                if (fabs(a[j + j * n]) >= DBL_MIN) {
+                    const double r = 1.0 / a[j + j * n];
+                    for (int i = j + 1; i < n; ++i) a[i + j * n] *= r;
+                } else
+                    for (int i = j + 1; i < n; ++i) a[i + j * n] /= a[j + j * n];
+            }
+        }
+        if (j < n - 1)
+            for (int c = j + 1; c < n; ++c) {
+                const double y = a[j + c * n];
+                if (y != 0.0) {
+                    const double t = -y;
+                    for (int i = j + 1; i < n; ++i) a[i + c * n] += a[i + j * n] * t;
+                }
+            }
+    }
+}
+
+static void lu_solve(int n, const double *a, const int *ipiv, double *b)
+{
+    for (int i = 0; i < n; ++i) {
+        const int ip = ipiv[i] - 1;
+        if (ip != i) { const double t = b[i]; b[i] = b[ip]; b[ip] = t; }
+    }
+    for (int k = 0; k < n; ++k)
+        if (b[k] != 0.0)
+            for (int i = k + 1; i < n; ++i) b[i] = b[i] - b[k] * a[i + k * n];
+    for (int k = n - 1; k >= 0; --k)
+        if (b[k] != 0.0) {
+            b[k] = b[k] / a[k + k * n];
+            for (int i = 0; i < k; ++i) b[i] = b[i] - b[k] * a[i + k * n];
+        }
+}
+
+API int oracle_analyzesimplex(const int *dtri, int numsimplex, const double *knots, int dim, int nknots,
+                              double *lumats, int *pivots, double *bbox)
+{
+    (void)nknots;
+    if (dim < 1 || dim >= ORACLE_MAXRANK) return 1;
+    const int N = dim + 1;
+    for (int s = 0; s < numsimplex; ++s) {
+        const int *tri = dtri + (int64_t)s * N;
+        double *lu = lumats + (int64_t)s * N * N, *m = bbox + (int64_t)s * 2 * dim;
+        for (int j = 0; j < dim; ++j) { m[2 * j] = 1e100; m[2 * j + 1] = -1e100; }
+        for (int v = 0; v < N; ++v) {
+            const double *knot = knots + (int64_t)(tri[v] - 1) * dim;
+            for (int j = 0; j < dim; ++j) {
+                lu[v * N + j] = knot[j];
+                if (knot[j] < m[2 * j]) m[2 * j] = knot[j];
+                if (knot[j] > m[2 * j + 1]) m[2 * j + 1] = knot[j];
+            }
+            lu[v * N + dim] = 1.0;
+        }
+        lu_factor(N, lu, pivots + (int64_t)s * N);
+    }
+    return 0;
+}
+
+static double sl_point(const double *x, const double *knots, const int *dtri, const double *lumats,
+                       const int *pivots, const double *bbox, int epol, const double *val, int dim,
+                       int numsimplex, int nknots, int blend)
+{
+    double vec[ORACLE_MAXRANK + 1];
+    const int N = dim + 1;
+    for (int s = 0; s < numsimplex; ++s) {
+        const double *box = bbox + (int64_t)s * 2 * dim;
+        int bad = 0;
+        for (int i = 0; i < dim; ++i)
+            if (x[i] < box[2 * i] || x[i] > box[2 * i + 1]) { bad = 1; break; }
+        if (bad) continue;
+        for (int d = 0; d < dim; ++d) vec[d] = x[d];
+        vec[dim] = 1.0;
+        lu_solve(N, lumats + (int64_t)s * N * N, pivots + (int64_t)s * N, vec);
+        for (int d = 0; d < N; ++d)
+            if (vec[d] < -1e-10) { bad = 1; break; }
+        if (bad) continue;
+        const int *tri = dtri + (int64_t)s * N;
+        double sum = 0.0, wsum = 0.0;
+        for (int d = 0; d < N; ++d) {
+            const double w = blend_weight(vec[d], blend);
+            wsum += w;
+            sum += w * val[tri[d] - 1];
+        }
+        return sum / wsum;
+    }
+    if (epol) {
+        double mindist = 1e99;
+        int near = 0;
+        for (int k = 0; k < nknots; ++k) {
+            double dist = 0.0;
+            for (int i = 0; i < dim; ++i) dist += (x[i] - knots[(int64_t)k * dim + i]) * (x[i] - knots[(int64_t)k * dim + i]);
+            if (dist < mindist) { mindist = dist; near = k; }
+        }
+        int nearest = -1;
+        for (int s = 0; s < numsimplex && nearest < 0; ++s)
+            for (int j = 0; j < N; ++j)
+                if (dtri[(int64_t)s * N + j] == near + 1) { nearest = s; break; }
+        if (nearest < 0) return oracle_na_real();
+        for (int d = 0; d < dim; ++d) vec[d] = x[d];
+        vec[dim] = 1.0;
+        lu_solve(N, lumats + (int64_t)nearest * N * N, pivots + (int64_t)nearest * N, vec);
+        const int *tri = dtri + (int64_t)nearest * N;
+        double sum = 0.0;
+        for (int d = 0; d <= dim; ++d) sum += vec[d] * val[tri[d] - 1];
+        return sum;
+    }
+    return oracle_na_real();
+}
+
+API int oracle_evalsl(const double *x, int64_t npts, const double *knots, int dim, int nknots, const int *dtri,
+                      int numsimplex, const double *lumats, const int *pivots, const double *bbox,
+                      const double *val, int epol, int threads, int blend, double *out)
+{
+    if (dim < 1 || dim >= ORACLE_MAXRANK) return 1;
+#pragma omp parallel for num_threads(threads) schedule(guided) if (npts > 1 && threads > 1)
+    for (int64_t i = 0; i < npts; ++i)
+        out[i] = sl_point(x + i * dim, knots, dtri, lumats, pivots, bbox, epol, val, dim, numsimplex, nknots, blend);
+    return 0;
+}

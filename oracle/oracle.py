@@ -273,6 +273,41 @@ class Oracle:
           c.ctypes.data_as(_dp), d.ctypes.data_as(_dp), threads, _ptr(out))
         return out
 
+    # -- simplex-linear on a Delaunay triangulation -----------------------------
+    def analyzesimplex(self, dtri, knots):
+        """dtri: (dim+1) x numsimplex 1-based knot indices; knots: dim x nknots.
+        Returns (lumats, pivots, bbox) as R_analyzesimplex lays them out."""
+        knots = np.asfortranarray(knots, dtype=np.float64)
+        dtri = np.asfortranarray(dtri, dtype=np.int32)
+        dim, nk = knots.shape
+        N, ns = dtri.shape
+        assert N == dim + 1
+        lu = np.empty(ns * N * N)
+        piv = np.empty(ns * N, dtype=np.int32)
+        bbox = np.empty(ns * 2 * dim)
+        f = getattr(self.lib, self.pfx + "analyzesimplex")
+        f.restype = None if self.kind == "reference" else C.c_int
+        f.argtypes = [_ip, C.c_int, _dp, C.c_int, C.c_int, _dp, _ip, _dp]
+        f(dtri.ctypes.data_as(_ip), ns, knots.ctypes.data_as(_dp), dim, nk, _ptr(lu), piv.ctypes.data_as(_ip), _ptr(bbox))
+        return lu, piv, bbox
+
+    def evalsl(self, x, knots, dtri, adata, val, epol: bool = False, blend: int = 3, threads: int = 1):
+        knots = np.asfortranarray(knots, dtype=np.float64)
+        dtri = np.asfortranarray(dtri, dtype=np.int32)
+        dim, nk = knots.shape
+        ns = dtri.shape[1]
+        lu, piv, bbox = adata
+        val = np.ascontiguousarray(val, dtype=np.float64)
+        assert val.size == nk
+        x = _as_pts(x, dim)
+        out = np.empty(x.shape[0], dtype=np.float64)
+        f = getattr(self.lib, self.pfx + "evalsl")
+        f.restype = None if self.kind == "reference" else C.c_int
+        f.argtypes = [_dp, C.c_int64, _dp, C.c_int, C.c_int, _ip, C.c_int, _dp, _ip, _dp, _dp, C.c_int, C.c_int, C.c_int, _dp]
+        f(_ptr(x), x.shape[0], knots.ctypes.data_as(_dp), dim, nk, dtri.ctypes.data_as(_ip), ns, _ptr(lu),
+          piv.ctypes.data_as(_ip), _ptr(bbox), _ptr(val), int(bool(epol)), threads, blend, _ptr(out))
+        return out
+
     # -- fit side (fixtures) -------------------------------------------------
     def fhweights(self, grid, d):
         d = np.broadcast_to(np.asarray(d, dtype=np.int64), (len(grid),))

@@ -11,8 +11,10 @@
  * (src/chebpol.c:375-378, :701-704, :259-262) with 64-bit point indices
  * (the reference's `int i`, `i*rank` overflow once P*K >= 2^31).
  *
- * Everything the R API would provide is a stub that aborts when executed:
- * the numeric kernels never call into R.
+ * The R API is a set of stubs that abort when executed -- the numeric kernels never call
+ * into R -- except for a minimal working vector object (REAL/INTEGER/nrows/ncols/VECTOR_ELT/
+ * allocVector ...) that lets the two simplex-linear wrappers at the end run the reference's
+ * real .Call entry points, and the LAPACK/BLAS routines restated below.
  */
 #include <stdio.h>
 #include <stdarg.h>
@@ -31,28 +33,49 @@ double R_NaReal;
 __attribute__((constructor)) static void shim_init_na(void) {
   union { double d; unsigned long long u; } v; v.u = 0x7FF00000000007A2ULL; R_NaReal = v.d;
 }
-double *REAL(SEXP s) { (void)s; SHIM_DIE("REAL"); }
-int *INTEGER(SEXP s) { (void)s; SHIM_DIE("INTEGER"); }
-int *LOGICAL(SEXP s) { (void)s; SHIM_DIE("LOGICAL"); }
-int LENGTH(SEXP s) { (void)s; SHIM_DIE("LENGTH"); }
-R_xlen_t XLENGTH(SEXP s) { (void)s; SHIM_DIE("XLENGTH"); }
-int Rf_length(SEXP s) { (void)s; SHIM_DIE("length"); }
+/* A minimal working vector object, used ONLY by the two simplex-linear wrappers at the end of
+ * this file, which run the reference's real .Call entry points R_analyzesimplex / R_evalsl
+ * (src/chebpol.c:803-875): type, length, matrix shape and a data pointer (borrowed from the
+ * caller or owned).  Every other wrapper passes plain C pointers to the static kernels and
+ * never reaches these accessors. */
+struct shim_sexprec { unsigned int type; R_xlen_t len; int nrow, ncol; void *data; int owned; };
+static SEXP shim_wrap(unsigned int type, R_xlen_t len, int nrow, int ncol, void *data) {
+  SEXP s = calloc(1, sizeof *s); s->type = type; s->len = len; s->nrow = nrow; s->ncol = ncol; s->data = data; return s;
+}
+static void shim_free(SEXP s) {
+  if (!s) return;
+  if (s->type == VECSXP && s->data) for (R_xlen_t i = 0; i < s->len; i++) shim_free(((SEXP *)s->data)[i]);
+  if (s->owned) free(s->data);
+  free(s);
+}
+double *REAL(SEXP s) { if (!s || s->type != REALSXP) SHIM_DIE("REAL"); return s->data; }
+int *INTEGER(SEXP s) { if (!s || s->type != INTSXP) SHIM_DIE("INTEGER"); return s->data; }
+int *LOGICAL(SEXP s) { if (!s || s->type != LGLSXP) SHIM_DIE("LOGICAL"); return s->data; }
+int LENGTH(SEXP s) { if (!s) SHIM_DIE("LENGTH"); return (int)s->len; }
+R_xlen_t XLENGTH(SEXP s) { if (!s) SHIM_DIE("XLENGTH"); return s->len; }
+int Rf_length(SEXP s) { if (!s) SHIM_DIE("length"); return (int)s->len; }
 SEXP Rf_getAttrib(SEXP a, SEXP b) { (void)a; (void)b; SHIM_DIE("getAttrib"); }
 SEXP Rf_setAttrib(SEXP a, SEXP b, SEXP c) { (void)a; (void)b; (void)c; SHIM_DIE("setAttrib"); }
-int Rf_isNull(SEXP s) { (void)s; SHIM_DIE("isNull"); }
+int Rf_isNull(SEXP s) { return s == NULL; } /* R_NilValue is the NULL pointer here */
 int Rf_isLogical(SEXP s) { (void)s; SHIM_DIE("isLogical"); }
 int Rf_isMatrix(SEXP s) { (void)s; SHIM_DIE("isMatrix"); }
 int Rf_isFunction(SEXP s) { (void)s; SHIM_DIE("isFunction"); }
 int Rf_isReal(SEXP s) { (void)s; SHIM_DIE("isReal"); }
-int Rf_nrows(SEXP s) { (void)s; SHIM_DIE("nrows"); }
-int Rf_ncols(SEXP s) { (void)s; SHIM_DIE("ncols"); }
-SEXP Rf_protect(SEXP s) { (void)s; SHIM_DIE("PROTECT"); }
-void Rf_unprotect(int n) { (void)n; SHIM_DIE("UNPROTECT"); }
-SEXP Rf_allocVector(unsigned int t, R_xlen_t n) { (void)t; (void)n; SHIM_DIE("allocVector"); }
-SEXP Rf_allocMatrix(unsigned int t, int a, int b) { (void)t; (void)a; (void)b; SHIM_DIE("allocMatrix"); }
-SEXP VECTOR_ELT(SEXP s, R_xlen_t i) { (void)s; (void)i; SHIM_DIE("VECTOR_ELT"); }
-SEXP SET_VECTOR_ELT(SEXP s, R_xlen_t i, SEXP v) { (void)s; (void)i; (void)v; SHIM_DIE("SET_VECTOR_ELT"); }
-SEXP Rf_coerceVector(SEXP s, unsigned int t) { (void)s; (void)t; SHIM_DIE("coerceVector"); }
+int Rf_nrows(SEXP s) { if (!s || s->nrow < 0) SHIM_DIE("nrows"); return s->nrow; }
+int Rf_ncols(SEXP s) { if (!s || s->ncol < 0) SHIM_DIE("ncols"); return s->ncol; }
+SEXP Rf_protect(SEXP s) { return s; }
+void Rf_unprotect(int n) { (void)n; }
+SEXP Rf_allocVector(unsigned int t, R_xlen_t n) {
+  size_t el = (t == REALSXP) ? sizeof(double) : (t == VECSXP) ? sizeof(SEXP) : sizeof(int);
+  SEXP s = shim_wrap(t, n, -1, -1, calloc(n > 0 ? n : 1, el)); s->owned = 1; return s;
+}
+SEXP Rf_allocMatrix(unsigned int t, int a, int b) {
+  SEXP s = Rf_allocVector(t, (R_xlen_t)a * b); s->nrow = a; s->ncol = b; return s;
+}
+SEXP VECTOR_ELT(SEXP s, R_xlen_t i) { if (!s || s->type != VECSXP || i >= s->len) SHIM_DIE("VECTOR_ELT"); return ((SEXP *)s->data)[i]; }
+SEXP SET_VECTOR_ELT(SEXP s, R_xlen_t i, SEXP v) { if (!s || s->type != VECSXP || i >= s->len) SHIM_DIE("SET_VECTOR_ELT"); ((SEXP *)s->data)[i] = v; return v; }
+/* AS_INTEGER / AS_LOGICAL of an object that already has the type: the object itself */
+SEXP Rf_coerceVector(SEXP s, unsigned int t) { if (!s || s->type != t) SHIM_DIE("coerceVector"); return s; }
 SEXP Rf_eval(SEXP a, SEXP b) { (void)a; (void)b; SHIM_DIE("eval"); }
 SEXP Rf_lang2(SEXP a, SEXP b) { (void)a; (void)b; SHIM_DIE("lang2"); }
 SEXP SETCADR(SEXP a, SEXP b) { (void)a; (void)b; SHIM_DIE("SETCADR"); }
@@ -89,10 +112,47 @@ int findInterval(double *xt, int n, double x, Rboolean rightmost_closed, Rboolea
   if (lo > n - 1) lo = n - 1;
   return lo;
 }
-void dgetrf_(const int *a, const int *b, double *c, const int *d, int *e, int *f)
-{ (void)a;(void)b;(void)c;(void)d;(void)e;(void)f; SHIM_DIE("dgetrf"); }
-void dgetrs_(const char *t, const int *a, const int *b, const double *c, const int *d, const int *e, double *f, const int *g, int *h)
-{ (void)t;(void)a;(void)b;(void)c;(void)d;(void)e;(void)f;(void)g;(void)h; SHIM_DIE("dgetrs"); }
+/* LAPACK dgetrf / dgetrs (and the BLAS they call) are not vendored under /root/reference and no
+ * LAPACK is installed here.  Restated from the published reference (netlib) algorithm: partial
+ * pivoting with the first largest |a| (idamax), row interchange, the multipliers scaled by the
+ * reciprocal of the pivot (dgetf2 / dgetrf2: dscal by 1/pivot when |pivot| >= sfmin), rank-one
+ * update of the trailing block (dger); dgetrs 'N': dlaswp, unit-lower then upper dtrsm, each
+ * skipping zero right-hand-side entries.  The recursive dgetrf2 of LAPACK >= 3.6 performs the
+ * same elementary operations on every entry in the same order, so it rounds identically. */
+void dgetrf_(const int *M, const int *N, double *A, const int *lda, int *ipiv, int *info)
+{
+  const int m = *M, n = *N, ld = *lda, mn = m < n ? m : n;
+  *info = 0;
+  for (int j = 0; j < mn; j++) {
+    int jp = j; double mx = fabs(A[j + (size_t)j * ld]);
+    for (int i = j + 1; i < m; i++) { const double v = fabs(A[i + (size_t)j * ld]); if (v > mx) { mx = v; jp = i; } }
+    ipiv[j] = jp + 1;
+    if (A[jp + (size_t)j * ld] != 0.0) {
+      if (jp != j) for (int c = 0; c < n; c++) { double t = A[j + (size_t)c * ld]; A[j + (size_t)c * ld] = A[jp + (size_t)c * ld]; A[jp + (size_t)c * ld] = t; }
+      if (j < m - 1) {
+        if (fabs(A[j + (size_t)j * ld]) >= DBL_MIN) { const double r = 1.0 / A[j + (size_t)j * ld]; for (int i = j + 1; i < m; i++) A[i + (size_t)j * ld] *= r; }
+        else for (int i = j + 1; i < m; i++) A[i + (size_t)j * ld] /= A[j + (size_t)j * ld];
+      }
+    } else if (*info == 0) *info = j + 1;
+    if (j < mn - 1)
+      for (int c = j + 1; c < n; c++) {
+        const double y = A[j + (size_t)c * ld];
+        if (y != 0.0) { const double t = -y; for (int i = j + 1; i < m; i++) A[i + (size_t)c * ld] += A[i + (size_t)j * ld] * t; }
+      }
+  }
+}
+void dgetrs_(const char *tr, const int *N, const int *nrhs, const double *A, const int *lda, const int *ipiv, double *B, const int *ldb, int *info)
+{
+  const int n = *N, ld = *lda;
+  if (tr[0] != 'N') SHIM_DIE("dgetrs (trans != N)");
+  *info = 0;
+  for (int r = 0; r < *nrhs; r++) {
+    double *b = B + (size_t)r * *ldb;
+    for (int i = 0; i < n; i++) { const int ip = ipiv[i] - 1; if (ip != i) { double t = b[i]; b[i] = b[ip]; b[ip] = t; } }
+    for (int k = 0; k < n; k++) if (b[k] != 0.0) for (int i = k + 1; i < n; i++) b[i] = b[i] - b[k] * A[i + (size_t)k * ld];
+    for (int k = n - 1; k >= 0; k--) if (b[k] != 0.0) { b[k] = b[k] / A[k + (size_t)k * ld]; for (int i = 0; i < k; i++) b[i] = b[i] - b[k] * A[i + (size_t)k * ld]; }
+  }
+}
 
 /* ---- the three non-stub services chebcoef's matrix path needs ---- */
 /* R_alloc: transient storage R frees at .Call exit; here a small arena the
@@ -216,3 +276,46 @@ EXPORT void ref_fhweights(int nknots, const double *grid, int d, double *w) {
 
 EXPORT double ref_blendfun(double w, int blend) { return blendfun(w, blend); }
 EXPORT int ref_binsearch(int n, const double *arr, double val) { return binsearch(n, (double *)arr, val); }
+
+/* Simplex-linear interpolation (slappx.real, R/simplexlinear.R): the reference's real .Call
+ * entry points, R_analyzesimplex (src/chebpol.c:830-875) and R_evalsl (:803-828) over
+ * findsimplex (:738-801), run on caller buffers wrapped as vector objects.  dtri is the
+ * (dim+1) x numsimplex matrix of 1-based knot indices, knots dim x nknots.  R_evalsl indexes
+ * points with `int`, so the batch is passed in chunks. */
+EXPORT void ref_analyzesimplex(const int *dtri, int numsimplex, const double *knots, int dim, int nknots,
+                               double *lumats, int *pivots, double *bbox) {
+  int one = 1;
+  SEXP Sd = shim_wrap(INTSXP, (R_xlen_t)(dim + 1) * numsimplex, dim + 1, numsimplex, (void *)dtri);
+  SEXP Sk = shim_wrap(REALSXP, (R_xlen_t)dim * nknots, dim, nknots, (void *)knots);
+  SEXP St = shim_wrap(INTSXP, 1, -1, -1, &one);
+  SEXP res = R_analyzesimplex(Sd, Sk, St);
+  const int N = dim + 1;
+  memcpy(lumats, REAL(VECTOR_ELT(res, 0)), sizeof(double) * (size_t)numsimplex * N * N);
+  memcpy(pivots, INTEGER(VECTOR_ELT(res, 1)), sizeof(int) * (size_t)numsimplex * N);
+  memcpy(bbox, REAL(VECTOR_ELT(res, 2)), sizeof(double) * (size_t)numsimplex * 2 * dim);
+  shim_free(res); shim_free(Sd); shim_free(Sk); shim_free(St);
+}
+EXPORT void ref_evalsl(const double *x, int64_t npts, const double *knots, int dim, int nknots, const int *dtri,
+                       int numsimplex, const double *lumats, const int *pivots, const double *bbox,
+                       const double *val, int epol, int threads, int blend, double *out) {
+  const int N = dim + 1;
+  SEXP Sk = shim_wrap(REALSXP, (R_xlen_t)dim * nknots, dim, nknots, (void *)knots);
+  SEXP Sd = shim_wrap(INTSXP, (R_xlen_t)N * numsimplex, N, numsimplex, (void *)dtri);
+  SEXP ad = Rf_allocVector(VECSXP, 3);
+  SET_VECTOR_ELT(ad, 0, shim_wrap(REALSXP, (R_xlen_t)numsimplex * N * N, -1, -1, (void *)lumats));
+  SET_VECTOR_ELT(ad, 1, shim_wrap(INTSXP, (R_xlen_t)numsimplex * N, -1, -1, (void *)pivots));
+  SET_VECTOR_ELT(ad, 2, shim_wrap(REALSXP, (R_xlen_t)numsimplex * 2 * dim, 2 * dim, numsimplex, (void *)bbox));
+  SEXP Sv = shim_wrap(REALSXP, nknots, -1, -1, (void *)val);
+  SEXP Se = shim_wrap(LGLSXP, 1, -1, -1, &epol);
+  SEXP St = shim_wrap(INTSXP, 1, -1, -1, &threads);
+  SEXP Sb = shim_wrap(INTSXP, 1, -1, -1, &blend);
+  const int64_t chunk = 1 << 24;
+  for (int64_t lo = 0; lo < npts; lo += chunk) {
+    const int64_t n = (npts - lo < chunk) ? npts - lo : chunk;
+    SEXP Sx = shim_wrap(REALSXP, (R_xlen_t)dim * n, dim, (int)n, (void *)(x + lo * dim));
+    SEXP r = R_evalsl(Sx, Sk, Sd, ad, Sv, Se, St, Sb);
+    memcpy(out + lo, REAL(r), sizeof(double) * (size_t)n);
+    shim_free(r); shim_free(Sx);
+  }
+  shim_free(ad); shim_free(Sk); shim_free(Sd); shim_free(Sv); shim_free(Se); shim_free(St); shim_free(Sb);
+}

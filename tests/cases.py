@@ -75,3 +75,20 @@ def polyh_case(rank, nknots, k=3, seed=45):
     knots = rng.uniform(-1.0, 1.0, (rank, nknots))
     ip = interp.polyh(lambda x: float(gfun(np.asarray(x).reshape(1, -1))[0]), knots, k=k, normalize=False)
     return ip.t["knots"], ip.t["weights"], ip.t["lweights"]
+
+
+def sl_case(dim, nknots, seed=46):
+    """Scattered knots in [-1,1]^dim, their Delaunay triangulation (qhull "Qt Pp", as
+    R/simplexlinear.R:30) and the values of gfun on them: (knots dim x nknots, dtri (dim+1) x ns
+    1-based int32, values)."""
+    from scipy.spatial import Delaunay
+
+    rng = np.random.default_rng(seed)
+    knots = np.asfortranarray(rng.uniform(-1.0, 1.0, (dim, nknots)))
+    if dim == 1:
+        o = np.argsort(knots[0], kind="stable")
+        simplices = np.stack([o[:-1], o[1:]], axis=1)
+    else:
+        simplices = Delaunay(knots.T, qhull_options="Qt Pp").simplices
+    dtri = np.asfortranarray((simplices.T + 1).astype(np.int32))
+    return knots, dtri, gfun(knots.T)

@@ -122,7 +122,12 @@ def test_ipol_front_end_checks():
     with pytest.raises(ValueError):
         cb.ipol(np.zeros(3), grid=[np.array([0.0, 2.0, 1.0])], method="fh")  # unsorted
     with pytest.raises(NotImplementedError):
-        cb.ipol(np.zeros(4), grid=[np.linspace(0, 1, 4)], method="simplexlinear")  # outside the GPU path
+        cb.ipol(np.zeros(4), grid=[np.linspace(0, 1, 4)], method="crbf")  # disabled in the reference too
+    with pytest.raises(ValueError):
+        cb.ipol(np.zeros(4), method="simplexlinear")  # knots must be specified
+    sl = cb.ipol(lambda x: float(np.sum(x)), knots=np.random.default_rng(0).uniform(0, 1, (2, 30)),
+                 method="simplexlinear", fit="host")
+    assert sl.kind == "simplexlinear" and sl.arity == 2 and sl.t["dtri"].shape[0] == 3 and len(sl.t["adata"]) == 3
     with pytest.raises(ValueError):
         cb.ipol(np.zeros(4), method="hstalker")  # grid must be specified
     hs = cb.ipol(lambda x: float(np.sum(x ** 2)), grid=[np.linspace(0, 1, 5)] * 2, method="hstalker")

@@ -1098,3 +1098,101 @@ def test_general_goldens_through_ipol(gpu_ok):
         t = ch.t["splines"]
         bad = [(t[0][0][::-1].copy(),) + tuple(t[0][1:])] + list(t[1:])
         _lib.Plan.chebg(ch.t["coef"], bad)
+
+
+# ------------------------------------------------- simplex-linear (slappx)
+def nan_aware_bits_equal(got, want):
+    """Bit-identical, NaN payloads included (NA_real_ outside the hull)."""
+    return np.array_equal(bits(got), bits(want))
+
+
+@pytest.mark.parametrize("dim,nk", [(1, 50), (2, 400), (3, 1000), (4, 200), (5, 60), (6, 30), (7, 20)])
+def test_simplexlinear_strict_and_cell(gpu_ok, port, dim, nk):
+    """R_evalsl (src/chebpol.c:738-828): both kernels issue the reference's operations in its order, so
+    both must be BIT-IDENTICAL to the oracle: every blend, with / without extrapolation, points
+    outside the hull (NA_real_ payload included), exact knot hits, NaN coordinates."""
+    knots, dtri, val = cases.sl_case(dim, nk)
+    ad = port.analyzesimplex(dtri, knots)
+    got_ad = _lib.analyzesimplex(dtri, knots)  # the fit step on the device
+    assert all(np.array_equal(u, v) for u, v in zip(ad, got_ad))
+    x = cases.points(30011, dim, lo=-1.1, hi=1.1)
+    x[:nk] = knots.T
+    x[nk, 0] = np.nan
+    x[nk + 1, dim - 1] = np.nan
+    plan = _lib.Plan.sl(knots, dtri, ad, val)
+    for epol in (0, 1):
+        plan.set(_lib.OPT_EPOL, epol)
+        for blend in range(6):
+            plan.set(_lib.OPT_BLEND, blend)
+            want = port.evalsl(x, knots, dtri, ad, val, epol, blend, threads=4)
+            got, k = eval_plan(plan, x, _lib.KERNEL_STRICT)
+            assert k == "sl_strict"
+            libm = blend in (1, 2)  # device exp vs libm exp
+            if libm:
+                assert np.array_equal(np.isnan(got), np.isnan(want))
+                f = np.isfinite(want)
+                assert np.abs(got[f] - want[f]).max() <= 1e-14 * np.abs(want[f]).max()
+            else:
+                assert nan_aware_bits_equal(got, want), (epol, blend)
+            if dim <= 6:
+                got2, k = eval_plan(plan, x, _lib.KERNEL_AUTO)
+                assert k == "sl_cell"
+                assert nan_aware_bits_equal(got2, got), (epol, blend)  # the two kernels agree bit for bit
+    if dim > 6:
+        got, k = eval_plan(plan, x, _lib.KERNEL_AUTO)
+        assert k == "sl_strict"
+        with pytest.raises(cb.ChebpolCudaError):
+            eval_plan(plan, x, _lib.KERNEL_FAST)
+    plan.close()
+
+
+def test_simplexlinear_cell_resolutions_and_stateless(gpu_ok, port, monkeypatch):
+    """The candidate lists give the reference's answer at any grid resolution (1 cell = the plain
+    scan ... much finer than the simplices), and the stateless entry point, sharded over all GPUs,
+    equals the plan path."""
+    knots, dtri, val = cases.sl_case(3, 800, seed=9)
+    ad = port.analyzesimplex(dtri, knots)
+    x = cases.points(200000, 3, lo=-1.05, hi=1.05, seed=2)
+    want = port.evalsl(x, knots, dtri, ad, val, True, 3, threads=8)
+    for cells in ("1", "2", "7", "64", "0"):
+        monkeypatch.setenv("CHEBPOL_CUDA_SL_CELLS", cells)
+        plan = _lib.Plan.sl(knots, dtri, ad, val)
+        plan.set(_lib.OPT_EPOL, 1)
+        got, k = eval_plan(plan, x, _lib.KERNEL_AUTO)
+        assert k == "sl_cell" and nan_aware_bits_equal(got, want), cells
+        plan.close()
+    monkeypatch.delenv("CHEBPOL_CUDA_SL_CELLS")
+    got = _lib.evalsl(x, knots, dtri, ad, val, True, 3, 0)
+    assert nan_aware_bits_equal(got, want)
+    got = _lib.evalsl(x, knots, dtri, ad, val, False, 0, 1)  # per-call blend / epol on a cached plan
+    assert nan_aware_bits_equal(got, port.evalsl(x, knots, dtri, ad, val, False, 0, threads=8))
+    # empty batch, single point, empty triangulation
+    assert _lib.evalsl(np.empty((0, 3)), knots, dtri, ad, val).shape == (0,)
+    one = _lib.evalsl(x[:1], knots, dtri, ad, val, True, 3)
+    assert nan_aware_bits_equal(one, want[:1])
+    with pytest.raises(cb.ChebpolCudaError):
+        bad = dtri.copy()
+        bad[0, 0] = 0
+        _lib.Plan.sl(knots, bad, ad, val)
+
+
+def test_simplexlinear_goldens_through_ipol(gpu_ok):
+    """chebpol-Ex.Rout.save:469,482-486, row 'sl': ipol(f, knots=knots, method='simplexlinear') at the
+    seven points of the example (set.seed(1) stream), default blend 'cubic'."""
+    from r_rng import RRng
+
+    f = lambda x: 10.0 / (1.0 + 25.0 * np.mean(np.asarray(x) ** 2))
+    r = RRng(1)
+    knots = r.runif(3000).reshape((3, 1000), order="F")
+    m = r.runif(21).reshape((3, 7), order="F")
+    sl = cb.ipol(f, knots=knots, method="simplexlinear")
+    want = [1.186031, 0.6786952, 1.550582, 0.9776420, 0.5247542, 1.478330, 0.7961787]
+    for kern in (_lib.KERNEL_AUTO, _lib.KERNEL_STRICT):
+        sl.kernel = kern
+        assert np.allclose(sl(m), want, rtol=6e-7)
+    assert np.isnan(sl(np.array([2.0, 2.0, 2.0]))[0]) and np.isfinite(sl(np.array([2.0, 2.0, 2.0]), epol=True)[0])
+    lin = sl(m, blend="linear")
+    assert np.all(np.abs(lin - want) < 0.05) and not np.allclose(lin, want, rtol=1e-9)
+    G = cb.evalongridV(sl, grid=[np.linspace(0.2, 0.8, 4)] * 3)
+    assert G.shape == (4, 4, 4) and np.isfinite(G).all()
+    sl.close()
