@@ -964,7 +964,7 @@ static int launch_plan(chebpol_cuda_plan *p, const double *d_x, int64_t npts, do
             e = launch_stalk_strict(a, s, &li);
         }
     } else if (p->kind == PLAN_SL) {
-        e = launch_sl(p->sl, p->kernel_opt, p->epol, p->blend, d_x, npts, d_out, p->num_sms, s, &li);
+        e = launch_sl(p->sl, p->kernel_opt, p->variant, p->epol, p->blend, d_x, npts, d_out, p->num_sms, s, &li);
         if (e == cudaErrorNotSupported)
             return fail(CHEBPOL_CUDA_EINVAL, "no cell-list kernel for %d-dimensional simplices", p->rank);
     } else {

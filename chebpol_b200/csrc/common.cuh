@@ -257,7 +257,7 @@ cudaError_t sl_create(const double *knots, int dim, int nknots, const int *dtri,
                       const int *pivots, const double *bbox, const double *val, int cells_per_dim, SlDevice **out);
 void sl_destroy(SlDevice *d);
 int64_t sl_bytes(const SlDevice *d);
-cudaError_t launch_sl(const SlDevice *d, int kernel, int epol, int blend, const double *x, int64_t npts, double *out,
-                      int num_sms, cudaStream_t s, LaunchInfo *li);
+cudaError_t launch_sl(SlDevice *d, int kernel, int variant, int epol, int blend, const double *x, int64_t npts,
+                      double *out, int num_sms, cudaStream_t s, LaunchInfo *li);
 cudaError_t sl_analyze_device(const int *d_dtri, int ns, const double *d_knots, int dim, double *d_lumats,
                               int *d_pivots, double *d_bbox, cudaStream_t s);

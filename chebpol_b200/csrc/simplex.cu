@@ -38,7 +38,10 @@ struct SlDevice {
     int G[SL_MAXCELLDIM] = {0};
     double lo[SL_MAXCELLDIM] = {0}, inv[SL_MAXCELLDIM] = {0};
     double glo[CP_MAXR] = {0}, ghi[CP_MAXR] = {0};  // bounding box of all simplices
-    int64_t bytes = 0, nitems = 0;
+    int64_t bytes = 0, nitems = 0, ncells = 0, cell_bytes = 0;
+    int forced_G = 0;
+    // host copies kept for (re)building the cell lists
+    std::vector<double> h_bbox, h_aff, h_tol;
 };
 
 struct SlArgs {
@@ -209,14 +212,21 @@ __global__ void __launch_bounds__(256) sl_strict_kernel(const __grid_constant__ 
 // record of simplex s at records + s*rs: [box lo/hi interleaved (2 DIM) | LU (N*N, column-major) |
 // vertex values (N) | row permutation (low 32 bits of one slot)]
 template <int DIM>
-__device__ __forceinline__ bool sl_try(const double *__restrict__ rec, const double (&x)[DIM], int blend, double *res)
+__device__ __forceinline__ bool sl_box(const double *__restrict__ rec, const double (&x)[DIM])
 {
-    constexpr int N = DIM + 1;
+    bool in = true;
 #pragma unroll
     for (int i = 0; i < DIM; ++i) {
         const double2 bx = __ldg(reinterpret_cast<const double2 *>(rec) + i);
-        if (x[i] < bx.x || x[i] > bx.y) return false;
+        in &= !(x[i] < bx.x || x[i] > bx.y);
     }
+    return in;
+}
+
+template <int DIM>
+__device__ __forceinline__ bool sl_accept(const double *__restrict__ rec, const double (&x)[DIM], int blend, double *res)
+{
+    constexpr int N = DIM + 1;
     double lu[N * N];
 #pragma unroll
     for (int i = 0; i < N * N; ++i) lu[i] = __ldg(rec + 2 * DIM + i);
@@ -238,8 +248,10 @@ __device__ __forceinline__ bool sl_try(const double *__restrict__ rec, const dou
     return true;
 }
 
-template <int DIM>
-__global__ void __launch_bounds__(128) sl_cell_kernel(const __grid_constant__ SlArgs a)
+// SL_BATCH candidates are box-tested together, so their loads are in flight at the same time; the
+// ones that pass are then solved in index order, which keeps "first accepted" the reference's
+template <int DIM, int SL_BATCH, int MINB>
+__global__ void __launch_bounds__(128, MINB) sl_cell_kernel(const __grid_constant__ SlArgs a)
 {
     for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < a.npts; p += (int64_t)gridDim.x * blockDim.x) {
         double x[DIM];
@@ -252,17 +264,35 @@ __global__ void __launch_bounds__(128) sl_cell_kernel(const __grid_constant__ Sl
         double res = 0.0;
         bool found = false;
         if (nan) {
-            // a NaN coordinate passes every box test of the reference; the scan is the reference's
-            // own, restricted to the finite coordinates, so fall back to it for this rare point
-            for (int s = 0; s < a.ns && !found; ++s) found = sl_try<DIM>(a.records + (int64_t)s * a.rs, x, a.blend, &res);
+            // a NaN coordinate passes every box test of the reference (comparisons are false), so its
+            // scan is over all simplices, restricted by the finite coordinates: do exactly that
+            for (int s = 0; s < a.ns && !found; ++s) {
+                const double *rec = a.records + (int64_t)s * a.rs;
+                if (sl_box<DIM>(rec, x)) found = sl_accept<DIM>(rec, x, a.blend, &res);
+            }
         } else {
             int cell = 0;
 #pragma unroll
             for (int d = DIM - 1; d >= 0; --d) cell = cell * a.G[d] + sl_cell_of(x[d], a.lo[d], a.inv[d], a.G[d]);
             const int beg = __ldg(a.cell_start + cell), end = __ldg(a.cell_start + cell + 1);
-            for (int it = beg; it < end && !found; ++it) {
-                const int s = __ldg(a.cell_items + it);
-                found = sl_try<DIM>(a.records + (int64_t)s * a.rs, x, a.blend, &res);
+            for (int it = beg; it < end && !found; it += SL_BATCH) {
+                int sid[SL_BATCH];
+                unsigned mask = 0;
+#pragma unroll
+                for (int j = 0; j < SL_BATCH; ++j) sid[j] = (it + j < end) ? __ldg(a.cell_items + it + j) : -1;
+#pragma unroll
+                for (int j = 0; j < SL_BATCH; ++j) {
+                    const double *rec = a.records + (int64_t)(sid[j] < 0 ? 0 : sid[j]) * a.rs;
+                    if (sl_box<DIM>(rec, x) && sid[j] >= 0) mask |= 1u << j;
+                }
+                while (mask && !found) {  // ascending j = ascending simplex index
+                    const int j = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    int sj = sid[0];
+#pragma unroll
+                    for (int q = 1; q < SL_BATCH; ++q) sj = (j == q) ? sid[q] : sj;
+                    found = sl_accept<DIM>(a.records + (int64_t)sj * a.rs, x, a.blend, &res);
+                }
             }
         }
         if (!found) {
@@ -361,7 +391,183 @@ static cudaError_t sl_upload(T **dst, const T *src, size_t n, int64_t *bytes)
     return n ? cudaMemcpy(*dst, src, sizeof(T) * n, cudaMemcpyHostToDevice) : cudaSuccess;
 }
 
-// cells_per_dim: 0 = automatic (about 4 cells per simplex), > 0 forces the resolution
+// Exact barycentric maps lambda_d(x) = a_d . x + c_d of every simplex (host, long double Gauss-Jordan
+// on [vertices; 1]), used ONLY to prune the cell lists: a simplex is left out of a cell's list when
+// some lambda_d stays below -tol on the whole (padded) cell, tol covering the -1e-10 acceptance slack
+// plus a bound on what the kernel's LU solve can deviate from the exact value
+// (1e-12 (1 + |M|)(1 + |M^-1|) max|lambda| -- ten times the classical GEPP bound).  Such a simplex cannot
+// be accepted for any point of the cell, so "first accepted candidate" is unchanged.  Degenerate
+// simplices (no inverse) are never pruned.
+static void sl_affine_maps(SlDevice *d, const double *knots, const int *dtri)
+{
+    const int dim = d->dim, N = dim + 1, ns = d->ns;
+    d->h_aff.assign((size_t)ns * N * N, 0.0);
+    d->h_tol.assign((size_t)ns, -1.0);  // < 0: do not prune
+#pragma omp parallel for schedule(static)
+    for (int s = 0; s < ns; ++s) {
+        long double m[SL_MAXCELLDIM + 1][2 * (SL_MAXCELLDIM + 1)];
+        double mnorm = (double)N;
+        for (int r = 0; r < N; ++r)
+            for (int c = 0; c < N; ++c) {
+                const int k = dtri[(size_t)s * N + c] - 1;
+                m[r][c] = (r < dim) ? (long double)knots[(size_t)k * dim + r] : 1.0L;
+                m[r][N + c] = (r == c) ? 1.0L : 0.0L;
+            }
+        for (int r = 0; r < dim; ++r) {
+            double rs = 0.0;
+            for (int c = 0; c < N; ++c) rs += fabs((double)m[r][c]);
+            mnorm = std::max(mnorm, rs);
+        }
+        bool ok = true;
+        for (int c = 0; c < N && ok; ++c) {
+            int pr = c;
+            for (int r = c + 1; r < N; ++r)
+                if (fabsl(m[r][c]) > fabsl(m[pr][c])) pr = r;
+            if (!(fabsl(m[pr][c]) > 0.0L) || !std::isfinite((double)m[pr][c])) { ok = false; break; }
+            if (pr != c)
+                for (int q = 0; q < 2 * N; ++q) std::swap(m[c][q], m[pr][q]);
+            const long double inv = 1.0L / m[c][c];
+            for (int q = 0; q < 2 * N; ++q) m[c][q] *= inv;
+            for (int r = 0; r < N; ++r)
+                if (r != c && m[r][c] != 0.0L) {
+                    const long double f = m[r][c];
+                    for (int q = 0; q < 2 * N; ++q) m[r][q] -= f * m[c][q];
+                }
+        }
+        if (!ok) continue;
+        // row v of the inverse: lambda_v = sum_j inv[v][j] x_j + inv[v][dim]
+        double inorm = 0.0, lam = 0.0;
+        const double *bx = &d->h_bbox[(size_t)s * 2 * dim];
+        for (int v = 0; v < N; ++v) {
+            double rs = 0.0, mag = 0.0;
+            for (int j = 0; j < N; ++j) {
+                const double a = (double)m[v][N + j];
+                d->h_aff[((size_t)s * N + v) * N + j] = a;
+                rs += fabs(a);
+                mag += (j < dim) ? fabs(a) * std::max(fabs(bx[2 * j]), fabs(bx[2 * j + 1])) : fabs(a);
+            }
+            inorm = std::max(inorm, rs);
+            lam = std::max(lam, mag);
+        }
+        const double tol = 1e-10 + 1e-12 * (1.0 + mnorm) * (1.0 + inorm) * lam + 1e-14 * lam;
+        if (std::isfinite(tol)) d->h_tol[s] = tol;
+    }
+}
+
+// (Re)build the cell lists with G cells per dimension.  Lists hold, in ascending order, the simplices
+// whose bounding box overlaps the cell and which the pruning test above cannot rule out.
+static cudaError_t sl_build_cells(SlDevice *d, int G)
+{
+    const int dim = d->dim, N = dim + 1, ns = d->ns;
+    if (G < 1) G = 1;
+    while (G > 1 && pow((double)G, dim) > (double)(1 << 24)) G = (G + 1) / 2;
+    const double *bbox = d->h_bbox.data();
+    std::vector<int> start;
+    std::vector<int> items;
+    for (;; G = (G + 1) / 2) {
+        double w[SL_MAXCELLDIM], pad[SL_MAXCELLDIM];
+        int64_t nc = 1;
+        for (int j = 0; j < dim; ++j) {
+            d->G[j] = G;
+            d->lo[j] = d->glo[j];
+            const double span = d->ghi[j] - d->glo[j];
+            const bool good = span > 0.0 && std::isfinite(span);
+            d->inv[j] = good ? (double)G / span : 0.0;
+            w[j] = good ? span / (double)G : 0.0;
+            pad[j] = 1e-6 * w[j] + 1e-12 * (fabs(d->glo[j]) + fabs(d->ghi[j]));
+            nc *= G;
+        }
+        std::vector<int> count((size_t)nc + 1, 0);
+        // a (simplex, cell) pair is kept unless some barycentric coordinate is surely below -tol on the cell
+        auto keep = [&](int s, const int *c) -> bool {
+            const double tol = d->h_tol[s];
+            if (tol < 0.0) return true;
+            const double *aff = &d->h_aff[(size_t)s * N * N];
+            for (int v = 0; v < N; ++v) {
+                double ub = aff[v * N + dim];
+                for (int j = 0; j < dim; ++j) {
+                    const double a = aff[v * N + j];
+                    const double lo = d->glo[j] + c[j] * w[j] - pad[j], hi = d->glo[j] + (c[j] + 1) * w[j] + pad[j];
+                    ub += std::max(a * lo, a * hi);
+                }
+                if (ub < -tol) return false;
+            }
+            return true;
+        };
+        auto visit = [&](int s, auto &&fn) {
+            int c0[SL_MAXCELLDIM], c1[SL_MAXCELLDIM], c[SL_MAXCELLDIM];
+            for (int j = 0; j < dim; ++j) {
+                c0[j] = sl_cell_of(bbox[(size_t)s * 2 * dim + 2 * j], d->lo[j], d->inv[j], G);
+                c1[j] = sl_cell_of(bbox[(size_t)s * 2 * dim + 2 * j + 1], d->lo[j], d->inv[j], G);
+                if (c1[j] < c0[j]) c1[j] = c0[j];  // NaN box: bin it somewhere, the box test rejects it anyway
+                c[j] = c0[j];
+            }
+            for (;;) {
+                if (keep(s, c)) {
+                    int64_t id = 0;
+                    for (int j = dim - 1; j >= 0; --j) id = id * G + c[j];
+                    fn(id);
+                }
+                int j = 0;
+                for (; j < dim; ++j) {
+                    if (++c[j] <= c1[j]) break;
+                    c[j] = c0[j];
+                }
+                if (j == dim) break;
+            }
+        };
+#pragma omp parallel for schedule(dynamic, 256)
+        for (int s = 0; s < ns; ++s)
+            visit(s, [&](int64_t id) {
+#pragma omp atomic
+                ++count[(size_t)id + 1];
+            });
+        int64_t total = 0;
+        for (int64_t i = 0; i < nc; ++i) total += count[(size_t)i + 1];
+        if (total > (int64_t(1) << 28) && G > 1) continue;  // too fine for the memory it takes: coarsen
+        for (int64_t i = 0; i < nc; ++i) count[(size_t)i + 1] += count[(size_t)i];
+        start.assign(count.begin(), count.end());
+        items.assign((size_t)total, 0);
+        std::vector<int> fill(count.begin(), count.end() - 1);
+#pragma omp parallel for schedule(dynamic, 256)
+        for (int s = 0; s < ns; ++s)
+            visit(s, [&](int64_t id) {
+                int pos;
+#pragma omp atomic capture
+                pos = fill[(size_t)id]++;
+                items[(size_t)pos] = s;
+            });
+        // the parallel fill loses the order inside a list: restore ascending simplex index
+#pragma omp parallel for schedule(dynamic, 4096)
+        for (int64_t i = 0; i < nc; ++i)
+            if (start[(size_t)i + 1] - start[(size_t)i] > 1) std::sort(items.begin() + start[(size_t)i], items.begin() + start[(size_t)i + 1]);
+        d->nitems = total;
+        d->ncells = nc;
+        break;
+    }
+    cudaError_t e = cudaDeviceSynchronize();  // a previous launch may still read the old lists
+    if (e != cudaSuccess) return e;
+    cudaFree(d->cell_start);
+    cudaFree(d->cell_items);
+    d->cell_start = d->cell_items = nullptr;
+    d->bytes -= d->cell_bytes;
+    int64_t nb = 0;
+    e = sl_upload(&d->cell_start, start.data(), start.size(), &nb);
+    if (e == cudaSuccess) e = sl_upload(&d->cell_items, items.data(), items.size(), &nb);
+    if (e != cudaSuccess) {
+        cudaFree(d->cell_start);
+        cudaFree(d->cell_items);
+        d->cell_start = d->cell_items = nullptr;
+        d->cell_bytes = 0;
+        d->ncells = 0;
+        return e;
+    }
+    d->cell_bytes = nb;
+    d->bytes += nb;
+    return cudaSuccess;
+}
+
+// cells_per_dim: 0 = the grid is built on first use, sized for the batch (launch_sl); > 0 forces it
 cudaError_t sl_create(const double *knots, int dim, int nknots, const int *dtri, int ns, const double *lumats,
                       const int *pivots, const double *bbox, const double *val, int cells_per_dim, SlDevice **out)
 {
@@ -369,6 +575,7 @@ cudaError_t sl_create(const double *knots, int dim, int nknots, const int *dtri,
     d->dim = dim;
     d->nknots = nknots;
     d->ns = ns;
+    d->forced_G = cells_per_dim > 0 ? cells_per_dim : 0;
     const int N = dim + 1;
     cudaError_t e;
 #define SL_TRY(call) do { e = (call); if (e != cudaSuccess) { sl_destroy(d); return e; } } while (0)
@@ -388,66 +595,15 @@ cudaError_t sl_create(const double *knots, int dim, int nknots, const int *dtri,
     SL_TRY(sl_upload(&d->knot_simplex, ks.data(), (size_t)nknots, &d->bytes));
     if (dim > SL_MAXCELLDIM || ns == 0) { *out = d; return cudaSuccess; }
 
-    // bounding box of all simplices and the cell grid over it
+    // bounding box of all simplices
+    d->h_bbox.assign(bbox, bbox + (size_t)2 * dim * ns);
     for (int j = 0; j < dim; ++j) { d->glo[j] = 1e300; d->ghi[j] = -1e300; }
     for (int s = 0; s < ns; ++s)
         for (int j = 0; j < dim; ++j) {
             d->glo[j] = std::min(d->glo[j], bbox[(size_t)s * 2 * dim + 2 * j]);
             d->ghi[j] = std::max(d->ghi[j], bbox[(size_t)s * 2 * dim + 2 * j + 1]);
         }
-    int G = cells_per_dim > 0 ? cells_per_dim : (int)ceil(pow(4.0 * ns, 1.0 / dim));
-    std::vector<int> start, items;
-    for (;; G = (G + 1) / 2) {
-        if (G < 1) G = 1;
-        double ncell = pow((double)G, dim);
-        if (ncell > (double)(1 << 24) && G > 1) continue;
-        for (int j = 0; j < dim; ++j) {
-            d->G[j] = G;
-            d->lo[j] = d->glo[j];
-            const double span = d->ghi[j] - d->glo[j];
-            d->inv[j] = (span > 0.0 && std::isfinite(span)) ? (double)G / span : 0.0;
-        }
-        const int64_t nc = (int64_t)ncell;
-        std::vector<int64_t> count(nc + 1, 0);
-        int c0[SL_MAXCELLDIM], c1[SL_MAXCELLDIM], c[SL_MAXCELLDIM];
-        auto range = [&](int s) {
-            for (int j = 0; j < dim; ++j) {
-                c0[j] = sl_cell_of(bbox[(size_t)s * 2 * dim + 2 * j], d->lo[j], d->inv[j], G);
-                c1[j] = sl_cell_of(bbox[(size_t)s * 2 * dim + 2 * j + 1], d->lo[j], d->inv[j], G);
-                if (c1[j] < c0[j]) c1[j] = c0[j];  // NaN box: bin it somewhere, the box test rejects it anyway
-            }
-        };
-        auto for_cells = [&](auto &&fn) {
-            for (int j = 0; j < dim; ++j) c[j] = c0[j];
-            for (;;) {
-                int64_t id = 0;
-                for (int j = dim - 1; j >= 0; --j) id = id * G + c[j];
-                fn(id);
-                int j = 0;
-                for (; j < dim; ++j) {
-                    if (++c[j] <= c1[j]) break;
-                    c[j] = c0[j];
-                }
-                if (j == dim) break;
-            }
-        };
-        int64_t total = 0;
-        for (int s = 0; s < ns; ++s) {
-            range(s);
-            for_cells([&](int64_t id) { ++count[id + 1]; ++total; });
-        }
-        if (total > (int64_t(1) << 27) && G > 1 && cells_per_dim <= 0) continue;  // too fine: coarsen
-        for (int64_t i = 0; i < nc; ++i) count[i + 1] += count[i];
-        start.assign(count.begin(), count.end());
-        items.assign((size_t)total, 0);
-        std::vector<int64_t> fill(count.begin(), count.end() - 1);
-        for (int s = 0; s < ns; ++s) {  // ascending s: every list comes out in index order
-            range(s);
-            for_cells([&](int64_t id) { items[(size_t)fill[id]++] = s; });
-        }
-        d->nitems = total;
-        break;
-    }
+    sl_affine_maps(d, knots, dtri);
     // packed records
     const int rs = ((2 * dim + N * N + N + 1) + 3) & ~3;
     std::vector<double> rec((size_t)ns * rs, 0.0);
@@ -471,19 +627,32 @@ cudaError_t sl_create(const double *knots, int dim, int nknots, const int *dtri,
         memcpy(&r[2 * dim + N * N + N], &code, sizeof code);
     }
     SL_TRY(sl_upload(&d->records, rec.data(), rec.size(), &d->bytes));
-    SL_TRY(sl_upload(&d->cell_start, start.data(), start.size(), &d->bytes));
-    SL_TRY(sl_upload(&d->cell_items, items.data(), items.size(), &d->bytes));
     d->rs = rs;
+    if (d->forced_G) SL_TRY(sl_build_cells(d, d->forced_G));
 #undef SL_TRY
     *out = d;
     return cudaSuccess;
 }
 
+// Cells wanted for a batch of npts points: building costs about one visit per (simplex, overlapped
+// cell), scanning costs about one box test per list entry per point; about one cell per two points,
+// between ns/4 and 32 ns (133k simplices in 3-D: 82 / 128 / 160 cells per dimension measured
+// 2.39 / 2.65 / 2.76e9 evals/s before pruning, tools/sl_sweep.sh).
+static int sl_wanted_G(const SlDevice *d, int64_t npts)
+{
+    double cells = (double)npts / 2.0;
+    cells = std::max(cells, (double)d->ns / 4.0);
+    cells = std::min(cells, 32.0 * (double)d->ns);
+    cells = std::min(cells, (double)(1 << 24));
+    return std::max(1, (int)ceil(pow(cells, 1.0 / d->dim)));
+}
+
 int64_t sl_bytes(const SlDevice *d) { return d ? d->bytes : 0; }
 
 // kernel: 0 auto, 1 strict, 2 fast (cudaErrorNotSupported if there is no cell structure)
-cudaError_t launch_sl(const SlDevice *d, int kernel, int epol, int blend, const double *x, int64_t npts, double *out,
-                      int num_sms, cudaStream_t s, LaunchInfo *li)
+#define SL_DEFAULT_VARIANT 804  // batch 4 at 64 registers: occupancy beats batching (tools/sl_sweep.sh)
+cudaError_t launch_sl(SlDevice *d, int kernel, int variant, int epol, int blend, const double *x, int64_t npts,
+                      double *out, int num_sms, cudaStream_t s, LaunchInfo *li)
 {
     SlArgs a;
     memset(&a, 0, sizeof a);
@@ -493,22 +662,57 @@ cudaError_t launch_sl(const SlDevice *d, int kernel, int epol, int blend, const 
     a.cell_start = d->cell_start; a.cell_items = d->cell_items;
     for (int j = 0; j < SL_MAXCELLDIM; ++j) { a.G[j] = d->G[j]; a.lo[j] = d->lo[j]; a.inv[j] = d->inv[j]; }
     a.x = x; a.npts = npts; a.out = out;
-    const bool cell_ok = d->rs > 0;
-    if (kernel == CHEBPOL_CUDA_KERNEL_FAST && !cell_ok) return cudaErrorNotSupported;
-    if (kernel != CHEBPOL_CUDA_KERNEL_STRICT && cell_ok) {
+    const bool can_cell = d->rs > 0;
+    if (kernel == CHEBPOL_CUDA_KERNEL_FAST && !can_cell) return cudaErrorNotSupported;
+    bool use_cell = can_cell && kernel != CHEBPOL_CUDA_KERNEL_STRICT;
+    if (use_cell && !d->forced_G) {
+        // a small first batch is cheaper through the plain scan than through building the lists
+        if (!d->cell_start && kernel == CHEBPOL_CUDA_KERNEL_AUTO && npts * (int64_t)d->ns < (int64_t(1) << 32)) use_cell = false;  // scan: ~2.5 ps per point and simplex
+        else {
+            const int G = sl_wanted_G(d, npts);
+            if (!d->cell_start || pow((double)G, d->dim) >= 8.0 * (double)d->ncells) {
+                cudaError_t be = sl_build_cells(d, G);
+                if (be != cudaSuccess) {
+                    (void)cudaGetLastError();
+                    if (kernel == CHEBPOL_CUDA_KERNEL_FAST || !d->cell_start) {
+                        if (kernel == CHEBPOL_CUDA_KERNEL_FAST) return be;
+                        use_cell = false;
+                    }
+                }
+            }
+        }
+    }
+    a.cell_start = d->cell_start; a.cell_items = d->cell_items;
+    for (int j = 0; j < SL_MAXCELLDIM; ++j) { a.G[j] = d->G[j]; a.lo[j] = d->lo[j]; a.inv[j] = d->inv[j]; }
+    if (use_cell) {
         const int block = 128;
         int64_t nb = (npts + block - 1) / block;
         const int64_t cap = (int64_t)num_sms * 16;
         if (nb > cap) nb = cap;
         if (nb < 1) nb = 1;
-        switch (d->dim) {
-        case 1: sl_cell_kernel<1><<<(int)nb, block, 0, s>>>(a); break;
-        case 2: sl_cell_kernel<2><<<(int)nb, block, 0, s>>>(a); break;
-        case 3: sl_cell_kernel<3><<<(int)nb, block, 0, s>>>(a); break;
-        case 4: sl_cell_kernel<4><<<(int)nb, block, 0, s>>>(a); break;
-        case 5: sl_cell_kernel<5><<<(int)nb, block, 0, s>>>(a); break;
-        default: sl_cell_kernel<6><<<(int)nb, block, 0, s>>>(a); break;
+        // variant = batch + 100*minblocks (tuning / ncu evidence); 0: the measured default
+        const int code = variant > 0 ? variant : SL_DEFAULT_VARIANT;
+#define SL_LAUNCH(D, B, M) sl_cell_kernel<D, B, M><<<(int)nb, block, 0, s>>>(a)
+#define SL_DIMS(B, M)                                                                                          \
+    switch (d->dim) {                                                                                          \
+    case 1: SL_LAUNCH(1, B, M); break;                                                                         \
+    case 2: SL_LAUNCH(2, B, M); break;                                                                         \
+    case 3: SL_LAUNCH(3, B, M); break;                                                                         \
+    case 4: SL_LAUNCH(4, B, M); break;                                                                         \
+    case 5: SL_LAUNCH(5, B, M); break;                                                                         \
+    default: SL_LAUNCH(6, B, M); break;                                                                        \
+    }
+        switch (code) {
+        case 1: SL_DIMS(1, 1); break;
+        case 2: SL_DIMS(2, 1); break;
+        case 8: SL_DIMS(8, 1); break;
+        case 802: SL_DIMS(2, 8); break;
+        case 804: SL_DIMS(4, 8); break;
+        case 4: SL_DIMS(4, 1); break;
+        default: SL_DIMS(4, 8); break;
         }
+#undef SL_DIMS
+#undef SL_LAUNCH
         if (li) { li->grid = (int)nb; li->block = block; li->smem = 0; li->kernel = K_SL_CELL; }
         return cudaGetLastError();
     }

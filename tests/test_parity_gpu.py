@@ -1135,7 +1135,7 @@ def test_simplexlinear_strict_and_cell(gpu_ok, port, dim, nk):
             else:
                 assert nan_aware_bits_equal(got, want), (epol, blend)
             if dim <= 6:
-                got2, k = eval_plan(plan, x, _lib.KERNEL_AUTO)
+                got2, k = eval_plan(plan, x, _lib.KERNEL_FAST)
                 assert k == "sl_cell"
                 assert nan_aware_bits_equal(got2, got), (epol, blend)  # the two kernels agree bit for bit
     if dim > 6:
@@ -1158,10 +1158,24 @@ def test_simplexlinear_cell_resolutions_and_stateless(gpu_ok, port, monkeypatch)
         monkeypatch.setenv("CHEBPOL_CUDA_SL_CELLS", cells)
         plan = _lib.Plan.sl(knots, dtri, ad, val)
         plan.set(_lib.OPT_EPOL, 1)
-        got, k = eval_plan(plan, x, _lib.KERNEL_AUTO)
+        got, k = eval_plan(plan, x, _lib.KERNEL_FAST)
         assert k == "sl_cell" and nan_aware_bits_equal(got, want), cells
         plan.close()
     monkeypatch.delenv("CHEBPOL_CUDA_SL_CELLS")
+    # AUTO: a small first batch goes through the plain scan, a large one builds the lists, and a much
+    # larger one rebuilds them finer; every route gives the same bits
+    plan = _lib.Plan.sl(knots, dtri, ad, val)
+    plan.set(_lib.OPT_EPOL, 1)
+    got, k = eval_plan(plan, x[:500], _lib.KERNEL_AUTO)
+    assert k == "sl_strict" and nan_aware_bits_equal(got, want[:500])
+    got, k = eval_plan(plan, x[:20000], _lib.KERNEL_FAST)
+    assert k == "sl_cell" and nan_aware_bits_equal(got, want[:20000])
+    got, k = eval_plan(plan, x[:500], _lib.KERNEL_AUTO)  # the lists exist now
+    assert k == "sl_cell" and nan_aware_bits_equal(got, want[:500])
+    xx = np.tile(x, (6, 1))
+    got, k = eval_plan(plan, xx, _lib.KERNEL_AUTO)
+    assert k == "sl_cell" and nan_aware_bits_equal(got, np.tile(want, 6))
+    plan.close()
     got = _lib.evalsl(x, knots, dtri, ad, val, True, 3, 0)
     assert nan_aware_bits_equal(got, want)
     got = _lib.evalsl(x, knots, dtri, ad, val, False, 0, 1)  # per-call blend / epol on a cached plan
