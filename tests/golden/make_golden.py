@@ -107,6 +107,22 @@ def main():
         out[f"stalk_y_blend{blend}"] = ref.evalstalk(sv, sg, b, c, r, x, blend=blend)
         out[f"hyp_y_blend{blend}"] = ref.evalhyp(sv, sg, a, hb, hc, hd, x, blend=blend)
 
+    # ---- simplex-linear: the reference's R_analyzesimplex / R_evalsl (LAPACK dgetrf/dgetrs restated
+    # in oracle/ref_wrap.c); triangulation by qhull through scipy, stored with the vectors
+    from scipy.spatial import Delaunay
+
+    kn = np.asfortranarray(rng.uniform(-1, 1, (3, 80)))
+    dtri = np.asfortranarray((Delaunay(kn.T, qhull_options="Qt Pp").simplices.T + 1).astype(np.float64))
+    kv = rng.standard_normal(80)
+    x = pts(257, 3, -1.1, 1.1)
+    x[:80] = kn.T
+    lu, piv, bb = ref.analyzesimplex(dtri.astype(np.int32), kn)
+    out["sl_knots"], out["sl_dtri"], out["sl_val"], out["sl_x"] = kn, dtri, kv, x
+    out["sl_lumats"], out["sl_pivots"], out["sl_bbox"] = lu, piv.astype(np.float64), bb
+    for epol in (0, 1):
+        for blend in (0, 3, 4, 5):
+            out[f"sl_y_epol{epol}_blend{blend}"] = ref.evalsl(x, kn, dtri.astype(np.int32), (lu, piv, bb), kv, epol, blend)
+
     path = os.path.join(HERE, "ref_vectors.npz")
     np.savez_compressed(path, **out)
     print(f"wrote {path}: {len(out)} arrays, {os.path.getsize(path)} bytes")

@@ -50,7 +50,7 @@ def mlip_x(blend):
 
 # ------------------------------------------------------------------ CPU: the restatement
 def test_fixture_is_complete():
-    assert len(G.files) == 63
+    assert len(G.files) == 78
     for k in G.files:
         assert G[k].dtype == np.float64
 
@@ -93,6 +93,21 @@ def test_port_stalker_fit_and_eval(port):
         assert same_bits(got, G[f"stalk_y_blend{blend}"])
         got = port.evalhyp(G["stalk_val"], SGRID, a, hb, hc, hd, G["stalk_x"], blend=blend)
         assert same_bits(got, G[f"hyp_y_blend{blend}"])
+
+
+def sl_tables():
+    dtri = np.asfortranarray(G["sl_dtri"].astype(np.int32))
+    return G["sl_knots"], dtri, (G["sl_lumats"], G["sl_pivots"].astype(np.int32), G["sl_bbox"])
+
+
+def test_port_simplexlinear(port):
+    kn, dtri, ad = sl_tables()
+    got = port.analyzesimplex(dtri, kn)
+    assert all(np.array_equal(a, b) for a, b in zip(got, ad))
+    for epol in (0, 1):
+        for blend in (0, 3, 4, 5):
+            y = port.evalsl(G["sl_x"], kn, dtri, ad, G["sl_val"], epol, blend)
+            assert same_bits(y, G[f"sl_y_epol{epol}_blend{blend}"])
 
 
 # ------------------------------------------------------------------ GPU: the CUDA kernels
@@ -194,4 +209,21 @@ def test_gpu_stalkers(gpu_ok, blend):
     got, k = run(plan, G["stalk_x"], _lib.KERNEL_FAST)
     assert k == "stalk_cell"
     close(got, want)
+    plan.close()
+
+
+@pytest.mark.gpu
+def test_gpu_simplexlinear(gpu_ok):
+    kn, dtri, ad = sl_tables()
+    assert all(np.array_equal(a, b) for a, b in zip(_lib.analyzesimplex(dtri, kn), ad))
+    plan = _lib.Plan.sl(kn, dtri, ad, G["sl_val"])
+    for epol in (0, 1):
+        plan.set(_lib.OPT_EPOL, epol)
+        for blend in (0, 3, 4, 5):
+            plan.set(_lib.OPT_BLEND, blend)
+            want = G[f"sl_y_epol{epol}_blend{blend}"]
+            got, k = run(plan, G["sl_x"], _lib.KERNEL_STRICT)
+            assert k == "sl_strict" and same_bits(got, want)
+            got, k = run(plan, G["sl_x"], _lib.KERNEL_FAST)
+            assert k == "sl_cell" and same_bits(got, want)
     plan.close()
