@@ -43,7 +43,7 @@ EXPORTS = [
     "chebpol_cuda_evalpolyh", "chebpol_cuda_plan_polyh",
     "chebpol_cuda_evalstalk", "chebpol_cuda_evalhyp", "chebpol_cuda_plan_stalk",
     "chebpol_cuda_evalchebg", "chebpol_cuda_plan_chebg",
-    "chebpol_cuda_evalsl", "chebpol_cuda_plan_sl", "chebpol_cuda_analyzesimplex",
+    "chebpol_cuda_evalsl", "chebpol_cuda_plan_sl", "chebpol_cuda_analyzesimplex", "chebpol_cuda_debug_sl_lists",
 ]
 
 
@@ -106,6 +106,8 @@ def lib() -> C.CDLL:
                                       C.c_int, C.c_int, _vp]
     L.chebpol_cuda_plan_sl.argtypes = [_vp, C.c_int, C.c_int, _vp, C.c_int, _vp, _vp, _vp, _vp, C.c_int, C.POINTER(_vp)]
     L.chebpol_cuda_analyzesimplex.argtypes = [_vp, C.c_int, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp]
+    L.chebpol_cuda_debug_sl_lists.argtypes = [_vp, C.c_int, C.c_int, _vp, C.c_int, _vp, C.c_int, _ip, _vp, _vp, _vp,
+                                              C.c_int64, _vp, C.c_int64, C.POINTER(C.c_int64)]
     L.chebpol_cuda_cache_clear.restype = None
     L.chebpol_cuda_cache_clear.argtypes = []
     L.chebpol_cuda_launch_count.restype = C.c_int64
@@ -375,6 +377,26 @@ def analyzesimplex(dtri, knots, device: int = 0):
     bb = np.empty(ns * 2 * dim)
     check(lib().chebpol_cuda_analyzesimplex(_addr(tri), ns, _addr(kn), dim, nk, device, _addr(lu), _addr(piv), _addr(bb)))
     return lu, piv, bb
+
+
+def debug_sl_lists(knots, dtri, bbox, cells_per_dim: int):
+    """Candidate lists of the sl_cell kernel, built on the host (no GPU): (G, lo, inv, start, items)."""
+    kn = f64(np.asarray(knots, dtype=np.float64), order="F")
+    tri = np.require(dtri, dtype=np.int32, requirements=["F", "A"])
+    dim, nk = kn.shape
+    ns = tri.shape[1]
+    bb = f64(np.ravel(bbox, order="F"))
+    g = max(1, int(cells_per_dim))
+    start = np.zeros(min(g, 256) ** dim + 1 if g ** dim <= (1 << 24) else (1 << 24) + 1, dtype=np.int32)
+    start = np.zeros(g ** dim + 1, dtype=np.int32)
+    cap = 1 << 26
+    items = np.zeros(cap, dtype=np.int32)
+    lo, inv = np.zeros(dim), np.zeros(dim)
+    gu, n = C.c_int(0), C.c_int64(0)
+    check(lib().chebpol_cuda_debug_sl_lists(_addr(kn), dim, nk, _addr(tri), ns, _addr(bb), g, C.byref(gu), _addr(lo),
+                                            _addr(inv), _addr(start), start.size, _addr(items), cap, C.byref(n)))
+    G = gu.value
+    return G, lo, inv, start[: G ** dim + 1], items[: n.value]
 
 
 def evalsl(x_pk, knots, dtri, adata, val, epol: bool = False, blend: int = 3, ngpus: int = 0) -> np.ndarray:

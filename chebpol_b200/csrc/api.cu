@@ -143,6 +143,19 @@ struct chebpol_cuda_plan {
     int64_t buf_points = 0;
 };
 
+// Plan constructors upload with synchronous cudaMemcpy from pageable memory, which may return while
+// the last DMA is still in flight on the legacy stream; evaluations run on non-blocking streams, so
+// a constructor only returns once everything it uploaded has landed.
+extern "C" void chebpol_cuda_plan_destroy(chebpol_cuda_plan *p);
+static int plan_ready(chebpol_cuda_plan **plan)
+{
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) return CHEBPOL_CUDA_OK;
+    chebpol_cuda_plan_destroy(*plan);
+    *plan = nullptr;
+    return cuda_fail(e, "plan upload");
+}
+
 static int check_dims(const int *dims, int rank, int64_t *nelem)
 {
     if (rank <= 0) return fail(CHEBPOL_CUDA_ERANK, "rank must be positive");
@@ -455,7 +468,7 @@ static int plan_cheb_impl(const double *coef, const int *dims, int rank, const d
     rc = configure_mma(p, 0, coef);
     if (rc) return bail(rc);
     *plan = p;
-    return CHEBPOL_CUDA_OK;
+    return plan_ready(plan);
 }
 
 extern "C" int chebpol_cuda_plan_mlip(const double *const *grid, const int *dims, int rank,
@@ -524,7 +537,7 @@ extern "C" int chebpol_cuda_plan_mlip(const double *const *grid, const int *dims
         if ((double)p->cell_bytes > cap_gb * 1e9) p->cell_bytes = 0;
     }
     *plan = p;
-    return CHEBPOL_CUDA_OK;
+    return plan_ready(plan);
 }
 
 extern "C" int chebpol_cuda_plan_fh(const double *vals, const double *const *grid,
@@ -552,7 +565,7 @@ extern "C" int chebpol_cuda_plan_fh(const double *vals, const double *const *gri
     rc = configure_mma(p, 1, vals);
     if (rc) return bail(rc);
     *plan = p;
-    return CHEBPOL_CUDA_OK;
+    return plan_ready(plan);
 }
 
 extern "C" int chebpol_cuda_plan_polyh(const double *knots, int rank, int nknots, const double *weights,
@@ -610,7 +623,7 @@ extern "C" int chebpol_cuda_plan_polyh(const double *knots, int rank, int nknots
     }
     p->tensor_bytes = sizeof(double) * ((int64_t)nknots * (rank + 1) + rank + 1);
     *plan = p;
-    return CHEBPOL_CUDA_OK;
+    return plan_ready(plan);
 }
 
 extern "C" int chebpol_cuda_plan_stalk(int kind, const double *val, const double *const *grid, const int *dims,
@@ -665,7 +678,7 @@ extern "C" int chebpol_cuda_plan_stalk(int kind, const double *val, const double
         }
     }
     *plan = p;
-    return CHEBPOL_CUDA_OK;
+    return plan_ready(plan);
 }
 
 static int check_sl(const double *knots, int dim, int nknots, const int *dtri, int ns, const double *lumats,
@@ -708,7 +721,7 @@ extern "C" int chebpol_cuda_plan_sl(const double *knots, int dim, int nknots, co
     }
     p->tensor_bytes = sl_bytes(p->sl);
     *plan = p;
-    return CHEBPOL_CUDA_OK;
+    return plan_ready(plan);
 }
 
 extern "C" int chebpol_cuda_analyzesimplex(const int *dtri, int numsimplex, const double *knots, int dim, int nknots,
@@ -742,6 +755,20 @@ extern "C" int chebpol_cuda_analyzesimplex(const int *dtri, int numsimplex, cons
     if (e == cudaSuccess) e = cudaMemcpy(bbox, d_bb, sizeof(double) * ns * 2 * dim, cudaMemcpyDeviceToHost);
     cudaFree(d_tri); cudaFree(d_piv); cudaFree(d_kn); cudaFree(d_lu); cudaFree(d_bb);
     if (e != cudaSuccess) return cuda_fail(e, "analyzesimplex");
+    return CHEBPOL_CUDA_OK;
+}
+
+extern "C" int chebpol_cuda_debug_sl_lists(const double *knots, int dim, int nknots, const int *dtri, int numsimplex,
+                                           const double *bbox, int cells_per_dim, int *cells_used, double *lo,
+                                           double *inv, int *start, int64_t start_cap, int *items,
+                                           int64_t items_cap, int64_t *nitems)
+{
+    if (!knots || !dtri || !bbox || !cells_used || !lo || !inv || !start || !items || !nitems)
+        return fail(CHEBPOL_CUDA_EINVAL, "a pointer is NULL");
+    const int rc = sl_debug_lists(knots, dim, nknots, dtri, numsimplex, bbox, cells_per_dim, cells_used, lo, inv, start,
+                                  start_cap, items, items_cap, nitems);
+    if (rc == 1) return fail(CHEBPOL_CUDA_ERANK, "cell lists exist for 1..6 dimensions and at least one simplex");
+    if (rc == 2) return fail(CHEBPOL_CUDA_ESIZE, "start / items buffers too small");
     return CHEBPOL_CUDA_OK;
 }
 

@@ -259,5 +259,8 @@ void sl_destroy(SlDevice *d);
 int64_t sl_bytes(const SlDevice *d);
 cudaError_t launch_sl(SlDevice *d, int kernel, int variant, int epol, int blend, const double *x, int64_t npts,
                       double *out, int num_sms, cudaStream_t s, LaunchInfo *li);
+int sl_debug_lists(const double *knots, int dim, int nknots, const int *dtri, int ns, const double *bbox, int G,
+                   int *G_used, double *lo, double *inv, int *start, int64_t start_cap, int *items, int64_t items_cap,
+                   int64_t *nitems);
 cudaError_t sl_analyze_device(const int *d_dtri, int ns, const double *d_knots, int dim, double *d_lumats,
                               int *d_pivots, double *d_bbox, cudaStream_t s);

@@ -456,14 +456,12 @@ static void sl_affine_maps(SlDevice *d, const double *knots, const int *dtri)
 
 // (Re)build the cell lists with G cells per dimension.  Lists hold, in ascending order, the simplices
 // whose bounding box overlaps the cell and which the pruning test above cannot rule out.
-static cudaError_t sl_build_cells(SlDevice *d, int G)
+static void sl_host_lists(SlDevice *d, int G, std::vector<int> &start, std::vector<int> &items)
 {
     const int dim = d->dim, N = dim + 1, ns = d->ns;
     if (G < 1) G = 1;
     while (G > 1 && pow((double)G, dim) > (double)(1 << 24)) G = (G + 1) / 2;
     const double *bbox = d->h_bbox.data();
-    std::vector<int> start;
-    std::vector<int> items;
     for (;; G = (G + 1) / 2) {
         double w[SL_MAXCELLDIM], pad[SL_MAXCELLDIM];
         int64_t nc = 1;
@@ -545,6 +543,12 @@ static cudaError_t sl_build_cells(SlDevice *d, int G)
         d->ncells = nc;
         break;
     }
+}
+
+static cudaError_t sl_build_cells(SlDevice *d, int G)
+{
+    std::vector<int> start, items;
+    sl_host_lists(d, G, start, items);
     cudaError_t e = cudaDeviceSynchronize();  // a previous launch may still read the old lists
     if (e != cudaSuccess) return e;
     cudaFree(d->cell_start);
@@ -564,7 +568,46 @@ static cudaError_t sl_build_cells(SlDevice *d, int G)
     }
     d->cell_bytes = nb;
     d->bytes += nb;
-    return cudaSuccess;
+    // a pageable cudaMemcpy may return while its DMA is still in flight on the legacy stream; the
+    // kernel that follows runs on a non-blocking stream, so wait for the lists to land
+    return cudaDeviceSynchronize();
+}
+
+// bounding box of all simplices and the barycentric maps: everything the list builder needs
+static void sl_host_setup(SlDevice *d, const double *knots, const int *dtri, const double *bbox)
+{
+    const int dim = d->dim, ns = d->ns;
+    d->h_bbox.assign(bbox, bbox + (size_t)2 * dim * ns);
+    for (int j = 0; j < dim; ++j) { d->glo[j] = 1e300; d->ghi[j] = -1e300; }
+    for (int s = 0; s < ns; ++s)
+        for (int j = 0; j < dim; ++j) {
+            d->glo[j] = std::min(d->glo[j], bbox[(size_t)s * 2 * dim + 2 * j]);
+            d->ghi[j] = std::max(d->ghi[j], bbox[(size_t)s * 2 * dim + 2 * j + 1]);
+        }
+    sl_affine_maps(d, knots, dtri);
+}
+
+// Host-only view of the candidate lists (no GPU needed): tests check, against the oracle, that the
+// simplex the reference accepts for a point is always in the list of the point's cell.
+int sl_debug_lists(const double *knots, int dim, int nknots, const int *dtri, int ns, const double *bbox, int G,
+                   int *G_used, double *lo, double *inv, int *start, int64_t start_cap, int *items, int64_t items_cap,
+                   int64_t *nitems)
+{
+    (void)nknots;
+    if (dim < 1 || dim > SL_MAXCELLDIM || ns < 1) return 1;
+    SlDevice d;
+    d.dim = dim;
+    d.ns = ns;
+    sl_host_setup(&d, knots, dtri, bbox);
+    std::vector<int> st, it;
+    sl_host_lists(&d, G, st, it);
+    if ((int64_t)st.size() > start_cap || (int64_t)it.size() > items_cap) return 2;
+    memcpy(start, st.data(), sizeof(int) * st.size());
+    memcpy(items, it.data(), sizeof(int) * it.size());
+    *nitems = (int64_t)it.size();
+    *G_used = d.G[0];
+    for (int j = 0; j < dim; ++j) { lo[j] = d.lo[j]; inv[j] = d.inv[j]; }
+    return 0;
 }
 
 // cells_per_dim: 0 = the grid is built on first use, sized for the batch (launch_sl); > 0 forces it
@@ -595,15 +638,7 @@ cudaError_t sl_create(const double *knots, int dim, int nknots, const int *dtri,
     SL_TRY(sl_upload(&d->knot_simplex, ks.data(), (size_t)nknots, &d->bytes));
     if (dim > SL_MAXCELLDIM || ns == 0) { *out = d; return cudaSuccess; }
 
-    // bounding box of all simplices
-    d->h_bbox.assign(bbox, bbox + (size_t)2 * dim * ns);
-    for (int j = 0; j < dim; ++j) { d->glo[j] = 1e300; d->ghi[j] = -1e300; }
-    for (int s = 0; s < ns; ++s)
-        for (int j = 0; j < dim; ++j) {
-            d->glo[j] = std::min(d->glo[j], bbox[(size_t)s * 2 * dim + 2 * j]);
-            d->ghi[j] = std::max(d->ghi[j], bbox[(size_t)s * 2 * dim + 2 * j + 1]);
-        }
-    sl_affine_maps(d, knots, dtri);
+    sl_host_setup(d, knots, dtri, bbox);
     // packed records
     const int rs = ((2 * dim + N * N + N + 1) + 3) & ~3;
     std::vector<double> rec((size_t)ns * rs, 0.0);

@@ -239,6 +239,14 @@ CHEBPOL_CUDA_API int chebpol_cuda_plan_sl(const double *knots, int dim, int nkno
 CHEBPOL_CUDA_API int chebpol_cuda_analyzesimplex(const int *dtri, int numsimplex, const double *knots, int dim,
                                                  int nknots, int device, double *lumats, int *pivots, double *bbox);
 
+/* Host-only (no GPU needed) view of the candidate lists sl_cell scans, for verification: cell
+ * c_d = clamp(floor((x_d - lo[d]) * inv[d]), 0, cells_used-1), cell id = sum_d c_d cells_used^d,
+ * candidates items[start[id] .. start[id+1]) in ascending simplex index. */
+CHEBPOL_CUDA_API int chebpol_cuda_debug_sl_lists(const double *knots, int dim, int nknots, const int *dtri,
+                                                 int numsimplex, const double *bbox, int cells_per_dim,
+                                                 int *cells_used, double *lo, double *inv, int *start,
+                                                 int64_t start_cap, int *items, int64_t items_cap, int64_t *nitems);
+
 /* ---- evaluation on a tensor grid (evalongridV of an interpolant, R/tools.R:132-137) ----
  * The reference expands the grid (expand.grid) and evaluates point by point; here the
  * structure is used: one basis matrix per dimension and one mode product per dimension.

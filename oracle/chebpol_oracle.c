@@ -918,3 +918,33 @@ API int oracle_evalsl(const double *x, int64_t npts, const double *knots, int di
         out[i] = sl_point(x + i * dim, knots, dtri, lumats, pivots, bbox, epol, val, dim, numsimplex, nknots, blend);
     return 0;
 }
+
+/* index (0-based) of the simplex findsimplex accepts for each point, -1 outside the hull: the
+ * scan of sl_point without the interpolation.  Lets tests check candidate-list structures. */
+API int oracle_sl_index(const double *x, int64_t npts, int dim, int numsimplex, const double *lumats,
+                        const int *pivots, const double *bbox, int threads, int *out)
+{
+    if (dim < 1 || dim >= ORACLE_MAXRANK) return 1;
+    const int N = dim + 1;
+#pragma omp parallel for num_threads(threads) schedule(guided) if (npts > 1 && threads > 1)
+    for (int64_t i = 0; i < npts; ++i) {
+        const double *xi = x + i * dim;
+        double vec[ORACLE_MAXRANK + 1];
+        int hit = -1;
+        for (int s = 0; s < numsimplex && hit < 0; ++s) {
+            const double *box = bbox + (int64_t)s * 2 * dim;
+            int bad = 0;
+            for (int k = 0; k < dim; ++k)
+                if (xi[k] < box[2 * k] || xi[k] > box[2 * k + 1]) { bad = 1; break; }
+            if (bad) continue;
+            for (int d = 0; d < dim; ++d) vec[d] = xi[d];
+            vec[dim] = 1.0;
+            lu_solve(N, lumats + (int64_t)s * N * N, pivots + (int64_t)s * N, vec);
+            for (int d = 0; d < N; ++d)
+                if (vec[d] < -1e-10) { bad = 1; break; }
+            if (!bad) hit = s;
+        }
+        out[i] = hit;
+    }
+    return 0;
+}

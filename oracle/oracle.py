@@ -308,6 +308,19 @@ class Oracle:
           piv.ctypes.data_as(_ip), _ptr(bbox), _ptr(val), int(bool(epol)), threads, blend, _ptr(out))
         return out
 
+    def sl_index(self, x, dim, adata, threads: int = 1):
+        """0-based index of the simplex the reference accepts for each point (-1: outside the hull)."""
+        lib = Oracle("port").lib if self.kind == "reference" else self.lib
+        lu, piv, bbox = adata
+        ns = bbox.size // (2 * dim)
+        x = _as_pts(x, dim)
+        out = np.empty(x.shape[0], dtype=np.int32)
+        f = lib.oracle_sl_index
+        f.restype = C.c_int
+        f.argtypes = [_dp, C.c_int64, C.c_int, C.c_int, _dp, _ip, _dp, C.c_int, _ip]
+        f(_ptr(x), x.shape[0], dim, ns, _ptr(lu), piv.ctypes.data_as(_ip), _ptr(bbox), threads, out.ctypes.data_as(_ip))
+        return out
+
     # -- fit side (fixtures) -------------------------------------------------
     def fhweights(self, grid, d):
         d = np.broadcast_to(np.asarray(d, dtype=np.int64), (len(grid),))
