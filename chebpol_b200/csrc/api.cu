@@ -793,6 +793,19 @@ extern "C" int chebpol_cuda_plan_set(chebpol_cuda_plan *p, int option, int64_t v
     case CHEBPOL_CUDA_OPT_VARIANT:
         p->variant = (int)value;
         return CHEBPOL_CUDA_OK;
+    case CHEBPOL_CUDA_OPT_SL_CELLS: {
+        if (p->kind != PLAN_SL) return fail(CHEBPOL_CUDA_EINVAL, "cell grid applies to simplex-linear plans");
+        if (value < 0 || value > 4096) return fail(CHEBPOL_CUDA_EINVAL, "cells per dimension %lld", (long long)value);
+        int cur = -1;
+        CU(cudaGetDevice(&cur));
+        if (cur != p->device) CU(cudaSetDevice(p->device));
+        cudaError_t e = sl_force_cells(p->sl, (int)value);
+        if (cur != p->device) cudaSetDevice(cur);
+        if (e == cudaErrorNotSupported) return fail(CHEBPOL_CUDA_EINVAL, "no cell-list kernel for %d-dimensional simplices", p->rank);
+        if (e != cudaSuccess) return cuda_fail(e, "cell lists");
+        p->tensor_bytes = sl_bytes(p->sl);
+        return CHEBPOL_CUDA_OK;
+    }
     case CHEBPOL_CUDA_OPT_EPOL:
         if (p->kind != PLAN_SL) return fail(CHEBPOL_CUDA_EINVAL, "epol applies to simplex-linear plans");
         p->epol = value != 0;

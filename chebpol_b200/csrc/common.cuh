@@ -257,6 +257,7 @@ cudaError_t sl_create(const double *knots, int dim, int nknots, const int *dtri,
                       const int *pivots, const double *bbox, const double *val, int cells_per_dim, SlDevice **out);
 void sl_destroy(SlDevice *d);
 int64_t sl_bytes(const SlDevice *d);
+cudaError_t sl_force_cells(SlDevice *d, int cells_per_dim);
 cudaError_t launch_sl(SlDevice *d, int kernel, int variant, int epol, int blend, const double *x, int64_t npts,
                       double *out, int num_sms, cudaStream_t s, LaunchInfo *li);
 int sl_debug_lists(const double *knots, int dim, int nknots, const int *dtri, int ns, const double *bbox, int G,

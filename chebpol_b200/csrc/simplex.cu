@@ -40,6 +40,7 @@ struct SlDevice {
     double glo[CP_MAXR] = {0}, ghi[CP_MAXR] = {0};  // bounding box of all simplices
     int64_t bytes = 0, nitems = 0, ncells = 0, cell_bytes = 0;
     int forced_G = 0;
+    int64_t points_seen = 0;  // evaluated by this plan so far: sizes the grid (sl_wanted_G)
     // host copies kept for (re)building the cell lists
     std::vector<double> h_bbox, h_aff, h_tol;
 };
@@ -669,17 +670,27 @@ cudaError_t sl_create(const double *knots, int dim, int nknots, const int *dtri,
     return cudaSuccess;
 }
 
-// Cells wanted for a batch of npts points: building costs about one visit per (simplex, overlapped
-// cell), scanning costs about one box test per list entry per point; about one cell per two points,
-// between ns/4 and 32 ns (133k simplices in 3-D: 82 / 128 / 160 cells per dimension measured
-// 2.39 / 2.65 / 2.76e9 evals/s before pruning, tools/sl_sweep.sh).
-static int sl_wanted_G(const SlDevice *d, int64_t npts)
+// Cells wanted once a plan has evaluated `seen` points in total.  Building visits every (simplex,
+// overlapped cell) pair on the host (133k simplices in 3-D, 8 cores: 0.07 / 0.22 / 0.97 / 2.7 s for
+// 41 / 82 / 163 / 256 cells per dimension) while a point costs 0.46 / 0.3 / 0.18 / 0.15 ns to
+// evaluate, so a fine grid only pays for a plan that lives long: about one cell per 64 points seen,
+// between ns/4 and 128 ns.  launch_sl rebuilds when this has grown 8-fold, so the total build time
+// stays a fraction of the evaluation time; CHEBPOL_CUDA_OPT_SL_CELLS / CHEBPOL_CUDA_SL_CELLS pin it.
+static int sl_wanted_G(const SlDevice *d, int64_t seen)
 {
-    double cells = (double)npts / 2.0;
+    double cells = (double)seen / 64.0;
     cells = std::max(cells, (double)d->ns / 4.0);
-    cells = std::min(cells, 32.0 * (double)d->ns);
+    cells = std::min(cells, 128.0 * (double)d->ns);
     cells = std::min(cells, (double)(1 << 24));
     return std::max(1, (int)ceil(pow(cells, 1.0 / d->dim)));
+}
+
+cudaError_t sl_force_cells(SlDevice *d, int cells_per_dim)
+{
+    if (!d || d->rs <= 0) return cudaErrorNotSupported;
+    d->forced_G = cells_per_dim > 0 ? cells_per_dim : 0;
+    if (!d->forced_G) return cudaSuccess;
+    return sl_build_cells(d, d->forced_G);
 }
 
 int64_t sl_bytes(const SlDevice *d) { return d ? d->bytes : 0; }
@@ -704,7 +715,7 @@ cudaError_t launch_sl(SlDevice *d, int kernel, int variant, int epol, int blend,
         // a small first batch is cheaper through the plain scan than through building the lists
         if (!d->cell_start && kernel == CHEBPOL_CUDA_KERNEL_AUTO && npts * (int64_t)d->ns < (int64_t(1) << 32)) use_cell = false;  // scan: ~2.5 ps per point and simplex
         else {
-            const int G = sl_wanted_G(d, npts);
+            const int G = sl_wanted_G(d, d->points_seen + npts);
             if (!d->cell_start || pow((double)G, d->dim) >= 8.0 * (double)d->ncells) {
                 cudaError_t be = sl_build_cells(d, G);
                 if (be != cudaSuccess) {
@@ -717,6 +728,7 @@ cudaError_t launch_sl(SlDevice *d, int kernel, int variant, int epol, int blend,
             }
         }
     }
+    d->points_seen += npts;
     a.cell_start = d->cell_start; a.cell_items = d->cell_items;
     for (int j = 0; j < SL_MAXCELLDIM; ++j) { a.G[j] = d->G[j]; a.lo[j] = d->lo[j]; a.inv[j] = d->inv[j]; }
     if (use_cell) {

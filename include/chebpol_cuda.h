@@ -139,6 +139,8 @@ CHEBPOL_CUDA_API int chebpol_cuda_plan_eval_host(chebpol_cuda_plan *plan, const 
 #define CHEBPOL_CUDA_OPT_CHUNK_POINTS 3 /* eval_host chunk size in points (0 = auto)      */
 #define CHEBPOL_CUDA_OPT_VARIANT 4     /* which fast kernel / layout (0 = auto), see below  */
 #define CHEBPOL_CUDA_OPT_EPOL 5        /* simplex-linear plans: extrapolate outside the hull */
+#define CHEBPOL_CUDA_OPT_SL_CELLS 6    /* simplex-linear plans: pin the candidate grid to this many cells
+                                          per dimension and build it now (0: back to automatic sizing)  */
 #define CHEBPOL_CUDA_GET_KERNEL_USED 101  /* kernel id of the most recent eval            */
 #define CHEBPOL_CUDA_GET_LAUNCHES 102     /* kernels launched by this plan so far         */
 #define CHEBPOL_CUDA_GET_TENSOR_BYTES 103 /* device bytes of the resident tensor          */

@@ -1172,9 +1172,13 @@ def test_simplexlinear_cell_resolutions_and_stateless(gpu_ok, port, monkeypatch)
     assert k == "sl_cell" and nan_aware_bits_equal(got, want[:20000])
     got, k = eval_plan(plan, x[:500], _lib.KERNEL_AUTO)  # the lists exist now
     assert k == "sl_cell" and nan_aware_bits_equal(got, want[:500])
-    xx = np.tile(x, (6, 1))
+    xx = np.tile(x, (20, 1))
     got, k = eval_plan(plan, xx, _lib.KERNEL_AUTO)
-    assert k == "sl_cell" and nan_aware_bits_equal(got, np.tile(want, 6))
+    assert k == "sl_cell" and nan_aware_bits_equal(got, np.tile(want, 20))
+    for cells in (33, 0, 5):  # pinned grid, back to automatic, pinned again
+        plan.set(_lib.OPT_SL_CELLS, cells)
+        got, k = eval_plan(plan, x, _lib.KERNEL_AUTO)
+        assert k == "sl_cell" and nan_aware_bits_equal(got, want), cells
     plan.close()
     got = _lib.evalsl(x, knots, dtri, ad, val, True, 3, 0)
     assert nan_aware_bits_equal(got, want)
