@@ -52,7 +52,7 @@ CONFIGS = {
             name="cfg7 (SURVEY 8f row 3): 3-D hyperbolic stalker spline on a 64^3 grid, cubic blend, 5e7 points"),
     8: dict(kind="sl", dims=(3,), rank=3, nknots=20000, points=50_000_000,
             name="cfg8 (beyond SURVEY 8f): 3-D simplex-linear on the Delaunay triangulation of 20000 scattered knots, cubic blend, 5e7 points"),
-    5: dict(kind="cheb", dims=(12,) * 6, points=20_000_000, name="cfg5: 6-D Chebyshev dims=rep(12,6), 2e7 points per GPU (1e9 total is ~3 min/step/8 GPUs)"),
+    5: dict(kind="cheb", dims=(12,) * 6, points=20_000_000, name="cfg5: 6-D Chebyshev dims=rep(12,6); default 2e7 points per GPU, --total-points 1000000000 for the full sharded batch"),
 }
 
 
@@ -292,6 +292,8 @@ def run_ours(args, cfg):
     if world > 1:
         shard.init_process_group("nccl")
     npts = args.points if args.points else cfg["points"]
+    if args.total_points:  # strong scaling: a fixed batch split into contiguous shards, one per GPU
+        npts = (args.total_points + world - 1) // world
     k = cfg.get("rank", len(cfg["dims"]))
     case = build_case(cfg)
     plan = make_plan(cfg, case, local_rank)
@@ -313,8 +315,9 @@ def run_ours(args, cfg):
     def step():
         plan.eval_device_ptr(x.data_ptr(), npts, out.data_ptr(), stream.cuda_stream)
 
+    wpts = min(npts, args.warmup_points) if args.warmup_points else npts
     for _ in range(args.warmup):
-        step()
+        plan.eval_device_ptr(x.data_ptr(), wpts, out.data_ptr(), stream.cuda_stream)
     torch.cuda.synchronize(dev)
 
     # FP64 peak (roofline denominator), measured now so clocks match the run
@@ -357,28 +360,29 @@ def run_ours(args, cfg):
 
     # ---- end to end through the host-pointer C ABI, pinned host buffers
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
-    hx = torch.empty((npts, k), dtype=torch.float64, pin_memory=True)
-    ho = torch.empty(npts, dtype=torch.float64, pin_memory=True)
-    hx.copy_(x)
+    epts = min(npts, args.e2e_points) if args.e2e_points else npts  # bounds the pinned host memory per rank
+    hx = torch.empty((epts, k), dtype=torch.float64, pin_memory=True)
+    ho = torch.empty(epts, dtype=torch.float64, pin_memory=True)
+    hx.copy_(x[:epts])
     torch.cuda.synchronize(dev)
     del x, out
     torch.cuda.empty_cache()
-    plan.eval_host_ptr(hx.data_ptr(), min(npts, 1 << 22), ho.data_ptr())  # warm the pipeline buffers
+    plan.eval_host_ptr(hx.data_ptr(), min(epts, 1 << 22), ho.data_ptr())  # warm the pipeline buffers
     shard.barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        plan.eval_host_ptr(hx.data_ptr(), npts, ho.data_ptr())
+        plan.eval_host_ptr(hx.data_ptr(), epts, ho.data_ptr())
     e2e_s = time.perf_counter() - t0
     shard.barrier()
     e2e_s = shard.max_over_ranks(e2e_s, dev)
-    e2e_value = npts * world * e2e_steps / e2e_s
+    e2e_value = epts * world * e2e_steps / e2e_s
 
     # ---- CPU baseline: rank 0, N = 1 only
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu:
         orc, okind = get_oracle()
         threads = os.cpu_count() or 1
-        n = min(cpu_sample_size(orc, cfg, case, threads, target_s=10.0), npts)
+        n = min(cpu_sample_size(orc, cfg, case, threads, target_s=10.0), epts)
         xs = hx[:n].numpy()
         dt = time_cpu(orc, cfg, case, np.ascontiguousarray(xs), threads)
         cpu_baseline = {"value": n / dt, "unit": UNIT, "cores": threads, "kind": okind,
@@ -434,11 +438,14 @@ def run_ours(args, cfg):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": "strong" if args.total_points else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": cfg["name"], "points_per_gpu": npts, "parallelism": f"points sharded over {world} GPU(s), tensor replicated",
+                       **({"total_points": args.total_points} if args.total_points else {}),
+                       **({"warmup_points": wpts} if wpts != npts else {}),
                        "l2": "inputs larger than L2 (point batch %.1f GB)" % (npts * k * 8 / 1e9) if npts * k * 8 > 126e6
                        else "inputs smaller than L2 (latency regime, reported not targeted)"},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": npts * k * 8, "d2h_bytes_per_step": npts * 8,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": epts * k * 8, "d2h_bytes_per_step": epts * 8,
+                    **({"points_per_gpu": epts} if epts != npts else {}),
                     "steps": e2e_steps, "api": "chebpol_cuda_plan_eval_host (pinned host buffers)"},
             "gpu_launches": int(launches),
             "clocks": clocks,
@@ -463,6 +470,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS))
     ap.add_argument("--points", type=int, default=0, help="override points per GPU")
+    ap.add_argument("--total-points", type=int, default=0, help="strong scaling: this many points split over the GPUs")
+    ap.add_argument("--warmup-points", type=int, default=0, help="points per warm-up step (default: a full step)")
+    ap.add_argument("--e2e-points", type=int, default=0, help="cap the points per GPU of the end-to-end leg (pinned host memory)")
     ap.add_argument("--variant", type=int, default=0, help="kernel tuning variant (0 = default)")
     ap.add_argument("--strict", action="store_true", help="use the reference-order kernels")
     ap.add_argument("--e2e-steps", type=int, default=2)

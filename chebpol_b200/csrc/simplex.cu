@@ -229,8 +229,16 @@ __device__ __forceinline__ bool sl_accept(const double *__restrict__ rec, const 
 {
     constexpr int N = DIM + 1;
     double lu[N * N];
+    {   // the LU block starts 16-byte aligned (2 DIM doubles into a 32-byte aligned record)
+        const double2 *q = reinterpret_cast<const double2 *>(rec + 2 * DIM);
 #pragma unroll
-    for (int i = 0; i < N * N; ++i) lu[i] = __ldg(rec + 2 * DIM + i);
+        for (int i = 0; i + 1 < N * N; i += 2) {
+            const double2 v = __ldg(q + i / 2);
+            lu[i] = v.x;
+            lu[i + 1] = v.y;
+        }
+        if ((N * N) & 1) lu[N * N - 1] = __ldg(rec + 2 * DIM + N * N - 1);
+    }
     const unsigned perm = (unsigned)__double_as_longlong(__ldg(rec + 2 * DIM + N * N + N));
     double b[N];
     sl_permuted_rhs<DIM>(x, perm, b);
@@ -306,6 +314,64 @@ __global__ void __launch_bounds__(128, MINB) sl_cell_kernel(const __grid_constan
                 res = sl_na_real();
         }
         a.out[p] = res;
+    }
+}
+
+// The same search as a per-lane state machine.  In sl_cell_kernel a warp stays on its 32 points until
+// the slowest lane has found its simplex (1 to 6+ LU solves per point, so half the issue slots go to
+// masked lanes).  Here every trip of the loop does, for each lane independently, "advance to the next
+// candidate whose box holds my point, solve it, and on acceptance (or an exhausted list) store the
+// result and move on to my next point": lanes progress through their own points at their own pace and
+// the expensive solve is executed by all lanes together.  Candidate order per point is unchanged, so
+// the result is the same bits.
+template <int DIM, int MINB>
+__global__ void __launch_bounds__(128, MINB) sl_cell_sm_kernel(const __grid_constant__ SlArgs a)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    double x[DIM];
+    int it = 0, end = 0;
+    bool ident = false;  // NaN coordinate: the candidates are all simplices in order (see sl_cell_kernel)
+    auto open_point = [&]() {
+        bool nan = false;
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) {
+            x[d] = a.x[p * DIM + d];
+            nan |= (x[d] != x[d]);
+        }
+        ident = nan;
+        if (nan) { it = 0; end = a.ns; return; }
+        int cell = 0;
+#pragma unroll
+        for (int d = DIM - 1; d >= 0; --d) cell = cell * a.G[d] + sl_cell_of(x[d], a.lo[d], a.inv[d], a.G[d]);
+        it = __ldg(a.cell_start + cell);
+        end = __ldg(a.cell_start + cell + 1);
+    };
+    if (p < a.npts) open_point();
+    while (p < a.npts) {
+        // next candidate whose box holds the point
+        const double *rec = nullptr;
+        while (it < end) {
+            const int s = ident ? it : __ldg(a.cell_items + it);
+            ++it;
+            const double *r = a.records + (int64_t)s * a.rs;
+            if (sl_box<DIM>(r, x)) { rec = r; break; }
+        }
+        double res = 0.0;
+        bool done = rec == nullptr;
+        if (rec) done = sl_accept<DIM>(rec, x, a.blend, &res);
+        else if (a.epol) {
+            double xl[DIM];
+#pragma unroll
+            for (int d = 0; d < DIM; ++d) xl[d] = x[d];
+            res = sl_extrapolate(a, xl);
+        } else
+            res = sl_na_real();
+        if (done) {
+            a.out[p] = res;
+            p += stride;
+            if (p < a.npts) open_point();
+        }
     }
 }
 
@@ -749,7 +815,18 @@ cudaError_t launch_sl(SlDevice *d, int kernel, int variant, int epol, int blend,
     case 5: SL_LAUNCH(5, B, M); break;                                                                         \
     default: SL_LAUNCH(6, B, M); break;                                                                        \
     }
+#define SL_SM(M)                                                                                               \
+    switch (d->dim) {                                                                                          \
+    case 1: sl_cell_sm_kernel<1, M><<<(int)nb, block, 0, s>>>(a); break;                                       \
+    case 2: sl_cell_sm_kernel<2, M><<<(int)nb, block, 0, s>>>(a); break;                                       \
+    case 3: sl_cell_sm_kernel<3, M><<<(int)nb, block, 0, s>>>(a); break;                                       \
+    case 4: sl_cell_sm_kernel<4, M><<<(int)nb, block, 0, s>>>(a); break;                                       \
+    case 5: sl_cell_sm_kernel<5, M><<<(int)nb, block, 0, s>>>(a); break;                                       \
+    default: sl_cell_sm_kernel<6, M><<<(int)nb, block, 0, s>>>(a); break;                                      \
+    }
         switch (code) {
+        case 900: SL_SM(8); break;
+        case 901: SL_SM(1); break;
         case 1: SL_DIMS(1, 1); break;
         case 2: SL_DIMS(2, 1); break;
         case 8: SL_DIMS(8, 1); break;
@@ -759,6 +836,7 @@ cudaError_t launch_sl(SlDevice *d, int kernel, int variant, int epol, int blend,
         default: SL_DIMS(4, 8); break;
         }
 #undef SL_DIMS
+#undef SL_SM
 #undef SL_LAUNCH
         if (li) { li->grid = (int)nb; li->block = block; li->smem = 0; li->kernel = K_SL_CELL; }
         return cudaGetLastError();

@@ -1135,9 +1135,10 @@ def test_simplexlinear_strict_and_cell(gpu_ok, port, dim, nk):
             else:
                 assert nan_aware_bits_equal(got, want), (epol, blend)
             if dim <= 6:
-                got2, k = eval_plan(plan, x, _lib.KERNEL_FAST)
-                assert k == "sl_cell"
-                assert nan_aware_bits_equal(got2, got), (epol, blend)  # the two kernels agree bit for bit
+                for variant in (0, 804, 900, 2):  # default, batched, per-lane state machine, 100-register build
+                    got2, k = eval_plan(plan, x, _lib.KERNEL_FAST, variant)
+                    assert k == "sl_cell"
+                    assert nan_aware_bits_equal(got2, got), (epol, blend, variant)  # the kernels agree bit for bit
     if dim > 6:
         got, k = eval_plan(plan, x, _lib.KERNEL_AUTO)
         assert k == "sl_strict"
