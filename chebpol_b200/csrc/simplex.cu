@@ -762,7 +762,7 @@ cudaError_t sl_force_cells(SlDevice *d, int cells_per_dim)
 int64_t sl_bytes(const SlDevice *d) { return d ? d->bytes : 0; }
 
 // kernel: 0 auto, 1 strict, 2 fast (cudaErrorNotSupported if there is no cell structure)
-#define SL_DEFAULT_VARIANT 804  // batch 4 at 64 registers: occupancy beats batching (tools/sl_sweep.sh)
+#define SL_DEFAULT_VARIANT 900  // per-lane state machine at 64 registers (tools/sl_sweep.sh: 8.6e9 vs 7.4e9 batched)
 cudaError_t launch_sl(SlDevice *d, int kernel, int variant, int epol, int blend, const double *x, int64_t npts,
                       double *out, int num_sms, cudaStream_t s, LaunchInfo *li)
 {
@@ -803,7 +803,8 @@ cudaError_t launch_sl(SlDevice *d, int kernel, int variant, int epol, int blend,
         const int64_t cap = (int64_t)num_sms * 16;
         if (nb > cap) nb = cap;
         if (nb < 1) nb = 1;
-        // variant = batch + 100*minblocks (tuning / ncu evidence); 0: the measured default
+        // variant (tuning / ncu evidence; 0: the measured default): 900 / 901 per-lane state machine at
+        // 64 registers / unconstrained; batch + 100*minblocks for the point-per-thread kernel
         const int code = variant > 0 ? variant : SL_DEFAULT_VARIANT;
 #define SL_LAUNCH(D, B, M) sl_cell_kernel<D, B, M><<<(int)nb, block, 0, s>>>(a)
 #define SL_DIMS(B, M)                                                                                          \
