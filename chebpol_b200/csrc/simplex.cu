@@ -779,7 +779,8 @@ cudaError_t launch_sl(SlDevice *d, int kernel, int variant, int epol, int blend,
     bool use_cell = can_cell && kernel != CHEBPOL_CUDA_KERNEL_STRICT;
     if (use_cell && !d->forced_G) {
         // a small first batch is cheaper through the plain scan than through building the lists
-        if (!d->cell_start && kernel == CHEBPOL_CUDA_KERNEL_AUTO && npts * (int64_t)d->ns < (int64_t(1) << 32)) use_cell = false;  // scan: ~2.5 ps per point and simplex
+        if (!d->cell_start && kernel == CHEBPOL_CUDA_KERNEL_AUTO && (d->points_seen + npts) * (int64_t)d->ns < (int64_t(1) << 32))
+            use_cell = false;  // scan: ~2.5 ps per point and simplex; counted over the plan's life, not per call
         else {
             const int G = sl_wanted_G(d, d->points_seen + npts);
             if (!d->cell_start || pow((double)G, d->dim) >= 8.0 * (double)d->ncells) {
