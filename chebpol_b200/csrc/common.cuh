@@ -54,7 +54,9 @@ __device__ __forceinline__ double premap_coord(const PreMap &pm, int d, double v
         const double n = pm.nd[d];
         v = sin(0.5 * 3.141592653589793 * v * (1.0 - n) / n);
     }
+#ifndef CP_NO_SPLINE  // A/B switch for measuring what the extra prologue branch costs the small kernels
     if (pm.mode & 4) v = premap_spline(pm, d, v);
+#endif
     return v;
 }
 
