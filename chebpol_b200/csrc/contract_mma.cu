@@ -248,7 +248,9 @@ bool mma_configure(MmaArgs &a, int kind, int rank, const int *dims, int *kc_out)
     a.nlg = a.nlev > 1 ? a.nlev - 1 : 0;
     // level A: the first unfolded dim (absent: one entry weighted by the table's ones row)
     a.nA = a.nlev >= 1 ? dims[best_nf] : 1;
-    a.ntb = 2;  // 4 N-tiles per step measured no faster for short K (FH 40^3: 0.725 vs 0.72)
+    // 4 N-tiles per step measured slower, twice: FH 40^3 0.725 vs 0.72 on the first engine, and with the
+    // current one (gpurun_out/ntb_sweep.log) FH 0.794 vs 0.828, cfg2 0.79 vs 0.945 of the FP64 peak
+    a.ntb = 2;
     a.nAp = (a.nA + a.ntb - 1) / a.ntb * a.ntb;
     a.boffA = a.nlev >= 1 ? a.boff[best_nf] : a.sumn;
     int64_t nrp = 1;
