@@ -13,6 +13,7 @@
 #include <string>
 #include <thread>
 #include <vector>
+#include <exception>
 
 // --------------------------------------------------------------- error state
 static thread_local std::string g_last_error;
@@ -714,7 +715,13 @@ extern "C" int chebpol_cuda_plan_sl(const double *knots, int dim, int nknots, co
     p->blend = 3;  // the closure's default, 'cubic' (R/simplexlinear.R:36)
     p->nknots = nknots;
     const char *env = getenv("CHEBPOL_CUDA_SL_CELLS");
-    cudaError_t e = sl_create(knots, dim, nknots, dtri, numsimplex, lumats, pivots, bbox, val, env ? atoi(env) : 0, &p->sl);
+    cudaError_t e = cudaSuccess;
+    try {  // host-side tables are std::vectors: an allocation failure must not cross the C boundary
+        e = sl_create(knots, dim, nknots, dtri, numsimplex, lumats, pivots, bbox, val, env ? atoi(env) : 0, &p->sl);
+    } catch (const std::exception &ex) {
+        chebpol_cuda_plan_destroy(p);
+        return fail(CHEBPOL_CUDA_ENOMEM, "simplex tables: %s", ex.what());
+    }
     if (e != cudaSuccess) {
         chebpol_cuda_plan_destroy(p);
         return cuda_fail(e, "simplex tables");
@@ -765,8 +772,13 @@ extern "C" int chebpol_cuda_debug_sl_lists(const double *knots, int dim, int nkn
 {
     if (!knots || !dtri || !bbox || !cells_used || !lo || !inv || !start || !items || !nitems)
         return fail(CHEBPOL_CUDA_EINVAL, "a pointer is NULL");
-    const int rc = sl_debug_lists(knots, dim, nknots, dtri, numsimplex, bbox, cells_per_dim, cells_used, lo, inv, start,
-                                  start_cap, items, items_cap, nitems);
+    int rc = 0;
+    try {
+        rc = sl_debug_lists(knots, dim, nknots, dtri, numsimplex, bbox, cells_per_dim, cells_used, lo, inv, start,
+                            start_cap, items, items_cap, nitems);
+    } catch (const std::exception &ex) {
+        return fail(CHEBPOL_CUDA_ENOMEM, "candidate lists: %s", ex.what());
+    }
     if (rc == 1) return fail(CHEBPOL_CUDA_ERANK, "cell lists exist for 1..6 dimensions and at least one simplex");
     if (rc == 2) return fail(CHEBPOL_CUDA_ESIZE, "start / items buffers too small");
     return CHEBPOL_CUDA_OK;
@@ -799,7 +811,13 @@ extern "C" int chebpol_cuda_plan_set(chebpol_cuda_plan *p, int option, int64_t v
         int cur = -1;
         CU(cudaGetDevice(&cur));
         if (cur != p->device) CU(cudaSetDevice(p->device));
-        cudaError_t e = sl_force_cells(p->sl, (int)value);
+        cudaError_t e = cudaSuccess;
+        try {
+            e = sl_force_cells(p->sl, (int)value);
+        } catch (const std::exception &ex) {
+            if (cur != p->device) cudaSetDevice(cur);
+            return fail(CHEBPOL_CUDA_ENOMEM, "candidate lists: %s", ex.what());
+        }
         if (cur != p->device) cudaSetDevice(cur);
         if (e == cudaErrorNotSupported) return fail(CHEBPOL_CUDA_EINVAL, "no cell-list kernel for %d-dimensional simplices", p->rank);
         if (e != cudaSuccess) return cuda_fail(e, "cell lists");
@@ -1004,7 +1022,11 @@ static int launch_plan(chebpol_cuda_plan *p, const double *d_x, int64_t npts, do
             e = launch_stalk_strict(a, s, &li);
         }
     } else if (p->kind == PLAN_SL) {
-        e = launch_sl(p->sl, p->kernel_opt, p->variant, p->epol, p->blend, d_x, npts, d_out, p->num_sms, s, &li);
+        try {  // may (re)build the candidate lists on the host
+            e = launch_sl(p->sl, p->kernel_opt, p->variant, p->epol, p->blend, d_x, npts, d_out, p->num_sms, s, &li);
+        } catch (const std::exception &ex) {
+            return fail(CHEBPOL_CUDA_ENOMEM, "candidate lists: %s", ex.what());
+        }
         if (e == cudaErrorNotSupported)
             return fail(CHEBPOL_CUDA_EINVAL, "no cell-list kernel for %d-dimensional simplices", p->rank);
     } else {

@@ -125,7 +125,9 @@ CHEBPOL_CUDA_API void chebpol_cuda_plan_destroy(chebpol_cuda_plan *plan);
 
 /* d_x (rank*npts doubles, point-major) and d_out (npts doubles) are DEVICE
  * pointers on the plan's device; `stream` is a cudaStream_t (NULL = default
- * stream).  Asynchronous: returns after enqueueing. */
+ * stream).  Asynchronous: returns after enqueueing -- except that a plan may first build a
+ * derived table it has not built yet (the multilinear cell-major table on the stream; the
+ * simplex-linear candidate lists on the host, which synchronises the device once). */
 CHEBPOL_CUDA_API int chebpol_cuda_plan_eval_device(chebpol_cuda_plan *plan, const double *d_x,
                                   int64_t npts, double *d_out, void *stream);
 /* Host pointers (pinned or pageable); chunked, double-buffered H2D -> kernel
