@@ -1215,3 +1215,47 @@ def test_simplexlinear_goldens_through_ipol(gpu_ok):
     G = cb.evalongridV(sl, grid=[np.linspace(0.2, 0.8, 4)] * 3)
     assert G.shape == (4, 4, 4) and np.isfinite(G).all()
     sl.close()
+
+
+def test_full_size_simplexlinear_properties(gpu_ok, port):
+    """Size-independent properties at 2e7 points (the oracle's linear scan would take minutes):
+    with the linear blend a simplex-linear interpolant reproduces every affine function inside the
+    hull; the set of points outside the hull (NA) and every value agree with the plain-scan kernel on
+    a strided sample; a contiguous slice evaluates to the same bits as the same points inside the
+    big batch (chunking / sharding independence)."""
+    import torch
+
+    knots, dtri, _ = cases.sl_case(3, 5000, seed=4)
+    ad = _lib.analyzesimplex(dtri, knots)
+    coef = np.array([0.7, -1.3, 0.4])
+    val = knots.T @ coef + 0.25  # affine in the knots
+    n = 20_000_000
+    g = torch.Generator(device="cuda").manual_seed(11)
+    x = torch.rand((n, 3), generator=g, device="cuda", dtype=torch.float64) * 2.1 - 1.05
+    plan = _lib.Plan.sl(knots, dtri, ad, val)
+    plan.set(_lib.OPT_BLEND, 0)
+    out = plan.eval_torch(x)
+    assert plan.kernel_used == "sl_cell"
+    want = x @ torch.tensor(coef, device="cuda") + 0.25
+    inside = ~torch.isnan(out)
+    frac = float(inside.double().mean())
+    assert 0.5 < frac < 0.95  # the hull of 5000 knots in [-1,1]^3 against points of [-1.05,1.05]^3
+    assert float((out[inside] - want[inside]).abs().max()) <= 1e-12
+    # strided sample against the plain scan (bit for bit, NA included)
+    idx = torch.arange(0, n, 997, device="cuda")
+    xs = x[idx].contiguous()
+    plan.set(_lib.OPT_KERNEL, _lib.KERNEL_STRICT)
+    ref = plan.eval_torch(xs)
+    assert plan.kernel_used == "sl_strict"
+    assert torch.equal(ref.view(torch.int64), out[idx].view(torch.int64))
+    # a slice evaluated on its own (host path, chunked) gives the same bits
+    plan.set(_lib.OPT_KERNEL, _lib.KERNEL_AUTO)
+    lo, hi = 7_000_001, 7_300_003
+    got = plan.eval_host(np.ascontiguousarray(x[lo:hi].cpu().numpy()))
+    assert np.array_equal(bits(got), bits(out[lo:hi].cpu().numpy()))
+    # extrapolation: affine functions are reproduced outside the hull too (barycentric combination)
+    plan.set(_lib.OPT_EPOL, 1)
+    oute = plan.eval_torch(x[:2_000_000].contiguous())
+    assert not bool(torch.isnan(oute).any())
+    assert float((oute - want[:2_000_000]).abs().max()) <= 1e-7  # slivers on the hull boundary amplify rounding
+    plan.close()
