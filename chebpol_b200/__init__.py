@@ -12,11 +12,11 @@ entry point fails with a ChebpolCudaError when no B200 is visible.
 from . import _lib
 from ._lib import ChebpolCudaError, Plan, device_count, fp64_peak_tflops, launch_count
 from .interp import (Interpolant, chebappx, chebappxf, chebappxg, chebappxgf, hyman_spline, chebcoef, chebeval, chebknots, evalongrid, evalongridV,
-                     fhappx, fhweights, hstalkerappx, ipol, mlappx, polyh, slappx, stalkerappx, ucappx, ucappxf)
+                     fhappx, fhweights, hstalkerappx, ipol, mlappx, oldstalkerappx, polyh, slappx, stalkerappx, ucappx, ucappxf)
 
 __version__ = "0.1.0"
 __all__ = [
-    "ipol", "chebappx", "chebappxf", "chebappxg", "chebappxgf", "hyman_spline", "mlappx", "fhappx", "polyh", "slappx", "stalkerappx", "hstalkerappx", "ucappx", "ucappxf", "chebeval", "chebknots",
+    "ipol", "chebappx", "chebappxf", "chebappxg", "chebappxgf", "hyman_spline", "mlappx", "fhappx", "polyh", "slappx", "oldstalkerappx", "stalkerappx", "hstalkerappx", "ucappx", "ucappxf", "chebeval", "chebknots",
     "chebcoef", "evalongrid", "evalongridV", "fhweights", "Interpolant", "Plan", "ChebpolCudaError", "device_count",
     "fp64_peak_tflops", "launch_count",
 ]

@@ -29,7 +29,7 @@ VARIANT_MLIP_PAIR, VARIANT_MLIP_CELL = 1, 2
 KERNEL_NAMES = {
     0: "none", 10: "cheb_strict", 11: "cheb_slab", 12: "cheb_mma", 20: "mlip_strict", 21: "mlip_pair", 22: "mlip_cell",
     30: "fh_strict", 32: "fh_mma", 40: "polyh_strict", 41: "polyh_tile", 50: "stalk_strict", 51: "stalk_cell",
-    60: "sl_strict", 61: "sl_cell",
+    52: "oldstalk", 60: "sl_strict", 61: "sl_cell",
 }
 
 EXPORTS = [
@@ -43,6 +43,7 @@ EXPORTS = [
     "chebpol_cuda_evalpolyh", "chebpol_cuda_plan_polyh",
     "chebpol_cuda_evalstalk", "chebpol_cuda_evalhyp", "chebpol_cuda_plan_stalk",
     "chebpol_cuda_evalchebg", "chebpol_cuda_plan_chebg",
+    "chebpol_cuda_evalstalker", "chebpol_cuda_plan_oldstalk",
     "chebpol_cuda_evalsl", "chebpol_cuda_plan_sl", "chebpol_cuda_analyzesimplex", "chebpol_cuda_debug_sl_lists",
 ]
 
@@ -108,6 +109,10 @@ def lib() -> C.CDLL:
     L.chebpol_cuda_analyzesimplex.argtypes = [_vp, C.c_int, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp]
     L.chebpol_cuda_debug_sl_lists.argtypes = [_vp, C.c_int, C.c_int, _vp, C.c_int, _vp, C.c_int, _ip, _vp, _vp, _vp,
                                               C.c_int64, _vp, C.c_int64, C.POINTER(C.c_int64)]
+    L.chebpol_cuda_evalstalker.argtypes = [_vp, _dpp, _ip, C.c_int, _vp, _dpp, _dpp, _dpp, _ip, C.c_int, _vp, C.c_int64,
+                                           C.c_int, _vp]
+    L.chebpol_cuda_plan_oldstalk.argtypes = [_vp, _dpp, _ip, C.c_int, _vp, _dpp, _dpp, _dpp, _ip, C.c_int, C.c_int,
+                                             C.POINTER(_vp)]
     L.chebpol_cuda_cache_clear.restype = None
     L.chebpol_cuda_cache_clear.argtypes = []
     L.chebpol_cuda_launch_count.restype = C.c_int64
@@ -282,6 +287,17 @@ class Plan:
         return Plan(h.value, len(grid), "stalk")
 
     @staticmethod
+    def oldstalk(val, grid, degree, ctx, uniform, blend: int = 0, device: int = 0) -> "Plan":
+        """Deprecated recursive stalker evaluator; ctx = (det, pmin, pplus), lists of per-dimension vectors."""
+        dims, v, deg, uni, lists = _oldstalk_args(val, grid, degree, ctx, uniform)
+        gl, keep = ptr_list(grid)
+        h = _vp()
+        check(lib().chebpol_cuda_plan_oldstalk(_addr(v), gl, dims.ctypes.data_as(_ip), len(grid), _addr(deg),
+                                               lists[0][0], lists[1][0], lists[2][0], uni.ctypes.data_as(_ip), blend,
+                                               device, C.byref(h)))
+        return Plan(h.value, len(grid), "oldstalk")
+
+    @staticmethod
     def sl(knots, dtri, adata, val, device: int = 0) -> "Plan":
         """Simplex-linear plan.  knots: dim x nknots; dtri: (dim+1) x numsimplex, 1-based;
         adata = (lumats, pivots, bbox) as analyzesimplex returns them."""
@@ -343,6 +359,35 @@ class Plan:
             self.close()
         except Exception:
             pass
+
+
+# ---- deprecated recursive stalker ---------------------------------------------
+def _oldstalk_args(val, grid, degree, ctx, uniform):
+    dims = _i32([len(g) for g in grid])
+    n = int(np.prod(dims.astype(np.int64)))
+    v = f64(np.asarray(val, dtype=np.float64).ravel(order="F"))
+    if v.size != n:
+        raise ValueError(f"number of values ({v.size}) does not match grid size ({n})")
+    deg = f64(np.ravel(degree))
+    if deg.size != len(grid):
+        raise ValueError(f"degree length must match dimension ({len(grid)})")
+    uni = _i32(np.ravel(uniform))
+    lists = [ptr_list(c) for c in ctx]
+    for c in ctx:
+        if len(c) != len(grid) or any(len(a) != len(g) for a, g in zip(c, grid)):
+            raise ValueError("stalker context does not match the grid")
+    return dims, v, deg, uni, lists
+
+
+def evalstalker(val, grid, degree, ctx, uniform, x_pk, blend: int = 0, ngpus: int = 0) -> np.ndarray:
+    dims, v, deg, uni, lists = _oldstalk_args(val, grid, degree, ctx, uniform)
+    gl, keep = ptr_list(grid)
+    x = f64(x_pk)
+    out = np.empty(x.shape[0], dtype=np.float64)
+    check(lib().chebpol_cuda_evalstalker(_addr(v), gl, dims.ctypes.data_as(_ip), len(grid), _addr(deg), lists[0][0],
+                                         lists[1][0], lists[2][0], uni.ctypes.data_as(_ip), blend, _addr(x), x.shape[0],
+                                         ngpus, _addr(out)))
+    return out
 
 
 # ---- simplex-linear ------------------------------------------------------------

@@ -81,7 +81,7 @@ extern "C" int chebpol_cuda_device_count(int *count)
 }
 
 // ---------------------------------------------------------------------- plan
-enum PlanKind { PLAN_CHEB = 1, PLAN_MLIP = 2, PLAN_FH = 3, PLAN_POLYH = 4, PLAN_STALK = 5, PLAN_SL = 6 };
+enum PlanKind { PLAN_CHEB = 1, PLAN_MLIP = 2, PLAN_FH = 3, PLAN_POLYH = 4, PLAN_STALK = 5, PLAN_SL = 6, PLAN_OLDSTALK = 7 };
 
 cudaError_t stalk_pack_records(const double *val, const double *aa, const double *b, const double *t1,
                                const double *t2, int rank, int64_t n, double *rec, cudaStream_t s);
@@ -133,6 +133,9 @@ struct chebpol_cuda_plan {
     // simplex-linear: every device table of the triangulation (simplex.cu)
     SlDevice *sl = nullptr;
     int epol = 0;
+    // deprecated recursive stalker: values in d_tensor, knots in d_grid, det / pmin / pplus in d_stalk[0..2]
+    double os_degree[CP_MAXR] = {0};
+    int os_uniform[CP_MAXR] = {0};
     // statistics
     LaunchInfo last = {0, 0, 0, 0};
     int64_t launches = 0;
@@ -682,6 +685,51 @@ extern "C" int chebpol_cuda_plan_stalk(int kind, const double *val, const double
     return plan_ready(plan);
 }
 
+// Deprecated recursive stalker evaluator (oldstalkerappx, R/stalker.R:11-49; R_evalstalker src/stalker.c:834-891)
+extern "C" int chebpol_cuda_plan_oldstalk(const double *val, const double *const *grid, const int *dims, int rank,
+                                          const double *degree, const double *const *det, const double *const *pmin,
+                                          const double *const *pplus, const int *uniform, int blend, int device,
+                                          chebpol_cuda_plan **plan)
+{
+    if (!plan) return fail(CHEBPOL_CUDA_EINVAL, "plan is NULL");
+    *plan = nullptr;
+    if (!val || !grid || !degree || !det || !pmin || !pplus || !uniform) return fail(CHEBPOL_CUDA_EINVAL, "a table pointer is NULL");
+    if (blend < 0 || blend > 5) return fail(CHEBPOL_CUDA_EBLEND, "blend %d not in 0..5", blend);
+    int64_t nelem = 0;
+    int rc = check_dims(dims, rank, &nelem);
+    if (rc) return rc;
+    for (int d = 0; d < rank; ++d) {
+        if (dims[d] < 2) return fail(CHEBPOL_CUDA_ESIZE, "stalker grid %d needs at least 2 knots", d);
+        if (!det[d] || !pmin[d] || !pplus[d]) return fail(CHEBPOL_CUDA_EINVAL, "context vector of dimension %d is NULL", d);
+        // the reference's message when it is built without GSL (src/stalker.c:871-874)
+        if (!uniform[d] && degree[d] != degree[d])
+            return fail(CHEBPOL_CUDA_EINVAL, "Non-uniform grid in dimension %d not supported without GSL", d + 1);
+    }
+    int sms = 0;
+    rc = select_device(device, &sms);
+    if (rc) return rc;
+    chebpol_cuda_plan *p = new_plan(PLAN_OLDSTALK, device, sms, dims, rank, nelem);
+    p->blend = blend;
+    for (int d = 0; d < rank; ++d) { p->os_degree[d] = degree[d]; p->os_uniform[d] = uniform[d] != 0; }
+    auto bail = [&](int code) { chebpol_cuda_plan_destroy(p); return code; };
+    rc = upload_lists(p, grid, nullptr);
+    if (rc) return bail(rc);
+    const double *const *ctx[3] = {det, pmin, pplus};
+    for (int j = 0; j < 3; ++j) {
+        std::vector<double> h(p->grid_elems);
+        for (int d = 0; d < rank; ++d) memcpy(&h[p->goff[d]], ctx[j][d], sizeof(double) * dims[d]);
+        cudaError_t e = cudaMalloc(&p->d_stalk[j], sizeof(double) * h.size());
+        if (e == cudaSuccess) e = cudaMemcpy(p->d_stalk[j], h.data(), sizeof(double) * h.size(), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) return bail(cuda_fail(e, "upload(stalker context)"));
+    }
+    cudaError_t e = cudaMalloc(&p->d_tensor, sizeof(double) * nelem);
+    if (e == cudaSuccess) e = cudaMemcpy(p->d_tensor, val, sizeof(double) * nelem, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return bail(cuda_fail(e, "upload(values)"));
+    p->tensor_bytes = sizeof(double) * (nelem + 4 * (int64_t)p->grid_elems);
+    *plan = p;
+    return plan_ready(plan);
+}
+
 static int check_sl(const double *knots, int dim, int nknots, const int *dtri, int ns, const double *lumats,
                     const int *pivots, const double *bbox, const double *val)
 {
@@ -793,7 +841,7 @@ extern "C" int chebpol_cuda_plan_set(chebpol_cuda_plan *p, int option, int64_t v
         p->kernel_opt = (int)value;
         return CHEBPOL_CUDA_OK;
     case CHEBPOL_CUDA_OPT_BLEND:
-        if (p->kind != PLAN_MLIP && p->kind != PLAN_STALK && p->kind != PLAN_SL)
+        if (p->kind != PLAN_MLIP && p->kind != PLAN_STALK && p->kind != PLAN_SL && p->kind != PLAN_OLDSTALK)
             return fail(CHEBPOL_CUDA_EINVAL, "blend applies to multilinear, stalker and simplex-linear plans");
         if (value < 0 || value > 5) return fail(CHEBPOL_CUDA_EBLEND, "blend %lld not in 0..5", (long long)value);
         p->blend = (int)value;
@@ -1021,6 +1069,9 @@ static int launch_plan(chebpol_cuda_plan *p, const double *d_x, int64_t npts, do
                 return fail(CHEBPOL_CUDA_EINVAL, "no fast stalker kernel for rank %d", p->rank);
             e = launch_stalk_strict(a, s, &li);
         }
+    } else if (p->kind == PLAN_OLDSTALK) {
+        e = launch_oldstalk(p->d_tensor, p->d_grid, p->d_stalk[0], p->d_stalk[1], p->d_stalk[2], p->goff, p->rank, p->dims,
+                            p->stride, p->os_degree, p->os_uniform, p->blend, d_x, npts, d_out, p->num_sms, s, &li);
     } else if (p->kind == PLAN_SL) {
         try {  // may (re)build the candidate lists on the host
             e = launch_sl(p->sl, p->kernel_opt, p->variant, p->epol, p->blend, d_x, npts, d_out, p->num_sms, s, &li);
@@ -1656,6 +1707,35 @@ extern "C" int chebpol_cuda_evalsl(const double *x, int64_t npts, const double *
     return run_sharded(dim, x, npts, ngpus, out, key, bytes, [&](int dev, chebpol_cuda_plan **p) {
         return chebpol_cuda_plan_sl(knots, dim, nknots, dtri, numsimplex, lumats, pivots, bbox, val, dev, p);
     }, blend, epol);
+}
+
+extern "C" int chebpol_cuda_evalstalker(const double *val, const double *const *grid, const int *dims, int rank,
+                                        const double *degree, const double *const *det, const double *const *pmin,
+                                        const double *const *pplus, const int *uniform, int blend, const double *x,
+                                        int64_t npts, int ngpus, double *out)
+{
+    int64_t nelem = 0;
+    if (!val || !grid || !degree || !det || !pmin || !pplus || !uniform) return fail(CHEBPOL_CUDA_EINVAL, "a table pointer is NULL");
+    int rc = check_dims(dims, rank, &nelem);
+    if (rc) return rc;
+    if (blend < 0 || blend > 5) return fail(CHEBPOL_CUDA_EBLEND, "blend %d not in 0..5", blend);
+    CacheKey key = make_key(PLAN_OLDSTALK, dims, rank);
+    if (cache_enabled() && nelem * 8 <= kCacheMaxBytes) {
+        uint64_t h = hash_bytes(val, (size_t)nelem * 8, 13);
+        h = hash_bytes(degree, (size_t)rank * 8, h);
+        h = hash_bytes(uniform, (size_t)rank * 4, h);
+        for (int d = 0; d < rank; ++d) {
+            if (!grid[d] || !det[d] || !pmin[d] || !pplus[d]) return fail(CHEBPOL_CUDA_EINVAL, "vector of dimension %d is NULL", d);
+            h = hash_bytes(grid[d], (size_t)dims[d] * 8, h);
+            h = hash_bytes(det[d], (size_t)dims[d] * 8, h);
+            h = hash_bytes(pmin[d], (size_t)dims[d] * 8, h);
+            h = hash_bytes(pplus[d], (size_t)dims[d] * 8, h);
+        }
+        key.hash = h;
+    }
+    return run_sharded(rank, x, npts, ngpus, out, key, nelem * 8, [&](int dev, chebpol_cuda_plan **p) {
+        return chebpol_cuda_plan_oldstalk(val, grid, dims, rank, degree, det, pmin, pplus, uniform, blend, dev, p);
+    }, blend);
 }
 
 extern "C" int chebpol_cuda_chebcoef(const double *val, const int *dims, int rank, int dct, int device, double *coef)

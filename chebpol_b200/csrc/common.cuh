@@ -75,6 +75,7 @@ enum KernelId {
     K_STALK_CELL = 51,   // packed per-grid-point records, blend weights hoisted, fast reciprocal
     K_POLYH_STRICT = 40, // thread-per-point radial sum, reference op order
     K_POLYH_TILE = 41,   // points in registers, knot rows broadcast from a TMA-filled ring
+    K_OLDSTALK = 52,     // deprecated recursive stalker evaluator, thread per point, reference op order
     K_SL_STRICT = 60,    // simplex-linear: the reference's linear scan over all simplices
     K_SL_CELL = 61,      // simplex-linear: candidates from a uniform cell grid, same acceptance test
 };
@@ -253,6 +254,11 @@ cudaError_t fit_evalgrid_device(int kind, const double *d_tensor, const int *dim
                                 const PreMap *pm, double *d_s0, double *d_s1, cudaStream_t s, double **result, int *launches);
 cudaError_t fit_fhweights_device(const double *d_grid, int nknots, int d, double *d_w, cudaStream_t s);
 cudaError_t run_fp64_peak(int num_sms, int repeats, cudaStream_t s, double *tflops);
+// deprecated recursive stalker evaluator (oldstalk.cu)
+cudaError_t launch_oldstalk(const double *val, const double *grid, const double *det, const double *pmin,
+                            const double *pplus, const int *goff, int rank, const int *dims, const int64_t *stride,
+                            const double *degree, const int *uniform, int blend, const double *x, int64_t npts,
+                            double *out, int num_sms, cudaStream_t s, LaunchInfo *li);
 // simplex-linear interpolation (simplex.cu): device tables of one triangulation
 struct SlDevice;
 cudaError_t sl_create(const double *knots, int dim, int nknots, const int *dtri, int ns, const double *lumats,

@@ -329,6 +329,42 @@ SEXP R_fhweights_cuda(SEXP Sgrid, SEXP Sd, SEXP Sthreads)
     return ret;
 }
 
+/* same arguments and return as R_evalstalker (src/stalker.c:834-891): stalker is the list
+ * c(list(val=, grid=), stalkercontext(...), uniform=) built by oldstalkerappx (R/stalker.R:29) */
+SEXP R_evalstalker_cuda(SEXP Sx, SEXP stalker, SEXP Sdegree, SEXP Sblend, SEXP Sthreads)
+{
+    SEXP Sgrid = VECTOR_ELT(stalker, 1);
+    const int nrank = LENGTH(Sgrid);
+    const int K = isMatrix(Sx) ? nrows(Sx) : LENGTH(Sx);
+    if (K != nrank) error("Rank of input(%d) does not match rank of spline", K, nrank);
+    if (nrank <= 0 || nrank > CHEBPOL_CUDA_MAXRANK) error("rank must be positive");
+    int dims[CHEBPOL_CUDA_MAXRANK], len = 1;
+    const double *grid[CHEBPOL_CUDA_MAXRANK], *det[CHEBPOL_CUDA_MAXRANK], *pmin[CHEBPOL_CUDA_MAXRANK],
+        *pplus[CHEBPOL_CUDA_MAXRANK];
+    for (int r = 0; r < nrank; r++) {
+        dims[r] = LENGTH(VECTOR_ELT(Sgrid, r));
+        len *= dims[r];
+        grid[r] = REAL(VECTOR_ELT(Sgrid, r));
+        det[r] = REAL(VECTOR_ELT(VECTOR_ELT(stalker, 2), r));
+        pmin[r] = REAL(VECTOR_ELT(VECTOR_ELT(stalker, 3), r));
+        pplus[r] = REAL(VECTOR_ELT(VECTOR_ELT(stalker, 4), r));
+    }
+    if (len != LENGTH(VECTOR_ELT(stalker, 0)))
+        error("number of values (%d) does not match grid size (%d)\n", LENGTH(VECTOR_ELT(stalker, 0)), len);
+    if (LENGTH(Sdegree) != nrank) error("degree length must match dimension (%d)", nrank);
+    const double *degree = REAL(AS_NUMERIC(Sdegree));
+    const int *uniform = LOGICAL(VECTOR_ELT(stalker, 5));
+    const int blend = INTEGER(AS_INTEGER(Sblend))[0];
+    const int ngpus = gpus_from_threads(Sthreads);
+    const R_xlen_t N = isMatrix(Sx) ? ncols(Sx) : 1;
+    SEXP ret = PROTECT(NEW_NUMERIC(N));
+    const int rc = chebpol_cuda_evalstalker(REAL(VECTOR_ELT(stalker, 0)), grid, dims, nrank, degree, det, pmin, pplus,
+                                            uniform, blend, REAL(Sx), (int64_t)N, ngpus, REAL(ret));
+    UNPROTECT(1);
+    raise(rc);
+    return ret;
+}
+
 /* same arguments and return as R_evalsl (src/chebpol.c:803-828), called by the closure of
  * slappx.real (R/simplexlinear.R:38) */
 SEXP R_evalsl_cuda(SEXP Sx, SEXP Sknots, SEXP Sdtri, SEXP adata, SEXP Sval, SEXP extrapolate, SEXP Sthreads,
@@ -384,6 +420,7 @@ const R_CallMethodDef chebpol_cuda_callMethods[] = {
     {"evalpolyh_cuda", (DL_FUNC)&R_evalpolyh_cuda, 7},
     {"evalstalk_cuda", (DL_FUNC)&R_evalstalk_cuda, 4},
     {"evalhyp_cuda", (DL_FUNC)&R_evalhyp_cuda, 4},
+    {"evalstalker_cuda", (DL_FUNC)&R_evalstalker_cuda, 5},
     {"evalsl_cuda", (DL_FUNC)&R_evalsl_cuda, 8},
     {"analyzesimplex_cuda", (DL_FUNC)&R_analyzesimplex_cuda, 3},
     {NULL, NULL, 0}};

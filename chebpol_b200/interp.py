@@ -28,7 +28,7 @@ import numpy as np
 from . import _lib
 
 __all__ = [
-    "ipol", "chebappx", "chebappxf", "chebappxg", "chebappxgf", "hyman_spline", "slappx", "mlappx", "fhappx", "ucappx", "ucappxf",
+    "ipol", "chebappx", "chebappxf", "chebappxg", "chebappxgf", "hyman_spline", "slappx", "oldstalkerappx", "mlappx", "fhappx", "ucappx", "ucappxf",
     "chebeval",
     "chebknots", "chebcoef", "evalongrid", "evalongridV", "fhweights", "Interpolant",
 ]
@@ -184,6 +184,8 @@ class Interpolant:
                 p = _lib.Plan.fh(t["values"], t["grid"], t["weights"], device)
             elif self.kind in ("stalker", "hstalker"):
                 p = _lib.Plan.stalk(1 if self.kind == "hstalker" else 0, t["values"], t["grid"], t["tables"], 3, device)
+            elif self.kind == "oldstalker":
+                p = _lib.Plan.oldstalk(t["values"], t["grid"], t["degree"], t["ctx"], t["uniform"], 0, device)
             elif self.kind == "simplexlinear":
                 p = _lib.Plan.sl(t["knots"], t["dtri"], t["adata"], t["values"], device)
             elif self.kind == "polyharmonic":
@@ -218,10 +220,10 @@ class Interpolant:
     def __call__(self, x, threads=None, blend: str | int | None = None, ngpus: int = 1, device: int = 0,
                  epol: bool = False):
         xp, _single = self._coerce(x)
-        blended = self.kind in ("multilinear", "stalker", "hstalker", "simplexlinear")
+        blended = self.kind in ("multilinear", "stalker", "hstalker", "simplexlinear", "oldstalker")
         if blended:
-            if blend is None:  # closure defaults: 'linear' (R/multilinear.R:63), 'cubic' (R/stalker.R:62,80; R/simplexlinear.R:36)
-                blend = "linear" if self.kind == "multilinear" else "cubic"
+            if blend is None:  # closure defaults: 'linear' (R/multilinear.R:63, R/stalker.R:36), 'cubic' (R/stalker.R:62,80; R/simplexlinear.R:36)
+                blend = "linear" if self.kind in ("multilinear", "oldstalker") else "cubic"
             b = BLENDS[blend] if isinstance(blend, str) else int(blend)
         if self.kind == "simplexlinear":
             t = self.t
@@ -243,6 +245,8 @@ class Interpolant:
                 return _lib.evalstalk(t["values"], t["grid"], *t["tables"], xp, b, ngpus)
             if self.kind == "hstalker":
                 return _lib.evalhyp(t["values"], t["grid"], *t["tables"], xp, b, ngpus)
+            if self.kind == "oldstalker":
+                return _lib.evalstalker(t["values"], t["grid"], t["degree"], t["ctx"], t["uniform"], xp, b, ngpus)
             if self.kind == "polyharmonic":
                 return _lib.evalpolyh(t["knots"], t["weights"], t["lweights"], t["k"], xp, t.get("norm_a"),
                                       t.get("norm_b"), ngpus)
@@ -566,6 +570,47 @@ def stalkerappx(val, grid) -> Interpolant:
                        values=np.asfortranarray(val), tables=makestalk(val, grid))
 
 
+def stalkercontext(grid, r):
+    """stalkercontext, R/stalker.R:2-10, with the dmin / dplus vectors of oldstalkerappx (:26-27):
+    (det, pmin, pplus), one vector per dimension.  R's `^` gives 1 for x^0 even when x is NaN."""
+    det, pmin, pplus = [], [], []
+    with np.errstate(invalid="ignore", divide="ignore"):
+        for g, ri in zip(grid, r):
+            dmin = np.concatenate([[np.nan], np.diff(g)])
+            dplus = np.concatenate([dmin[1:], [np.nan]])
+            pm = np.ones_like(dmin) if ri == 0 else dmin ** ri
+            pp = np.ones_like(dplus) if ri == 0 else dplus ** ri
+            det.append(1.0 / (dmin * pp + dplus * pm))
+            pmin.append(pm)
+            pplus.append(pp)
+    return det, pmin, pplus
+
+
+def oldstalkerappx(val, grid, r=2) -> Interpolant:
+    """oldstalkerappx, R/stalker.R:11-49 (deprecated in the reference; ipol(method='oldstalker'))."""
+    if np.isscalar(grid[0]):
+        grid = [grid]
+    grid = [np.asarray(g, dtype=np.float64) for g in grid]
+    if any(np.any(np.diff(g) < 0) for g in grid):
+        if not callable(val):
+            raise ValueError("Grid points must be ordered in increasing order")
+        grid = [np.sort(g) for g in grid]
+    if callable(val):
+        val = evalongrid(val, grid=grid)
+    val = np.asarray(val, dtype=np.float64)
+    gl = int(np.prod([len(g) for g in grid]))
+    if val.size != gl:
+        raise ValueError(f"length of values {val.size} do not match size of grid {gl}")
+    deg = np.resize(np.asarray(r, dtype=np.float64), len(grid))
+    uniform = np.array([bool(np.all(np.abs(np.diff(g, n=2)) < 1e-8)) for g in grid])
+    if np.any(np.isnan(deg) & ~uniform):
+        raise ValueError("Non-uniform grid and varying degree needs GSL. Recompile with GSL.")
+    values = val.ravel(order="F") if val.ndim > 1 else val
+    return Interpolant("oldstalker", len(grid), [(g.min(), g.max()) for g in grid], grid=grid,
+                       values=np.ascontiguousarray(values), degree=deg, ctx=stalkercontext(grid, deg),
+                       uniform=uniform.astype(np.int32))
+
+
 def analyzesimplex(dtri, knots):
     """Host (numpy) counterpart of C_analyzesimplex, src/chebpol.c:830-875, vectorised over the
     simplices: the matrix [vertices; 1 ... 1] of every simplex LU-factorised with partial pivoting
@@ -728,7 +773,8 @@ def ucappxf(fun, dims, intervals=None) -> Interpolant:
 
 _METHODS = ["chebyshev", "multilinear", "fh", "uniform", "general", "polyharmonic", "simplexlinear",
             "hstalker", "stalker", "crbf", "oldstalker"]
-_ON_PATH = {"chebyshev", "multilinear", "fh", "uniform", "general", "polyharmonic", "simplexlinear", "stalker", "hstalker"}
+_ON_PATH = {"chebyshev", "multilinear", "fh", "uniform", "general", "polyharmonic", "simplexlinear", "stalker", "hstalker",
+            "oldstalker"}
 
 
 def ipol(val, dims=None, intervals=None, grid=None, knots=None, k=None, method="chebyshev", **kw) -> Interpolant:
@@ -750,6 +796,14 @@ def ipol(val, dims=None, intervals=None, grid=None, knots=None, k=None, method="
         if any(_unsorted(np.asarray(g, dtype=np.float64)) for g in grid):
             raise ValueError("grid must be distinct ordered values")
         return (hstalkerappx if method == "hstalker" else stalkerappx)(val, grid)
+    if method == "oldstalker":  # R/ipol.R:187-197
+        if grid is None:
+            raise ValueError("grid must be specified for stalker interpolation")
+        if np.isscalar(grid[0]):
+            grid = [grid]
+        if any(_unsorted(np.asarray(g, dtype=np.float64)) for g in grid):
+            raise ValueError("grid must be distinct ordered values")
+        return oldstalkerappx(val, grid, r=2 if k is None else k)
     if method == "simplexlinear":  # R/ipol.R:131-142
         if knots is None:
             if grid is None:

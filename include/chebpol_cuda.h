@@ -218,6 +218,24 @@ CHEBPOL_CUDA_API int chebpol_cuda_plan_stalk(int kind, const double *val, const 
                                              const double *t1, const double *t2, int blend, int device,
                                              chebpol_cuda_plan **plan);
 
+/* ---- the deprecated recursive stalker evaluator (ipol(method='oldstalker')) -----------------
+ * Replaces R_evalstalker / evalstalker, src/stalker.c:617-678, 834-891, as called by the closure of
+ * oldstalkerappx (R/stalker.R:35-46).  val: R array of values; grid[d]: dims[d] >= 2 increasing knots;
+ * degree[rank]: the degree r of every dimension (0: hyperbolic, NaN: per-basis degree); det, pmin,
+ * pplus: the per-dimension vectors of stalkercontext (R/stalker.R:2-10), dims[d] entries each;
+ * uniform[d] != 0 when grid d is uniform.  Like a reference build without GSL, a NaN degree on a
+ * non-uniform grid is refused (src/stalker.c:871-874).  Kernel id 52 (oldstalk). */
+CHEBPOL_CUDA_API int chebpol_cuda_evalstalker(const double *val, const double *const *grid, const int *dims, int rank,
+                                              const double *degree, const double *const *det,
+                                              const double *const *pmin, const double *const *pplus,
+                                              const int *uniform, int blend, const double *x, int64_t npts,
+                                              int ngpus, double *out);
+CHEBPOL_CUDA_API int chebpol_cuda_plan_oldstalk(const double *val, const double *const *grid, const int *dims,
+                                                int rank, const double *degree, const double *const *det,
+                                                const double *const *pmin, const double *const *pplus,
+                                                const int *uniform, int blend, int device,
+                                                chebpol_cuda_plan **plan);
+
 /* ---- simplex-linear interpolation on a Delaunay triangulation -------------
  * Replaces R_evalsl / findsimplex (src/chebpol.c:738-828), as called by the closure of
  * slappx.real (R/simplexlinear.R:34-39), and the fit step R_analyzesimplex (:830-875).

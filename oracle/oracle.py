@@ -321,6 +321,26 @@ class Oracle:
         f(_ptr(x), x.shape[0], dim, ns, _ptr(lu), piv.ctypes.data_as(_ip), _ptr(bbox), threads, out.ctypes.data_as(_ip))
         return out
 
+    def evalstalker_old(self, val, grid, degree, det, pmin, pplus, uniform, x, blend: int = 0, threads: int = 1):
+        """The deprecated recursive stalker evaluator; reference library only (it IS the reference's code)."""
+        assert self.kind == "reference"
+        dims, gl, keep = self._grid_args(grid)
+        rank = len(grid)
+        v = np.ascontiguousarray(np.asarray(val, dtype=np.float64).ravel(order="F"))
+        deg = np.ascontiguousarray(degree, dtype=np.float64)
+        uni = np.ascontiguousarray(uniform, dtype=np.int32)
+        dl, k1 = _ptr_list(det)
+        pl, k2 = _ptr_list(pmin)
+        ql, k3 = _ptr_list(pplus)
+        x = _as_pts(x, rank)
+        out = np.empty(x.shape[0], dtype=np.float64)
+        f = self.lib.ref_evalstalker
+        f.restype = None
+        f.argtypes = [_dp, C.c_int64, C.c_int, _ip, _dpp, _dp, C.c_int, _dp, _dpp, _dpp, _dpp, _ip, C.c_int, _dp]
+        f(_ptr(x), x.shape[0], rank, dims.ctypes.data_as(_ip), gl, _ptr(v), blend, _ptr(deg), dl, pl, ql,
+          uni.ctypes.data_as(_ip), threads, _ptr(out))
+        return out
+
     # -- fit side (fixtures) -------------------------------------------------
     def fhweights(self, grid, d):
         d = np.broadcast_to(np.asarray(d, dtype=np.int64), (len(grid),))

@@ -319,3 +319,20 @@ EXPORT void ref_evalsl(const double *x, int64_t npts, const double *knots, int d
   }
   shim_free(ad); shim_free(Sk); shim_free(Sd); shim_free(Sv); shim_free(Se); shim_free(St); shim_free(Sb);
 }
+
+/* The deprecated recursive stalker evaluator (ipol(method='oldstalker'), R/stalker.R:11-49): the point loop
+ * of R_evalstalker (src/stalker.c:881-884) over the reference's evalstalker (:617-678).  det, pmin, pplus
+ * are the per-dimension vectors of stalkercontext (R/stalker.R:2-10); this build has no GSL, so a NaN
+ * degree is only legal on a uniform grid (:871-874). */
+EXPORT void ref_evalstalker(const double *x, int64_t npts, int rank, const int *dims, const double *const *grid,
+                            const double *val, int blend, const double *degree, const double *const *det,
+                            const double *const *pmin, const double *const *pplus, const int *uniform, int threads,
+                            double *out) {
+  precomp pc[rank > 0 ? rank : 1];
+  for (int i = 0; i < rank; i++) {
+    pc[i].det = (double *)det[i]; pc[i].pmin = (double *)pmin[i]; pc[i].pplus = (double *)pplus[i]; pc[i].uniform = uniform[i];
+  }
+#pragma omp parallel for num_threads(threads) schedule(guided) if (npts > 1 && threads > 1)
+  for (int64_t i = 0; i < npts; i++)
+    out[i] = evalstalker(x + i * rank, rank, dims, (double **)grid, val, blend, degree, pc);
+}

@@ -1259,3 +1259,42 @@ def test_full_size_simplexlinear_properties(gpu_ok, port):
     assert not bool(torch.isnan(oute).any())
     assert float((oute - want[:2_000_000]).abs().max()) <= 1e-7  # slivers on the hull boundary amplify rounding
     plan.close()
+
+
+# ------------------------------------------------- the deprecated recursive stalker ('oldstalker')
+@pytest.mark.parametrize("dims,uniform", [((9,), True), ((7, 6), False), ((6, 5, 7), True), ((4, 5, 4, 3), False),
+                                          ((2, 2), True)])
+def test_oldstalker_matches_reference(gpu_ok, ref, dims, uniform):
+    """R_evalstalker (src/stalker.c:617-678, 834-891) against the compiled reference: every degree the
+    no-GSL build accepts (2, 1, fractional, 0 = hyperbolic, NaN = per-basis on uniform grids), blends
+    0-4, points outside the grid, exact knot hits.  Same operation order, so only pow / exp differ."""
+    rng = np.random.default_rng(12)
+    grid = [np.linspace(-1, 1, n) if uniform else np.sort(rng.uniform(-1, 1, n)) for n in dims]
+    val = np.asfortranarray(rng.standard_normal(dims))
+    K = len(dims)
+    x = cases.points(4001, K, lo=-1.15, hi=1.15)
+    x[:4] = np.array([g[min(1, len(g) - 1)] for g in grid])
+    x[4] = [g[-1] for g in grid]
+    x[5] = [g[0] for g in grid]
+    degs = [[2.0], [1.0], [1.5], [0.0], list(np.resize([2.0, 1.3, 0.0], K))] + ([[np.nan]] if uniform else [])
+    for r in degs:
+        ip = cb.ipol(val, grid=grid, k=r, method="oldstalker")
+        t = ip.t
+        for blend, name in enumerate(["linear", "sigmoid", "parodic", "cubic", "square"]):
+            want = ref.evalstalker_old(t["values"], t["grid"], t["degree"], *t["ctx"], t["uniform"], x, blend=blend, threads=4)
+            got = ip(x.T, blend=name)
+            assert ip.plan().kernel_used == "oldstalk"
+            fin = np.isfinite(want)
+            assert np.array_equal(fin, np.isfinite(got)), (r, blend)
+            exact = (r == [2.0] or r == [1.0]) and blend in (0, 3, 4)
+            if exact and dims != (2, 2):
+                pass  # pow(|x|, 2) and pow(|x|, 1) are exact in both libraries, but keep one tolerance for all
+            scale = max(1.0, np.abs(want[fin]).max())
+            assert np.abs(got[fin] - want[fin]).max() <= 1e-13 * scale, (r, blend, np.abs(got[fin] - want[fin]).max())
+        # stateless entry point (all GPUs) equals the plan path
+        st = _lib.evalstalker(t["values"], t["grid"], t["degree"], t["ctx"], t["uniform"], x, 3, 0)
+        assert np.array_equal(bits(st), bits(ip(x.T, blend="cubic")))
+        ip.close()
+    with pytest.raises(cb.ChebpolCudaError):  # NaN degree on a non-uniform grid: refused like the no-GSL reference
+        g2 = [np.array([0.0, 0.1, 0.4, 1.0])]
+        _lib.Plan.oldstalk(np.zeros(4), g2, [np.nan], cb.interp.stalkercontext(g2, [2.0]), [0])
