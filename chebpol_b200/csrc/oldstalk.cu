@@ -3,7 +3,8 @@
 // One thread per point, the reference's operation order (compiled with -fmad=false); the recursion
 // over the dimensions (last dimension outermost, up to four lower-dimensional values per level) is
 // unrolled into an explicit stack so no device call stack is needed.  Differences from the reference
-// C are confined to pow / exp (device libm, <= 2 ulp).  As in a reference build without GSL, a NaN
+// C are confined to pow for fractional degrees and exp (device libm, <= 2 ulp; |x|^1 and |x|^2 are formed
+// exactly).  As in a reference build without GSL, a NaN
 // degree (per-basis degree) is supported on uniform grids only.
 #include "common.cuh"
 #include <float.h>
@@ -61,6 +62,16 @@ __device__ double os_stalkhyp(double x, double vmin, double vplus, double dmin, 
     return a + b * x - a / (1 + c * x);
 }
 
+// |x|^r as libm's pow returns it where the result is exact (r = 1) or a single rounding (r = 2); the
+// device pow is only accurate to 2 ulp, and outside the grid the blend amplifies every ulp
+__device__ __forceinline__ double os_powabs(double x, double r)
+{
+    const double ax = fabs(x);
+    if (r == 1.0) return ax;
+    if (r == 2.0) return ax * ax;
+    return pow(ax, r);
+}
+
 // stalk1, src/stalker.c:190-260 without GSL
 __device__ double os_stalk1(double x, double vmin, double v0, double vplus, double dmin, double dplus, double r,
                             double iD, double powmin, double powplus)
@@ -73,7 +84,7 @@ __device__ double os_stalk1(double x, double vmin, double v0, double vplus, doub
     if (r == r) {
         const double b = (vplus * powmin - vmin * powplus) * iD;
         const double c = (vplus * dmin + vmin * dplus) * iD;
-        return v0 + b * x + c * pow(fabs(x), r);
+        return v0 + b * x + c * os_powabs(x, r);
     }
     // per-basis degree on a uniform grid
     x /= dplus;
@@ -84,7 +95,7 @@ __device__ double os_stalk1(double x, double vmin, double v0, double vplus, doub
     if (os_sign(vplus * vmin) <= 0) r = (ab < 2.0 * ac) ? ab / ac : 2.0;
     else r = (ac < 2.0 * ab) ? ac / ab : 2.0;
     if (r == 2.0) return v0 + b * x + c * x * x;
-    if (r != 1.0) return v0 + b * x + c * pow(fabs(x), r);
+    if (r != 1.0) return v0 + b * x + c * os_powabs(x, r);
     return v0 + b * x + c * fabs(x);
 }
 
