@@ -193,6 +193,7 @@ static int select_device(int device, int *num_sms)
 
 static chebpol_cuda_plan *new_plan(int kind, int device, int num_sms, const int *dims, int rank, int64_t nelem)
 {
+    nvtxMarkA("chebpol_cuda:plan_build");
     chebpol_cuda_plan *p = new chebpol_cuda_plan();
     p->kind = kind;
     p->device = device;
@@ -1228,6 +1229,7 @@ extern "C" int chebpol_cuda_plan_eval_host(chebpol_cuda_plan *p, const double *x
     if (npts < 0) return fail(CHEBPOL_CUDA_EINVAL, "negative point count");
     if (npts == 0) return CHEBPOL_CUDA_OK;
     if (!x || !out) return fail(CHEBPOL_CUDA_EINVAL, "x or out is NULL");
+    NvtxRange nvtx("chebpol_cuda:eval_host");
     int cur = -1;
     CU(cudaGetDevice(&cur));
     if (cur != p->device) CU(cudaSetDevice(p->device));

@@ -6,6 +6,16 @@
 
 #define CP_MAXR 32  // CHEBPOL_CUDA_MAXRANK + 1
 
+// NVTX ranges around the host-side phases (plan build, staged evaluation, list building) so a timeline
+// tool shows where a call spends its time; header-only NVTX3 costs nothing when no tool is attached.
+#include <nvtx3/nvToolsExt.h>
+struct NvtxRange {
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange &) = delete;
+    NvtxRange &operator=(const NvtxRange &) = delete;
+};
+
 // Pre-map applied to every coordinate before evaluation (Chebyshev plans):
 //   bit 0: x <- (x - mid)*ispan                 R/chebyshev.R:223-227 (imap)
 //   bit 1: x <- sin(0.5*pi*x*(1-n)/n)           R/uniform.R:6 (ugm)

@@ -614,6 +614,7 @@ static void sl_host_lists(SlDevice *d, int G, std::vector<int> &start, std::vect
 
 static cudaError_t sl_build_cells(SlDevice *d, int G)
 {
+    NvtxRange nvtx("chebpol_cuda:sl_candidate_lists");
     std::vector<int> start, items;
     sl_host_lists(d, G, start, items);
     cudaError_t e = cudaDeviceSynchronize();  // a previous launch may still read the old lists
