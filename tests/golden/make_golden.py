@@ -123,6 +123,19 @@ def main():
         for blend in (0, 3, 4, 5):
             out[f"sl_y_epol{epol}_blend{blend}"] = ref.evalsl(x, kn, dtri.astype(np.int32), (lu, piv, bb), kv, epol, blend)
 
+    # ---- the deprecated recursive stalker evaluator (reference's evalstalker, no restatement exists)
+    from chebpol_b200 import interp
+
+    og = [np.linspace(-1.0, 1.0, 6), np.sort(np.concatenate([[-1.0, 1.0], rng.uniform(-1, 1, 3)]))]
+    ov = np.asfortranarray(rng.standard_normal((6, 5)))
+    ox = pts(129, 2, -1.02, 1.02)
+    out["oldst_grid0"], out["oldst_grid1"], out["oldst_val"], out["oldst_x"] = og[0], og[1], ov, ox
+    for tag, r in (("r2", [2.0, 2.0]), ("r15", [1.5, 1.0]), ("r0", [0.0, 2.0])):
+        t = interp.oldstalkerappx(ov, og, r=r).t
+        for blend in (0, 3):
+            out[f"oldst_y_{tag}_blend{blend}"] = ref.evalstalker_old(t["values"], t["grid"], t["degree"], *t["ctx"],
+                                                                     t["uniform"], ox, blend=blend)
+
     path = os.path.join(HERE, "ref_vectors.npz")
     np.savez_compressed(path, **out)
     print(f"wrote {path}: {len(out)} arrays, {os.path.getsize(path)} bytes")

@@ -50,7 +50,7 @@ def mlip_x(blend):
 
 # ------------------------------------------------------------------ CPU: the restatement
 def test_fixture_is_complete():
-    assert len(G.files) == 78
+    assert len(G.files) == 88
     for k in G.files:
         assert G[k].dtype == np.float64
 
@@ -227,3 +227,18 @@ def test_gpu_simplexlinear(gpu_ok):
             got, k = run(plan, G["sl_x"], _lib.KERNEL_FAST)
             assert k == "sl_cell" and same_bits(got, want)
     plan.close()
+
+
+@pytest.mark.gpu
+def test_gpu_oldstalker(gpu_ok):
+    import chebpol_b200 as cb
+
+    grid = [G["oldst_grid0"], G["oldst_grid1"]]
+    for tag, r in (("r2", [2.0, 2.0]), ("r15", [1.5, 1.0]), ("r0", [0.0, 2.0])):
+        ip = cb.ipol(G["oldst_val"], grid=grid, k=r, method="oldstalker")
+        for blend, name in ((0, "linear"), (3, "cubic")):
+            want = G[f"oldst_y_{tag}_blend{blend}"]
+            got = ip(G["oldst_x"].T, blend=name)
+            assert ip.plan().kernel_used == "oldstalk"
+            close(got, want, tol=1e-12)
+        ip.close()
