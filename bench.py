@@ -52,6 +52,8 @@ CONFIGS = {
             name="cfg7 (SURVEY 8f row 3): 3-D hyperbolic stalker spline on a 64^3 grid, cubic blend, 5e7 points"),
     8: dict(kind="sl", dims=(3,), rank=3, nknots=20000, points=50_000_000,
             name="cfg8 (beyond SURVEY 8f): 3-D simplex-linear on the Delaunay triangulation of 20000 scattered knots, cubic blend, 5e7 points"),
+    9: dict(kind="chebg", dims=(10,) * 5, points=100_000_000,
+            name="cfg9 (beyond SURVEY 8f): 5-D 'general' method (hyman-spline grid maps + Chebyshev) on an irregular 10^5 grid, 1e8 points"),
     5: dict(kind="cheb", dims=(12,) * 6, points=20_000_000, name="cfg5: 6-D Chebyshev dims=rep(12,6); default 2e7 points per GPU, --total-points 1000000000 for the full sharded batch"),
 }
 
@@ -94,6 +96,12 @@ def build_case(cfg):
     kind, dims = cfg["kind"], cfg["dims"]
     if kind == "cheb":
         return dict(coef=cases.cheb_fitted(dims))
+    if kind == "chebg":
+        from chebpol_b200 import interp
+
+        grid = [np.linspace(-1.0, 1.0, n) ** 3 if d % 2 == 0 else np.linspace(-1.0, 1.0, n) for d, n in enumerate(dims)]
+        ip = interp.chebappxg(cases.grid_values(grid), grid)
+        return dict(coef=ip.t["coef"], splines=ip.t["splines"])
     if kind == "mlip":
         grid, values = cases.mlip_case(dims)
         return dict(grid=grid, values=values)
@@ -120,6 +128,8 @@ def make_plan(cfg, case, device):
 
     if cfg["kind"] == "cheb":
         return _lib.Plan.cheb(case["coef"], device=device)
+    if cfg["kind"] == "chebg":
+        return _lib.Plan.chebg(case["coef"], case["splines"], device=device)
     if cfg["kind"] == "mlip":
         return _lib.Plan.mlip(case["grid"], case["values"], 0, device=device)
     if cfg["kind"] == "hstalk":
@@ -137,6 +147,8 @@ def make_plan(cfg, case, device):
 def oracle_eval(orc, cfg, case, x, threads):
     if cfg["kind"] == "cheb":
         return orc.evalcheb(case["coef"], x, threads=threads)
+    if cfg["kind"] == "chebg":
+        return orc.evalcheb(case["coef"], orc.splinemap(x, case["splines"], threads=threads), threads=threads)
     if cfg["kind"] == "mlip":
         return orc.evalmlip(case["grid"], case["values"], x, threads=threads)
     if cfg["kind"] == "hstalk":
@@ -411,7 +423,7 @@ def run_ours(args, cfg):
                         "frac": achieved / peaks["hbm_gbs"], "traffic": load_traffic(kernel_used, args.config, npts),
                         "peak_source": f"MEASURED_PEAKS.json ({peak_src}); the simplex records are gathered from L2",
                         "bytes_per_eval": byts, "kernel": kernel_used, "kernel_ms": kernel_ms}
-        elif cfg["kind"] in ("cheb", "fh", "polyh"):
+        elif cfg["kind"] in ("cheb", "chebg", "fh", "polyh"):
             # polyharmonic: per knot a subtract and a multiply-add per coordinate plus the weight
             # multiply-add, 3*rank + 2 flop as the reference executes them; the basis function
             # (sqrt / log / exp) is not counted.  Half of those instruction slots are not FMAs, so
