@@ -76,6 +76,43 @@ def test_argument_validation_precedes_device():
 
 
 @pytest.mark.skipif(_lib.device_count() > 0, reason="a GPU is visible")
+def test_argument_validation_of_the_widened_entry_points():
+    """general / simplex-linear / oldstalker: argument checks run before any device is touched, with the
+    reference's messages where it has one (src/stalker.c:871-874)."""
+    from chebpol_b200 import interp
+
+    # general: spline knots must be strictly increasing, one table per dimension
+    g = np.linspace(0, 1, 5) ** 2
+    tab = interp.hyman_spline(g, interp.chebknots([5])[0])
+    bad = (tab[0][::-1].copy(),) + tuple(tab[1:])
+    with pytest.raises(_lib.ChebpolCudaError) as e:
+        _lib.Plan.chebg(np.zeros(5), [bad])
+    assert e.value.code == 1 and "strictly increasing" in str(e.value)
+    with pytest.raises(ValueError):
+        _lib.Plan.chebg(np.zeros((5, 5)), [tab])
+    # simplex-linear: knot indices of the triangulation are checked
+    knots = np.array([[0.0, 1.0, 0.0, 1.0], [0.0, 0.0, 1.0, 1.0]])
+    dtri = np.array([[1, 2], [2, 3], [3, 5]], dtype=np.int32)  # 5 is not a knot
+    ad = interp.analyzesimplex(np.array([[1, 2], [2, 3], [3, 4]], dtype=np.int32), knots)
+    with pytest.raises(_lib.ChebpolCudaError) as e:
+        _lib.Plan.sl(knots, dtri, ad, np.zeros(4))
+    assert e.value.code == 1 and "not a knot index" in str(e.value)
+    with pytest.raises(ValueError):
+        _lib.Plan.sl(knots, dtri[:2], ad, np.zeros(4))  # dtri must have dim+1 rows
+    with pytest.raises(_lib.ChebpolCudaError) as e:
+        _lib.evalsl(np.zeros((1, 2)), knots, np.array([[1, 2], [2, 3], [3, 4]], dtype=np.int32), ad, np.zeros(4), blend=9)
+    assert e.value.code == 4  # EBLEND
+    # oldstalker: NaN degree on a non-uniform grid is refused like the reference built without GSL
+    g2 = [np.array([0.0, 0.1, 0.4, 1.0])]
+    with pytest.raises(_lib.ChebpolCudaError) as e:
+        _lib.Plan.oldstalk(np.zeros(4), g2, [np.nan], interp.stalkercontext(g2, [2.0]), [0])
+    assert "not supported without GSL" in str(e.value)
+    with pytest.raises(_lib.ChebpolCudaError) as e:
+        _lib.Plan.oldstalk(np.zeros(1), [np.array([0.0])], [2.0], interp.stalkercontext([np.array([0.0, 1.0])], [2.0])[:0] or
+                           ([np.zeros(1)], [np.zeros(1)], [np.zeros(1)]), [1])
+    assert e.value.code == 3  # a stalker grid needs at least two knots
+
+
 def test_no_cpu_fallback_without_gpu():
     cf = np.ones((3, 3))
     with pytest.raises(cb.ChebpolCudaError) as e:
