@@ -52,6 +52,8 @@ CONFIGS = {
             name="cfg7 (SURVEY 8f row 3): 3-D hyperbolic stalker spline on a 64^3 grid, cubic blend, 5e7 points"),
     8: dict(kind="sl", dims=(3,), rank=3, nknots=20000, points=50_000_000,
             name="cfg8 (beyond SURVEY 8f): 3-D simplex-linear on the Delaunay triangulation of 20000 scattered knots, cubic blend, 5e7 points"),
+    10: dict(kind="sl", dims=(2,), rank=2, nknots=100000, points=100_000_000,
+             name="cfg10 (beyond SURVEY 8f): 2-D simplex-linear on the Delaunay triangulation of 100000 scattered knots, cubic blend, 1e8 points"),
     9: dict(kind="chebg", dims=(10,) * 5, points=100_000_000,
             name="cfg9 (beyond SURVEY 8f): 5-D 'general' method (hyman-spline grid maps + Chebyshev) on an irregular 10^5 grid, 1e8 points"),
     5: dict(kind="cheb", dims=(12,) * 6, points=20_000_000, name="cfg5: 6-D Chebyshev dims=rep(12,6); default 2e7 points per GPU, --total-points 1000000000 for the full sharded batch"),
@@ -140,7 +142,9 @@ def make_plan(cfg, case, device):
         # the candidate grid is part of the plan (untimed, like the fit): sized as for a long-lived
         # interpolant instead of letting it refine itself in the middle of the timed steps
         p = _lib.Plan.sl(case["knots"], case["dtri"], case["adata"], case["val"], device=device)
-        return p.set(_lib.OPT_SL_CELLS, int(os.environ.get("CHEBPOL_CUDA_SL_CELLS", "256")))
+        ns, dim = case["dtri"].shape[1], cfg["rank"]
+        cells = int(np.ceil(min((8.0 if dim <= 2 else 128.0) * ns, float(1 << 24)) ** (1.0 / dim)))  # the library's own upper size (sl_wanted_G)
+        return p.set(_lib.OPT_SL_CELLS, int(os.environ.get("CHEBPOL_CUDA_SL_CELLS", cells)))
     return _lib.Plan.fh(case["vals"], case["grid"], case["weights"], device=device)
 
 

@@ -741,13 +741,15 @@ cudaError_t sl_create(const double *knots, int dim, int nknots, const int *dtri,
 // overlapped cell) pair on the host (133k simplices in 3-D, 8 cores: 0.07 / 0.22 / 0.97 / 2.7 s for
 // 41 / 82 / 163 / 256 cells per dimension) while a point costs 0.46 / 0.3 / 0.18 / 0.15 ns to
 // evaluate, so a fine grid only pays for a plan that lives long: about one cell per 64 points seen,
-// between ns/4 and 128 ns.  launch_sl rebuilds when this has grown 8-fold, so the total build time
+// between ns/4 and 128 ns (8 ns in 1-D and 2-D).  launch_sl rebuilds when this has grown 8-fold, so the total build time
 // stays a fraction of the evaluation time; CHEBPOL_CUDA_OPT_SL_CELLS / CHEBPOL_CUDA_SL_CELLS pin it.
 static int sl_wanted_G(const SlDevice *d, int64_t seen)
 {
     double cells = (double)seen / 64.0;
     cells = std::max(cells, (double)d->ns / 4.0);
-    cells = std::min(cells, 128.0 * (double)d->ns);
+    // measured upper sizes: 3-D (133k simplices) is fastest at the finest grid tried, 126 cells per simplex;
+    // 2-D (200k triangles) peaks at ~5 cells per triangle (1.62e10 evals/s; 1.45e10 at 84 per triangle)
+    cells = std::min(cells, (d->dim <= 2 ? 8.0 : 128.0) * (double)d->ns);
     cells = std::min(cells, (double)(1 << 24));
     return std::max(1, (int)ceil(pow(cells, 1.0 / d->dim)));
 }
