@@ -1081,6 +1081,7 @@ static int launch_plan(chebpol_cuda_plan *p, const double *d_x, int64_t npts, do
         }
         if (e == cudaErrorNotSupported)
             return fail(CHEBPOL_CUDA_EINVAL, "no cell-list kernel for %d-dimensional simplices", p->rank);
+        p->tensor_bytes = sl_bytes(p->sl);  // the candidate lists may just have been (re)built
     } else {
         return fail(CHEBPOL_CUDA_EINVAL, "corrupt plan");
     }
