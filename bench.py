@@ -269,7 +269,7 @@ def run_reference(args, cfg):
     case = build_case(cfg)
     threads = os.cpu_count() or 1
     k = cfg.get("rank", len(cfg["dims"]))
-    n = min(cpu_sample_size(orc, cfg, case, threads, target_s=8.0), 50_000_000)
+    n = min(cpu_sample_size(orc, cfg, case, threads, target_s=args.ref_seconds), 50_000_000)
     x = cpu_points(n, k)
     for _ in range(args.warmup):
         time_cpu(orc, cfg, case, x[: max(1000, n // 8)], threads)
@@ -493,6 +493,7 @@ def main():
     ap.add_argument("--strict", action="store_true", help="use the reference-order kernels")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--ref-seconds", type=float, default=8.0, help="--impl reference: CPU seconds per step the sample is sized for")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
     if args.impl == "reference":
