@@ -169,6 +169,17 @@ class Interpolant:
         self._plans: dict[int, _lib.Plan] = {}
         self.kernel = _lib.KERNEL_AUTO
 
+    # save()/load() of the R closures (R/chebpol-package.R:18-22): an interpolant is its host tensors;
+    # device plans are dropped on pickling and rebuilt on first use after loading
+    def __getstate__(self):
+        st = self.__dict__.copy()
+        st["_plans"] = {}
+        return st
+
+    def __setstate__(self, st):
+        self.__dict__.update(st)
+        self._plans = {}
+
     # device-resident copy, re-creatable from the host tensors at any time
     def plan(self, device: int = 0) -> _lib.Plan:
         p = self._plans.get(device)

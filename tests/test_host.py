@@ -306,3 +306,19 @@ def test_bench_reference_arm_contract():
     env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_interpolants_pickle_like_saved_r_closures():
+    """R interpolants survive save()/load() because they are plain closures over their tensors
+    (R/chebpol-package.R:18-22, SURVEY 5 "checkpoint / resume"): the mirror pickles the host tensors and
+    drops device plans, which are rebuilt on first use."""
+    import pickle
+
+    ip = cb.ipol(lambda x: float(np.sum(x)), grid=[np.linspace(0, 1, 5) ** 2, np.linspace(0, 2, 4)], method="general")
+    ip._plans[0] = object()  # stands for a live device plan (a ctypes handle cannot be pickled)
+    ip2 = pickle.loads(pickle.dumps(ip))
+    assert ip2.kind == "general" and ip2._plans == {} and ip2.arity == 2
+    assert np.array_equal(ip2.t["coef"], ip.t["coef"]) and len(ip2.t["splines"]) == 2
+    ip._plans.clear()
+    ml = pickle.loads(pickle.dumps(cb.ipol(np.arange(9.0), grid=[np.linspace(0, 1, 3)] * 2, method="multilinear")))
+    assert ml.kind == "multilinear" and np.array_equal(ml.t["values"], np.arange(9.0))
