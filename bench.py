@@ -1,24 +1,37 @@
 #!/usr/bin/env python
 """bench.py -- interpolant evaluations/sec (FP64) on B200, BASELINE.json's metric.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--config C] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--config C] [--workloads all|none|1,3,4,5] [--dropin 2,3|none]
 
-A "step" is one evaluation pass of the fitted interpolant over one batch of synthetic
-points.  Default workload = BASELINE.json configs[1]: 5-D Chebyshev, dims = rep(10,5),
-1e8 uniform random points per GPU (weak scaling: every rank evaluates its own 1e8 points
-against its replica of the coefficient tensor; no data-path collective).
+A "step" is one evaluation pass of the fitted interpolant over one batch of synthetic points.
+The HEADLINE workload (top-level `value`, `e2e`, `roofline`, ...) is BASELINE.json configs[1]:
+5-D Chebyshev, dims = rep(10,5), 1e8 points per GPU (weak scaling: rank r evaluates global points
+[r*1e8, (r+1)*1e8) of one counter-based batch against its replica of the coefficient tensor; no
+data-path collective).  The same JSON line carries
 
-One JSON line is printed by rank 0:
-  value      evaluations/s over all GPUs, inputs resident in HBM, CUDA-event timed
-  e2e        the same metric through the host-pointer C ABI (chebpol_cuda_plan_eval_host)
-             with pinned HOST buffers: H2D of the points and D2H of the results are inside
-             the timed region
-  roofline   the dominant kernel against the FP64-FMA roofline (Chebyshev, FH) or the HBM
-             roofline (multilinear); the FP64 peak is measured in-run with a DFMA-only
-             kernel (MEASURED_PEAKS.json has no FP64 figure), HBM peak from that file
-  cpu_baseline  the reference's own C evaluator (oracle/_ref, compiled from
-             /root/reference/src/chebpol.c) or its C restatement, all host cores, on a
-             bounded prefix of the same points
+  workloads   one sub-record per other BASELINE config -- cfg1 (2-D Chebyshev 20x20, 1e6 points),
+              cfg3 (4-D multilinear 64^4, 1e8 points), cfg4 (3-D Floater-Hormann 40^3, 1e7 points)
+              per GPU, and cfg5 (6-D Chebyshev 12^6) as BASELINE states it: 1e9 points SHARDED over
+              the GPUs when world >= 2 (strong scaling, one timed pass), a 2e7-point slice at N = 1.
+              Each has value, ms_per_step, roofline, e2e, cpu_baseline (N = 1), parity and clocks.
+  e2e_dropin  the path R takes: ONE process, numpy PAGEABLE arrays, the stateless C ABI
+              (chebpol_cuda_evalcheb / _evalmlip with ngpus = 1 and ngpus = world), tensor re-passed
+              on every call.  Under torchrun rank 0 drives all GPUs while the others wait on a
+              host-side (gloo) barrier.
+
+Fields of a record
+  value      evaluations/s over all GPUs, inputs resident in HBM, CUDA-event timed, max over ranks
+  e2e        the same metric through chebpol_cuda_plan_eval_host with pinned HOST buffers: H2D of
+             the points and D2H of the results are inside the timed region
+  roofline   the dominant kernel against the FP64-FMA roofline (Chebyshev, FH; peak measured in-run
+             with DFMA / DMMA-only kernels because MEASURED_PEAKS.json has no FP64 figure) or the
+             HBM roofline (multilinear; peak from MEASURED_PEAKS.json)
+  parity     every rank compares >= 1e5 strided points of ITS shard with the CPU oracle (the
+             reference's own C, oracle/_ref); worst error over ranks; plus an order-independent
+             checksum of all results (wrapping 64-bit sum of the bit patterns, summed over ranks)
+  cpu_baseline  the reference's C evaluator on all host cores, bounded prefix of the same batch,
+             timed with the same warm multi-step procedure as --impl reference
 
 --impl reference times only that CPU evaluator (rank 0), same metric / config / unit.
 """
@@ -26,6 +39,7 @@ from __future__ import annotations
 
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -40,6 +54,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 METRIC = "interpolant evaluations/sec (FP64) at 1/2/4/8 B200 vs FP64/HBM roofline"  # BASELINE.json "metric", verbatim
 UNIT = "evals/s"
+SEED = 42
 
 CONFIGS = {
     1: dict(kind="cheb", dims=(20, 20), points=1_000_000, name="cfg1: 2-D Chebyshev dims=c(20,20), 1e6 points"),
@@ -56,8 +71,10 @@ CONFIGS = {
              name="cfg10 (beyond SURVEY 8f): 2-D simplex-linear on the Delaunay triangulation of 100000 scattered knots, cubic blend, 1e8 points"),
     9: dict(kind="chebg", dims=(10,) * 5, points=100_000_000,
             name="cfg9 (beyond SURVEY 8f): 5-D 'general' method (hyman-spline grid maps + Chebyshev) on an irregular 10^5 grid, 1e8 points"),
-    5: dict(kind="cheb", dims=(12,) * 6, points=20_000_000, name="cfg5: 6-D Chebyshev dims=rep(12,6); default 2e7 points per GPU, --total-points 1000000000 for the full sharded batch"),
+    5: dict(kind="cheb", dims=(12,) * 6, points=20_000_000, total_points=1_000_000_000,
+            name="cfg5: 6-D Chebyshev dims=rep(12,6), 1e9 points sharded over the GPUs (2e7-point slice on one GPU)"),
 }
+BASELINE_WORKLOADS = (1, 3, 4, 5)  # beside the headline cfg2
 
 
 def steps_per_eval(dims):
@@ -69,17 +86,21 @@ def steps_per_eval(dims):
     return s
 
 
+TRAFFIC_FILES = ("traffic_r02.json", "traffic_r01.json")
+
+
 def load_traffic(kernel, cfg_id, npts):
-    """DRAM bytes per launch from the committed ncu capture of this kernel (None if not captured for this config)."""
-    p = os.path.join(ROOT, "profiles", "traffic_r01.json")
-    try:
-        with open(p) as f:
-            t = json.load(f).get(kernel)
-        if t and t.get("cfg") == cfg_id:
-            return t["bytes_per_point"] * npts
-    except (OSError, ValueError):
-        pass
-    return None
+    """DRAM bytes per launch from the COMMITTED ncu capture of this kernel on this config (static:
+    bytes per point x points of the launch; None when that pair has not been captured)."""
+    for name in TRAFFIC_FILES:
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                t = json.load(f).get(kernel)
+            if t and t.get("cfg") == cfg_id:
+                return t["bytes_per_point"] * npts, f"profiles/{name} (static: ncu dram__bytes per point of this kernel on this config x points per launch; not measured in this run)"
+        except (OSError, ValueError):
+            pass
+    return None, None
 
 
 def load_peaks():
@@ -148,6 +169,18 @@ def make_plan(cfg, case, device):
     return _lib.Plan.fh(case["vals"], case["grid"], case["weights"], device=device)
 
 
+def make_stateless(cfg, case):
+    from chebpol_b200 import _lib
+
+    if cfg["kind"] == "cheb":
+        return _lib.Stateless.cheb(case["coef"])
+    if cfg["kind"] == "mlip":
+        return _lib.Stateless.mlip(case["grid"], case["values"], 0)
+    if cfg["kind"] == "fh":
+        return _lib.Stateless.fh(case["vals"], case["grid"], case["weights"])
+    raise ValueError(cfg["kind"])
+
+
 def oracle_eval(orc, cfg, case, x, threads):
     if cfg["kind"] == "cheb":
         return orc.evalcheb(case["coef"], x, threads=threads)
@@ -172,9 +205,15 @@ def get_oracle():
     return Oracle("port"), "port"
 
 
-def cpu_points(npts, rank_dims, seed=42):
-    rng = np.random.Generator(np.random.Philox(key=seed))
-    return np.ascontiguousarray(rng.random((npts, rank_dims)) * 2.0 - 1.0)
+def cfg_rank(cfg):
+    return cfg.get("rank", len(cfg["dims"]))
+
+
+def cpu_points(npts, k, first=0):
+    """First points of the seed-42 counter-based batch (the GPU arm evaluates the same values)."""
+    from chebpol_b200 import synth
+
+    return synth.points(first, npts, k, seed=SEED)
 
 
 def time_cpu(orc, cfg, case, x, threads):
@@ -183,16 +222,31 @@ def time_cpu(orc, cfg, case, x, threads):
     return time.perf_counter() - t0
 
 
-def cpu_sample_size(orc, cfg, case, threads, target_s):
+def cpu_sample_size(orc, cfg, case, threads, target_s, cap=50_000_000):
     """Calibrate a prefix length that takes about target_s seconds of CPU work."""
-    k = cfg.get("rank", len(cfg["dims"]))
+    k = cfg_rank(cfg)
     n = 2000
+    dt = max(time_cpu(orc, cfg, case, cpu_points(n, k), threads), 1e-4)
+    n2 = int(min(max(n * 0.3 / dt, 2000), 4e6))  # ~0.3 s probe (first-touch and thread start-up amortised)
+    dt = max(time_cpu(orc, cfg, case, cpu_points(n2, k), threads), 1e-4)
+    return int(min(max(n2 * target_s / dt, 2000), cap))
+
+
+def cpu_reference_rate(orc, okind, cfg, case, threads, seconds_per_step, steps, warmup):
+    """The ONE procedure both arms use for the CPU figure: a prefix of the seed-42 batch sized for
+    about seconds_per_step, `warmup` untimed passes over an eighth of it, then `steps` timed passes."""
+    k = cfg_rank(cfg)
+    n = cpu_sample_size(orc, cfg, case, threads, seconds_per_step)
     x = cpu_points(n, k)
-    dt = max(time_cpu(orc, cfg, case, x, threads), 1e-4)
-    n2 = int(min(max(n * 0.5 / dt, 2000), 4e6))  # ~0.5 s probe (first-touch and thread start-up amortised)
-    x = cpu_points(n2, k)
-    dt = max(time_cpu(orc, cfg, case, x, threads), 1e-4)
-    return int(min(max(n2 * target_s / dt, 2000), 4e8))
+    for _ in range(warmup):
+        time_cpu(orc, cfg, case, x[: max(1000, n // 8)], threads)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        oracle_eval(orc, cfg, case, x, threads)
+    dt = time.perf_counter() - t0
+    return {"value": n * steps / dt, "unit": UNIT, "cores": threads, "kind": okind,
+            "sample": f"first {n} points of the seed-{SEED} batch x {steps} timed passes after {warmup} warm-up, {dt:.1f} s wall",
+            "points_per_step": n, "ms_per_step": 1e3 * dt / steps}
 
 
 # --------------------------------------------------------------- clock sampler
@@ -200,6 +254,7 @@ class ClockSampler:
     FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
+    PERIOD_MS = 100
 
     def __init__(self, gpu_index):
         self.gpu_index = gpu_index
@@ -208,8 +263,9 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                                       "-lms", "200"], stdout=self.f, stderr=subprocess.DEVNULL)
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu_index), f"--query-gpu={self.FIELDS}",
+                                       "--format=csv,noheader,nounits", "-lms", str(self.PERIOD_MS)],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
@@ -217,7 +273,7 @@ class ClockSampler:
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if self.p is None:
             return out
-        time.sleep(0.25)
+        time.sleep(0.12)
         self.p.terminate()
         try:
             self.p.wait(timeout=5)
@@ -225,7 +281,7 @@ class ClockSampler:
             self.p.kill()
         self.f.flush()
         self.f.seek(0)
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in self.f.read().splitlines():
             parts = [s.strip() for s in line.split(",")]
@@ -236,6 +292,7 @@ class ClockSampler:
                     continue
                 sm.append(float(parts[1]))
                 mx.append(float(parts[2]))
+                pw.append(float(parts[3]))
             except ValueError:
                 continue
             for nm, v in zip(names, parts[4:8]):
@@ -246,7 +303,9 @@ class ClockSampler:
         except OSError:
             pass
         if sm:
-            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+            out.update(sm_mhz=float(np.median(sm)), sm_min_mhz=float(min(sm)), sm_max_mhz=float(max(mx)),
+                       power_w_max=float(max(pw)) if pw else None, reasons=sorted(reasons), samples=len(sm),
+                       period_ms=self.PERIOD_MS)
         return out
 
 
@@ -266,117 +325,307 @@ def run_reference(args, cfg):
     if rank != 0:
         return 0
     orc, kind = get_oracle()
-    case = build_case(cfg)
     threads = os.cpu_count() or 1
-    k = cfg.get("rank", len(cfg["dims"]))
-    n = min(cpu_sample_size(orc, cfg, case, threads, target_s=args.ref_seconds), 50_000_000)
-    x = cpu_points(n, k)
-    for _ in range(args.warmup):
-        time_cpu(orc, cfg, case, x[: max(1000, n // 8)], threads)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        oracle_eval(orc, cfg, case, x, threads)
-    dt = time.perf_counter() - t0
-    value = n * args.steps / dt
+    case = build_case(cfg)
+    rec = cpu_reference_rate(orc, kind, cfg, case, threads, args.ref_seconds, args.steps, max(1, args.warmup))
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "impl": "reference", "metric": METRIC, "value": rec["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": rec["ms_per_step"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": cfg["name"], "points_per_step": n,
+        "config": {"workload": cfg["name"], "points_per_step": rec["points_per_step"],
                    "note": "reference C evaluator (OpenMP over points) on the host cores; bounded sample of the workload"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind,
-                         "sample": f"{n} points/step x {args.steps} steps, first points of the seed-42 stream"},
-        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "cpu_baseline": {k: rec[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": rec["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    # the other BASELINE configs, same procedure (shorter passes), so every `workloads` record of the
+    # GPU arm has its CPU counterpart from this arm too
+    wl = []
+    for cid in parse_workloads(args):
+        c = CONFIGS[cid]
+        r = cpu_reference_rate(orc, kind, c, build_case(c), threads, args.sub_cpu_seconds, 3, 1)
+        wl.append({"config": cid, "workload": c["name"], **r})
+    if wl:
+        line["workloads"] = wl
     print(json.dumps(line), flush=True)
     return 0
 
 
+def parse_workloads(args):
+    if args.workloads in ("none", "", "0"):
+        return []
+    if args.workloads == "all":
+        return [c for c in BASELINE_WORKLOADS if c != args.config]
+    return [int(t) for t in args.workloads.split(",") if t]
+
+
 # ------------------------------------------------------------------------ ours
-def run_ours(args, cfg):
+class Ctx:
+    """Per-process state of the GPU arm."""
+
+    def __init__(self, args):
+        import torch
+
+        from chebpol_b200 import shard
+
+        self.args = args
+        self.rank, self.local_rank, self.world = shard.dist_env()
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device; chebpol_b200 has no CPU path")
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        self.gloo = None
+        if self.world > 1:
+            import datetime
+
+            import torch.distributed as dist
+
+            shard.init_process_group("nccl")
+            # host-side barrier for the drop-in leg: ranks that wait must not spin on their GPU
+            self.gloo = dist.new_group(backend="gloo", timeout=datetime.timedelta(minutes=30))
+        self.stream = torch.cuda.current_stream(self.dev)
+        self.fp64_peak = None
+        self.peaks, self.peak_src = load_peaks()
+        self.oracle = None
+
+    def get_oracle(self):
+        if self.oracle is None:
+            self.oracle = get_oracle()
+        return self.oracle
+
+    def host_barrier(self):
+        if self.gloo is not None:
+            import torch.distributed as dist
+
+            dist.barrier(group=self.gloo)
+
+
+def sum_u64_over_ranks(ctx, value):
+    """Sum modulo 2^64 of one unsigned value per rank (gathered, added on the host)."""
+    import torch
+    import torch.distributed as dist
+
+    if ctx.world == 1:
+        return value & 0xFFFFFFFFFFFFFFFF
+    parts = torch.tensor([value & 0xFFFFFFFF, (value >> 32) & 0xFFFFFFFF], dtype=torch.int64, device=ctx.dev)
+    allp = [torch.zeros_like(parts) for _ in range(ctx.world)]
+    dist.all_gather(allp, parts)
+    tot = 0
+    for t in allp:
+        lo, hi = (int(v) for v in t.tolist())
+        tot = (tot + lo + (hi << 32)) & 0xFFFFFFFFFFFFFFFF
+    return tot
+
+
+def roofline_record(ctx, cfg, cfg_id, npts, kernel_ms, kernel_used):
+    k = cfg_rank(cfg)
+    traffic, traffic_src = load_traffic(kernel_used, cfg_id, npts)
+    peaks, peak_src = ctx.peaks, ctx.peak_src
+    if cfg["kind"] == "hstalk":
+        # 2^D corners, each one packed record of 3D+1 doubles, plus the point and the result.  The
+        # 21 MB record table is L2-resident, so this is the L2-side byte count set against the HBM
+        # peak: a reference line for the gather rate, not a bound (DESIGN 3.6).
+        byts = 8.0 * (k + 1 + 2 ** k * (3 * k + 1))
+        achieved = byts * npts / (kernel_ms * 1e-3) / 1e9
+        return {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "traffic_source": traffic_src,
+                "peak_source": f"MEASURED_PEAKS.json ({peak_src}); bytes are gathered from L2, not HBM",
+                "bytes_per_eval": byts, "kernel": kernel_used, "kernel_ms": kernel_ms}
+    if cfg["kind"] == "sl":
+        # streamed point + result, plus the one packed simplex record that is accepted; the candidate
+        # records rejected on the way and the cell lists are L2-side traffic.  A reference line for
+        # a gather-latency kernel, not a bound (DESIGN 3.7).
+        n1 = k + 1
+        byts = 8.0 * (k + 1) + 8.0 * (((2 * k + n1 * n1 + n1 + 1) + 3) // 4 * 4)
+        achieved = byts * npts / (kernel_ms * 1e-3) / 1e9
+        return {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "traffic_source": traffic_src,
+                "peak_source": f"MEASURED_PEAKS.json ({peak_src}); the simplex records are gathered from L2",
+                "bytes_per_eval": byts, "kernel": kernel_used, "kernel_ms": kernel_ms}
+    if cfg["kind"] in ("cheb", "chebg", "fh", "polyh"):
+        # polyharmonic: per knot a subtract and a multiply-add per coordinate plus the weight
+        # multiply-add, 3*rank + 2 flop as the reference executes them; the basis function
+        # (sqrt / log / exp) is not counted.  Half of those instruction slots are not FMAs, so
+        # this fraction tops out near 0.45; ncu's FP64-pipe-active figure is in profiles/.
+        flop = (2.0 * steps_per_eval(cfg["dims"]) if cfg["kind"] != "polyh"
+                else float(cfg["nknots"]) * (3.0 * cfg["rank"] + 2.0))
+        achieved = flop * npts / (kernel_ms * 1e-3) / 1e12
+        # "tensor": the kernel's multiply-adds run as DMMA (FP64 tensor-core instructions); the DFMA
+        # kernels are bounded by the same FP64 peak (B200's DMMA and DFMA rates are equal, DESIGN 3)
+        bound = "tensor" if kernel_used in ("cheb_mma", "fh_mma") else "fp64"
+        return {"bound": bound, "precision": "fp64", "achieved": achieved, "peak": ctx.fp64_peak, "unit": "TFLOP/s",
+                "frac": achieved / ctx.fp64_peak if ctx.fp64_peak else None,
+                "traffic": traffic, "traffic_source": traffic_src,
+                "peak_source": "best of a DFMA-only and a DMMA-only kernel measured in this run (MEASURED_PEAKS.json has no FP64 peak); "
+                               "nominal 148 SM x 64 FMA/clk x 2 x 1.965 GHz = 37.2",
+                "flop_per_eval": flop, "kernel": kernel_used, "kernel_ms": kernel_ms}
+    byts = 8.0 * (k + 1 + 2 ** k)
+    achieved = byts * npts / (kernel_ms * 1e-3) / 1e9
+    return {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+            "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "traffic_source": traffic_src,
+            "peak_source": f"MEASURED_PEAKS.json ({peak_src})",
+            "bytes_per_eval": byts, "kernel": kernel_used, "kernel_ms": kernel_ms}
+
+
+def parity_check(ctx, cfg, case, plan, x, out, first_point, npts, n_want, oracle_seconds):
+    """Strided sample of this rank's shard against the CPU oracle (the points are regenerated on
+    the host from their global indices).  When the oracle cannot do all n_want points in
+    oracle_seconds (12^6: ~1e3 evals/s), the rest is checked against the STRICT kernel, after that
+    kernel has been shown bit-identical to the oracle on the oracle's share of the sample."""
+    import torch
+
+    from chebpol_b200 import _lib, synth
+
+    k = cfg_rank(cfg)
+    orc, okind = ctx.get_oracle()
+    threads = max(1, (os.cpu_count() or 1) // ctx.world)
+    stride = max(1, npts // n_want)
+    idx = torch.arange(0, npts, stride, device=ctx.dev)[:n_want]
+    n = int(idx.numel())
+    got = out[idx].cpu().numpy()
+    xs = synth.points_at(idx.cpu().numpy().astype(np.uint64) + np.uint64(first_point), k, seed=SEED)
+    same_points = bool(np.array_equal(xs[:64], x[idx[:64]].cpu().numpy()))  # host twin == device generator
+    # how many points the oracle manages in its time budget
+    probe = min(n, 500)
+    dt = max(time_cpu(orc, cfg, case, xs[:probe], threads), 1e-5)
+    n_orc = int(min(n, max(probe, probe * oracle_seconds / dt)))
+    want = oracle_eval(orc, cfg, case, xs[:n_orc], threads)
+    rec = {"n": n, "stride": stride, "oracle": okind, "n_oracle": n_orc, "host_points_match_device": same_points}
+    ref = want
+    if n_orc < n:
+        plan.set(_lib.OPT_KERNEL, _lib.KERNEL_STRICT)
+        xs_d = x[idx].contiguous()
+        st = torch.empty(n, dtype=torch.float64, device=ctx.dev)
+        plan.eval_device_ptr(xs_d.data_ptr(), n, st.data_ptr(), ctx.stream.cuda_stream)
+        torch.cuda.synchronize(ctx.dev)
+        plan.set(_lib.OPT_KERNEL, _lib.KERNEL_AUTO)
+        strict = st.cpu().numpy()
+        rec["strict_kernel_bit_identical_to_oracle"] = bool(np.array_equal(strict[:n_orc].view(np.uint64), want.view(np.uint64)))
+        rec["checked_against"] = (f"oracle on the first {n_orc} sample points; the strict kernel (bit-identical to the "
+                                  f"oracle on those) on all {n}")
+        ref = strict
+    else:
+        rec["checked_against"] = f"oracle on all {n} sample points"
+    fin = np.isfinite(ref)  # simplex-linear: NA outside the convex hull, on both sides
+    err = float(np.abs(got[fin] - ref[fin]).max()) if fin.any() else 0.0
+    scale = float(np.abs(ref[fin]).max()) if fin.any() else 0.0
+    rec.update(max_abs_err=err, max_abs_f=scale, rel_err=err / scale if scale else 0.0,
+               non_finite=int((~fin).sum()), non_finite_agree=bool(np.array_equal(fin, np.isfinite(got))))
+    return rec
+
+
+def measure_workload(ctx, cfg_id, headline):
+    """One BASELINE config on this rank's GPU: device-resident timing, parity, pinned e2e, CPU baseline."""
     import torch
 
     import chebpol_b200 as cb
     from chebpol_b200 import _lib, shard
 
-    rank, local_rank, world = shard.dist_env()
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device; chebpol_b200 has no CPU path")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        shard.init_process_group("nccl")
-    npts = args.points if args.points else cfg["points"]
-    if args.total_points:  # strong scaling: a fixed batch split into contiguous shards, one per GPU
-        npts = (args.total_points + world - 1) // world
-    k = cfg.get("rank", len(cfg["dims"]))
+    args, cfg = ctx.args, CONFIGS[cfg_id]
+    k = cfg_rank(cfg)
+    rank, world, dev, stream = ctx.rank, ctx.world, ctx.dev, ctx.stream
+    npts = args.points if (args.points and headline) else cfg["points"]
+    total = 0
+    if headline and args.total_points:
+        total = args.total_points
+    elif not headline and world > 1 and cfg.get("total_points"):
+        total = cfg["total_points"]  # BASELINE cfg5: the batch is sharded over the GPUs of the box
+    if total:  # strong scaling: a fixed batch split into contiguous shards, one per GPU
+        lo, hi = shard.shard_range(total, rank, world)
+        first_point, npts = lo, hi - lo
+    else:      # weak scaling: rank r owns global points [r*npts, (r+1)*npts)
+        first_point = rank * npts
     case = build_case(cfg)
-    plan = make_plan(cfg, case, local_rank)
-    if args.variant:
+    plan = make_plan(cfg, case, ctx.local_rank)
+    if headline and args.variant:
         plan.set(_lib.OPT_VARIANT, args.variant)
-    if args.strict:
+    if headline and args.strict:
         plan.set(_lib.OPT_KERNEL, _lib.KERNEL_STRICT)
 
-    # synthetic points generated on the device, per-rank seed (weak scaling: npts per GPU)
-    g = torch.Generator(device=dev).manual_seed(42 + rank)
     x = torch.empty((npts, k), dtype=torch.float64, device=dev)
-    blk = 1 << 24
-    for lo in range(0, npts, blk):
-        hi = min(npts, lo + blk)
-        x[lo:hi] = torch.rand((hi - lo, k), generator=g, device=dev, dtype=torch.float64) * 2.0 - 1.0
+    _lib.synth_points_device(x.data_ptr(), first_point, npts, k, seed=SEED, device=ctx.local_rank, stream=stream.cuda_stream)
     out = torch.empty(npts, dtype=torch.float64, device=dev)
-    stream = torch.cuda.current_stream(dev)
 
-    def step():
-        plan.eval_device_ptr(x.data_ptr(), npts, out.data_ptr(), stream.cuda_stream)
+    def step(n=npts):
+        plan.eval_device_ptr(x.data_ptr(), n, out.data_ptr(), stream.cuda_stream)
 
-    wpts = min(npts, args.warmup_points) if args.warmup_points else npts
-    for _ in range(args.warmup):
-        plan.eval_device_ptr(x.data_ptr(), wpts, out.data_ptr(), stream.cuda_stream)
+    # warm-up: full steps, except for the sharded 12^6 batch (a pass is tens of seconds) where a
+    # 2e6-point prefix warms the kernel, the TMA ring and the clocks
+    wpts = npts
+    if headline and args.warmup_points:
+        wpts = min(npts, args.warmup_points)
+    elif total and npts > 4_000_000:
+        wpts = 2_000_000
+    t0 = time.perf_counter()
+    for _ in range(max(args.warmup, 3)):
+        step(wpts)
     torch.cuda.synchronize(dev)
+    warm_s = (time.perf_counter() - t0) / max(args.warmup, 3) * (npts / wpts)  # ~seconds per full step
 
-    # FP64 peak (roofline denominator), measured now so clocks match the run
-    fp64_peak = cb.fp64_peak_tflops(local_rank, 5) if rank == 0 else 0.0
-    torch.cuda.synchronize(dev)
+    if ctx.fp64_peak is None:  # FP64 roofline denominator, measured now so clocks match the run
+        ctx.fp64_peak = cb.fp64_peak_tflops(ctx.local_rank, 5) if rank == 0 else 0.0
+        torch.cuda.synchronize(dev)
 
-    sampler = ClockSampler(physical_gpu_index(local_rank))
+    # the headline times EXACTLY --steps steps; a sub-workload repeats its step until the clock
+    # sampler (100 ms period) has seen >= 20 samples -- except the sharded batch: one pass
+    if headline:
+        steps = args.steps
+    elif total and world > 1:
+        steps = 1
+    else:
+        steps = int(min(max(args.steps, math.ceil(args.sub_seconds / max(warm_s, 1e-6))), 200000))
+        steps = int(shard.max_over_ranks(steps, dev))
+
+    sampler = ClockSampler(physical_gpu_index(ctx.local_rank)) if rank == 0 else None
     shard.barrier()
     torch.cuda.synchronize(dev)
-    sampler.start()
+    if sampler:
+        sampler.start()
+        time.sleep(0.15)  # the first sample lands inside the timed region
     l0 = cb.launch_count()
-    evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    nev = min(steps, 64)  # per-step events for the first 64 steps (kernel_ms), one pair around everything
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(nev + 1)]
+    ev_end = torch.cuda.Event(enable_timing=True)
     evs[0].record(stream)
-    for i in range(args.steps):
+    for i in range(steps):
         step()
-        evs[i + 1].record(stream)
+        if i < nev:
+            evs[i + 1].record(stream)
+    ev_end.record(stream)
     torch.cuda.synchronize(dev)
     shard.barrier()
     launches = int(shard.sum_over_ranks(cb.launch_count() - l0, dev))
-    clocks = sampler.stop()
-    total_ms = evs[0].elapsed_time(evs[-1])
-    step_ms = [evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps)]
-    total_ms = shard.max_over_ranks(total_ms, dev)
-    value = npts * world * args.steps / (total_ms * 1e-3)
-    kernel_ms = float(np.mean(step_ms))  # one kernel launch per step
+    clocks = sampler.stop() if sampler else None
+    total_ms = shard.max_over_ranks(evs[0].elapsed_time(ev_end), dev)
+    kernel_ms = float(np.mean([evs[i].elapsed_time(evs[i + 1]) for i in range(nev)]))  # one kernel launch per step
+    all_pts = total if total else npts * world
+    value = all_pts * steps / (total_ms * 1e-3)
     kernel_used = plan.kernel_used
 
-    # ---- parity spot check (untimed): strided sample against the oracle
-    parity = None
-    if rank == 0:
-        orc, okind = get_oracle()
-        idx = torch.arange(0, npts, max(1, npts // 2000), device=dev)[:2000]
-        xs = x[idx].cpu().numpy()
-        want = oracle_eval(orc, cfg, case, xs, os.cpu_count() or 1)
-        got = out[idx].cpu().numpy()
-        fin = np.isfinite(want)  # simplex-linear: NA outside the convex hull, on both sides
-        parity = {"n": int(len(want)), "max_abs_err": float(np.abs(got[fin] - want[fin]).max()) if fin.any() else 0.0,
-                  "max_abs_f": float(np.abs(want[fin]).max()) if fin.any() else 0.0, "oracle": okind,
-                  "non_finite": int((~fin).sum()), "non_finite_agree": bool(np.array_equal(fin, np.isfinite(got)))}
+    # ---- parity: every rank, >= 1e5 strided points of its shard; checksum over ALL results
+    par = parity_check(ctx, cfg, case, plan, x, out, first_point, npts, args.parity_points,
+                       args.parity_oracle_seconds)
+    bits_sum = int(out.view(torch.int64).sum().item()) & 0xFFFFFFFFFFFFFFFF
+    fsum = float(out.sum().item())
+    worst = shard.max_over_ranks(par["rel_err"], dev)
+    worst_abs = shard.max_over_ranks(par["max_abs_err"], dev)
+    all_ok = shard.max_over_ranks(0.0 if (par["non_finite_agree"] and par["host_points_match_device"]
+                                          and par.get("strict_kernel_bit_identical_to_oracle", True)) else 1.0, dev) == 0.0
+    n_all = int(shard.sum_over_ranks(par["n"], dev))
+    checksum = {"bits_sum_mod_2_64": f"{sum_u64_over_ranks(ctx, bits_sum):016x}", "sum": shard.sum_over_ranks(fsum, dev),
+                "over": f"all {all_pts} results of the last step, all ranks",
+                "note": "wrapping 64-bit sum of the IEEE bit patterns: independent of order and of how the batch is sharded"}
+    parity = {**par, "ranks_checked": world, "n_all_ranks": n_all, "worst_rel_err_over_ranks": worst,
+              "worst_abs_err_over_ranks": worst_abs, "all_ranks_ok": bool(all_ok), "checksum": checksum}
 
     # ---- end to end through the host-pointer C ABI, pinned host buffers
-    e2e_steps = max(1, min(args.steps, args.e2e_steps))
-    epts = min(npts, args.e2e_points) if args.e2e_points else npts  # bounds the pinned host memory per rank
+    e2e_steps = max(1, args.e2e_steps)
+    epts = npts
+    if headline and args.e2e_points:
+        epts = min(npts, args.e2e_points)
+    elif total and npts > cfg["points"]:
+        epts = cfg["points"]  # bounds the pinned host memory and the time of the sharded batch's e2e leg
+        e2e_steps = min(e2e_steps, 3)
     hx = torch.empty((epts, k), dtype=torch.float64, pin_memory=True)
     ho = torch.empty(epts, dtype=torch.float64, pin_memory=True)
     hx.copy_(x[:epts])
@@ -392,86 +641,144 @@ def run_ours(args, cfg):
     shard.barrier()
     e2e_s = shard.max_over_ranks(e2e_s, dev)
     e2e_value = epts * world * e2e_steps / e2e_s
+    e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": epts * k * 8, "d2h_bytes_per_step": epts * 8,
+           **({"points_per_gpu": epts} if epts != npts else {}),
+           "steps": e2e_steps, "api": "chebpol_cuda_plan_eval_host (pinned host buffers)"}
 
-    # ---- CPU baseline: rank 0, N = 1 only
+    # ---- CPU baseline: rank 0, N = 1 only; the reference arm's procedure
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        orc, okind = get_oracle()
-        threads = os.cpu_count() or 1
-        n = min(cpu_sample_size(orc, cfg, case, threads, target_s=10.0), epts)
-        xs = hx[:n].numpy()
-        dt = time_cpu(orc, cfg, case, np.ascontiguousarray(xs), threads)
-        cpu_baseline = {"value": n / dt, "unit": UNIT, "cores": threads, "kind": okind,
-                        "sample": f"first {n} points of the rank-0 batch, {dt:.1f} s wall"}
+        orc, okind = ctx.get_oracle()
+        secs = args.cpu_seconds if headline else args.sub_cpu_seconds
+        r = cpu_reference_rate(orc, okind, cfg, case, os.cpu_count() or 1, secs, 3, 1)
+        cpu_baseline = {kk: r[kk] for kk in ("value", "unit", "cores", "kind", "sample")}
 
-    if rank == 0:
-        peaks, peak_src = load_peaks()
-        if cfg["kind"] == "hstalk":
-            # 2^D corners, each one packed record of 3D+1 doubles, plus the point and the result.  The
-            # 21 MB record table is L2-resident, so this is the L2-side byte count set against the HBM
-            # peak: a reference line for the gather rate, not a bound.
-            byts = 8.0 * (k + 1 + 2 ** k * (3 * k + 1))
-            achieved = byts * npts / (kernel_ms * 1e-3) / 1e9
-            roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                        "frac": achieved / peaks["hbm_gbs"], "traffic": load_traffic(kernel_used, args.config, npts),
-                        "peak_source": f"MEASURED_PEAKS.json ({peak_src}); bytes are gathered from L2, not HBM",
-                        "bytes_per_eval": byts, "kernel": kernel_used, "kernel_ms": kernel_ms}
-        elif cfg["kind"] == "sl":
-            # streamed point + result, plus the one packed simplex record that is accepted; the candidate
-            # records rejected on the way and the cell lists are L2-side traffic.  A reference line for
-            # a gather-latency kernel, not a bound.
-            n1 = k + 1
-            byts = 8.0 * (k + 1) + 8.0 * (((2 * k + n1 * n1 + n1 + 1) + 3) // 4 * 4)
-            achieved = byts * npts / (kernel_ms * 1e-3) / 1e9
-            roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                        "frac": achieved / peaks["hbm_gbs"], "traffic": load_traffic(kernel_used, args.config, npts),
-                        "peak_source": f"MEASURED_PEAKS.json ({peak_src}); the simplex records are gathered from L2",
-                        "bytes_per_eval": byts, "kernel": kernel_used, "kernel_ms": kernel_ms}
-        elif cfg["kind"] in ("cheb", "chebg", "fh", "polyh"):
-            # polyharmonic: per knot a subtract and a multiply-add per coordinate plus the weight
-            # multiply-add, 3*rank + 2 flop as the reference executes them; the basis function
-            # (sqrt / log / exp) is not counted.  Half of those instruction slots are not FMAs, so
-            # this fraction tops out near 0.45; ncu's FP64-pipe-active figure is in profiles/.
-            flop = (2.0 * steps_per_eval(cfg["dims"]) if cfg["kind"] != "polyh"
-                    else float(cfg["nknots"]) * (3.0 * cfg["rank"] + 2.0))
-            achieved = flop * npts / (kernel_ms * 1e-3) / 1e12
-            # "tensor": the kernel's multiply-adds run as DMMA (FP64 tensor-core instructions); the DFMA
-            # kernels are bounded by the same FP64 peak (B200's DMMA and DFMA rates are equal)
-            bound = "tensor" if kernel_used in ("cheb_mma", "fh_mma") else "fp64"
-            roofline = {"bound": bound, "precision": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
-                        "frac": achieved / fp64_peak if fp64_peak else None,
-                        "traffic": load_traffic(kernel_used, args.config, npts),
-                        "peak_source": "best of a DFMA-only and a DMMA-only kernel measured in this run (MEASURED_PEAKS.json has no FP64 peak); "
-                                       "nominal 148 SM x 64 FMA/clk x 2 x 1.965 GHz = 37.2",
-                        "flop_per_eval": flop, "kernel": kernel_used, "kernel_ms": kernel_ms}
-        else:
-            byts = 8.0 * (k + 1 + 2 ** k)
-            achieved = byts * npts / (kernel_ms * 1e-3) / 1e9
-            roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                        "frac": achieved / peaks["hbm_gbs"], "traffic": load_traffic(kernel_used, args.config, npts),
-                        "peak_source": f"MEASURED_PEAKS.json ({peak_src})",
-                        "bytes_per_eval": byts, "kernel": kernel_used, "kernel_ms": kernel_ms}
+    del hx, ho
+    plan.close()
+    if rank != 0:
+        return None
+    roof = roofline_record(ctx, cfg, cfg_id, npts, kernel_ms, kernel_used)
+    rec = {
+        "value": value, "unit": UNIT, "steps": steps, "ms_per_step": total_ms / steps,
+        "scaling": "strong" if total else "weak",
+        "config": {"workload": cfg["name"], "points_per_gpu": npts,
+                   "parallelism": f"points sharded over {world} GPU(s), tensor replicated",
+                   **({"total_points": total} if total else {}),
+                   **({"warmup_points": wpts} if wpts != npts else {}),
+                   "points": f"counter-based generator, seed {SEED}, global points [{first_point}, {first_point + npts}) on rank 0",
+                   "l2": "inputs larger than L2 (point batch %.1f GB)" % (npts * k * 8 / 1e9) if npts * k * 8 > 126e6
+                   else "inputs smaller than L2 (latency regime, reported not targeted)"},
+        "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roof,
+        "cpu_baseline": cpu_baseline, "parity": parity,
+    }
+    return rec
+
+
+def fill_pageable(npts, k, threads=8):
+    """(npts, k) PAGEABLE numpy array holding the seed-42 batch: the first 2^22 points are generated,
+    the rest repeats them (first touch and copy spread over a few threads)."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    from chebpol_b200 import synth
+
+    base_n = min(npts, 1 << 22)
+    base = synth.points(0, base_n, k, seed=SEED)
+    x = np.empty((npts, k), dtype=np.float64)
+    blocks = [(lo, min(npts, lo + base_n)) for lo in range(0, npts, base_n)]
+
+    def put(b):
+        x[b[0]:b[1]] = base[: b[1] - b[0]]
+
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        list(ex.map(put, blocks))
+    return x
+
+
+def measure_dropin(ctx, cfg_id, ngpus, pinned_e2e_per_gpu):
+    """The path the R closure takes: one process, pageable numpy arrays, the stateless C ABI with the
+    interpolant re-passed on every call, points split over `ngpus` devices inside the library."""
+    from chebpol_b200 import _lib
+
+    args, cfg = ctx.args, CONFIGS[cfg_id]
+    k = cfg_rank(cfg)
+    per_gpu = min(cfg["points"], args.dropin_points)
+    npts = per_gpu * ngpus
+    case = build_case(cfg)
+    call = make_stateless(cfg, case)
+    x = fill_pageable(npts, k)
+    out = np.empty(npts, dtype=np.float64)
+    out[:] = 0.0  # touch the result pages once; R's allocVector result is fresh memory on every call
+    t0 = time.perf_counter()
+    call(x, out, ngpus)  # first call: plans built on every device, cell table expanded, staging pinned
+    first_s = time.perf_counter() - t0
+    steps = max(5, args.e2e_steps)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        call(x, out, ngpus)
+    dt = time.perf_counter() - t0
+    # spot check against the oracle (same points as the counter-based batch)
+    orc, okind = ctx.get_oracle()
+    idx = np.arange(0, npts, max(1, npts // 2000))[:2000]
+    want = oracle_eval(orc, cfg, case, np.ascontiguousarray(x[idx]), os.cpu_count() or 1)
+    err = float(np.abs(out[idx] - want).max())
+    value = npts * steps / dt
+    rec = {"config": cfg_id, "workload": cfg["name"], "n_gpus": ngpus, "points": npts, "steps": steps,
+           "value": value, "unit": UNIT, "ms_per_step": 1e3 * dt / steps, "first_call_ms": 1e3 * first_s,
+           "host_gbs": npts * (k + 1) * 8 * steps / dt / 1e9,
+           "h2d_bytes_per_step": npts * k * 8, "d2h_bytes_per_step": npts * 8,
+           "api": f"stateless C ABI from ONE process, numpy pageable x and out, tensor re-passed every call, ngpus={ngpus}",
+           "host_threads": os.environ.get("CHEBPOL_CUDA_HOST_THREADS", "default min(16, cores/2), divided among the GPUs"),
+           "cache": _lib.cache_stats(),
+           "parity": {"n": int(len(idx)), "max_abs_err": err, "max_abs_f": float(np.abs(want).max()), "oracle": okind}}
+    if pinned_e2e_per_gpu:
+        rec["vs_pinned_plan_e2e"] = value / (pinned_e2e_per_gpu * ngpus)
+    del x, out
+    _lib.cache_clear()
+    return rec
+
+
+def run_ours(args, cfg_id):
+    import torch
+
+    ctx = Ctx(args)
+    head = measure_workload(ctx, cfg_id, headline=True)
+    subs = []
+    for cid in parse_workloads(args):
+        r = measure_workload(ctx, cid, headline=False)
+        if r is not None:
+            subs.append({"config": cid, **r})
+
+    # ---- drop-in leg: rank 0 alone, every GPU of the box through ONE process
+    dropin = []
+    if args.dropin not in ("none", "", "0"):
+        torch.cuda.synchronize(ctx.dev)
+        torch.cuda.empty_cache()
+        ctx.host_barrier()
+        if ctx.rank == 0:
+            pinned = {cfg_id: head["e2e"]["value"] / ctx.world}
+            for s in subs:
+                pinned[s["config"]] = s["e2e"]["value"] / ctx.world
+            for cid in [int(t) for t in args.dropin.split(",") if t]:
+                for ng in sorted({1, ctx.world}):
+                    try:
+                        dropin.append(measure_dropin(ctx, cid, ng, pinned.get(cid)))
+                    except Exception as ex:  # reported, never hidden
+                        dropin.append({"config": cid, "n_gpus": ng, "error": f"{type(ex).__name__}: {ex}"})
+        ctx.host_barrier()
+
+    if ctx.rank == 0:
+        cfg = CONFIGS[cfg_id]
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
-            "scaling": "strong" if args.total_points else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": cfg["name"], "points_per_gpu": npts, "parallelism": f"points sharded over {world} GPU(s), tensor replicated",
-                       **({"total_points": args.total_points} if args.total_points else {}),
-                       **({"warmup_points": wpts} if wpts != npts else {}),
-                       "l2": "inputs larger than L2 (point batch %.1f GB)" % (npts * k * 8 / 1e9) if npts * k * 8 > 126e6
-                       else "inputs smaller than L2 (latency regime, reported not targeted)"},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": epts * k * 8, "d2h_bytes_per_step": epts * 8,
-                    **({"points_per_gpu": epts} if epts != npts else {}),
-                    "steps": e2e_steps, "api": "chebpol_cuda_plan_eval_host (pinned host buffers)"},
-            "gpu_launches": int(launches),
-            "clocks": clocks,
-            "roofline": roofline,
-            "cpu_baseline": cpu_baseline,
-            "parity": parity,
+            "metric": METRIC, "value": head["value"], "unit": UNIT, "n_gpus": ctx.world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": head["ms_per_step"], "higher_is_better": True,
+            "scaling": head["scaling"], "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": head["config"], "e2e": head["e2e"], "gpu_launches": head["gpu_launches"],
+            "clocks": head["clocks"], "roofline": head["roofline"], "cpu_baseline": head["cpu_baseline"],
+            "parity": head["parity"],
+            "workloads": subs, "e2e_dropin": dropin,
         }
         print(json.dumps(line), flush=True)
-    plan.close()
-    if world > 1:
+    if ctx.world > 1:
         import torch.distributed as dist
 
         dist.destroy_process_group()
@@ -484,21 +791,30 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS))
-    ap.add_argument("--points", type=int, default=0, help="override points per GPU")
-    ap.add_argument("--total-points", type=int, default=0, help="strong scaling: this many points split over the GPUs")
+    ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS), help="headline workload")
+    ap.add_argument("--workloads", default="all", help="sub-records: all (BASELINE cfg1,3,4,5), none, or a list like 3,4")
+    ap.add_argument("--dropin", default="2,3", help="configs of the one-process pageable stateless leg, or none")
+    ap.add_argument("--dropin-points", type=int, default=50_000_000, help="points per GPU of the drop-in leg")
+    ap.add_argument("--points", type=int, default=0, help="override points per GPU (headline)")
+    ap.add_argument("--total-points", type=int, default=0, help="headline strong scaling: this many points split over the GPUs")
     ap.add_argument("--warmup-points", type=int, default=0, help="points per warm-up step (default: a full step)")
     ap.add_argument("--e2e-points", type=int, default=0, help="cap the points per GPU of the end-to-end leg (pinned host memory)")
     ap.add_argument("--variant", type=int, default=0, help="kernel tuning variant (0 = default)")
     ap.add_argument("--strict", action="store_true", help="use the reference-order kernels")
-    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--sub-seconds", type=float, default=2.6, help="minimum timed seconds of a sub-workload (>= 20 clock samples)")
+    ap.add_argument("--parity-points", type=int, default=100_000)
+    ap.add_argument("--parity-oracle-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=3.0, help="CPU seconds per timed pass of the headline cpu_baseline")
+    ap.add_argument("--sub-cpu-seconds", type=float, default=1.5, help="CPU seconds per timed pass of a sub-workload's baseline")
     ap.add_argument("--ref-seconds", type=float, default=8.0, help="--impl reference: CPU seconds per step the sample is sized for")
     args = ap.parse_args()
-    cfg = CONFIGS[args.config]
+    if args.config not in (1, 2, 3, 4, 5) and args.dropin == "2,3":
+        args.dropin = "none"
     if args.impl == "reference":
-        return run_reference(args, cfg)
-    return run_ours(args, cfg)
+        return run_reference(args, CONFIGS[args.config])
+    return run_ours(args, args.config)
 
 
 if __name__ == "__main__":

@@ -45,6 +45,8 @@ EXPORTS = [
     "chebpol_cuda_evalchebg", "chebpol_cuda_plan_chebg",
     "chebpol_cuda_evalstalker", "chebpol_cuda_plan_oldstalk",
     "chebpol_cuda_evalsl", "chebpol_cuda_plan_sl", "chebpol_cuda_analyzesimplex", "chebpol_cuda_debug_sl_lists",
+    "chebpol_cuda_synth_points", "chebpol_cuda_debug_cache_stats", "chebpol_cuda_debug_cache_weak_hash",
+    "chebpol_cuda_debug_fingerprint", "chebpol_cuda_debug_cache_would_hit",
 ]
 
 
@@ -115,6 +117,14 @@ def lib() -> C.CDLL:
                                              C.POINTER(_vp)]
     L.chebpol_cuda_cache_clear.restype = None
     L.chebpol_cuda_cache_clear.argtypes = []
+    L.chebpol_cuda_synth_points.argtypes = [C.c_uint64, C.c_int64, C.c_int64, C.c_int, C.c_double, C.c_double, _vp,
+                                            C.c_int, _vp]
+    _i64p = C.POINTER(C.c_int64)
+    L.chebpol_cuda_debug_cache_stats.argtypes = [_i64p, _i64p, _i64p, _i64p, _i64p]
+    L.chebpol_cuda_debug_cache_weak_hash.restype = None
+    L.chebpol_cuda_debug_cache_weak_hash.argtypes = [C.c_int]
+    L.chebpol_cuda_debug_fingerprint.argtypes = [_vp, C.c_int64, C.c_int, C.POINTER(C.c_uint64)]
+    L.chebpol_cuda_debug_cache_would_hit.argtypes = [_vp, C.c_int64, _vp, C.c_int64, C.c_int, _ip]
     L.chebpol_cuda_launch_count.restype = C.c_int64
     L.chebpol_cuda_launch_count.argtypes = []
     _lib = L
@@ -137,6 +147,38 @@ def device_count() -> int:
 
 def cache_clear() -> None:
     lib().chebpol_cuda_cache_clear()
+
+
+def cache_stats() -> dict:
+    """Facts of the stateless entry points' plan cache (csrc/api.cu)."""
+    v = [C.c_int64(0) for _ in range(5)]
+    check(lib().chebpol_cuda_debug_cache_stats(*[C.byref(t) for t in v]))
+    return dict(zip(("entries", "hits", "misses", "rejected", "device_bytes"), (int(t.value) for t in v)))
+
+
+def cache_weak_hash(on: bool) -> None:
+    lib().chebpol_cuda_debug_cache_weak_hash(1 if on else 0)
+
+
+def fingerprint(a: np.ndarray, threads: int = 1) -> tuple[int, int]:
+    a = np.ascontiguousarray(a)
+    out = (C.c_uint64 * 2)()
+    check(lib().chebpol_cuda_debug_fingerprint(_addr(a), a.nbytes, threads, out))
+    return int(out[0]), int(out[1])
+
+
+def cache_would_hit(a: np.ndarray, b: np.ndarray, retain: bool = True) -> bool:
+    a, b = np.ascontiguousarray(a), np.ascontiguousarray(b)
+    hit = C.c_int(0)
+    check(lib().chebpol_cuda_debug_cache_would_hit(_addr(a), a.nbytes, _addr(b), b.nbytes, 1 if retain else 0,
+                                                   C.byref(hit)))
+    return bool(hit.value)
+
+
+def synth_points_device(x_ptr: int, first_point: int, npts: int, rank: int, seed: int = 42, lo: float = -1.0,
+                        hi: float = 1.0, device: int = 0, stream: int = 0) -> None:
+    """Fill a device buffer with the counter-based synthetic batch (twin of chebpol_b200.synth.points)."""
+    check(lib().chebpol_cuda_synth_points(seed, first_point, npts, rank, lo, hi, x_ptr, device, stream))
 
 
 def launch_count() -> int:
@@ -612,3 +654,47 @@ def fh(vals, grid, weights, x_pk, ngpus: int = 0) -> np.ndarray:
     check(lib().chebpol_cuda_fh(_addr(v), gl, wl, dims.ctypes.data_as(_ip), len(grid), _addr(x_pk), x_pk.shape[0],
                                 ngpus, _addr(out)))
     return out
+
+
+class Stateless:
+    """One stateless entry point with its interpolant arguments marshalled once: calling the object
+    is the bare C call a ``.Call`` from the R closure makes (tensor re-passed every time, host
+    pointers in and out), without per-call numpy conversions."""
+
+    def __init__(self, fn, head, tail, rank, keep):
+        self._fn, self._head, self._tail, self.rank, self._keep = fn, head, tail, rank, keep
+
+    @staticmethod
+    def cheb(coef, mid=None, ispan=None, ugm_n=None) -> "Stateless":
+        coef = np.asarray(coef, dtype=np.float64)
+        dims, cf = _i32(coef.shape), f64(coef, order="F")
+        mid_a = f64(mid) if mid is not None else None
+        isp_a = f64(ispan) if ispan is not None else None
+        ugm_a = _i32(ugm_n) if ugm_n is not None else None
+        return Stateless(lib().chebpol_cuda_evalcheb, (_addr(cf), dims.ctypes.data_as(_ip), coef.ndim),
+                         (_addr(mid_a), _addr(isp_a), _addr(ugm_a)), coef.ndim, (cf, dims, mid_a, isp_a, ugm_a))
+
+    @staticmethod
+    def mlip(grid, values, blend: int = 0) -> "Stateless":
+        dims = _i32([len(g) for g in grid])
+        vals = f64(np.asarray(values, dtype=np.float64).ravel(order="F"))
+        gl, keep = ptr_list(grid)
+        return Stateless(lib().chebpol_cuda_evalmlip, (gl, dims.ctypes.data_as(_ip), len(grid), _addr(vals)), (blend,),
+                         len(grid), (dims, vals, gl, keep))
+
+    @staticmethod
+    def fh(vals, grid, weights) -> "Stateless":
+        dims = _i32([len(g) for g in grid])
+        v = f64(np.asarray(vals, dtype=np.float64).ravel(order="F"))
+        gl, k1 = ptr_list(grid)
+        wl, k2 = ptr_list(weights)
+        return Stateless(lib().chebpol_cuda_fh, (_addr(v), gl, wl, dims.ctypes.data_as(_ip), len(grid)), (), len(grid),
+                         (dims, v, gl, k1, wl, k2))
+
+    def __call__(self, x_pk: np.ndarray, out: np.ndarray | None = None, ngpus: int = 0) -> np.ndarray:
+        assert x_pk.dtype == np.float64 and x_pk.flags.c_contiguous and x_pk.shape[1] == self.rank
+        n = x_pk.shape[0]
+        if out is None:
+            out = np.empty(n, dtype=np.float64)
+        check(self._fn(*self._head, _addr(x_pk), n, *self._tail, ngpus, _addr(out)))
+        return out

@@ -145,6 +145,12 @@ struct chebpol_cuda_plan {
     cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_k[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
     double *d_x[2] = {nullptr, nullptr}, *d_o[2] = {nullptr, nullptr};
     int64_t buf_points = 0;
+    int host_threads = 0;  // threads that fill / drain the pinned staging buffers (0: staging_threads())
+    // derived tables built lazily on the stream of the evaluation that first needs them (padded
+    // slab tensor, multilinear cell-major table): later evaluations on another stream wait for this
+    cudaEvent_t ev_build = nullptr;
+    cudaStream_t build_stream = nullptr;
+    bool built_lazily = false;
 };
 
 // Plan constructors upload with synchronous cudaMemcpy from pageable memory, which may return while
@@ -235,6 +241,7 @@ extern "C" void chebpol_cuda_plan_destroy(chebpol_cuda_plan *p)
         cudaFree(p->d_x[i]);
         cudaFree(p->d_o[i]);
     }
+    if (p->ev_build) cudaEventDestroy(p->ev_build);
     cudaFree(p->d_tensor);
     cudaFree(p->d_padded);
     cudaFree(p->d_mma);
@@ -744,6 +751,15 @@ static int check_sl(const double *knots, int dim, int nknots, const int *dtri, i
     for (int64_t i = 0; i < (int64_t)ns * (dim + 1); ++i)
         if (dtri[i] < 1 || dtri[i] > nknots)
             return fail(CHEBPOL_CUDA_EINVAL, "dtri[%lld] = %d is not a knot index in 1..%d", (long long)i, dtri[i], nknots);
+    // LAPACK's dgetrf records, for row r (1-based), the row it was interchanged with: r <= piv <= dim+1.
+    // The kernels apply the interchanges without bounds checks.
+    const int N = dim + 1;
+    for (int64_t j = 0; j < (int64_t)ns; ++j)
+        for (int r = 0; r < N; ++r) {
+            const int pv = pivots[j * N + r];
+            if (pv < r + 1 || pv > N)
+                return fail(CHEBPOL_CUDA_EINVAL, "pivots[%lld] = %d is not a dgetrf pivot (%d..%d)", (long long)(j * N + r), pv, r + 1, N);
+        }
     return CHEBPOL_CUDA_OK;
 }
 
@@ -896,6 +912,17 @@ extern "C" int chebpol_cuda_plan_get(chebpol_cuda_plan *p, int what, int64_t *va
     return CHEBPOL_CUDA_OK;
 }
 
+// A derived table has just been enqueued on stream s: remember where, so that an evaluation on
+// any other stream (chebpol_cuda_plan_eval_device takes the caller's) is ordered after the build.
+static int mark_lazy_build(chebpol_cuda_plan *p, cudaStream_t s)
+{
+    if (!p->ev_build) CU(cudaEventCreateWithFlags(&p->ev_build, cudaEventDisableTiming));
+    CU(cudaEventRecord(p->ev_build, s));
+    p->build_stream = s;
+    p->built_lazily = true;
+    return CHEBPOL_CUDA_OK;
+}
+
 // Row-padded copy of the tensor for the DFMA slab kernel, made on the device from the
 // resident R-layout tensor the first time that kernel is asked for.
 static int ensure_slab_tensor(chebpol_cuda_plan *p, cudaStream_t s)
@@ -907,7 +934,7 @@ static int ensure_slab_tensor(chebpol_cuda_plan *p, cudaStream_t s)
     CU(cudaMemcpy2DAsync(p->d_padded, n0p * 8, p->d_tensor, n0 * 8, n0 * 8, rows, cudaMemcpyDeviceToDevice, s));
     p->slab.cf = p->d_padded;
     p->tensor_bytes += sizeof(double) * rows * n0p;
-    return CHEBPOL_CUDA_OK;
+    return mark_lazy_build(p, s);
 }
 
 // ------------------------------------------------------------------- launch
@@ -915,6 +942,7 @@ static int ensure_slab_tensor(chebpol_cuda_plan *p, cudaStream_t s)
 static int launch_plan(chebpol_cuda_plan *p, const double *d_x, int64_t npts, double *d_out, cudaStream_t s)
 {
     if (npts == 0) return CHEBPOL_CUDA_OK;
+    if (p->built_lazily && s != p->build_stream) CU(cudaStreamWaitEvent(s, p->ev_build, 0));
     cudaError_t e = cudaErrorNotSupported;
     LaunchInfo li = {0, 0, 0, 0};
     const bool want_fast = p->kernel_opt != CHEBPOL_CUDA_KERNEL_STRICT;
@@ -997,6 +1025,8 @@ static int launch_plan(chebpol_cuda_plan *p, const double *d_x, int64_t npts, do
                 p->tensor_bytes += p->cell_bytes;
                 p->launches += 1;
                 g_launches.fetch_add(1);
+                const int rcb = mark_lazy_build(p, s);
+                if (rcb) return rcb;
             }
         }
         if (want_fast && allow_cell && p->d_cells) e = launch_mlip_cell(a, p->d_cells, p->variant, p->num_sms, s, &li);
@@ -1173,9 +1203,8 @@ static int staging_threads()
     return n;
 }
 
-static void par_memcpy(void *dst, const void *src, size_t bytes)
+static void par_memcpy(void *dst, const void *src, size_t bytes, int T)
 {
-    const int T = staging_threads();
     if (T == 1 || bytes < (4u << 20)) { memcpy(dst, src, bytes); return; }
     const size_t slice = ((bytes + T - 1) / T + 4095) & ~(size_t)4095;
 #pragma omp parallel for num_threads(T) schedule(static)
@@ -1250,6 +1279,7 @@ extern "C" int chebpol_cuda_plan_eval_host(chebpol_cuda_plan *p, const double *x
     if (chunk > npts) chunk = npts;
     int rc = ensure_pipeline(p, chunk);
     if (rc) { if (stg) staging_put(stg); return rc; }
+    const int nthreads = p->host_threads > 0 ? p->host_threads : staging_threads();
     if (stg) {
         // chunk c: threads fill in[b]; H2D -> kernel -> D2H into out[b]; chunk c-1 is drained to
         // the caller's buffer while chunk c runs on the GPU
@@ -1267,7 +1297,7 @@ extern "C" int chebpol_cuda_plan_eval_host(chebpol_cuda_plan *p, const double *x
             const int64_t off = c * chunk, n = (off + chunk <= npts) ? chunk : npts - off;
             cudaError_t e = cudaEventSynchronize(p->ev_out[b]);
             if (e != cudaSuccess) return cuda_fail(e, "D2H (staged)");
-            par_memcpy(out + off, stg->out[b], sizeof(double) * n);
+            par_memcpy(out + off, stg->out[b], sizeof(double) * n, nthreads);
             return CHEBPOL_CUDA_OK;
         };
         for (int64_t c = 0; c < nch; ++c) {
@@ -1277,7 +1307,7 @@ extern "C" int chebpol_cuda_plan_eval_host(chebpol_cuda_plan *p, const double *x
                 cudaError_t e = cudaEventSynchronize(p->ev_in[b]);  // staging buffer b has been read
                 if (e != cudaSuccess) return bail(cuda_fail(e, "H2D (staged)"));
             }
-            par_memcpy(stg->in[b], x + off * p->rank, sizeof(double) * n * p->rank);
+            par_memcpy(stg->in[b], x + off * p->rank, sizeof(double) * n * p->rank, nthreads);
             cudaError_t e = cudaSuccess;
             if (c >= 2) e = cudaStreamWaitEvent(p->st_in, p->ev_k[b], 0);
             if (e == cudaSuccess) e = cudaMemcpyAsync(p->d_x[b], stg->in[b], sizeof(double) * n * p->rank, cudaMemcpyHostToDevice, p->st_in);
@@ -1304,29 +1334,31 @@ extern "C" int chebpol_cuda_plan_eval_host(chebpol_cuda_plan *p, const double *x
     // chunk c uses buffer c&1:  H2D(c) -> kernel(c) -> D2H(c); D2H(c-1) is
     // enqueued after kernel(c) so that a blocking (pageable) copy-out overlaps
     // the next kernel.
+    // Nothing in the loop returns early: asynchronous copies that touch the caller's x / out may be
+    // in flight, so every exit goes through the stream synchronisation below.
     auto copy_out = [&](int64_t c) -> int {
         const int b = (int)(c & 1);
         const int64_t off = c * chunk, n = (off + chunk <= npts) ? chunk : npts - off;
-        CU(cudaStreamWaitEvent(p->st_out, p->ev_k[b], 0));
-        CU(cudaMemcpyAsync(out + off, p->d_o[b], sizeof(double) * n, cudaMemcpyDeviceToHost, p->st_out));
-        CU(cudaEventRecord(p->ev_out[b], p->st_out));
-        return CHEBPOL_CUDA_OK;
+        cudaError_t e = cudaStreamWaitEvent(p->st_out, p->ev_k[b], 0);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(out + off, p->d_o[b], sizeof(double) * n, cudaMemcpyDeviceToHost, p->st_out);
+        if (e == cudaSuccess) e = cudaEventRecord(p->ev_out[b], p->st_out);
+        return e == cudaSuccess ? CHEBPOL_CUDA_OK : cuda_fail(e, "D2H pipeline");
     };
-    for (int64_t c = 0; c < nchunks; ++c) {
+    for (int64_t c = 0; c < nchunks && !rc; ++c) {
         const int b = (int)(c & 1);
         const int64_t off = c * chunk, n = (off + chunk <= npts) ? chunk : npts - off;
-        if (c >= 2) CU(cudaStreamWaitEvent(p->st_in, p->ev_k[b], 0));  // x buffer free
-        CU(cudaMemcpyAsync(p->d_x[b], x + off * p->rank, sizeof(double) * n * p->rank, cudaMemcpyHostToDevice, p->st_in));
-        CU(cudaEventRecord(p->ev_in[b], p->st_in));
-        CU(cudaStreamWaitEvent(p->st_k, p->ev_in[b], 0));
-        if (c >= 2) CU(cudaStreamWaitEvent(p->st_k, p->ev_out[b], 0));  // out buffer free
+        cudaError_t e = cudaSuccess;
+        if (c >= 2) e = cudaStreamWaitEvent(p->st_in, p->ev_k[b], 0);  // x buffer free
+        if (e == cudaSuccess) e = cudaMemcpyAsync(p->d_x[b], x + off * p->rank, sizeof(double) * n * p->rank, cudaMemcpyHostToDevice, p->st_in);
+        if (e == cudaSuccess) e = cudaEventRecord(p->ev_in[b], p->st_in);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(p->st_k, p->ev_in[b], 0);
+        if (e == cudaSuccess && c >= 2) e = cudaStreamWaitEvent(p->st_k, p->ev_out[b], 0);  // out buffer free
+        if (e != cudaSuccess) { rc = cuda_fail(e, "H2D pipeline"); break; }
         rc = launch_plan(p, p->d_x[b], n, p->d_o[b], p->st_k);
         if (rc) break;
-        CU(cudaEventRecord(p->ev_k[b], p->st_k));
-        if (c >= 1) {
-            rc = copy_out(c - 1);
-            if (rc) break;
-        }
+        e = cudaEventRecord(p->ev_k[b], p->st_k);
+        if (e != cudaSuccess) { rc = cuda_fail(e, "kernel event"); break; }
+        if (c >= 1) rc = copy_out(c - 1);
     }
     if (!rc) rc = copy_out(nchunks - 1);
     cudaError_t e1 = cudaStreamSynchronize(p->st_in);
@@ -1342,52 +1374,48 @@ extern "C" int chebpol_cuda_plan_eval_host(chebpol_cuda_plan *p, const double *x
 
 // ---------------------------------------------------------------- plan cache
 // The R closures re-pass the tensor on every call (no C-side state in the reference), so a
-// stateless call would rebuild and re-upload its plan each time (~4 ms).  Small interpolants
-// are therefore kept in a process-wide cache keyed by the CONTENT of everything that defines
-// the plan (64-bit hash of tensor, knots, weights, pre-map; plus kind, device, dims), so a
-// closure restored by load() or a tensor re-allocated at another address still hits, and a
-// modified tensor never does.  CHEBPOL_CUDA_PLAN_CACHE=0 disables it.
-static uint64_t hash_bytes(const void *data, size_t n, uint64_t seed)
-{
-    const uint64_t M = 0x9E3779B97F4A7C15ull;
-    uint64_t h[4] = {seed ^ 0x243F6A8885A308D3ull, seed ^ 0x13198A2E03707344ull, seed ^ 0xA4093822299F31D0ull, seed ^ 0x082EFA98EC4E6C89ull};
-    const uint64_t *w = static_cast<const uint64_t *>(data);
-    const size_t nw = n / 8;
-    size_t i = 0;
-    for (; i + 4 <= nw; i += 4)
-        for (int j = 0; j < 4; ++j) {
-            h[j] = (h[j] ^ w[i + j]) * M;
-            h[j] ^= h[j] >> 29;
-        }
-    for (; i < nw; ++i) {
-        h[0] = (h[0] ^ w[i]) * M;
-        h[0] ^= h[0] >> 29;
-    }
-    const unsigned char *tail = static_cast<const unsigned char *>(data) + nw * 8;
-    for (size_t k = 0; k < n % 8; ++k) h[1] = (h[1] ^ tail[k]) * M;
-    uint64_t r = (h[0] * 31 + h[1]) * M ^ (h[2] * 17 + h[3]);
-    r ^= r >> 32;
-    return r * M ^ n;
-}
+// stateless call would rebuild and re-upload its plan each time (4 ms for a small tensor; 134 MB
+// of upload plus a 2 GB cell-table expansion for the 64^4 multilinear table).  Interpolants are
+// therefore kept in a process-wide cache keyed by the CONTENT of everything that defines the plan
+// (kind, device, dims, byte count and a 128-bit fingerprint of tensor, knots, weights, pre-map:
+// hash128.h), so a closure restored by load() or a tensor re-allocated at another address still
+// hits, and a modified tensor never does.  A hit is verified: entries up to 32 MB keep a host copy
+// of their defining arrays and the bytes are compared; larger ones rely on the 128-bit fingerprint
+// (collision probability ~2^-128 per pair, see hash128.h).  Per device at most 8 entries and
+// CHEBPOL_CUDA_CACHE_MAX_GB (default 16) of device memory, least recently used out first.
+// CHEBPOL_CUDA_PLAN_CACHE=0 disables the cache.
+#include "hash128.h"
+#include <memory>
+
+typedef std::shared_ptr<const std::vector<unsigned char>> KeptBytes;
 
 struct CacheKey {
     int kind, device, rank;
     int dims[CP_MAXR];
-    uint64_t hash;
+    uint64_t bytes;
+    cphash::H128 hash;
     bool operator==(const CacheKey &o) const
     {
-        if (kind != o.kind || device != o.device || rank != o.rank || hash != o.hash) return false;
+        if (kind != o.kind || device != o.device || rank != o.rank || bytes != o.bytes || !(hash == o.hash)) return false;
         for (int i = 0; i < rank; ++i)
             if (dims[i] != o.dims[i]) return false;
         return true;
     }
 };
-struct CacheEntry { CacheKey key; chebpol_cuda_plan *plan; uint64_t stamp; bool busy; };
+struct CacheEntry {
+    CacheKey key;
+    chebpol_cuda_plan *plan;
+    uint64_t stamp;
+    bool busy, doomed;
+    KeptBytes kept;  // null: fingerprint only (> kRetainMaxBytes)
+};
 static std::mutex g_cache_mu;
 static std::vector<CacheEntry> g_cache;
 static uint64_t g_cache_clock = 0;
-static const size_t kCacheSlots = 8;
-static const int64_t kCacheMaxBytes = 32ll << 20;  // per tensor; larger ones are cheaper to upload than to hash
+static std::atomic<int64_t> g_cache_hits{0}, g_cache_misses{0}, g_cache_rejected{0};
+static std::atomic<int> g_weak_hash{0};
+static const size_t kCacheSlotsPerDevice = 8;
+static const uint64_t kRetainMaxBytes = 32ull << 20;
 
 static bool cache_enabled()
 {
@@ -1399,62 +1427,302 @@ static bool cache_enabled()
     return on == 1;
 }
 
-static chebpol_cuda_plan *cache_take(const CacheKey &k)
+static int64_t cache_budget_bytes()
 {
-    std::lock_guard<std::mutex> lk(g_cache_mu);
-    for (auto &e : g_cache)
-        if (!e.busy && e.key == k) {
-            e.busy = true;
-            e.stamp = ++g_cache_clock;
-            return e.plan;
+    static int64_t b = -1;
+    if (b < 0) {
+        double gb = 16.0;
+        if (const char *e = getenv("CHEBPOL_CUDA_CACHE_MAX_GB")) gb = atof(e);
+        b = gb > 0 ? (int64_t)(gb * 1e9) : 0;
+    }
+    return b;
+}
+
+static int host_threads_total()
+{
+    static int n = 0;
+    if (n == 0) {
+        const char *e = getenv("CHEBPOL_CUDA_HOST_THREADS");
+        n = e ? atoi(e) : 0;
+        if (n <= 0) {
+            n = (int)std::thread::hardware_concurrency() / 2;
+            if (n > 16) n = 16;
         }
-    return nullptr;
+        if (n < 1) n = 1;
+    }
+    return n;
+}
+
+// Opt-in (CHEBPOL_CUDA_CACHE_TRUST_ADDRESS=1), for interpolants of 8 MB and more: identify them by
+// the ADDRESSES and lengths of their arrays plus a sparse sample of the content (both ends and 512
+// strided words of every array) instead of reading every byte -- the exact fingerprint of the
+// 134 MB 64^4 table costs milliseconds of host memory bandwidth per call.  This is NOT exact: an
+// array modified in place between two calls, outside the sampled words, is served from the stale
+// device copy.  R only modifies a vector in place when nothing else references it, which is not
+// how the closures use their tensors, but the default stays the exact content key.
+static bool cache_trust_address()
+{
+    static int on = -1;
+    if (on < 0) {
+        const char *e = getenv("CHEBPOL_CUDA_CACHE_TRUST_ADDRESS");
+        on = (e && atoi(e) != 0) ? 1 : 0;
+    }
+    return on == 1;
+}
+
+// everything that identifies the interpolant of one stateless call
+struct Identity {
+    CacheKey key;
+    std::vector<cphash::Blob> blobs;
+    bool cacheable = false;
+    bool by_address = false;
+    KeptBytes kept;          // made on the first miss of this call, shared by the per-device entries
+    const void *verified = nullptr;  // a retained copy this call has already compared equal
+    std::mutex mu;
+};
+
+static void make_identity(Identity &id, int kind, const int *dims, int rank, uint64_t seed)
+{
+    memset(&id.key, 0, sizeof id.key);
+    id.key.kind = kind;
+    id.key.rank = rank;
+    for (int i = 0; i < rank && i < CP_MAXR; ++i) id.key.dims[i] = dims[i];
+    id.key.bytes = cphash::blobs_bytes(id.blobs);
+    id.cacheable = cache_enabled() && (int64_t)id.key.bytes <= cache_budget_bytes();
+    if (!id.cacheable) return;
+    if (cache_trust_address() && id.key.bytes >= (8ull << 20)) {
+        std::vector<uint64_t> sample;
+        for (const cphash::Blob &b : id.blobs) {
+            sample.push_back((uint64_t)(uintptr_t)b.p);
+            sample.push_back((uint64_t)b.n);
+            const unsigned char *p = static_cast<const unsigned char *>(b.p);
+            const size_t nw = b.n / 8;
+            if (nw <= 2048) {
+                for (size_t i = 0; i < nw; ++i) sample.push_back(cphash::rd64(p + 8 * i));
+            } else {
+                for (size_t i = 0; i < 512; ++i) sample.push_back(cphash::rd64(p + 8 * i));
+                for (size_t i = nw - 512; i < nw; ++i) sample.push_back(cphash::rd64(p + 8 * i));
+                const size_t step = nw / 512;
+                for (size_t i = 0; i < 512; ++i) sample.push_back(cphash::rd64(p + 8 * (i * step + step / 2)));
+            }
+        }
+        std::vector<cphash::Blob> sb{{sample.data(), sample.size() * 8}};
+        id.key.hash = cphash::hash_blobs(sb, seed ^ 0xADD2E55ull, 1);
+        id.by_address = true;
+        return;
+    }
+    if (!g_weak_hash.load()) id.key.hash = cphash::hash_blobs(id.blobs, seed, host_threads_total());
+}
+
+// does a cached entry hold exactly the interpolant of this call?
+static bool identity_matches(Identity &id, const CacheKey &ekey, const KeptBytes &ekept)
+{
+    if (!(ekey == id.key)) return false;
+    if (!ekept) return true;  // fingerprint-only entry
+    {
+        std::lock_guard<std::mutex> lk(id.mu);
+        if (id.verified == ekept.get() || id.kept.get() == ekept.get()) return true;
+    }
+    if (!cphash::blobs_equal(id.blobs, *ekept, host_threads_total())) return false;
+    std::lock_guard<std::mutex> lk(id.mu);
+    id.verified = ekept.get();
+    return true;
+}
+
+static int64_t plan_device_bytes(const chebpol_cuda_plan *p)
+{
+    return p->tensor_bytes + 2 * p->buf_points * (int64_t)(p->rank + 1) * 8;
+}
+
+static chebpol_cuda_plan *cache_take(Identity &id, int device)
+{
+    CacheKey k = id.key;
+    k.device = device;
+    std::vector<chebpol_cuda_plan *> skipped;
+    for (;;) {
+        chebpol_cuda_plan *cand = nullptr;
+        KeptBytes kept;
+        {
+            std::lock_guard<std::mutex> lk(g_cache_mu);
+            for (auto &e : g_cache) {
+                if (e.busy || e.doomed || !(e.key == k)) continue;
+                bool seen = false;
+                for (auto *q : skipped) seen |= (q == e.plan);
+                if (seen) continue;
+                e.busy = true;  // held while the bytes are compared outside the lock
+                cand = e.plan;
+                kept = e.kept;
+                break;
+            }
+        }
+        if (!cand) {
+            g_cache_misses.fetch_add(1);
+            return nullptr;
+        }
+        Identity &idr = id;
+        CacheKey kk = k;
+        if (identity_matches(idr, kk, kept)) {
+            std::lock_guard<std::mutex> lk(g_cache_mu);
+            for (auto &e : g_cache)
+                if (e.plan == cand) e.stamp = ++g_cache_clock;
+            g_cache_hits.fetch_add(1);
+            return cand;
+        }
+        // same fingerprint, different bytes: not this interpolant
+        g_cache_rejected.fetch_add(1);
+        skipped.push_back(cand);
+        chebpol_cuda_plan *doomed = nullptr;
+        {
+            std::lock_guard<std::mutex> lk(g_cache_mu);
+            for (size_t i = 0; i < g_cache.size(); ++i)
+                if (g_cache[i].plan == cand) {
+                    g_cache[i].busy = false;
+                    if (g_cache[i].doomed) { doomed = cand; g_cache.erase(g_cache.begin() + i); }
+                    break;
+                }
+        }
+        if (doomed) chebpol_cuda_plan_destroy(doomed);
+    }
 }
 
 // give a plan (back) to the cache; takes ownership
-static void cache_put(const CacheKey &k, chebpol_cuda_plan *p)
+static void cache_put(Identity &id, int device, chebpol_cuda_plan *p)
 {
-    chebpol_cuda_plan *evict = nullptr;
+    CacheKey k = id.key;
+    k.device = device;
+    std::vector<chebpol_cuda_plan *> evict;
+    bool known = false;
     {
         std::lock_guard<std::mutex> lk(g_cache_mu);
-        for (auto &e : g_cache)
-            if (e.plan == p) {
-                e.busy = false;
-                return;
+        for (size_t i = 0; i < g_cache.size(); ++i)
+            if (g_cache[i].plan == p) {
+                known = true;
+                g_cache[i].busy = false;
+                if (g_cache[i].doomed) { evict.push_back(p); g_cache.erase(g_cache.begin() + i); }
+                break;
             }
-        if (g_cache.size() >= kCacheSlots) {
-            size_t victim = g_cache.size();
-            for (size_t i = 0; i < g_cache.size(); ++i)
-                if (!g_cache[i].busy && (victim == g_cache.size() || g_cache[i].stamp < g_cache[victim].stamp)) victim = i;
-            if (victim == g_cache.size()) {
-                evict = p;  // everything busy: do not cache this one
-            } else {
-                evict = g_cache[victim].plan;
-                g_cache.erase(g_cache.begin() + victim);
-            }
-        }
-        if (evict != p) g_cache.push_back({k, p, ++g_cache_clock, false});
     }
-    if (evict) chebpol_cuda_plan_destroy(evict);
+    if (!known) {
+        KeptBytes kept;
+        if (id.key.bytes <= kRetainMaxBytes && !id.by_address) {
+            std::lock_guard<std::mutex> lk(id.mu);
+            if (!id.kept) {
+                auto v = std::make_shared<std::vector<unsigned char>>();
+                cphash::blobs_copy(id.blobs, *v);
+                id.kept = v;
+            }
+            kept = id.kept;
+        }
+        std::lock_guard<std::mutex> lk(g_cache_mu);
+        g_cache.push_back({k, p, ++g_cache_clock, false, false, kept});
+    }
+    {
+        // per-device limits: slots and device bytes; least recently used idle entries go first
+        std::lock_guard<std::mutex> lk(g_cache_mu);
+        for (;;) {
+            size_t count = 0, victim = g_cache.size();
+            int64_t bytes = 0;
+            for (size_t i = 0; i < g_cache.size(); ++i) {
+                if (g_cache[i].key.device != device) continue;
+                ++count;
+                bytes += plan_device_bytes(g_cache[i].plan);
+                if (!g_cache[i].busy && (victim == g_cache.size() || g_cache[i].stamp < g_cache[victim].stamp)) victim = i;
+            }
+            if ((count <= kCacheSlotsPerDevice && bytes <= cache_budget_bytes()) || victim == g_cache.size()) break;
+            evict.push_back(g_cache[victim].plan);
+            g_cache.erase(g_cache.begin() + victim);
+        }
+    }
+    for (auto *q : evict) chebpol_cuda_plan_destroy(q);
+}
+
+// a plan that failed: never goes back
+static void cache_drop(chebpol_cuda_plan *p)
+{
+    {
+        std::lock_guard<std::mutex> lk(g_cache_mu);
+        for (size_t i = 0; i < g_cache.size(); ++i)
+            if (g_cache[i].plan == p) { g_cache.erase(g_cache.begin() + i); break; }
+    }
+    chebpol_cuda_plan_destroy(p);
 }
 
 extern "C" void chebpol_cuda_cache_clear(void)
 {
-    std::vector<CacheEntry> old;
+    std::vector<chebpol_cuda_plan *> old;
     {
         std::lock_guard<std::mutex> lk(g_cache_mu);
-        old.swap(g_cache);
+        for (size_t i = 0; i < g_cache.size();) {
+            if (g_cache[i].busy) {  // another thread is evaluating it: destroyed when it comes back
+                g_cache[i].doomed = true;
+                ++i;
+            } else {
+                old.push_back(g_cache[i].plan);
+                g_cache.erase(g_cache.begin() + i);
+            }
+        }
     }
-    for (auto &e : old) chebpol_cuda_plan_destroy(e.plan);
+    for (auto *p : old) chebpol_cuda_plan_destroy(p);
+}
+
+extern "C" int chebpol_cuda_debug_cache_stats(int64_t *entries, int64_t *hits, int64_t *misses, int64_t *rejected,
+                                              int64_t *device_bytes)
+{
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    int64_t bytes = 0;
+    for (auto &e : g_cache) bytes += plan_device_bytes(e.plan);
+    if (entries) *entries = (int64_t)g_cache.size();
+    if (hits) *hits = g_cache_hits.load();
+    if (misses) *misses = g_cache_misses.load();
+    if (rejected) *rejected = g_cache_rejected.load();
+    if (device_bytes) *device_bytes = bytes;
+    return CHEBPOL_CUDA_OK;
+}
+
+extern "C" void chebpol_cuda_debug_cache_weak_hash(int on) { g_weak_hash.store(on ? 1 : 0); }
+
+extern "C" int chebpol_cuda_debug_fingerprint(const void *data, int64_t nbytes, int threads, uint64_t *out2)
+{
+    if (!out2 || nbytes < 0 || (nbytes > 0 && !data)) return fail(CHEBPOL_CUDA_EINVAL, "NULL argument");
+    std::vector<cphash::Blob> b{{data, (size_t)nbytes}};
+    const cphash::H128 h = cphash::hash_blobs(b, 1, threads);
+    out2[0] = h.a;
+    out2[1] = h.b;
+    return CHEBPOL_CUDA_OK;
+}
+
+// Host-only model of one cache decision (no device needed): an entry is made from array a as a
+// stateless call would make it, then a call with array b looks it up.  *hit = 1 when b would be
+// served by a's entry.  retain = 0 models an entry above the 32 MB retention limit.
+extern "C" int chebpol_cuda_debug_cache_would_hit(const void *a, int64_t na, const void *b, int64_t nb, int retain, int *hit)
+{
+    if (!hit || na < 0 || nb < 0 || (na > 0 && !a) || (nb > 0 && !b)) return fail(CHEBPOL_CUDA_EINVAL, "NULL argument");
+    const int dims[1] = {1};
+    Identity ia, ib;
+    ia.blobs.push_back({a, (size_t)na});
+    ib.blobs.push_back({b, (size_t)nb});
+    make_identity(ia, PLAN_CHEB, dims, 1, 1);
+    make_identity(ib, PLAN_CHEB, dims, 1, 1);
+    KeptBytes kept;
+    if (retain) {
+        auto v = std::make_shared<std::vector<unsigned char>>();
+        cphash::blobs_copy(ia.blobs, *v);
+        kept = v;
+    }
+    *hit = identity_matches(ib, ia.key, kept) ? 1 : 0;
+    return CHEBPOL_CUDA_OK;
 }
 
 // -------------------------------------------------- stateless entry points
 // Split [0, npts) into contiguous ranges over `ngpus` devices; one host thread
 // per device builds a plan there (replicating the tensor) and runs the host
 // pipeline on its slice.  No collective: every GPU writes its own slice.
+// The host threads that copy pageable batches into the pinned staging buffers are a
+// per-process budget (CHEBPOL_CUDA_HOST_THREADS, default min(16, cores/2)) divided among the
+// devices, not a team per device.
 template <class MakePlan>
-static int run_sharded(int rank, const double *x, int64_t npts, int ngpus, double *out, CacheKey key,
-                       int64_t tensor_bytes, MakePlan make_plan, int blend = -1, int epol = -1)
+static int run_sharded(int rank, const double *x, int64_t npts, int ngpus, double *out, Identity &id,
+                       MakePlan make_plan, int blend = -1, int epol = -1)
 {
     if (npts < 0) return fail(CHEBPOL_CUDA_EINVAL, "negative point count");
     if (npts > 0 && (!x || !out)) return fail(CHEBPOL_CUDA_EINVAL, "x or out is NULL");
@@ -1466,27 +1734,23 @@ static int run_sharded(int rank, const double *x, int64_t npts, int ngpus, doubl
     // do not spread tiny batches
     const int64_t min_per_gpu = 1 << 16;
     while (ngpus > 1 && npts / ngpus < min_per_gpu) --ngpus;
-    const bool cacheable = cache_enabled() && tensor_bytes <= kCacheMaxBytes;
+    const bool cacheable = id.cacheable;
+    int per_dev_threads = host_threads_total() / ngpus;
+    if (per_dev_threads < 1) per_dev_threads = 1;
+    if (per_dev_threads > 8) per_dev_threads = 8;
 
     auto on_device = [&](int dev, const double *xs, int64_t n, double *os) -> int {
-        CacheKey k = key;
-        k.device = dev;
-        chebpol_cuda_plan *p = cacheable ? cache_take(k) : nullptr;
+        chebpol_cuda_plan *p = cacheable ? cache_take(id, dev) : nullptr;
         int r = CHEBPOL_CUDA_OK;
         if (!p) r = make_plan(dev, &p);
         if (!r && blend >= 0) p->blend = blend;  // per-call argument of the multilinear closure, not part of the key
         if (!r && epol >= 0) p->epol = epol;
+        if (!r) p->host_threads = per_dev_threads;
         if (!r && n > 0) r = chebpol_cuda_plan_eval_host(p, xs, n, os);
         if (p) {
-            if (cacheable && !r) cache_put(k, p);
-            else {
-                if (cacheable) {  // failed: drop it from the cache if it came from there
-                    std::lock_guard<std::mutex> lk(g_cache_mu);
-                    for (size_t i = 0; i < g_cache.size(); ++i)
-                        if (g_cache[i].plan == p) { g_cache.erase(g_cache.begin() + i); break; }
-                }
-                chebpol_cuda_plan_destroy(p);
-            }
+            if (cacheable && !r) cache_put(id, dev, p);
+            else if (cacheable) cache_drop(p);  // failed: remove it from the cache if it came from there
+            else chebpol_cuda_plan_destroy(p);
         }
         return r;
     };
@@ -1513,16 +1777,6 @@ static int run_sharded(int rank, const double *x, int64_t npts, int ngpus, doubl
     return CHEBPOL_CUDA_OK;
 }
 
-static CacheKey make_key(int kind, const int *dims, int rank)
-{
-    CacheKey k;
-    memset(&k, 0, sizeof k);
-    k.kind = kind;
-    k.rank = rank;
-    for (int i = 0; i < rank && i < CP_MAXR; ++i) k.dims[i] = dims[i];
-    return k;
-}
-
 extern "C" int chebpol_cuda_evalcheb(const double *coef, const int *dims, int rank, const double *x,
                                      int64_t npts, const double *mid, const double *ispan,
                                      const int *ugm_n, int ngpus, double *out)
@@ -1531,14 +1785,14 @@ extern "C" int chebpol_cuda_evalcheb(const double *coef, const int *dims, int ra
     if (!coef) return fail(CHEBPOL_CUDA_EINVAL, "coef is NULL");
     int rc = check_dims(dims, rank, &nelem);
     if (rc) return rc;
-    CacheKey key = make_key(PLAN_CHEB, dims, rank);
-    if (cache_enabled() && nelem * 8 <= kCacheMaxBytes) {
-        uint64_t h = hash_bytes(coef, (size_t)nelem * 8, 1);
-        if (mid && ispan) { h = hash_bytes(mid, rank * 8, h); h = hash_bytes(ispan, rank * 8, h); }
-        if (ugm_n) h = hash_bytes(ugm_n, rank * 4, h ^ 0x55);
-        key.hash = h;
-    }
-    return run_sharded(rank, x, npts, ngpus, out, key, nelem * 8, [&](int dev, chebpol_cuda_plan **p) {
+    if ((mid == nullptr) != (ispan == nullptr)) return fail(CHEBPOL_CUDA_EINVAL, "mid and ispan must be given together");
+    Identity id;
+    const int32_t have[2] = {mid ? 1 : 0, ugm_n ? 1 : 0};
+    id.blobs = {{have, sizeof have}, {coef, (size_t)nelem * 8}};
+    if (mid) { id.blobs.push_back({mid, (size_t)rank * 8}); id.blobs.push_back({ispan, (size_t)rank * 8}); }
+    if (ugm_n) id.blobs.push_back({ugm_n, (size_t)rank * 4});
+    make_identity(id, PLAN_CHEB, dims, rank, 1);
+    return run_sharded(rank, x, npts, ngpus, out, id, [&](int dev, chebpol_cuda_plan **p) {
         return chebpol_cuda_plan_cheb(coef, dims, rank, mid, ispan, ugm_n, dev, p);
     });
 }
@@ -1554,15 +1808,15 @@ extern "C" int chebpol_cuda_evalchebg(const double *coef, const int *dims, int r
     if (rc) return rc;
     SplineTabs t = {sn, sx, sy, sb, sc, sd};
     if ((rc = check_spline_tabs(t, rank))) return rc;
-    CacheKey key = make_key(PLAN_CHEB, dims, rank);
-    if (cache_enabled() && nelem * 8 <= kCacheMaxBytes) {
-        uint64_t h = hash_bytes(coef, (size_t)nelem * 8, 7);
+    Identity id;
+    id.blobs = {{coef, (size_t)nelem * 8}, {sn, (size_t)rank * 4}};
+    {
         const double *const *tabs[5] = {sx, sy, sb, sc, sd};
         for (int k = 0; k < rank; ++k)
-            for (int j = 0; j < 5; ++j) h = hash_bytes(tabs[j][k], (size_t)sn[k] * 8, h + j);
-        key.hash = h;
+            for (int j = 0; j < 5; ++j) id.blobs.push_back({tabs[j][k], (size_t)sn[k] * 8});
     }
-    return run_sharded(rank, x, npts, ngpus, out, key, nelem * 8, [&](int dev, chebpol_cuda_plan **p) {
+    make_identity(id, PLAN_CHEB, dims, rank, 7);
+    return run_sharded(rank, x, npts, ngpus, out, id, [&](int dev, chebpol_cuda_plan **p) {
         return plan_cheb_impl(coef, dims, rank, nullptr, nullptr, nullptr, &t, dev, p);
     });
 }
@@ -1576,16 +1830,14 @@ extern "C" int chebpol_cuda_evalmlip(const double *const *grid, const int *dims,
     if (blend < 0 || blend > 5) return fail(CHEBPOL_CUDA_EBLEND, "blend %d not in 0..5", blend);
     int rc = check_dims(dims, rank, &nelem);
     if (rc) return rc;
-    CacheKey key = make_key(PLAN_MLIP, dims, rank);
-    if (cache_enabled() && nelem * 8 <= kCacheMaxBytes) {
-        uint64_t h = hash_bytes(values, (size_t)nelem * 8, 2);
-        for (int d = 0; d < rank; ++d) {
-            if (!grid[d]) return fail(CHEBPOL_CUDA_EINVAL, "grid[%d] is NULL", d);
-            h = hash_bytes(grid[d], (size_t)dims[d] * 8, h);
-        }
-        key.hash = h;
+    Identity id;
+    id.blobs = {{values, (size_t)nelem * 8}};
+    for (int d = 0; d < rank; ++d) {
+        if (!grid[d]) return fail(CHEBPOL_CUDA_EINVAL, "grid[%d] is NULL", d);
+        id.blobs.push_back({grid[d], (size_t)dims[d] * 8});
     }
-    return run_sharded(rank, x, npts, ngpus, out, key, nelem * 8, [&](int dev, chebpol_cuda_plan **p) {
+    make_identity(id, PLAN_MLIP, dims, rank, 2);
+    return run_sharded(rank, x, npts, ngpus, out, id, [&](int dev, chebpol_cuda_plan **p) {
         return chebpol_cuda_plan_mlip(grid, dims, rank, values, blend, dev, p);
     }, blend);
 }
@@ -1598,17 +1850,15 @@ extern "C" int chebpol_cuda_fh(const double *vals, const double *const *grid,
     if (!vals || !grid || !weights) return fail(CHEBPOL_CUDA_EINVAL, "vals, grid or weights is NULL");
     int rc = check_dims(dims, rank, &nelem);
     if (rc) return rc;
-    CacheKey key = make_key(PLAN_FH, dims, rank);
-    if (cache_enabled() && nelem * 8 <= kCacheMaxBytes) {
-        uint64_t h = hash_bytes(vals, (size_t)nelem * 8, 3);
-        for (int d = 0; d < rank; ++d) {
-            if (!grid[d] || !weights[d]) return fail(CHEBPOL_CUDA_EINVAL, "grid/weights[%d] is NULL", d);
-            h = hash_bytes(grid[d], (size_t)dims[d] * 8, h);
-            h = hash_bytes(weights[d], (size_t)dims[d] * 8, h);
-        }
-        key.hash = h;
+    Identity id;
+    id.blobs = {{vals, (size_t)nelem * 8}};
+    for (int d = 0; d < rank; ++d) {
+        if (!grid[d] || !weights[d]) return fail(CHEBPOL_CUDA_EINVAL, "grid/weights[%d] is NULL", d);
+        id.blobs.push_back({grid[d], (size_t)dims[d] * 8});
+        id.blobs.push_back({weights[d], (size_t)dims[d] * 8});
     }
-    return run_sharded(rank, x, npts, ngpus, out, key, nelem * 8, [&](int dev, chebpol_cuda_plan **p) {
+    make_identity(id, PLAN_FH, dims, rank, 3);
+    return run_sharded(rank, x, npts, ngpus, out, id, [&](int dev, chebpol_cuda_plan **p) {
         return chebpol_cuda_plan_fh(vals, grid, weights, dims, rank, dev, p);
     });
 }
@@ -1622,22 +1872,20 @@ extern "C" int chebpol_cuda_evalpolyh(const double *knots, int rank, int nknots,
     if (!lweights || (nknots > 0 && (!knots || !weights))) return fail(CHEBPOL_CUDA_EINVAL, "knots, weights or lweights is NULL");
     int dims[CP_MAXR];
     for (int i = 0; i < rank; ++i) dims[i] = nknots;
-    CacheKey key = make_key(PLAN_POLYH, dims, rank);
-    const int64_t bytes = 8ll * ((int64_t)nknots * (rank + 1) + rank + 1);
-    if (cache_enabled() && bytes <= kCacheMaxBytes) {
-        uint64_t h = hash_bytes(&k, sizeof k, 4);
-        if (nknots > 0) {
-            h = hash_bytes(knots, (size_t)nknots * rank * 8, h);
-            h = hash_bytes(weights, (size_t)nknots * 8, h);
-        }
-        h = hash_bytes(lweights, (size_t)(rank + 1) * 8, h);
-        if (norm_a && norm_b) {
-            h = hash_bytes(norm_a, (size_t)rank * 8, h);
-            h = hash_bytes(norm_b, (size_t)rank * 8, h);
-        }
-        key.hash = h;
+    if ((norm_a == nullptr) != (norm_b == nullptr)) return fail(CHEBPOL_CUDA_EINVAL, "norm_a and norm_b go together");
+    Identity id;
+    const int32_t have[2] = {norm_a ? 1 : 0, nknots};
+    id.blobs = {{have, sizeof have}, {&k, sizeof k}, {lweights, (size_t)(rank + 1) * 8}};
+    if (nknots > 0) {
+        id.blobs.push_back({knots, (size_t)nknots * rank * 8});
+        id.blobs.push_back({weights, (size_t)nknots * 8});
     }
-    return run_sharded(rank, x, npts, ngpus, out, key, bytes, [&](int dev, chebpol_cuda_plan **p) {
+    if (norm_a) {
+        id.blobs.push_back({norm_a, (size_t)rank * 8});
+        id.blobs.push_back({norm_b, (size_t)rank * 8});
+    }
+    make_identity(id, PLAN_POLYH, dims, rank, 4);
+    return run_sharded(rank, x, npts, ngpus, out, id, [&](int dev, chebpol_cuda_plan **p) {
         return chebpol_cuda_plan_polyh(knots, rank, nknots, weights, lweights, k, norm_a, norm_b, dev, p);
     });
 }
@@ -1651,21 +1899,18 @@ static int stalk_stateless(int kind, const double *val, const double *const *gri
     int rc = check_dims(dims, rank, &nelem);
     if (rc) return rc;
     if (blend < 0 || blend > 5) return fail(CHEBPOL_CUDA_EBLEND, "blend %d not in 0..5", blend);
-    CacheKey key = make_key(PLAN_STALK, dims, rank);
-    const int64_t bytes = 8 * (nelem * (kind == 1 ? 2 : 1) + 3 * nelem * rank);
-    if (cache_enabled() && bytes <= kCacheMaxBytes) {
-        uint64_t h = hash_bytes(val, (size_t)nelem * 8, 5 + kind);
-        if (kind == 1) h = hash_bytes(a, (size_t)nelem * 8, h);
-        h = hash_bytes(b, (size_t)nelem * rank * 8, h);
-        h = hash_bytes(t1, (size_t)nelem * rank * 8, h);
-        h = hash_bytes(t2, (size_t)nelem * rank * 8, h);
-        for (int d = 0; d < rank; ++d) {
-            if (!grid[d]) return fail(CHEBPOL_CUDA_EINVAL, "grid[%d] is NULL", d);
-            h = hash_bytes(grid[d], (size_t)dims[d] * 8, h);
-        }
-        key.hash = h;
+    Identity id;
+    id.blobs = {{val, (size_t)nelem * 8}};
+    if (kind == 1) id.blobs.push_back({a, (size_t)nelem * 8});
+    id.blobs.push_back({b, (size_t)nelem * rank * 8});
+    id.blobs.push_back({t1, (size_t)nelem * rank * 8});
+    id.blobs.push_back({t2, (size_t)nelem * rank * 8});
+    for (int d = 0; d < rank; ++d) {
+        if (!grid[d]) return fail(CHEBPOL_CUDA_EINVAL, "grid[%d] is NULL", d);
+        id.blobs.push_back({grid[d], (size_t)dims[d] * 8});
     }
-    return run_sharded(rank, x, npts, ngpus, out, key, bytes, [&](int dev, chebpol_cuda_plan **p) {
+    make_identity(id, PLAN_STALK, dims, rank, 5 + kind);
+    return run_sharded(rank, x, npts, ngpus, out, id, [&](int dev, chebpol_cuda_plan **p) {
         return chebpol_cuda_plan_stalk(kind, val, grid, dims, rank, a, b, t1, t2, blend, dev, p);
     }, blend);
 }
@@ -1694,20 +1939,19 @@ extern "C" int chebpol_cuda_evalsl(const double *x, int64_t npts, const double *
     if (blend < 0 || blend > 5) return fail(CHEBPOL_CUDA_EBLEND, "blend %d not in 0..5", blend);
     int dims[CP_MAXR];
     for (int i = 0; i < dim; ++i) dims[i] = nknots > 0 ? nknots : 1;
-    CacheKey key = make_key(PLAN_SL, dims, dim);
     const int N = dim + 1;
-    const int64_t bytes = (int64_t)numsimplex * (N * N * 8 + N * 8 + 2 * dim * 8) + (int64_t)nknots * (dim + 1) * 8;
-    if (cache_enabled() && bytes <= kCacheMaxBytes) {
-        uint64_t h = hash_bytes(knots, (size_t)nknots * dim * 8, 11);
-        h = hash_bytes(val, (size_t)nknots * 8, h);
-        h = hash_bytes(dtri, (size_t)numsimplex * N * 4, h);
-        h = hash_bytes(lumats, (size_t)numsimplex * N * N * 8, h);
-        h = hash_bytes(pivots, (size_t)numsimplex * N * 4, h);
-        h = hash_bytes(bbox, (size_t)numsimplex * 2 * dim * 8, h);
-        key.hash = h ^ (uint64_t)numsimplex;
-    }
+    Identity id;
+    const int32_t counts[2] = {nknots, numsimplex};
+    id.blobs = {{counts, sizeof counts},
+                {knots, (size_t)nknots * dim * 8},
+                {val, (size_t)nknots * 8},
+                {dtri, (size_t)numsimplex * N * 4},
+                {lumats, (size_t)numsimplex * N * N * 8},
+                {pivots, (size_t)numsimplex * N * 4},
+                {bbox, (size_t)numsimplex * 2 * dim * 8}};
+    make_identity(id, PLAN_SL, dims, dim, 11);
     // blend and epol are per-call arguments of the closure (R/simplexlinear.R:34-38), not part of the key
-    return run_sharded(dim, x, npts, ngpus, out, key, bytes, [&](int dev, chebpol_cuda_plan **p) {
+    return run_sharded(dim, x, npts, ngpus, out, id, [&](int dev, chebpol_cuda_plan **p) {
         return chebpol_cuda_plan_sl(knots, dim, nknots, dtri, numsimplex, lumats, pivots, bbox, val, dev, p);
     }, blend, epol);
 }
@@ -1722,21 +1966,17 @@ extern "C" int chebpol_cuda_evalstalker(const double *val, const double *const *
     int rc = check_dims(dims, rank, &nelem);
     if (rc) return rc;
     if (blend < 0 || blend > 5) return fail(CHEBPOL_CUDA_EBLEND, "blend %d not in 0..5", blend);
-    CacheKey key = make_key(PLAN_OLDSTALK, dims, rank);
-    if (cache_enabled() && nelem * 8 <= kCacheMaxBytes) {
-        uint64_t h = hash_bytes(val, (size_t)nelem * 8, 13);
-        h = hash_bytes(degree, (size_t)rank * 8, h);
-        h = hash_bytes(uniform, (size_t)rank * 4, h);
-        for (int d = 0; d < rank; ++d) {
-            if (!grid[d] || !det[d] || !pmin[d] || !pplus[d]) return fail(CHEBPOL_CUDA_EINVAL, "vector of dimension %d is NULL", d);
-            h = hash_bytes(grid[d], (size_t)dims[d] * 8, h);
-            h = hash_bytes(det[d], (size_t)dims[d] * 8, h);
-            h = hash_bytes(pmin[d], (size_t)dims[d] * 8, h);
-            h = hash_bytes(pplus[d], (size_t)dims[d] * 8, h);
-        }
-        key.hash = h;
+    Identity id;
+    id.blobs = {{val, (size_t)nelem * 8}, {degree, (size_t)rank * 8}, {uniform, (size_t)rank * 4}};
+    for (int d = 0; d < rank; ++d) {
+        if (!grid[d] || !det[d] || !pmin[d] || !pplus[d]) return fail(CHEBPOL_CUDA_EINVAL, "vector of dimension %d is NULL", d);
+        id.blobs.push_back({grid[d], (size_t)dims[d] * 8});
+        id.blobs.push_back({det[d], (size_t)dims[d] * 8});
+        id.blobs.push_back({pmin[d], (size_t)dims[d] * 8});
+        id.blobs.push_back({pplus[d], (size_t)dims[d] * 8});
     }
-    return run_sharded(rank, x, npts, ngpus, out, key, nelem * 8, [&](int dev, chebpol_cuda_plan **p) {
+    make_identity(id, PLAN_OLDSTALK, dims, rank, 13);
+    return run_sharded(rank, x, npts, ngpus, out, id, [&](int dev, chebpol_cuda_plan **p) {
         return chebpol_cuda_plan_oldstalk(val, grid, dims, rank, degree, det, pmin, pplus, uniform, blend, dev, p);
     }, blend);
 }
@@ -1871,6 +2111,22 @@ extern "C" int chebpol_cuda_evalgrid_fh(const double *vals, const double *const 
 {
     if (!grid || !weights) return fail(CHEBPOL_CUDA_EINVAL, "grid or weights is NULL");
     return evalgrid_common(1, vals, dims, rank, pts, gdims, grid, weights, 0, nullptr, device, out);
+}
+
+extern "C" int chebpol_cuda_synth_points(uint64_t seed, int64_t first_point, int64_t npts, int rank, double lo, double hi,
+                                         double *d_x, int device, void *stream)
+{
+    if (npts < 0 || rank <= 0) return fail(CHEBPOL_CUDA_EINVAL, "negative point count or non-positive rank");
+    if (npts > 0 && !d_x) return fail(CHEBPOL_CUDA_EINVAL, "d_x is NULL");
+    int cur = -1, sms = 0;
+    CU(cudaGetDevice(&cur));
+    if (cur != device) CU(cudaSetDevice(device));
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    cudaError_t e = synth_fill_points(seed, first_point, npts, rank, lo, hi, d_x, sms, (cudaStream_t)stream);
+    if (cur != device) cudaSetDevice(cur);
+    if (e != cudaSuccess) return cuda_fail(e, "synthetic point generator");
+    g_launches.fetch_add(1);
+    return CHEBPOL_CUDA_OK;
 }
 
 extern "C" int chebpol_cuda_fp64_peak(int device, int repeats, double *tflops)

@@ -263,6 +263,9 @@ cudaError_t fit_evalgrid_device(int kind, const double *d_tensor, const int *dim
                                 const int *gdims, const double *const *d_knots, const double *const *d_weights, int blend,
                                 const PreMap *pm, double *d_s0, double *d_s1, cudaStream_t s, double **result, int *launches);
 cudaError_t fit_fhweights_device(const double *d_grid, int nknots, int d, double *d_w, cudaStream_t s);
+// counter-based synthetic points (synth.cu)
+cudaError_t synth_fill_points(uint64_t seed, int64_t first_point, int64_t npts, int rank, double lo, double hi, double *d_x,
+                              int num_sms, cudaStream_t s);
 cudaError_t run_fp64_peak(int num_sms, int repeats, cudaStream_t s, double *tflops);
 // deprecated recursive stalker evaluator (oldstalk.cu)
 cudaError_t launch_oldstalk(const double *val, const double *grid, const double *det, const double *pmin,

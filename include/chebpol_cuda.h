@@ -286,16 +286,44 @@ CHEBPOL_CUDA_API int chebpol_cuda_evalgrid_fh(const double *vals, const double *
                                               const double *const *pts, const int *gdims, int device,
                                               double *out);
 
+/* ---- measurement support ------------------------------------------------ */
+/* Counter-based synthetic points: fills d_x (DEVICE pointer, npts*rank doubles,
+ * point-major) with global points first_point .. first_point+npts-1 of the batch `seed`, every
+ * coordinate uniform in [lo, hi) and a pure function of (seed, point index, dimension), so any
+ * split of a batch over GPUs or onto the CPU regenerates identical values.  Asynchronous on
+ * `stream`.  chebpol_b200/synth.py is the bit-identical numpy twin. */
+CHEBPOL_CUDA_API int chebpol_cuda_synth_points(uint64_t seed, int64_t first_point, int64_t npts, int rank,
+                                               double lo, double hi, double *d_x, int device, void *stream);
+
 /* ---- diagnostics -------------------------------------------------------- */
 /* The FP64 roofline denominator (MEASURED_PEAKS.json has none): the better of a
  * register-resident DFMA chain and a DMMA-only kernel on every SM of `device`.
  * Returns TFLOP/s (2 flop/FMA). */
 CHEBPOL_CUDA_API int chebpol_cuda_fp64_peak(int device, int repeats, double *tflops);
-/* The stateless entry points keep up to 8 small (<= 32 MB) interpolants resident between
- * calls, keyed by a 64-bit hash of their content (tensor, knots, weights, pre-map), so the
- * closure that re-passes its tensor on every call does not re-upload it.  Clearing is never
- * required for correctness; CHEBPOL_CUDA_PLAN_CACHE=0 disables the cache. */
+/* The stateless entry points keep interpolants resident between calls (per device up to 8
+ * entries and CHEBPOL_CUDA_CACHE_MAX_GB, default 16, of device memory; least recently used out
+ * first), so the closure that re-passes its tensor on every call (src/chebpol.c:340-381) does not
+ * re-upload it, and a multilinear plan keeps its expanded cell table.  The key is the CONTENT:
+ * kind, device, dims, byte count and a 128-bit fingerprint of every defining array (tensor,
+ * knots, weights, pre-map).  A hit is verified: entries up to 32 MB retain a host copy and the
+ * bytes are compared, larger ones rely on the fingerprint (collision probability ~2^-128 per
+ * pair).  Clearing is never required for correctness; CHEBPOL_CUDA_PLAN_CACHE=0 disables the
+ * cache.  Entries another thread is evaluating are destroyed when that evaluation returns. */
 CHEBPOL_CUDA_API void chebpol_cuda_cache_clear(void);
+/* cache facts (any pointer may be NULL): live entries, verified hits, misses, fingerprint matches
+ * whose bytes differed, device bytes held */
+CHEBPOL_CUDA_API int chebpol_cuda_debug_cache_stats(int64_t *entries, int64_t *hits, int64_t *misses,
+                                                    int64_t *rejected, int64_t *device_bytes);
+/* test hook: on != 0 makes every fingerprint equal, so that only the byte comparison separates
+ * interpolants of the same shape */
+CHEBPOL_CUDA_API void chebpol_cuda_debug_cache_weak_hash(int on);
+/* host only: the 128-bit fingerprint of one array, computed by `threads` host threads (the value
+ * does not depend on the thread count) */
+CHEBPOL_CUDA_API int chebpol_cuda_debug_fingerprint(const void *data, int64_t nbytes, int threads, uint64_t *out2);
+/* host only: would a call defined by array b be served by the cache entry made from array a?
+ * retain = 0 models an entry above the 32 MB retention limit (fingerprint only) */
+CHEBPOL_CUDA_API int chebpol_cuda_debug_cache_would_hit(const void *a, int64_t na, const void *b, int64_t nb,
+                                                        int retain, int *hit);
 /* total kernels launched by this library in this process */
 CHEBPOL_CUDA_API int64_t chebpol_cuda_launch_count(void);
 

@@ -291,7 +291,7 @@ def test_bench_reference_arm_contract():
     import sys
 
     cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--config", "1", "--steps", "1",
-           "--warmup", "1", "--ref-seconds", "0.3"]
+           "--warmup", "1", "--ref-seconds", "0.3", "--workloads", "4", "--sub-cpu-seconds", "0.2"]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr
     lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
@@ -303,6 +303,9 @@ def test_bench_reference_arm_contract():
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
     assert "workload" in d["config"] and "model" not in d["config"]
+    # the other BASELINE configs ride in `workloads`, timed by the same procedure
+    assert [w["config"] for w in d["workloads"]] == [4] and d["workloads"][0]["value"] > 0
+    assert d["workloads"][0]["kind"] == d["cpu_baseline"]["kind"]
     env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env)
     assert r.returncode == 0 and r.stdout.strip() == ""
@@ -322,3 +325,73 @@ def test_interpolants_pickle_like_saved_r_closures():
     ip._plans.clear()
     ml = pickle.loads(pickle.dumps(cb.ipol(np.arange(9.0), grid=[np.linspace(0, 1, 3)] * 2, method="multilinear")))
     assert ml.kind == "multilinear" and np.array_equal(ml.t["values"], np.arange(9.0))
+
+
+def test_synthetic_points_are_partition_independent():
+    """coordinate d of global point i depends on (seed, i, d) only, so any slice of a batch --
+    another GPU's shard, the CPU baseline's prefix, a strided parity sample -- regenerates identical values."""
+    from chebpol_b200 import synth
+
+    whole = synth.points(0, 5000, 6)
+    assert whole.shape == (5000, 6) and whole.flags.c_contiguous
+    assert np.array_equal(synth.points(1234, 777, 6), whole[1234:2011])
+    idx = np.arange(3, 5000, 97)
+    assert np.array_equal(synth.points_at(idx, 6), whole[idx])
+    assert not np.array_equal(synth.points(0, 100, 6, seed=43), whole[:100])
+    assert -1.0 <= whole.min() and whole.max() < 1.0 and abs(whole.mean()) < 0.02
+    big = synth.points(10**9 - 3, 3, 6)  # 64-bit element counters: cfg5's last points
+    assert np.array_equal(big, synth.points_at([10**9 - 3, 10**9 - 2, 10**9 - 1], 6))
+    lo_hi = synth.points(0, 1000, 2, lo=-1.2, hi=1.2)
+    assert lo_hi.min() >= -1.2 and lo_hi.max() < 1.2
+
+
+def test_fingerprint_is_thread_independent_and_sensitive():
+    """The plan cache's 128-bit content fingerprint (csrc/hash128.h): the same value whatever the
+    number of host threads, different for any single changed word, length and order sensitive."""
+    rng = np.random.default_rng(5)
+    a = rng.random(3 * (1 << 20) + 12345)  # > 8 MB: the threaded path; ragged last segment
+    h1 = _lib.fingerprint(a, 1)
+    assert _lib.fingerprint(a, 4) == h1 and _lib.fingerprint(a, 7) == h1
+    for i in (0, 1, 131071, 131072, a.size // 2, a.size - 1):
+        b = a.copy()
+        b[i] = np.nextafter(b[i], 2.0)
+        assert _lib.fingerprint(b, 4) != h1, i
+    assert _lib.fingerprint(a[:-1], 1) != h1
+    assert _lib.fingerprint(np.zeros(0), 1) != _lib.fingerprint(np.zeros(1), 1)
+    small = rng.integers(0, 255, 1001).astype(np.uint8)  # unaligned tail, 4-byte aligned int arrays are legal input
+    assert _lib.fingerprint(small, 1) != _lib.fingerprint(small[::-1].copy(), 1)
+    assert _lib.fingerprint(small[1:], 1) == _lib.fingerprint(small[1:].copy(), 1)  # odd address, same bytes
+
+
+def test_plan_cache_never_aliases_two_interpolants():
+    """with every fingerprint forced equal, two different tensors of the same shape
+    must still be told apart -- the cache compares the bytes of the retained host copy."""
+    rng = np.random.default_rng(6)
+    a = rng.random(4096)
+    b = a.copy()
+    b[2048] += 1e-9
+    assert _lib.cache_would_hit(a, a.copy()) and not _lib.cache_would_hit(a, b)
+    assert not _lib.cache_would_hit(a, a[:-1])
+    _lib.cache_weak_hash(True)
+    try:
+        assert _lib.cache_would_hit(a, a.copy(), retain=True)
+        assert not _lib.cache_would_hit(a, b, retain=True)       # bytes decide
+        assert not _lib.cache_would_hit(a, a[:-1], retain=True)  # byte count is part of the key
+        assert _lib.cache_would_hit(a, b, retain=False)          # what the hook removes: only the fingerprint separates entries above 32 MB
+    finally:
+        _lib.cache_weak_hash(False)
+    assert not _lib.cache_would_hit(a, b, retain=False)
+
+
+def test_sl_rejects_malformed_pivots(port):
+    """pivots outside dgetrf's range would index out of bounds on the device; the check runs
+    before any device is touched."""
+    import cases
+
+    kn, dtri, kv = cases.sl_case(2, 50)
+    lu, piv, bb = port.analyzesimplex(dtri, kn)
+    bad = np.array(piv, dtype=np.int32, copy=True)
+    bad.flat[1] = 7
+    with pytest.raises(_lib.ChebpolCudaError) as ei:
+        _lib.Plan.sl(kn, dtri, (lu, bad, bb), kv)
+    assert ei.value.code == 1 and "pivot" in str(ei.value)

@@ -11,6 +11,8 @@ accounting for summation order"):
     for the adversarial "stress" tensor (slowly decaying random coefficients, points
     outside the domain) scale = sum|c| * max_k|T_k(x)|, the natural conditioning bound.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -87,18 +89,61 @@ def test_cheb_fast_fitted(gpu_ok, port, dims, family, variant):
 
 
 @pytest.mark.parametrize("family,variant", FAST)
-@pytest.mark.parametrize("dims", [(20, 20), (10,) * 5, (12, 12, 12, 3), (6, 5, 4, 3, 2, 2), (40, 7), (150,)])
+@pytest.mark.parametrize("dims", [(20, 20), (10,) * 5, (12, 12, 12, 3), (6, 5, 4, 3, 2, 2), (40, 7), (150,), (8, 7, 6)])
 def test_cheb_fast_stress_outside_domain(gpu_ok, port, dims, family, variant):
+    """The reference evaluates outside [-1,1] too (R/chebyshev.R:152-153; C_evalcheb's recurrence is
+    valid for any real x).  Adversarial case: slowly decaying random coefficients, points up to
+    |x| = 1.2.  The bar is north_star's: |diff| <= 1e-12 * max|f| with max|f| the largest |reference
+    value| over the evaluated points -- NOT the conditioning product sum|c| * prod max|T_k|, which is
+    10^3-10^4 times larger for (8,7,6); that product is printed beside the measured error."""
     cf = cases.cheb_stress(dims)
     x = cases.points(5003, len(dims), lo=-1.2, hi=1.2)
     plan = _lib.Plan.cheb(cf)
     got, k = eval_plan(plan, x, _lib.KERNEL_AUTO, variant)
     assert k == expected_kernel(family, dims)
     want = port.evalcheb(cf, x, threads=4)
-    # conditioning bound: sum|c| * prod_d max_k |T_k(x_d)|, |T_k(1.2)| <= cosh(k*acosh(1.2))
-    tmax = np.prod([np.cosh((n - 1) * np.arccosh(1.2)) for n in dims])
-    scale = np.abs(cf).sum() * tmax
-    assert np.abs(got - want).max() <= TOL_REL * scale
+    err, maxf = np.abs(got - want).max(), np.abs(want).max()
+    cond = np.abs(cf).sum() * np.prod([np.cosh((n - 1) * np.arccosh(1.2)) for n in dims])
+    print(f"stress {dims} {k}: |diff| = {err:.3e}, max|f| = {maxf:.3e}, |diff|/max|f| = {err / maxf:.2e}, "
+          f"conditioning product = {cond:.3e}")
+    assert err <= TOL_REL * maxf, (err, maxf, err / maxf)
+    # and inside the domain alone, against max|f| there
+    xi = cases.points(5003, len(dims), seed=7)
+    gi, _ = eval_plan(plan, xi, _lib.KERNEL_AUTO, variant)
+    wi = port.evalcheb(cf, xi, threads=4)
+    assert np.abs(gi - wi).max() <= TOL_REL * np.abs(wi).max()
+    plan.close()
+
+
+@pytest.mark.parametrize("family,variant", FAST)
+def test_cheb_12pow6_strided_sample(gpu_ok, port, family, variant):
+    """BASELINE config 5's tensor (6-D, 12^6 = 2 985 984 coefficients): >= 1e5 strided points of a 1e7-point
+    counter-based batch through each fast kernel.  The CPU oracle manages ~1e3 evaluations/s on this
+    shape (3.3e6 recurrence steps each), so it checks the first 4000 sample points; the strict kernel is
+    required to be BIT-IDENTICAL to the oracle on those and then stands in for it on all 1e5."""
+    import torch
+
+    from chebpol_b200 import synth
+
+    dims = (12,) * 6
+    cf = cases.cheb_fitted(dims)
+    n, stride = 100_000, 100
+    idx = np.arange(n, dtype=np.uint64) * np.uint64(stride)
+    x = synth.points_at(idx, 6)
+    plan = _lib.Plan.cheb(cf)
+    got, k = eval_plan(plan, x, _lib.KERNEL_AUTO, variant)
+    assert k == ("cheb_mma" if family == "mma" else "cheb_slab")
+    strict, ks = eval_plan(plan, x, _lib.KERNEL_STRICT)
+    assert ks == "cheb_strict"
+    n_orc = 4000
+    want = port.evalcheb(cf, x[:n_orc], threads=os.cpu_count() or 4)
+    assert np.array_equal(bits(strict[:n_orc]), bits(want))
+    maxf = np.abs(strict).max()
+    err = np.abs(got - strict).max()
+    print(f"12^6 {k}: |diff| = {err:.3e} on {n} points, max|f| = {maxf:.3e}, ratio {err / maxf:.2e}; Kahan-free checksum "
+          f"{int(bits(got).astype(np.uint64).sum(dtype=np.uint64)):016x}")
+    assert err <= TOL_REL * maxf, (err, maxf)
+    assert np.abs(got[:n_orc] - want).max() <= TOL_REL * np.abs(want).max()
     plan.close()
 
 
@@ -1317,3 +1362,136 @@ def test_oldstalker_matches_reference(gpu_ok, ref, dims, uniform):
     with pytest.raises(cb.ChebpolCudaError):  # NaN degree on a non-uniform grid: refused like the no-GSL reference
         g2 = [np.array([0.0, 0.1, 0.4, 1.0])]
         _lib.Plan.oldstalk(np.zeros(4), g2, [np.nan], cb.interp.stalkercontext(g2, [2.0]), [0])
+
+
+# ------------------------------------------------- round 2: cache, generator, stream ordering
+def test_synth_points_device_equals_numpy_twin(gpu_ok):
+    import torch
+
+    from chebpol_b200 import synth
+
+    for first, n, k, lo, hi in [(0, 100_003, 5, -1.0, 1.0), (10**9 - 7, 7, 6, -1.0, 1.0), (123_456_789, 4099, 3, -1.2, 1.2)]:
+        d = torch.empty((n, k), dtype=torch.float64, device="cuda")
+        _lib.synth_points_device(d.data_ptr(), first, n, k, seed=42, lo=lo, hi=hi)
+        torch.cuda.synchronize()
+        assert np.array_equal(bits(d.cpu().numpy()), bits(synth.points(first, n, k, seed=42, lo=lo, hi=hi)))
+
+
+def test_checksum_is_independent_of_sharding(gpu_ok):
+    """What bench.py's cross-rank checksum relies on: the wrapping 64-bit sum of the result bit patterns of a
+    counter-based batch does not depend on how the batch is cut into shards (here 1, 2 and 3 pieces)."""
+    import torch
+
+    for plan, k in [(_lib.Plan.cheb(cases.cheb_fitted((10,) * 5)), 5), (_lib.Plan.mlip(*cases.mlip_case((16,) * 4), 0), 4),
+                    (_lib.Plan.fh(*cases.fh_case((12, 11, 10))), 3)]:
+        n = 400_003
+        sums = []
+        for pieces in (1, 2, 3):
+            tot = 0
+            per = (n + pieces - 1) // pieces
+            for r in range(pieces):
+                lo, hi = min(n, r * per), min(n, (r + 1) * per)
+                d = torch.empty((hi - lo, k), dtype=torch.float64, device="cuda")
+                _lib.synth_points_device(d.data_ptr(), lo, hi - lo, k)
+                o = plan.eval_torch(d)
+                tot = (tot + int(o.view(torch.int64).sum().item())) & 0xFFFFFFFFFFFFFFFF
+            sums.append(tot)
+        assert sums[0] == sums[1] == sums[2], sums
+        plan.close()
+
+
+def test_cache_tells_apart_tensors_with_equal_fingerprints(gpu_ok, port):
+    """VERDICT r1 item 7 on the device path: every fingerprint forced equal, so two coefficient tensors of
+    the same shape collide in the key; the byte comparison must keep them apart."""
+    cf1 = cases.cheb_fitted((8, 7, 6))
+    cf2 = cf1.copy(order="F")
+    cf2[3, 2, 1] += 0.25
+    x = cases.points(4000, 3)
+    _lib.cache_clear()
+    _lib.cache_weak_hash(True)
+    try:
+        s0 = _lib.cache_stats()
+        a1 = _lib.evalcheb(cf1, x, ngpus=1)
+        a2 = _lib.evalcheb(cf2, x, ngpus=1)   # same key as cf1: must be rejected by the byte comparison
+        b1 = _lib.evalcheb(cf1.copy(order="F"), x, ngpus=1)
+        b2 = _lib.evalcheb(cf2, x, ngpus=1)
+        s1 = _lib.cache_stats()
+    finally:
+        _lib.cache_weak_hash(False)
+        _lib.cache_clear()
+    assert np.array_equal(bits(a1), bits(b1)) and np.array_equal(bits(a2), bits(b2))
+    assert not np.array_equal(bits(a1), bits(a2))
+    for got, cf in ((a1, cf1), (a2, cf2)):
+        want = port.evalcheb(cf, x)
+        assert np.abs(got - want).max() <= TOL_REL * np.abs(want).max()
+    assert s1["rejected"] - s0["rejected"] >= 1 and s1["hits"] - s0["hits"] >= 2
+
+
+def test_cache_keeps_large_tables_and_their_cell_tables(gpu_ok, port):
+    """an interpolant above the 32 MB retention limit (48^4 doubles = 42 MB) is cached by
+    fingerprint; the second call neither re-uploads it nor rebuilds the cell-major table."""
+    grid, values = cases.mlip_case((48,) * 4)
+    call = _lib.Stateless.mlip(grid, values, 0)
+    x = cases.points(700_000, 4)  # >= cells/8: the first call expands the cell-major table
+    _lib.cache_clear()
+    s0, l0 = _lib.cache_stats(), cb.launch_count()
+    a = call(x, ngpus=1)
+    s1, l1 = _lib.cache_stats(), cb.launch_count()
+    b = call(x[:1000], ngpus=1)
+    s2, l2 = _lib.cache_stats(), cb.launch_count()
+    assert s1["misses"] - s0["misses"] == 1 and s1["entries"] == 1
+    assert s1["device_bytes"] >= values.nbytes * 17  # table + 16x cell-major expansion held
+    assert s2["hits"] - s1["hits"] == 1 and s2["entries"] == 1
+    assert l1 - l0 >= 2 and l2 - l1 == 1  # expansion + evaluation, then one evaluation only
+    assert np.array_equal(bits(a[:1000]), bits(b)) or np.abs(a[:1000] - b).max() <= 1e-14  # (kernel may differ with batch size)
+    want = port.evalmlip(grid, values, x[:20000])
+    assert np.abs(a[:20000] - want).max() <= TOL_REL
+    values2 = values.copy(order="F")
+    values2[5, 6, 7, 8] += 1.0
+    c = _lib.evalmlip(grid, values2, x[:20000], 0, 1)
+    assert np.abs(c - port.evalmlip(grid, values2, x[:20000])).max() <= TOL_REL
+    assert _lib.cache_stats()["misses"] - s2["misses"] == 1
+    _lib.cache_clear()
+    assert _lib.cache_stats()["entries"] == 0
+
+
+def test_lazy_tables_are_ordered_across_streams(gpu_ok, port):
+    """a derived table built lazily on the first evaluation's stream must be
+    complete before an evaluation on ANOTHER stream reads it (chebpol_cuda_plan_eval_device takes
+    the caller's stream)."""
+    import torch
+
+    grid, values = cases.mlip_case((40,) * 4)
+    x = cases.points(400_000, 4)
+    want = port.evalmlip(grid, values, x[:20000])
+    xd = torch.from_numpy(x).cuda()
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    for _ in range(3):
+        plan = _lib.Plan.mlip(grid, values, 0)
+        plan.set(_lib.OPT_VARIANT, _lib.VARIANT_MLIP_CELL)  # expand on first use
+        o1 = torch.empty(x.shape[0], dtype=torch.float64, device="cuda")
+        o2 = torch.empty(x.shape[0], dtype=torch.float64, device="cuda")
+        torch.cuda.synchronize()
+        plan.eval_device_ptr(xd.data_ptr(), x.shape[0], o1.data_ptr(), s1.cuda_stream)  # builds the table on s1
+        plan.eval_device_ptr(xd.data_ptr(), x.shape[0], o2.data_ptr(), s2.cuda_stream)  # must wait for it
+        torch.cuda.synchronize()
+        assert plan.kernel_used == "mlip_cell"
+        assert torch.equal(o1, o2)
+        assert np.abs(o2[:20000].cpu().numpy() - want).max() <= TOL_REL
+        plan.close()
+    # the padded slab tensor of the DFMA Chebyshev kernel is built the same way
+    cf = cases.cheb_fitted((10, 10, 10))
+    x3 = cases.points(300_000, 3)
+    x3d = torch.from_numpy(x3).cuda()
+    plan = _lib.Plan.cheb(cf)
+    plan.set(_lib.OPT_VARIANT, _lib.VARIANT_SLAB)
+    o1 = torch.empty(x3.shape[0], dtype=torch.float64, device="cuda")
+    o2 = torch.empty(x3.shape[0], dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()
+    plan.eval_device_ptr(x3d.data_ptr(), x3.shape[0], o1.data_ptr(), s1.cuda_stream)
+    plan.eval_device_ptr(x3d.data_ptr(), x3.shape[0], o2.data_ptr(), s2.cuda_stream)
+    torch.cuda.synchronize()
+    assert torch.equal(o1, o2)
+    w3 = port.evalcheb(cf, x3[:20000])
+    assert np.abs(o2[:20000].cpu().numpy() - w3).max() <= TOL_REL * np.abs(w3).max()
+    plan.close()
