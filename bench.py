@@ -344,7 +344,7 @@ def run_reference(args, cfg):
     for cid in parse_workloads(args):
         c = CONFIGS[cid]
         r = cpu_reference_rate(orc, kind, c, build_case(c), threads, args.sub_cpu_seconds, 3, 1)
-        wl.append({"config": cid, "workload": c["name"], **r})
+        wl.append({"cfg": cid, "workload": c["name"], **r})
     if wl:
         line["workloads"] = wl
     print(json.dumps(line), flush=True)
@@ -722,7 +722,7 @@ def measure_dropin(ctx, cfg_id, ngpus, pinned_e2e_per_gpu):
     want = oracle_eval(orc, cfg, case, np.ascontiguousarray(x[idx]), os.cpu_count() or 1)
     err = float(np.abs(out[idx] - want).max())
     value = npts * steps / dt
-    rec = {"config": cfg_id, "workload": cfg["name"], "n_gpus": ngpus, "points": npts, "steps": steps,
+    rec = {"cfg": cfg_id, "workload": cfg["name"], "n_gpus": ngpus, "points": npts, "steps": steps,
            "value": value, "unit": UNIT, "ms_per_step": 1e3 * dt / steps, "first_call_ms": 1e3 * first_s,
            "host_gbs": npts * (k + 1) * 8 * steps / dt / 1e9,
            "h2d_bytes_per_step": npts * k * 8, "d2h_bytes_per_step": npts * 8,
@@ -746,7 +746,7 @@ def run_ours(args, cfg_id):
     for cid in parse_workloads(args):
         r = measure_workload(ctx, cid, headline=False)
         if r is not None:
-            subs.append({"config": cid, **r})
+            subs.append({"cfg": cid, **r})
 
     # ---- drop-in leg: rank 0 alone, every GPU of the box through ONE process
     dropin = []
@@ -757,13 +757,13 @@ def run_ours(args, cfg_id):
         if ctx.rank == 0:
             pinned = {cfg_id: head["e2e"]["value"] / ctx.world}
             for s in subs:
-                pinned[s["config"]] = s["e2e"]["value"] / ctx.world
+                pinned[s["cfg"]] = s["e2e"]["value"] / ctx.world
             for cid in [int(t) for t in args.dropin.split(",") if t]:
                 for ng in sorted({1, ctx.world}):
                     try:
                         dropin.append(measure_dropin(ctx, cid, ng, pinned.get(cid)))
                     except Exception as ex:  # reported, never hidden
-                        dropin.append({"config": cid, "n_gpus": ng, "error": f"{type(ex).__name__}: {ex}"})
+                        dropin.append({"cfg": cid, "n_gpus": ng, "error": f"{type(ex).__name__}: {ex}"})
         ctx.host_barrier()
 
     if ctx.rank == 0:

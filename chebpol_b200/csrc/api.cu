@@ -123,6 +123,10 @@ struct chebpol_cuda_plan {
     int64_t cell_bytes = 0;   // 0: shape not supported / disabled
     int64_t ncells = 0;
     bool cells_failed = false;
+    // multilinear: row-pair-interleaved table (mlip_quad.cu, 2x the values), built on first use
+    double *d_quads = nullptr;
+    int64_t quad_bytes = 0;   // 0: shape not supported
+    bool quads_failed = false;
     // polyharmonic spline: knots in d_tensor, weights in d_weights, affine part in d_grid,
     // packed [w, knot, pad] rows in d_padded
     int nknots = 0;
@@ -247,6 +251,7 @@ extern "C" void chebpol_cuda_plan_destroy(chebpol_cuda_plan *p)
     cudaFree(p->d_mma);
     cudaFree(p->d_ktab);
     cudaFree(p->d_cells);
+    cudaFree(p->d_quads);
     cudaFree(p->d_lut);
     cudaFree(p->d_grid);
     cudaFree(p->d_weights);
@@ -547,6 +552,15 @@ extern "C" int chebpol_cuda_plan_mlip(const double *const *grid, const int *dims
         double cap_gb = 16.0;
         if (const char *env = getenv("CHEBPOL_CUDA_CELL_MAX_GB")) cap_gb = atof(env);
         if ((double)p->cell_bytes > cap_gb * 1e9) p->cell_bytes = 0;
+    }
+    p->quad_bytes = mlip_quad_bytes(rank, dims);
+    // A random gather wants the smallest DRAM fetch the L2 offers: with the default granularity every
+    // missed 16-byte pair costs 64 bytes of HBM traffic.  A hint, per device; streaming kernels do not care.
+    {
+        size_t gran = 32;
+        if (const char *env = getenv("CHEBPOL_CUDA_L2_FETCH")) gran = (size_t)atoi(env);
+        if (gran) (void)cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran);
+        (void)cudaGetLastError();
     }
     *plan = p;
     return plan_ready(plan);
@@ -995,6 +1009,39 @@ static int launch_plan(chebpol_cuda_plan *p, const double *d_x, int64_t npts, do
             e = launch_cheb_strict(a, s, &li);
         }
     } else if (p->kind == PLAN_MLIP) {
+        // experiment switch: pin as much of the value table as the device allows in the persisting part of L2
+        static const int persist_mb = getenv("CHEBPOL_CUDA_MLIP_PERSIST_MB") ? atoi(getenv("CHEBPOL_CUDA_MLIP_PERSIST_MB")) : 0;
+        struct WindowGuard {
+            cudaStream_t s;
+            bool on = false;
+            ~WindowGuard()
+            {
+                if (!on) return;
+                cudaStreamAttrValue av;
+                memset(&av, 0, sizeof av);
+                cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &av);
+            }
+        } guard{s};
+        if (persist_mb > 0) {
+            int max_persist = 0, max_window = 0;
+            cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, p->device);
+            cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, p->device);
+            size_t want = (size_t)persist_mb << 20;
+            if (want > (size_t)max_persist) want = (size_t)max_persist;
+            cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
+            const double *tab = p->d_quads ? p->d_quads : p->d_tensor;
+            size_t bytes = p->d_quads ? (size_t)p->quad_bytes : (size_t)p->nelem * 8;
+            if (bytes > (size_t)max_window) bytes = (size_t)max_window;
+            cudaStreamAttrValue av;
+            memset(&av, 0, sizeof av);
+            av.accessPolicyWindow.base_ptr = const_cast<double *>(tab);
+            av.accessPolicyWindow.num_bytes = bytes;
+            av.accessPolicyWindow.hitRatio = bytes ? (float)((double)want / (double)bytes > 1.0 ? 1.0 : (double)want / (double)bytes) : 0.f;
+            av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            if (cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &av) == cudaSuccess) guard.on = true;
+            (void)cudaGetLastError();
+        }
         MlipArgs a;
         a.values = p->d_tensor;
         a.grid = p->d_grid;
@@ -1006,9 +1053,14 @@ static int launch_plan(chebpol_cuda_plan *p, const double *d_x, int64_t npts, do
         a.out = d_out;
         a.lut = p->d_lut;
         for (int i = 0; i < p->rank; ++i) { a.loff[i] = p->loff[i]; a.nb[i] = p->nbk[i]; a.lscale[i] = p->lscale[i]; }
-        // variant: 0 auto, 1 pair-gather kernel, 2 cell-major kernel (always expand),
-        // >= 20 cell-major kernel with layout code warps*10 + stages
-        const bool allow_cell = p->variant == 0 || p->variant >= 2;
+        // variant: 0 auto, 1 pair-gather kernel, 2 cell-major kernel (always expand), 3 quad kernel
+        // (always expand), 20..199 cell-major kernel with layout code warps*10 + stages,
+        // 300+c quad kernel with c CTAs per SM.
+        // AUTO: the cell-major table (2^D x the values) when it fits and the batch has at least
+        // cells/8 points; else the row-pair-interleaved table (2 x) once a batch has at least
+        // half as many points as the table has values; else the pair gather on the values as given.
+        const bool want_quad = p->variant == 3 || (p->variant >= 300 && p->variant < 400);
+        const bool allow_cell = p->variant == 0 || p->variant == 2 || (p->variant >= 20 && p->variant < 200);
         if (want_fast && allow_cell && p->cell_bytes > 0 && !p->d_cells && !p->cells_failed &&
             (p->variant >= 2 || npts >= p->ncells / 8)) {
             size_t free_b = 0, total_b = 0;
@@ -1030,6 +1082,28 @@ static int launch_plan(chebpol_cuda_plan *p, const double *d_x, int64_t npts, do
             }
         }
         if (want_fast && allow_cell && p->d_cells) e = launch_mlip_cell(a, p->d_cells, p->variant, p->num_sms, s, &li);
+        if (e == cudaErrorNotSupported && want_fast && (want_quad || p->variant == 0) && p->quad_bytes > 0 && !p->quads_failed) {
+            if (!p->d_quads && (want_quad || npts >= p->nelem / 2)) {
+                size_t free_b = 0, total_b = 0;
+                cudaError_t ce = cudaMemGetInfo(&free_b, &total_b);
+                if (ce == cudaSuccess && (size_t)p->quad_bytes < free_b / 2) ce = cudaMalloc(&p->d_quads, (size_t)p->quad_bytes);
+                else if (ce == cudaSuccess) ce = cudaErrorMemoryAllocation;
+                if (ce == cudaSuccess) ce = mlip_quad_expand(a, p->d_tensor, p->d_quads, s);
+                if (ce != cudaSuccess) {
+                    (void)cudaGetLastError();
+                    cudaFree(p->d_quads);
+                    p->d_quads = nullptr;
+                    p->quads_failed = true;  // the pair kernel serves the plan
+                } else {
+                    p->tensor_bytes += p->quad_bytes;
+                    p->launches += 1;
+                    g_launches.fetch_add(1);
+                    const int rcb = mark_lazy_build(p, s);
+                    if (rcb) return rcb;
+                }
+            }
+            if (p->d_quads) e = launch_mlip_quad(a, p->d_quads, want_quad && p->variant >= 300 ? p->variant - 300 : 0, p->num_sms, s, &li);
+        }
         if (e == cudaErrorNotSupported && want_fast && p->variant < 2 && aligned16 && mlip_pair_supported(p->rank, p->blend))
             e = launch_mlip_pair(a, p->variant, p->num_sms, s, &li);
         if (e == cudaErrorNotSupported) {

@@ -79,6 +79,7 @@ enum KernelId {
     K_MLIP_STRICT = 20,  // thread-per-point, reference op order
     K_MLIP_PAIR = 21,    // lane-pair gather kernel
     K_MLIP_CELL = 22,    // cell-major table: one contiguous 2^D block per point
+    K_MLIP_QUAD = 23,    // row-pair-interleaved table (2x): one 32-byte quad per (dim 0, dim 1) corner set
     K_FH_STRICT = 30,    // thread-per-point nested barycentric, reference op order
     K_FH_MMA = 32,       // barycentric-basis DMMA contraction, TMA-streamed rows
     K_STALK_STRICT = 50, // stalker / hstalker, thread per point, reference op order
@@ -257,6 +258,9 @@ bool mlip_pair_supported(int rank, int blend);
 int64_t mlip_cell_bytes(int rank, const int *dims);
 cudaError_t mlip_expand(const MlipArgs &a, const double *values, double *cells, cudaStream_t s);
 cudaError_t launch_mlip_cell(const MlipArgs &a, const double *cells, int variant, int num_sms, cudaStream_t s, LaunchInfo *li);
+int64_t mlip_quad_bytes(int rank, const int *dims);
+cudaError_t mlip_quad_expand(const MlipArgs &a, const double *values, double *quads, cudaStream_t s);
+cudaError_t launch_mlip_quad(const MlipArgs &a, const double *quads, int variant, int num_sms, cudaStream_t s, LaunchInfo *li);
 cudaError_t fit_chebcoef_device(double *d_a, double *d_b, const int *dims, int rank, int dct, cudaStream_t s,
                                 double **result, int *launches);
 cudaError_t fit_evalgrid_device(int kind, const double *d_tensor, const int *dims, int rank, const double *const *d_pts,

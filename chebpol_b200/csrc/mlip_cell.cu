@@ -20,22 +20,12 @@
 // the reference (blend weights once per dimension, running products in the order
 // g = 0..D-1 as at :654-662); the 2^D corner terms are summed in corner order like the
 // reference for D <= 4.
-#include "common.cuh"
-#include "ptx.cuh"
+#include "mlip_common.cuh"
 
 namespace {
 
-__device__ __forceinline__ double blend_w(double w, int blend)
-{
-    switch (blend) {
-    case 1: return w < 0.5 ? 0.5 * exp(2 - 1 / w) : 1 - 0.5 * exp(2 - 1 / (1 - w));
-    case 2: return w < 0.5 ? 0.5 * exp(4 - 1 / (w * w)) : 1 - 0.5 * exp(4 - 1 / ((1 - w) * (1 - w)));
-    case 3: return (-2 * w + 3) * w * w;
-    case 4: return (w < 0.5) ? 0.0 : 1.0;
-    case 5: return 0.5;
-    default: return w;
-    }
-}
+using mlip::blend_w;
+using mlip::cell_search;
 
 // ---- expansion: values (R layout) -> cell-major blocks -------------------------------
 __global__ void __launch_bounds__(256) mlip_expand_kernel(const double *__restrict__ values, double *__restrict__ cells,
@@ -78,34 +68,6 @@ __device__ __forceinline__ void cp_async16(void *dst_smem, const void *src)
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-// Cell search: upper knot index in [1, n-1], identical to the reference's bisection
-// (src/chebpol.c:543-556: smallest index with g[idx] >= v, clamped) for every sorted grid.
-// The bucket table gives a starting index; the two fix-up scans use the real knots, so the
-// result does not depend on the table's rounding.  Also returns the cell's two knots.
-__device__ __forceinline__ int cell_search(const double *g, int n, const int *lut, int nb, double scale, double v,
-                                           double &g0, double &g1)
-{
-    double t = (v - g[0]) * scale;
-    t = t > 0.0 ? t : 0.0;  // NaN -> 0
-    const double tmax = (double)(nb - 1);
-    t = t < tmax ? t : tmax;
-    int k = lut[(int)t];
-    double hi = g[k], lo = g[k - 1];
-    while (k < n - 1 && hi < v) {
-        ++k;
-        lo = hi;
-        hi = g[k];
-    }
-    while (k > 1 && lo >= v) {
-        --k;
-        hi = lo;
-        lo = g[k - 1];
-    }
-    g0 = lo;
-    g1 = hi;
-    return k;
-}
 
 // One thread per point.  The cell blocks travel global -> shared memory with cp.async
 // (LDGSTS): in round k the 32 lanes of a warp copy the blocks of 32/CH points, CH = 2^(D-1)

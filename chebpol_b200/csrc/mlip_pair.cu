@@ -19,22 +19,11 @@
 // Rounding: corner terms are accumulated in two interleaved partial sums
 // instead of one (few-ulp differences); everything else is the reference's
 // arithmetic.
-#include "common.cuh"
-#include "ptx.cuh"
+#include "mlip_common.cuh"
 
 namespace {
 
-__device__ __forceinline__ double blend_w(double w, int blend)
-{
-    switch (blend) {
-    case 1: return w < 0.5 ? 0.5 * exp(2 - 1 / w) : 1 - 0.5 * exp(2 - 1 / (1 - w));
-    case 2: return w < 0.5 ? 0.5 * exp(4 - 1 / (w * w)) : 1 - 0.5 * exp(4 - 1 / ((1 - w) * (1 - w)));
-    case 3: return (-2 * w + 3) * w * w;
-    case 4: return (w < 0.5) ? 0.0 : 1.0;
-    case 5: return 0.5;
-    default: return w;
-    }
-}
+using mlip::blend_w;
 
 constexpr int kBlock = 256;
 

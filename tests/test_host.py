@@ -304,7 +304,7 @@ def test_bench_reference_arm_contract():
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
     assert "workload" in d["config"] and "model" not in d["config"]
     # the other BASELINE configs ride in `workloads`, timed by the same procedure
-    assert [w["config"] for w in d["workloads"]] == [4] and d["workloads"][0]["value"] > 0
+    assert [w["cfg"] for w in d["workloads"]] == [4] and d["workloads"][0]["value"] > 0
     assert d["workloads"][0]["kind"] == d["cpu_baseline"]["kind"]
     env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env)

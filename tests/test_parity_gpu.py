@@ -241,7 +241,8 @@ def test_mlip_strict(gpu_ok, port, dims, blend):
     plan.close()
 
 
-@pytest.mark.parametrize("family,variant", [("mlip_pair", _lib.VARIANT_MLIP_PAIR), ("mlip_cell", _lib.VARIANT_MLIP_CELL)])
+@pytest.mark.parametrize("family,variant", [("mlip_pair", _lib.VARIANT_MLIP_PAIR), ("mlip_cell", _lib.VARIANT_MLIP_CELL),
+                                            ("mlip_quad", _lib.VARIANT_MLIP_QUAD)])
 @pytest.mark.parametrize("blend", [0, 1, 2, 3, 4, 5])
 @pytest.mark.parametrize("dims", [(10,), (7, 9), (11, 11, 11), (16, 16, 16, 16), (5, 4, 3, 6, 4), (3, 4, 3, 2, 5, 3)])
 def test_mlip_fast(gpu_ok, port, dims, blend, family, variant):
@@ -255,7 +256,10 @@ def test_mlip_fast(gpu_ok, port, dims, blend, family, variant):
     x[:50, 0] = np.resize(grid[0], 50)
     plan = _lib.Plan.mlip(grid, values, blend)
     got, k = eval_plan(plan, x, _lib.KERNEL_AUTO, variant)
-    assert k == family
+    if family == "mlip_quad" and len(dims) == 1:
+        assert k == "mlip_strict"  # the quad layout interleaves rows of dimension 1: rank >= 2
+    else:
+        assert k == family
     want = port.evalmlip(grid, values, x, blend=blend, threads=4)
     assert_close(got, want, TOL_REL)
     plan.close()
@@ -275,6 +279,32 @@ def test_mlip_auto_picks_cell_layout_when_amortised(gpu_ok, port):
     assert_close(got, port.evalmlip(grid, values, big, threads=4), TOL_REL)
     _, k = eval_plan(plan, small, _lib.KERNEL_AUTO)
     assert k == "mlip_cell"
+    plan.close()
+
+
+def test_mlip_auto_uses_quads_when_cells_do_not_fit(gpu_ok, port, monkeypatch):
+    """AUTO without the cell-major table (here: capped away, as for a 64^5-class table whose 2^D-fold
+    expansion does not fit): small batches gather pairs from the values as given, a batch of at least
+    half as many points as the table has values builds the row-pair-interleaved table (2x) and stays on it."""
+    monkeypatch.setenv("CHEBPOL_CUDA_CELL_MAX_GB", "0")
+    grid, values = cases.mlip_case((12, 11, 10, 9), uniform=False)
+    plan = _lib.Plan.mlip(grid, values, 0)
+    small = cases.points(1000, 4)
+    _, k = eval_plan(plan, small, _lib.KERNEL_AUTO)
+    assert k == "mlip_pair"
+    b0 = plan.get(_lib.GET_TENSOR_BYTES)
+    big = cases.points(8000, 4, lo=-1.2, hi=1.2)
+    big[:12, 0] = grid[0]
+    got, k = eval_plan(plan, big, _lib.KERNEL_AUTO)
+    assert k == "mlip_quad"
+    assert plan.get(_lib.GET_TENSOR_BYTES) - b0 == 2 * 12 * 10 * 10 * 9 * 8  # 2 * n0 * (n1 - 1) * rest doubles
+    assert_close(got, port.evalmlip(grid, values, big, threads=4), TOL_REL)
+    _, k = eval_plan(plan, small, _lib.KERNEL_AUTO)
+    assert k == "mlip_quad"
+    nan = small.copy()
+    nan[3, 2] = np.nan
+    out, _ = eval_plan(plan, nan, _lib.KERNEL_AUTO)
+    assert np.isnan(out[3]) and np.isfinite(np.delete(out, 3)).all()
     plan.close()
 
 
