@@ -25,9 +25,9 @@ OPT_EPOL, OPT_SL_CELLS = 5, 6
 GET_KERNEL_USED, GET_LAUNCHES, GET_TENSOR_BYTES, GET_DEVICE, GET_SMEM_BYTES, GET_GRID = 101, 102, 103, 104, 105, 106
 KERNEL_AUTO, KERNEL_STRICT, KERNEL_FAST = 0, 1, 2
 VARIANT_AUTO, VARIANT_SLAB, VARIANT_MMA = 0, 1, 100000  # OPT_VARIANT families (csrc/api.cu: launch_plan)
-VARIANT_MLIP_PAIR, VARIANT_MLIP_CELL, VARIANT_MLIP_QUAD = 1, 2, 3
+VARIANT_MLIP_PAIR, VARIANT_MLIP_CELL, VARIANT_MLIP_QUAD, VARIANT_MLIP_BIN = 1, 2, 3, 4
 KERNEL_NAMES = {
-    0: "none", 10: "cheb_strict", 11: "cheb_slab", 12: "cheb_mma", 20: "mlip_strict", 21: "mlip_pair", 22: "mlip_cell", 23: "mlip_quad",
+    0: "none", 10: "cheb_strict", 11: "cheb_slab", 12: "cheb_mma", 20: "mlip_strict", 21: "mlip_pair", 22: "mlip_cell", 23: "mlip_quad", 24: "mlip_bin",
     30: "fh_strict", 32: "fh_mma", 40: "polyh_strict", 41: "polyh_tile", 50: "stalk_strict", 51: "stalk_cell",
     52: "oldstalk", 60: "sl_strict", 61: "sl_cell",
 }

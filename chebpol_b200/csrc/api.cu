@@ -127,6 +127,9 @@ struct chebpol_cuda_plan {
     double *d_quads = nullptr;
     int64_t quad_bytes = 0;   // 0: shape not supported
     bool quads_failed = false;
+    // multilinear: workspace of the binned (cache-blocked) path, mlip_bin.cu
+    MlipBinState *bin = nullptr;
+    bool bin_failed = false;
     // polyharmonic spline: knots in d_tensor, weights in d_weights, affine part in d_grid,
     // packed [w, knot, pad] rows in d_padded
     int nknots = 0;
@@ -252,6 +255,7 @@ extern "C" void chebpol_cuda_plan_destroy(chebpol_cuda_plan *p)
     cudaFree(p->d_ktab);
     cudaFree(p->d_cells);
     cudaFree(p->d_quads);
+    mlip_bin_destroy(p->bin);
     cudaFree(p->d_lut);
     cudaFree(p->d_grid);
     cudaFree(p->d_weights);
@@ -1059,7 +1063,11 @@ static int launch_plan(chebpol_cuda_plan *p, const double *d_x, int64_t npts, do
         // AUTO: the cell-major table (2^D x the values) when it fits and the batch has at least
         // cells/8 points; else the row-pair-interleaved table (2 x) once a batch has at least
         // half as many points as the table has values; else the pair gather on the values as given.
+        // 4: binned path (no extra table memory: the points are reordered so that a bin's sub-table
+        // is staged in shared memory); AUTO takes it, when the cell-major table is not available,
+        // for batches with enough points per bin to pay for the staging.
         const bool want_quad = p->variant == 3 || (p->variant >= 300 && p->variant < 400);
+        const bool want_bin = p->variant == 4;
         const bool allow_cell = p->variant == 0 || p->variant == 2 || (p->variant >= 20 && p->variant < 200);
         if (want_fast && allow_cell && p->cell_bytes > 0 && !p->d_cells && !p->cells_failed &&
             (p->variant >= 2 || npts >= p->ncells / 8)) {
@@ -1082,6 +1090,21 @@ static int launch_plan(chebpol_cuda_plan *p, const double *d_x, int64_t npts, do
             }
         }
         if (want_fast && allow_cell && p->d_cells) e = launch_mlip_cell(a, p->d_cells, p->variant, p->num_sms, s, &li);
+        if (e == cudaErrorNotSupported && want_fast && (want_bin || p->variant == 0) && !p->bin_failed && aligned16 &&
+            (want_bin || p->nelem * 8 > (48ll << 20)) && mlip_bin_supported(p->rank, p->dims, npts, p->blend)) {
+            cudaError_t ce = mlip_bin_prepare(&p->bin, p->rank, p->dims, npts);
+            if (ce == cudaSuccess) {
+                int nl = 0;
+                e = launch_mlip_bin(a, p->bin, p->num_sms, s, &li, &nl);
+                if (e == cudaSuccess && nl > 1) {
+                    p->launches += nl - 1;
+                    g_launches.fetch_add(nl - 1);
+                }
+            } else {
+                (void)cudaGetLastError();
+                if (ce != cudaErrorNotSupported) p->bin_failed = true;  // no room for the workspace
+            }
+        }
         if (e == cudaErrorNotSupported && want_fast && (want_quad || p->variant == 0) && p->quad_bytes > 0 && !p->quads_failed) {
             if (!p->d_quads && (want_quad || npts >= p->nelem / 2)) {
                 size_t free_b = 0, total_b = 0;
@@ -1277,14 +1300,52 @@ static int staging_threads()
     return n;
 }
 
+// Copy with non-temporal stores: the destination (a pinned staging buffer about to be read by the
+// DMA engine, or the caller's result vector) is not read again by this core, so the write-allocate
+// read of every destination line is pure waste on a path that is bound by host memory bandwidth.
+#include <immintrin.h>
+__attribute__((target("avx2"))) static void copy_stream_avx2(void *dst, const void *src, size_t bytes)
+{
+    char *d = static_cast<char *>(dst);
+    const char *s = static_cast<const char *>(src);
+    size_t head = (32 - ((uintptr_t)d & 31)) & 31;
+    if (head > bytes) head = bytes;
+    memcpy(d, s, head);
+    d += head; s += head; bytes -= head;
+    size_t i = 0;
+    for (; i + 128 <= bytes; i += 128) {
+        const __m256i a = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(s + i));
+        const __m256i b = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(s + i + 32));
+        const __m256i c = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(s + i + 64));
+        const __m256i e = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(s + i + 96));
+        _mm256_stream_si256(reinterpret_cast<__m256i *>(d + i), a);
+        _mm256_stream_si256(reinterpret_cast<__m256i *>(d + i + 32), b);
+        _mm256_stream_si256(reinterpret_cast<__m256i *>(d + i + 64), c);
+        _mm256_stream_si256(reinterpret_cast<__m256i *>(d + i + 96), e);
+    }
+    _mm_sfence();
+    memcpy(d + i, s + i, bytes - i);
+}
+
+static void copy_stream(void *dst, const void *src, size_t bytes)
+{
+    static const int mode = [] {
+        const char *e = getenv("CHEBPOL_CUDA_STAGING_NT");
+        if (e && atoi(e) == 0) return 0;
+        return __builtin_cpu_supports("avx2") ? 1 : 0;
+    }();
+    if (mode == 1 && bytes >= 4096) copy_stream_avx2(dst, src, bytes);
+    else memcpy(dst, src, bytes);
+}
+
 static void par_memcpy(void *dst, const void *src, size_t bytes, int T)
 {
-    if (T == 1 || bytes < (4u << 20)) { memcpy(dst, src, bytes); return; }
+    if (T == 1 || bytes < (4u << 20)) { copy_stream(dst, src, bytes); return; }
     const size_t slice = ((bytes + T - 1) / T + 4095) & ~(size_t)4095;
 #pragma omp parallel for num_threads(T) schedule(static)
     for (int i = 0; i < T; ++i) {
         const size_t lo = (size_t)i * slice;
-        if (lo < bytes) memcpy((char *)dst + lo, (const char *)src + lo, (lo + slice <= bytes) ? slice : bytes - lo);
+        if (lo < bytes) copy_stream((char *)dst + lo, (const char *)src + lo, (lo + slice <= bytes) ? slice : bytes - lo);
     }
 }
 

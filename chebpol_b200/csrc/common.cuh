@@ -79,6 +79,7 @@ enum KernelId {
     K_MLIP_STRICT = 20,  // thread-per-point, reference op order
     K_MLIP_PAIR = 21,    // lane-pair gather kernel
     K_MLIP_CELL = 22,    // cell-major table: one contiguous 2^D block per point
+    K_MLIP_BIN = 24,     // points binned by upper-dimension cell, sub-table staged in shared memory (no extra table memory)
     K_MLIP_QUAD = 23,    // row-pair-interleaved table (2x): one 32-byte quad per (dim 0, dim 1) corner set
     K_FH_STRICT = 30,    // thread-per-point nested barycentric, reference op order
     K_FH_MMA = 32,       // barycentric-basis DMMA contraction, TMA-streamed rows
@@ -258,6 +259,12 @@ bool mlip_pair_supported(int rank, int blend);
 int64_t mlip_cell_bytes(int rank, const int *dims);
 cudaError_t mlip_expand(const MlipArgs &a, const double *values, double *cells, cudaStream_t s);
 cudaError_t launch_mlip_cell(const MlipArgs &a, const double *cells, int variant, int num_sms, cudaStream_t s, LaunchInfo *li);
+struct MlipBinState;
+bool mlip_bin_supported(int rank, const int *dims, int64_t npts, int blend);
+cudaError_t mlip_bin_prepare(MlipBinState **st, int rank, const int *dims, int64_t npts);
+void mlip_bin_destroy(MlipBinState *st);
+int64_t mlip_bin_bytes(const MlipBinState *st);
+cudaError_t launch_mlip_bin(const MlipArgs &a, MlipBinState *st, int num_sms, cudaStream_t s, LaunchInfo *li, int *launches);
 int64_t mlip_quad_bytes(int rank, const int *dims);
 cudaError_t mlip_quad_expand(const MlipArgs &a, const double *values, double *quads, cudaStream_t s);
 cudaError_t launch_mlip_quad(const MlipArgs &a, const double *quads, int variant, int num_sms, cudaStream_t s, LaunchInfo *li);

@@ -164,11 +164,13 @@ CHEBPOL_CUDA_API int chebpol_cuda_plan_eval_host(chebpol_cuda_plan *plan, const 
  *                     100000       DMMA contraction engine, default layout
  *                     100000+c     DMMA engine, layout c = MT*100 + WARPS
  *   multilinear plans 1 pair-gather kernel on the R layout; 2 cell-major kernel (2^D x the table);
- *                     3 quad kernel (row pairs interleaved, 2 x the table); 20..199 cell-major
+ *                     3 quad kernel (row pairs interleaved, 2 x the table); 4 binned path (points
+ *                     reordered by cell, sub-tables staged in shared memory, 1 x the table plus a
+ *                     workspace proportional to the batch); 20..199 cell-major
  *                     kernel with WARPS*10 + STAGES; 300+c quad kernel with c CTAs per SM
  *   FH plans          100000+c as for Chebyshev
  * CHEBPOL_CUDA_GET_KERNEL_USED: 10 cheb_strict, 11 cheb_slab (DFMA), 12 cheb_mma (DMMA),
- *   20 mlip_strict, 21 mlip_pair, 22 mlip_cell, 23 mlip_quad, 30 fh_strict, 32 fh_mma, 40/41 polyh, 50/51 stalk,
+ *   20 mlip_strict, 21 mlip_pair, 22 mlip_cell, 23 mlip_quad, 24 mlip_bin, 30 fh_strict, 32 fh_mma, 40/41 polyh, 50/51 stalk,
  *   60 sl_strict, 61 sl_cell. */
 CHEBPOL_CUDA_API int chebpol_cuda_plan_set(chebpol_cuda_plan *plan, int option, int64_t value);
 CHEBPOL_CUDA_API int chebpol_cuda_plan_get(chebpol_cuda_plan *plan, int what, int64_t *value);

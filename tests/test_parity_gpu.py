@@ -242,7 +242,7 @@ def test_mlip_strict(gpu_ok, port, dims, blend):
 
 
 @pytest.mark.parametrize("family,variant", [("mlip_pair", _lib.VARIANT_MLIP_PAIR), ("mlip_cell", _lib.VARIANT_MLIP_CELL),
-                                            ("mlip_quad", _lib.VARIANT_MLIP_QUAD)])
+                                            ("mlip_quad", _lib.VARIANT_MLIP_QUAD), ("mlip_bin", _lib.VARIANT_MLIP_BIN)])
 @pytest.mark.parametrize("blend", [0, 1, 2, 3, 4, 5])
 @pytest.mark.parametrize("dims", [(10,), (7, 9), (11, 11, 11), (16, 16, 16, 16), (5, 4, 3, 6, 4), (3, 4, 3, 2, 5, 3)])
 def test_mlip_fast(gpu_ok, port, dims, blend, family, variant):
@@ -256,8 +256,8 @@ def test_mlip_fast(gpu_ok, port, dims, blend, family, variant):
     x[:50, 0] = np.resize(grid[0], 50)
     plan = _lib.Plan.mlip(grid, values, blend)
     got, k = eval_plan(plan, x, _lib.KERNEL_AUTO, variant)
-    if family == "mlip_quad" and len(dims) == 1:
-        assert k == "mlip_strict"  # the quad layout interleaves rows of dimension 1: rank >= 2
+    if family in ("mlip_quad", "mlip_bin") and len(dims) == 1:
+        assert k == "mlip_strict"  # both need a second dimension (rows to interleave / upper cells to bin by)
     else:
         assert k == family
     want = port.evalmlip(grid, values, x, blend=blend, threads=4)
@@ -305,6 +305,33 @@ def test_mlip_auto_uses_quads_when_cells_do_not_fit(gpu_ok, port, monkeypatch):
     nan[3, 2] = np.nan
     out, _ = eval_plan(plan, nan, _lib.KERNEL_AUTO)
     assert np.isnan(out[3]) and np.isfinite(np.delete(out, 3)).all()
+    plan.close()
+
+
+def test_mlip_binned_path_handles_clustered_and_ragged_batches(gpu_ok, port):
+    """The binned path (points reordered by upper-dimension cell, sub-tables staged in shared memory):
+    uniform batches, a batch clustered in one cell (every bin but one empty, most points overflow the
+    bin capacity and take the gather kernel), points on knots / outside the grid / NaN, batch sizes
+    around the bin count, and results restored to the caller's order."""
+    grid, values = cases.mlip_case((12, 10, 9, 8), uniform=False)
+    plan = _lib.Plan.mlip(grid, values, 0)
+    plan.set(_lib.OPT_VARIANT, _lib.VARIANT_MLIP_BIN)
+    rng = np.random.default_rng(11)
+    for n in (1, 7, 500, 4001, 60_000):
+        x = cases.points(n, 4, seed=n, lo=-1.2, hi=1.2)
+        x[: min(n, 12), 0] = grid[0][: min(n, 12)]
+        got = plan.eval_host(x)
+        assert plan.kernel_used == "mlip_bin"
+        assert_close(got, port.evalmlip(grid, values, x, threads=4), TOL_REL)
+    cl = np.ascontiguousarray(np.array([0.31, -0.42, 0.11, 0.73]) + 1e-3 * rng.standard_normal((50_000, 4)))
+    cl[17, 1] = np.nan
+    got = plan.eval_host(cl)
+    want = port.evalmlip(grid, values, np.where(np.isnan(cl), 0.0, cl), threads=4)
+    assert np.isnan(got[17]) and np.abs(np.delete(got - want, 17)).max() <= TOL_REL
+    for blend in (3, 5):
+        plan.set(_lib.OPT_BLEND, blend)
+        x = cases.points(30_000, 4, seed=blend)
+        assert_close(plan.eval_host(x), port.evalmlip(grid, values, x, blend=blend, threads=4), TOL_REL)
     plan.close()
 
 
