@@ -121,6 +121,7 @@ struct chebpol_cuda_plan {
     int loff[CP_MAXR] = {0}, nbk[CP_MAXR] = {0};
     double lscale[CP_MAXR] = {0};
     int64_t cell_bytes = 0;   // 0: shape not supported / disabled
+    int cell_m = 0;           // leading dimensions expanded into bricks of 2^m corners (rank: cell-major)
     int64_t ncells = 0;
     bool cells_failed = false;
     // multilinear: row-pair-interleaved table (mlip_quad.cu, 2x the values), built on first use
@@ -549,13 +550,30 @@ extern "C" int chebpol_cuda_plan_mlip(const double *const *grid, const int *dims
     }
     // cell-major expansion (mlip_cell.cu) is built lazily, on the first evaluation large
     // enough to amortise it; capped by CHEBPOL_CUDA_CELL_MAX_GB (default 16) and free memory
-    p->cell_bytes = mlip_cell_bytes(rank, dims);
+    // The largest expansion that fits the cap: all rank dimensions (cell-major, 2^rank x the table),
+    // else bricks over the first m >= 3 of them (2^m x; 64-byte bricks are the DRAM access
+    // granularity, smaller ones waste half of every burst -- the 2 x quad table covers that end).
+    // CHEBPOL_CUDA_CELL_M pins m (tests, tuning).
     p->ncells = 1;
     for (int d = 0; d < rank; ++d) p->ncells *= dims[d] - 1;
     {
         double cap_gb = 16.0;
         if (const char *env = getenv("CHEBPOL_CUDA_CELL_MAX_GB")) cap_gb = atof(env);
-        if ((double)p->cell_bytes > cap_gb * 1e9) p->cell_bytes = 0;
+        int m_lo = rank < 3 ? rank : 3, m_hi = rank;
+        if (const char *env = getenv("CHEBPOL_CUDA_CELL_M")) {
+            const int mm = atoi(env);
+            if (mm >= 1 && mm <= rank) m_lo = m_hi = mm;
+        }
+        p->cell_bytes = 0;
+        p->cell_m = 0;
+        for (int m = m_hi; m >= m_lo; --m) {
+            const int64_t b = mlip_cell_bytes(rank, dims, m);
+            if (b > 0 && (double)b <= cap_gb * 1e9) {
+                p->cell_bytes = b;
+                p->cell_m = m;
+                break;
+            }
+        }
     }
     p->quad_bytes = mlip_quad_bytes(rank, dims);
     // A random gather wants the smallest DRAM fetch the L2 offers: with the default granularity every
@@ -925,6 +943,7 @@ extern "C" int chebpol_cuda_plan_get(chebpol_cuda_plan *p, int what, int64_t *va
     case CHEBPOL_CUDA_GET_DEVICE: *value = p->device; break;
     case CHEBPOL_CUDA_GET_SMEM_BYTES: *value = p->last.smem; break;
     case CHEBPOL_CUDA_GET_GRID: *value = p->last.grid; break;
+    case CHEBPOL_CUDA_GET_RANK: *value = p->rank; break;
     default: return fail(CHEBPOL_CUDA_EINVAL, "unknown query %d", what);
     }
     return CHEBPOL_CUDA_OK;
@@ -1075,7 +1094,7 @@ static int launch_plan(chebpol_cuda_plan *p, const double *d_x, int64_t npts, do
             cudaError_t ce = cudaMemGetInfo(&free_b, &total_b);
             if (ce == cudaSuccess && (size_t)p->cell_bytes < free_b / 2) ce = cudaMalloc(&p->d_cells, (size_t)p->cell_bytes);
             else if (ce == cudaSuccess) ce = cudaErrorMemoryAllocation;
-            if (ce == cudaSuccess) ce = mlip_expand(a, p->d_tensor, p->d_cells, s);
+            if (ce == cudaSuccess) ce = mlip_expand(a, p->d_tensor, p->d_cells, p->cell_m, s);
             if (ce != cudaSuccess) {
                 (void)cudaGetLastError();
                 cudaFree(p->d_cells);
@@ -1089,9 +1108,9 @@ static int launch_plan(chebpol_cuda_plan *p, const double *d_x, int64_t npts, do
                 if (rcb) return rcb;
             }
         }
-        if (want_fast && allow_cell && p->d_cells) e = launch_mlip_cell(a, p->d_cells, p->variant, p->num_sms, s, &li);
+        if (want_fast && allow_cell && p->d_cells) e = launch_mlip_cell(a, p->d_cells, p->cell_m, p->variant, p->num_sms, s, &li);
         if (e == cudaErrorNotSupported && want_fast && (want_bin || p->variant == 0) && !p->bin_failed && aligned16 &&
-            (want_bin || p->nelem * 8 > (48ll << 20)) && mlip_bin_supported(p->rank, p->dims, npts, p->blend)) {
+            (want_bin || p->nelem * 8 > (48ll << 20)) && mlip_bin_supported(p->rank, p->dims, npts, p->blend, want_bin)) {
             cudaError_t ce = mlip_bin_prepare(&p->bin, p->rank, p->dims, npts);
             if (ce == cudaSuccess) {
                 int nl = 0;
@@ -1466,6 +1485,20 @@ extern "C" int chebpol_cuda_plan_eval_host(chebpol_cuda_plan *p, const double *x
         return bail(rc);
     }
     const int64_t nchunks = (npts + chunk - 1) / chunk;
+    if (nchunks == 1) {
+        // a small call (the closure on one or a few points): one stream, one synchronisation
+        cudaError_t e = cudaMemcpyAsync(p->d_x[0], x, sizeof(double) * npts * p->rank, cudaMemcpyHostToDevice, p->st_k);
+        if (e == cudaSuccess) {
+            rc = launch_plan(p, p->d_x[0], npts, p->d_o[0], p->st_k);
+            if (!rc) e = cudaMemcpyAsync(out, p->d_o[0], sizeof(double) * npts, cudaMemcpyDeviceToHost, p->st_k);
+        }
+        const cudaError_t es = cudaStreamSynchronize(p->st_k);
+        if (cur != p->device) cudaSetDevice(cur);
+        if (rc) return rc;
+        if (e != cudaSuccess) return cuda_fail(e, "small-call pipeline");
+        if (es != cudaSuccess) return cuda_fail(es, "kernel stream");
+        return CHEBPOL_CUDA_OK;
+    }
     // chunk c uses buffer c&1:  H2D(c) -> kernel(c) -> D2H(c); D2H(c-1) is
     // enqueued after kernel(c) so that a blocking (pageable) copy-out overlaps
     // the next kernel.
@@ -1616,7 +1649,7 @@ struct Identity {
     std::mutex mu;
 };
 
-static void make_identity(Identity &id, int kind, const int *dims, int rank, uint64_t seed)
+static void make_identity(Identity &id, int kind, const int *dims, int rank, uint64_t seed, bool as_large = false)
 {
     memset(&id.key, 0, sizeof id.key);
     id.key.kind = kind;
@@ -1646,7 +1679,10 @@ static void make_identity(Identity &id, int kind, const int *dims, int rank, uin
         id.by_address = true;
         return;
     }
-    if (!g_weak_hash.load()) id.key.hash = cphash::hash_blobs(id.blobs, seed, host_threads_total());
+    // Interpolants small enough to be retained are told apart by the byte comparison alone (one pass
+    // over the arrays on a hit instead of two); the fingerprint is for the large ones.
+    if ((id.key.bytes > kRetainMaxBytes || as_large) && !g_weak_hash.load())
+        id.key.hash = cphash::hash_blobs(id.blobs, seed, host_threads_total());
 }
 
 // does a cached entry hold exactly the interpolant of this call?
@@ -1836,8 +1872,8 @@ extern "C" int chebpol_cuda_debug_cache_would_hit(const void *a, int64_t na, con
     Identity ia, ib;
     ia.blobs.push_back({a, (size_t)na});
     ib.blobs.push_back({b, (size_t)nb});
-    make_identity(ia, PLAN_CHEB, dims, 1, 1);
-    make_identity(ib, PLAN_CHEB, dims, 1, 1);
+    make_identity(ia, PLAN_CHEB, dims, 1, 1, !retain);
+    make_identity(ib, PLAN_CHEB, dims, 1, 1, !retain);
     KeptBytes kept;
     if (retain) {
         auto v = std::make_shared<std::vector<unsigned char>>();

@@ -256,11 +256,11 @@ cudaError_t launch_cheb_slab(const SlabArgs &a, int variant, int num_sms, cudaSt
 int cheb_slab_pick_n0p(int n0);
 cudaError_t launch_mlip_pair(const MlipArgs &a, int variant, int num_sms, cudaStream_t s, LaunchInfo *li);
 bool mlip_pair_supported(int rank, int blend);
-int64_t mlip_cell_bytes(int rank, const int *dims);
-cudaError_t mlip_expand(const MlipArgs &a, const double *values, double *cells, cudaStream_t s);
-cudaError_t launch_mlip_cell(const MlipArgs &a, const double *cells, int variant, int num_sms, cudaStream_t s, LaunchInfo *li);
+int64_t mlip_cell_bytes(int rank, const int *dims, int m);
+cudaError_t mlip_expand(const MlipArgs &a, const double *values, double *cells, int m, cudaStream_t s);
+cudaError_t launch_mlip_cell(const MlipArgs &a, const double *cells, int m, int variant, int num_sms, cudaStream_t s, LaunchInfo *li);
 struct MlipBinState;
-bool mlip_bin_supported(int rank, const int *dims, int64_t npts, int blend);
+bool mlip_bin_supported(int rank, const int *dims, int64_t npts, int blend, bool force);
 cudaError_t mlip_bin_prepare(MlipBinState **st, int rank, const int *dims, int64_t npts);
 void mlip_bin_destroy(MlipBinState *st);
 int64_t mlip_bin_bytes(const MlipBinState *st);

@@ -13,15 +13,15 @@
 //                2^(D-m) contiguous runs of the R array (131 KB for 64^4 with m = 2: 3969 bins);
 //   2. evaluate  one CTA per bin: the runs travel to shared memory by TMA bulk copy, the bin's
 //                points stream through, all 2^D corner reads are shared-memory loads;
-//   3. restore   results are gathered back into the caller's order (out[i] = res[pos[i]]): the
-//                positions of consecutive points of a bin are consecutive, so each 64-byte piece of
-//                res is fetched once and reused from L2.
+//                every result goes straight to out[index of the point] (the index travels with the
+//                point), so nothing has to be un-permuted afterwards.
 //
-// DRAM traffic per point: 32 + 32 + 4 (scatter), 32 + 8 (evaluate), 4 + 8 + 8 (restore) = 128 B for
-// D = 4, all of it streaming, plus the table once per chunk of points.  Bins have a fixed capacity
-// (1.25 x the mean + 64); points that do not fit (a clustered batch) go to an overflow list that is
-// evaluated by a plain gather kernel -- so no counting pass and no host synchronisation.
-// Workspace is proportional to the batch chunk (<= 2^25 points: ~3 GB), not to the table.
+// DRAM traffic per point for D = 4: 32 + 32 + 4 (scatter: read the point, write it and its index),
+// 32 + 4 (evaluate: read them back) plus the scattered 8-byte result, and the table once per chunk
+// of points (15 B/point at 2^25 points) -- streaming except for the result.  Bins have a fixed
+// capacity (1.25 x the mean + 64); points that do not fit (a clustered batch) are listed by index
+// and evaluated by a plain gather kernel -- so no counting pass and no host synchronisation.
+// Workspace is proportional to the batch chunk (<= 2^25 points: 1.7 GB), not to the table.
 //
 // Arithmetic: weights, blend functions and the final division are the reference's; the corner terms
 // are accumulated in the reference's corner order (bit d of the corner index = upper knot of dim d).
@@ -35,6 +35,7 @@ using mlip::cell_search;
 constexpr int kTileBudget = 160 * 1024;  // bytes of value table per bin in shared memory
 constexpr int kEvalThreads = 1024;
 constexpr int kScatterThreads = 256;
+constexpr int kCursorStride = 64;  // ints between two bins' cursors: one per 256 bytes, so the atomics spread over every L2 slice
 
 struct BinGeom {
     int rank, mf;            // dims < mf are whole inside a bin
@@ -48,19 +49,59 @@ struct BinGeom {
 
 struct BinWork {
     double *bx;              // [nbins*cap][rank] binned points
-    double *res;             // [nbins*cap] results in bin order
-    int *pos;                // [chunk] position of point i in bin order, or -1 - (overflow position)
+    int *bidx;               // [nbins*cap] index (within the chunk) of each binned point
     int *cursor;             // [nbins] points appended to each bin (may exceed cap: the excess overflowed)
     int *counters;           // [0] overflow count, [1] work counter of the evaluate kernel
-    double *ox;              // [ocap][rank] overflow points
-    double *ores;            // [ocap]
-    int ocap;
+    int *oidx;               // [chunk] indices of the points that did not fit their bin
 };
 
-// ------------------------------------------------------------------------------ 1. scatter
+// one point, RANK doubles: a single 256-bit access for RANK = 4 on 32-byte aligned storage
+// (LDG.E.ENL2.256 / STG.E.ENL2.256), 128-bit pairs for other even ranks, scalars otherwise
 template <int RANK>
+__device__ __forceinline__ void load_point(const double *p, double (&x)[RANK], bool al32)
+{
+    if constexpr (RANK == 4) {
+        if (al32) {
+            asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];"
+                         : "=d"(x[0]), "=d"(x[1]), "=d"(x[2]), "=d"(x[3])
+                         : "l"(p));
+            return;
+        }
+    }
+    if constexpr ((RANK & 1) == 0) {
+#pragma unroll
+        for (int d = 0; d < RANK; d += 2) {
+            const double2 v = ldg_stream_f64x2(p + d);
+            x[d] = v.x;
+            x[d + 1] = v.y;
+        }
+    } else {
+#pragma unroll
+        for (int d = 0; d < RANK; ++d) x[d] = ldg_stream_f64(p + d);
+    }
+}
+
+template <int RANK>
+__device__ __forceinline__ void store_point(double *p, const double (&x)[RANK])
+{
+    if constexpr (RANK == 4) {
+        asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(x[0]), "d"(x[1]), "d"(x[2]), "d"(x[3]) : "memory");
+    } else if constexpr ((RANK & 1) == 0) {
+#pragma unroll
+        for (int d = 0; d < RANK; d += 2) reinterpret_cast<double2 *>(p)[d / 2] = make_double2(x[d], x[d + 1]);
+    } else {
+#pragma unroll
+        for (int d = 0; d < RANK; ++d) p[d] = x[d];
+    }
+}
+
+// ------------------------------------------------------------------------------ 1. scatter
+// U points per thread are in flight together: their loads, then their searches, then their slot
+// reservations (one atomic each), then their stores -- the kernel is a chain of dependent memory
+// round trips per point, so the only lever is how many chains overlap.
+template <int RANK, int U>
 __global__ void __launch_bounds__(kScatterThreads) mlip_bin_scatter(const __grid_constant__ MlipArgs a, const BinGeom gm,
-                                                                    const BinWork w, int grid_elems, int lut_elems)
+                                                                    const BinWork w, int grid_elems, int lut_elems, int x32)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *sgrid = reinterpret_cast<double *>(smem_raw);
@@ -68,47 +109,47 @@ __global__ void __launch_bounds__(kScatterThreads) mlip_bin_scatter(const __grid
     for (int i = threadIdx.x; i < grid_elems; i += blockDim.x) sgrid[i] = a.grid[i];
     for (int i = threadIdx.x; i < lut_elems; i += blockDim.x) slut[i] = a.lut[i];
     __syncthreads();
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.npts; i += stride) {
-        double x[RANK];
-        const double *xp = a.x + i * RANK;
-        if constexpr ((RANK & 1) == 0) {
+    const int64_t tile = (int64_t)kScatterThreads * U;
+    for (int64_t base = (int64_t)blockIdx.x * tile; base < a.npts; base += (int64_t)gridDim.x * tile) {
+        double x[U][RANK];
+        int bin[U], slot[U];
 #pragma unroll
-            for (int d = 0; d < RANK; d += 2) {
-                const double2 v = ldg_stream_f64x2(xp + d);
-                x[d] = v.x;
-                x[d + 1] = v.y;
+        for (int u = 0; u < U; ++u) {
+            const int64_t i = base + u * kScatterThreads + threadIdx.x;
+            if (i < a.npts) load_point<RANK>(a.x + i * RANK, x[u], x32 != 0);
+            else {
+#pragma unroll
+                for (int d = 0; d < RANK; ++d) x[u][d] = 0.0;
             }
-        } else {
-#pragma unroll
-            for (int d = 0; d < RANK; ++d) x[d] = ldg_stream_f64(xp + d);
         }
-        int bin = 0;
 #pragma unroll
-        for (int d = 0; d < RANK; ++d) {
-            if (d < gm.mf) continue;
-            double g0, g1;
-            const int hi = cell_search(sgrid + a.goff[d], a.dims[d], slut + a.loff[d], a.nb[d], a.lscale[d], x[d], g0, g1);
-            bin += (hi - 1) * gm.bstride[d];
+        for (int u = 0; u < U; ++u) {
+            int b = 0;
+#pragma unroll
+            for (int d = 0; d < RANK; ++d) {
+                if (d < gm.mf) continue;
+                double g0, g1;
+                const int hi = cell_search(sgrid + a.goff[d], a.dims[d], slut + a.loff[d], a.nb[d], a.lscale[d], x[u][d], g0, g1);
+                b += (hi - 1) * gm.bstride[d];
+            }
+            bin[u] = b;
         }
-        const int slot = atomicAdd(w.cursor + bin, 1);
-        double *dst;
-        int where;
-        if (slot < gm.cap) {
-            where = bin * gm.cap + slot;
-            dst = w.bx + (int64_t)where * RANK;
-        } else {
-            const int o = atomicAdd(w.counters, 1);  // cannot exceed ocap = the chunk size
-            where = -1 - o;
-            dst = w.ox + (int64_t)o * RANK;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t i = base + u * kScatterThreads + threadIdx.x;
+            slot[u] = i < a.npts ? atomicAdd(w.cursor + (int64_t)bin[u] * kCursorStride, 1) : 0;
         }
-        w.pos[i] = where;
-        if constexpr ((RANK & 1) == 0) {
 #pragma unroll
-            for (int d = 0; d < RANK; d += 2) reinterpret_cast<double2 *>(dst)[d / 2] = make_double2(x[d], x[d + 1]);
-        } else {
-#pragma unroll
-            for (int d = 0; d < RANK; ++d) dst[d] = x[d];
+        for (int u = 0; u < U; ++u) {
+            const int64_t i = base + u * kScatterThreads + threadIdx.x;
+            if (i >= a.npts) continue;
+            if (slot[u] < gm.cap) {
+                const int64_t where = (int64_t)bin[u] * gm.cap + slot[u];
+                store_point<RANK>(w.bx + where * RANK, x[u]);
+                w.bidx[where] = (int)i;
+            } else {
+                w.oidx[atomicAdd(w.counters, 1)] = (int)i;  // cannot exceed the chunk size
+            }
         }
     }
 }
@@ -223,7 +264,7 @@ __global__ void __launch_bounds__(kEvalThreads, 1) mlip_bin_eval(const __grid_co
         __syncthreads();
         const int b = *sbin;
         if (b >= gm.nbins) break;
-        int npt = w.cursor[b];
+        int npt = w.cursor[(int64_t)b * kCursorStride];
         npt = npt < gm.cap ? npt : gm.cap;
         // knots of the bin's cell in the upper dimensions (the same for every point of the bin)
         double ug0[RANK], uinv[RANK];
@@ -239,29 +280,22 @@ __global__ void __launch_bounds__(kEvalThreads, 1) mlip_bin_eval(const __grid_co
             }
         }
         const double *bx = w.bx + (int64_t)b * gm.cap * RANK;
-        double *bres = w.res + (int64_t)b * gm.cap;
+        const int *bi = w.bidx + (int64_t)b * gm.cap;
 
-        auto load_x = [&](int i, double (&x)[RANK]) {
+        auto load_x = [&](int i, double (&x)[RANK], int &idx) {
             if (i < npt) {
-                if constexpr ((RANK & 1) == 0) {
-#pragma unroll
-                    for (int d = 0; d < RANK; d += 2) {
-                        const double2 v = ldg_stream_f64x2(bx + (int64_t)i * RANK + d);
-                        x[d] = v.x;
-                        x[d + 1] = v.y;
-                    }
-                } else {
-#pragma unroll
-                    for (int d = 0; d < RANK; ++d) x[d] = ldg_stream_f64(bx + (int64_t)i * RANK + d);
-                }
+                load_point<RANK>(bx + (int64_t)i * RANK, x, true);
+                idx = __ldg(bi + i);
             } else {
 #pragma unroll
                 for (int d = 0; d < RANK; ++d) x[d] = 0.0;
+                idx = 0;
             }
         };
         double xc[RANK], xn[RANK];
-        load_x(threadIdx.x, xc);
-        load_x(threadIdx.x + kEvalThreads, xn);
+        int ic, in;
+        load_x(threadIdx.x, xc, ic);
+        load_x(threadIdx.x + kEvalThreads, xn, in);
         if (gm.tma) {
             mbar_wait(bar, phase);
             phase ^= 1u;
@@ -287,7 +321,8 @@ __global__ void __launch_bounds__(kEvalThreads, 1) mlip_bin_eval(const __grid_co
         }
         for (int i = threadIdx.x; i < npt; i += kEvalThreads) {
             double xnn[RANK];
-            load_x(i + 2 * kEvalThreads, xnn);  // two iterations ahead: the stream stays in flight
+            int inn;
+            load_x(i + 2 * kEvalThreads, xnn, inn);  // two iterations ahead: the stream stays in flight
             double wt[RANK];
             bool nn = false;
             int lidx = 0;
@@ -312,9 +347,11 @@ __global__ void __launch_bounds__(kEvalThreads, 1) mlip_bin_eval(const __grid_co
                     if ((corner >> d) & 1) off += (int)a.stride[d];
                 return tp[(size_t)(corner >> MF) * gm.low_elems + off];
             });
-            stg_stream_f64(bres + i, r);
+            a.out[ic] = r;  // the caller's order, straight from here
 #pragma unroll
             for (int d = 0; d < RANK; ++d) { xc[d] = xn[d]; xn[d] = xnn[d]; }
+            ic = in;
+            in = inn;
         }
         __syncthreads();  // everyone is done with the tile and with *sbin
     }
@@ -332,13 +369,14 @@ __global__ void __launch_bounds__(256) mlip_bin_overflow(const __grid_constant__
     for (int i = threadIdx.x; i < lut_elems; i += blockDim.x) slut[i] = a.lut[i];
     __syncthreads();
     const int n = w.counters[0];
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+        const int i = w.oidx[j];
         double wt[RANK];
         bool nn = false;
         int64_t base = 0;
 #pragma unroll
         for (int d = 0; d < RANK; ++d) {
-            const double v = w.ox[(int64_t)i * RANK + d];
+            const double v = a.x[(int64_t)i * RANK + d];
             nn |= (v != v);
             double g0, g1;
             const int hi = cell_search(sgrid + a.goff[d], a.dims[d], slut + a.loff[d], a.nb[d], a.lscale[d], v, g0, g1);
@@ -346,24 +384,13 @@ __global__ void __launch_bounds__(256) mlip_bin_overflow(const __grid_constant__
             base += (int64_t)(hi - 1) * a.stride[d];
         }
         const double *vp = a.values + base;
-        w.ores[i] = corner_sum<RANK, LINEAR>(wt, a.blend, nn, [&](int corner) -> double {
+        a.out[i] = corner_sum<RANK, LINEAR>(wt, a.blend, nn, [&](int corner) -> double {
             int64_t off = 0;
 #pragma unroll
             for (int d = 0; d < RANK; ++d)
                 if ((corner >> d) & 1) off += a.stride[d];
             return __ldg(vp + off);
         });
-    }
-}
-
-// ------------------------------------------------------------------------------ 3. restore
-__global__ void __launch_bounds__(256) mlip_bin_restore(const BinWork w, int64_t npts, double *__restrict__ out)
-{
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < npts; i += stride) {
-        const int p = w.pos[i];
-        const double r = p >= 0 ? __ldg(w.res + p) : __ldg(w.ores + (-1 - p));
-        stg_stream_f64(out + i, r);
     }
 }
 
@@ -443,16 +470,17 @@ cudaError_t run_chunk(const MlipArgs &a, const BinGeom &gm, const BinWork &w, in
     int ge = 0, le = 0;
     for (int d = 0; d < RANK; ++d) { ge += a.dims[d]; le += a.nb[d]; }
     const int head = ge * 8 + le * 4;
-    cudaError_t e = cudaMemsetAsync(w.cursor, 0, sizeof(int) * (size_t)gm.nbins, s);
+    cudaError_t e = cudaMemsetAsync(w.cursor, 0, sizeof(int) * (size_t)gm.nbins * kCursorStride, s);
     if (e == cudaSuccess) e = cudaMemsetAsync(w.counters, 0, sizeof(int) * 2, s);
     if (e != cudaSuccess) return e;
     {
-        auto k = mlip_bin_scatter<RANK>;
+        constexpr int U = 4;
+        auto k = mlip_bin_scatter<RANK, U>;
         e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, head);
         if (e != cudaSuccess) return e;
-        int64_t nb = (a.npts + kScatterThreads - 1) / kScatterThreads;
+        int64_t nb = (a.npts + kScatterThreads * U - 1) / (kScatterThreads * U);
         if (nb > (int64_t)num_sms * 8) nb = (int64_t)num_sms * 8;
-        k<<<(int)nb, kScatterThreads, head, s>>>(a, gm, w, ge, le);
+        k<<<(int)nb, kScatterThreads, head, s>>>(a, gm, w, ge, le, (((uintptr_t)a.x) & 31) == 0 ? 1 : 0);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
     const int smem = ((16 + head + 127) & ~127) + gm.nslots * gm.low_elems * 8;
@@ -467,13 +495,7 @@ cudaError_t run_chunk(const MlipArgs &a, const BinGeom &gm, const BinWork &w, in
         k<<<num_sms * 4, 256, head, s>>>(a, w, ge, le);
     }
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
-    {
-        int64_t nb = (a.npts + 255) / 256;
-        if (nb > (int64_t)num_sms * 16) nb = (int64_t)num_sms * 16;
-        mlip_bin_restore<<<(int)nb, 256, 0, s>>>(w, a.npts, a.out);
-        if ((e = cudaGetLastError()) != cudaSuccess) return e;
-    }
-    *launches += 4;
+    *launches += 3;
     if (li) { li->grid = num_sms; li->block = kEvalThreads; li->smem = smem; li->kernel = K_MLIP_BIN; }
     return cudaSuccess;
 }
@@ -493,14 +515,14 @@ int64_t mlip_bin_chunk_points() { return int64_t(1) << 25; }
 
 // can this shape take the binned path for a batch of npts points, and is it worth it (enough points
 // per bin to pay for loading the bin's runs)?
-bool mlip_bin_supported(int rank, const int *dims, int64_t npts, int blend)
+bool mlip_bin_supported(int rank, const int *dims, int64_t npts, int blend, bool force)
 {
     if (blend < 0 || blend > 5) return false;
     BinGeom gm;
     const int64_t chunk = npts < mlip_bin_chunk_points() ? npts : mlip_bin_chunk_points();
     if (!bin_geometry(rank, dims, chunk, gm)) return false;
     const int64_t tile_bytes = (int64_t)gm.nslots * gm.low_elems * 8;
-    return chunk / gm.nbins * 64 >= tile_bytes;  // staging the runs costs at most 64 bytes per point
+    return force || chunk / gm.nbins * 64 >= tile_bytes;  // staging the runs costs at most 64 bytes per point
 }
 
 void mlip_bin_destroy(MlipBinState *st)
@@ -525,20 +547,17 @@ cudaError_t mlip_bin_prepare(MlipBinState **pst, int rank, const int *dims, int6
     const BinGeom &gm = st->gm;
     auto up = [](size_t b) { return (b + 255) & ~size_t(255); };
     const size_t slots = (size_t)gm.nbins * gm.cap;
-    const size_t b_bx = up(slots * rank * 8), b_res = up(slots * 8), b_pos = up((size_t)chunk * 4), b_cur = up((size_t)gm.nbins * 4),
-                 b_cnt = 256, b_ox = up((size_t)chunk * rank * 8), b_ores = up((size_t)chunk * 8);
-    st->bytes = b_bx + b_res + b_pos + b_cur + b_cnt + b_ox + b_ores;
+    const size_t b_bx = up(slots * rank * 8), b_bidx = up(slots * 4), b_cur = up((size_t)gm.nbins * 4 * kCursorStride), b_cnt = 256,
+                 b_oidx = up((size_t)chunk * 4);
+    st->bytes = b_bx + b_bidx + b_cur + b_cnt + b_oidx;
     cudaError_t e = cudaMalloc(&st->block, st->bytes);
     if (e != cudaSuccess) { delete st; return e; }
     unsigned char *p = static_cast<unsigned char *>(st->block);
     st->w.bx = reinterpret_cast<double *>(p); p += b_bx;
-    st->w.res = reinterpret_cast<double *>(p); p += b_res;
-    st->w.pos = reinterpret_cast<int *>(p); p += b_pos;
+    st->w.bidx = reinterpret_cast<int *>(p); p += b_bidx;
     st->w.cursor = reinterpret_cast<int *>(p); p += b_cur;
     st->w.counters = reinterpret_cast<int *>(p); p += b_cnt;
-    st->w.ox = reinterpret_cast<double *>(p); p += b_ox;
-    st->w.ores = reinterpret_cast<double *>(p);
-    st->w.ocap = (int)chunk;
+    st->w.oidx = reinterpret_cast<int *>(p);
     *pst = st;
     return cudaSuccess;
 }

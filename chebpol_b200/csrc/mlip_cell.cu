@@ -12,6 +12,13 @@
 // upper knot).  For D = 4 that is one aligned 128-byte line per cell (2.0 GB for 64^4), so
 // a point reads exactly its algorithmic bytes: D coordinates, one cell block, one result.
 //
+// When 2^D times the table does not fit (64^5: 275 GB), the expansion stops after the first m
+// dimensions: BRICKS of 2^m corner values, one per cell of dims < m and per GRID INDEX of dims >= m
+// (2^m x the memory; m = 3: 64-byte bricks, the DRAM access granularity; m = D: the cell-major table
+// above).  A point then reads 2^(D-m) bricks -- still only bytes it uses -- and because the corner
+// index has the upper dimensions in its high bits, the bricks land in the staging row in exactly the
+// cell-major order, so only the address of each 16-byte piece changes (a per-lane constant offset).
+//
 // Mapping: one thread per point for D <= 4 (a lane holds up to 16 corner values; for D = 5, 6
 // two or four adjacent lanes share a point and reduce by shuffle).  The kernel is bounded by
 // DRAM latency x points in flight, so per-point state is kept private to one thread (most
@@ -27,21 +34,23 @@ namespace {
 using mlip::blend_w;
 using mlip::cell_search;
 
-// ---- expansion: values (R layout) -> cell-major blocks -------------------------------
+// ---- expansion: values (R layout) -> bricks of 2^m corners -------------------------------
+// brick index = upper * nlow + lowcell:  lowcell over the cells of dims < m (dim 0 fastest), upper
+// over the GRID indices of dims >= m (dim m fastest)
 __global__ void __launch_bounds__(256) mlip_expand_kernel(const double *__restrict__ values, double *__restrict__ cells,
-                                                          const __grid_constant__ MlipArgs a, int64_t ncells)
+                                                          const __grid_constant__ MlipArgs a, int64_t nbricks, int m)
 {
     const int D = a.rank;
-    const int64_t total = ncells << D;
+    const int64_t total = nbricks << m;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int corner = (int)(i & ((1 << D) - 1));
-        int64_t cell = i >> D;
+        const int corner = (int)(i & ((1 << m) - 1));
+        int64_t rem = i >> m;
         int64_t pos = 0;
         for (int d = 0; d < D; ++d) {
-            const int nc = a.dims[d] - 1;
-            const int id = (int)(cell % nc);
-            cell /= nc;
-            pos += (int64_t)(id + ((corner >> d) & 1)) * a.stride[d];
+            const int n = d < m ? a.dims[d] - 1 : a.dims[d];
+            const int id = (int)(rem % n);
+            rem /= n;
+            pos += (int64_t)(id + (d < m ? ((corner >> d) & 1) : 0)) * a.stride[d];
         }
         cells[i] = __ldg(values + pos);
     }
@@ -79,7 +88,7 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // point's coordinates are prefetched in registers.
 template <int RANK, bool LINEAR>
 __global__ void __launch_bounds__(512) mlip_cell_kernel(const __grid_constant__ MlipArgs a, const double *__restrict__ cells,
-                                                        int grid_elems, int lut_elems, int S, int rowb)
+                                                        int grid_elems, int lut_elems, int S, int rowb, int m)
 {
     constexpr int NCORN = 1 << RANK;
     constexpr int CH = NCORN / 2;                  // 16-byte pieces per block (RANK >= 1)
@@ -101,6 +110,25 @@ __global__ void __launch_bounds__(512) mlip_cell_kernel(const __grid_constant__ 
     const int64_t niter = (a.npts + stride_pts - 1) / stride_pts;  // iterations that issue
     const int64_t total = niter + (S - 1);
     const int64_t pbase = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    // brick strides: dims < m count cells, dims >= m count grid indices; this lane's 16-byte piece
+    // (lane % CH) lies in brick (piece >> (m-1)) of the point, i.e. at upper-dimension corner bits b
+    int64_t bstr[RANK];
+    unsigned long long lane_off;
+    {
+        int64_t sacc = 1;
+#pragma unroll
+        for (int d = 0; d < RANK; ++d) {
+            bstr[d] = sacc;
+            sacc *= d < m ? a.dims[d] - 1 : a.dims[d];
+        }
+        const int piece = lane % CH;
+        const int b = m >= 1 ? piece >> (m - 1) : 0;
+        int64_t boff = 0;
+#pragma unroll
+        for (int d = 0; d < RANK; ++d)
+            if (d >= m && ((b >> (d - m)) & 1)) boff += bstr[d];
+        lane_off = ((unsigned long long)boff << (m + 3)) + 16ull * (unsigned)(piece & ((1 << (m - 1)) - 1));
+    }
 
     auto load_x = [&](int64_t p, double (&xv)[RANK]) {
         const bool ok = p < a.npts;
@@ -130,7 +158,7 @@ __global__ void __launch_bounds__(512) mlip_cell_kernel(const __grid_constant__ 
             load_x(p + stride_pts, xnext);
             unsigned char *st = wstage + (size_t)si * 32 * rowb;
             double *wrow = reinterpret_cast<double *>(st + (size_t)lane * rowb + NCORN * 8);
-            int64_t cell = 0, cs = 1;
+            int64_t cell = 0;
             bool nn = false;
 #pragma unroll
             for (int d = 0; d < RANK; ++d) {
@@ -139,17 +167,16 @@ __global__ void __launch_bounds__(512) mlip_cell_kernel(const __grid_constant__ 
                 double g0, g1;
                 const int hi = cell_search(sgrid + a.goff[d], a.dims[d], slut + a.loff[d], a.nb[d], a.lscale[d], v, g0, g1);
                 wrow[d] = (v - g0) / (g1 - g0);
-                cell += cs * (hi - 1);
-                cs *= a.dims[d] - 1;
+                cell += bstr[d] * (hi - 1);
             }
             if (nn) wrow[0] = __longlong_as_double(0x7ff8000000000000LL);  // NaN in -> NaN out, whatever the blend
             if (p >= a.npts) cell = 0;
-            const unsigned long long base = reinterpret_cast<unsigned long long>(cells) + ((unsigned long long)cell << (RANK + 3));
+            const unsigned long long base = reinterpret_cast<unsigned long long>(cells) + ((unsigned long long)cell << (m + 3));
 #pragma unroll
             for (int k = 0; k < CH; ++k) {
                 const int pt = lane / CH + PPI * k;  // the lane whose point this lane serves in round k
                 const unsigned long long b = __shfl_sync(full, base, pt);
-                cp_async16(st + (size_t)pt * rowb + 16 * (lane % CH), reinterpret_cast<const void *>(b + 16 * (lane % CH)));
+                cp_async16(st + (size_t)pt * rowb + 16 * (lane % CH), reinterpret_cast<const void *>(b + lane_off));
             }
 #pragma unroll
             for (int d = 0; d < RANK; ++d) xcur[d] = xnext[d];
@@ -233,13 +260,13 @@ int stage_row_bytes(int rank)
 }
 
 template <int RANK>
-cudaError_t launch_rank(const MlipArgs &a, const double *cells, int variant, int num_sms, cudaStream_t s, LaunchInfo *li)
+cudaError_t launch_rank(const MlipArgs &a, const double *cells, int m, int variant, int num_sms, cudaStream_t s, LaunchInfo *li)
 {
     int grid_elems = 0, lut_elems = 0;
     for (int d = 0; d < RANK; ++d) { grid_elems += a.dims[d]; lut_elems += a.nb[d]; }
     const int head_bytes = (grid_elems * 8 + lut_elems * 4 + 15) & ~15;
     const int rowb = stage_row_bytes(RANK);
-    if ((((uintptr_t)a.x) & 15) != 0 || !a.lut) return cudaErrorNotSupported;
+    if ((((uintptr_t)a.x) & 15) != 0 || !a.lut || m < 1 || m > RANK) return cudaErrorNotSupported;
     // layout: `warps` warps per CTA, S stages each; tuning code = warps*10 + S (0: default)
     int warps = 16, S = 2;
     if (variant >= 20) { warps = variant / 10; S = variant % 10; }
@@ -260,12 +287,12 @@ cudaError_t launch_rank(const MlipArgs &a, const double *cells, int variant, int
         auto k = mlip_cell_kernel<RANK, true>;
         e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
-        k<<<grid, block, smem, s>>>(a, cells, grid_elems, lut_elems, S, rowb);
+        k<<<grid, block, smem, s>>>(a, cells, grid_elems, lut_elems, S, rowb, m);
     } else {
         auto k = mlip_cell_kernel<RANK, false>;
         e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
-        k<<<grid, block, smem, s>>>(a, cells, grid_elems, lut_elems, S, rowb);
+        k<<<grid, block, smem, s>>>(a, cells, grid_elems, lut_elems, S, rowb, m);
     }
     if (li) { li->grid = grid; li->block = block; li->smem = smem; li->kernel = K_MLIP_CELL; }
     return cudaGetLastError();
@@ -273,39 +300,40 @@ cudaError_t launch_rank(const MlipArgs &a, const double *cells, int variant, int
 
 }  // namespace
 
-// bytes of the cell-major table, 0 if the shape is not supported
-int64_t mlip_cell_bytes(int rank, const int *dims)
+// bytes of the brick table with the first m dimensions expanded (m = rank: cell-major), 0 if the
+// shape is not supported
+int64_t mlip_cell_bytes(int rank, const int *dims, int m)
 {
-    if (rank < 1 || rank > 6) return 0;
-    int64_t cells = 1;
+    if (rank < 1 || rank > 6 || m < 1 || m > rank) return 0;
+    int64_t bricks = 1;
     for (int d = 0; d < rank; ++d) {
         if (dims[d] < 2) return 0;
-        cells *= dims[d] - 1;
-        if (cells > (int64_t(1) << 40)) return 0;
+        bricks *= d < m ? dims[d] - 1 : dims[d];
+        if (bricks > (int64_t(1) << 40)) return 0;
     }
-    return (cells << rank) * 8;
+    return (bricks << m) * 8;
 }
 
-cudaError_t mlip_expand(const MlipArgs &a, const double *values, double *cells, cudaStream_t s)
+cudaError_t mlip_expand(const MlipArgs &a, const double *values, double *cells, int m, cudaStream_t s)
 {
-    int64_t ncells = 1;
-    for (int d = 0; d < a.rank; ++d) ncells *= a.dims[d] - 1;
-    const int64_t total = ncells << a.rank;
+    int64_t nbricks = 1;
+    for (int d = 0; d < a.rank; ++d) nbricks *= d < m ? a.dims[d] - 1 : a.dims[d];
+    const int64_t total = nbricks << m;
     int64_t nb = (total + 255) / 256;
     if (nb > 148 * 32) nb = 148 * 32;
-    mlip_expand_kernel<<<(int)nb, 256, 0, s>>>(values, cells, a, ncells);
+    mlip_expand_kernel<<<(int)nb, 256, 0, s>>>(values, cells, a, nbricks, m);
     return cudaGetLastError();
 }
 
-cudaError_t launch_mlip_cell(const MlipArgs &a, const double *cells, int variant, int num_sms, cudaStream_t s, LaunchInfo *li)
+cudaError_t launch_mlip_cell(const MlipArgs &a, const double *cells, int m, int variant, int num_sms, cudaStream_t s, LaunchInfo *li)
 {
     switch (a.rank) {
-    case 1: return launch_rank<1>(a, cells, variant, num_sms, s, li);
-    case 2: return launch_rank<2>(a, cells, variant, num_sms, s, li);
-    case 3: return launch_rank<3>(a, cells, variant, num_sms, s, li);
-    case 4: return launch_rank<4>(a, cells, variant, num_sms, s, li);
-    case 5: return launch_rank<5>(a, cells, variant, num_sms, s, li);
-    case 6: return launch_rank<6>(a, cells, variant, num_sms, s, li);
+    case 1: return launch_rank<1>(a, cells, m, variant, num_sms, s, li);
+    case 2: return launch_rank<2>(a, cells, m, variant, num_sms, s, li);
+    case 3: return launch_rank<3>(a, cells, m, variant, num_sms, s, li);
+    case 4: return launch_rank<4>(a, cells, m, variant, num_sms, s, li);
+    case 5: return launch_rank<5>(a, cells, m, variant, num_sms, s, li);
+    case 6: return launch_rank<6>(a, cells, m, variant, num_sms, s, li);
     default: return cudaErrorNotSupported;
     }
 }

@@ -409,6 +409,116 @@ SEXP R_analyzesimplex_cuda(SEXP Sdtri, SEXP Sknots, SEXP Sthreads)
     return retlist;
 }
 
+/* ---- resident interpolants ------------------------------------------------------------------
+ * The stateless entries above re-receive the tensor on every call, as the reference does, and
+ * recognise it by content (one pass over its bytes per call: 3 ms for the 134 MB 64^4 table).
+ * A closure that is called many times on few points can instead keep the device copy alive:
+ *     plan <- .Call(C_plan_mlip_cuda, grid, values, blend, 0L)       # once, when the closure is made
+ *     function(x, threads, blend) .Call(C_plan_eval_cuda, plan, x, blendcode)
+ * The plan is an R external pointer; R's garbage collector destroys the device copy with the
+ * closure (finalizer), so no C-side state outlives the R object that owns it. */
+static void plan_finalizer(SEXP ptr)
+{
+    chebpol_cuda_plan *p = (chebpol_cuda_plan *)R_ExternalPtrAddr(ptr);
+    if (p) {
+        chebpol_cuda_plan_destroy(p);
+        R_ClearExternalPtr(ptr);
+    }
+}
+
+static SEXP wrap_plan(chebpol_cuda_plan *p, int rank)
+{
+    SEXP tag = PROTECT(NEW_INTEGER(1));
+    INTEGER(tag)[0] = rank;
+    SEXP ptr = PROTECT(R_MakeExternalPtr(p, tag, R_NilValue));
+    R_RegisterCFinalizerEx(ptr, plan_finalizer, TRUE);
+    UNPROTECT(2);
+    return ptr;
+}
+
+SEXP R_plan_cheb_cuda(SEXP coef, SEXP spare, SEXP Sdevice)
+{
+    SEXP dim = getAttrib(coef, R_DimSymbol);
+    const int rank = LENGTH(dim);
+    int siz = 1;
+    if (rank <= 0) error("rank must be positive");
+    for (int i = 0; i < rank; i++) siz *= INTEGER(dim)[i];
+    if (LENGTH(coef) != siz) error("coefficient length(%d) does not match data length(%d)", LENGTH(coef), siz);
+    SEXP smid = list_elt(spare, "mid"), sispan = list_elt(spare, "ispan"), sugm = list_elt(spare, "ugm");
+    const int have_map = !isNull(smid) && !isNull(sispan);
+    if (have_map && (LENGTH(smid) != rank || LENGTH(sispan) != rank)) error("mid/ispan must have one entry per dimension");
+    if (!isNull(sugm) && LENGTH(sugm) != rank) error("ugm must have one entry per dimension");
+    chebpol_cuda_plan *p = NULL;
+    raise(chebpol_cuda_plan_cheb(REAL(coef), INTEGER(dim), rank, have_map ? REAL(smid) : NULL, have_map ? REAL(sispan) : NULL,
+                                 isNull(sugm) ? NULL : INTEGER(sugm), INTEGER(AS_INTEGER(Sdevice))[0], &p));
+    return wrap_plan(p, rank);
+}
+
+SEXP R_plan_mlip_cuda(SEXP sgrid, SEXP values, SEXP Sblend, SEXP Sdevice)
+{
+    const int rank = LENGTH(sgrid);
+    int gridsize = 1;
+    if (!IS_NUMERIC(values)) error("values must be numeric");
+    if (rank <= 0 || rank > CHEBPOL_CUDA_MAXRANK) error("rank must be positive");
+    int dims[CHEBPOL_CUDA_MAXRANK];
+    const double *grid[CHEBPOL_CUDA_MAXRANK];
+    for (int i = 0; i < rank; i++) {
+        dims[i] = LENGTH(VECTOR_ELT(sgrid, i));
+        grid[i] = REAL(VECTOR_ELT(sgrid, i));
+        gridsize *= dims[i];
+    }
+    if (LENGTH(values) != gridsize) error("grid has size %d, you supplied %d values", gridsize, LENGTH(values));
+    chebpol_cuda_plan *p = NULL;
+    raise(chebpol_cuda_plan_mlip(grid, dims, rank, REAL(values), isNull(Sblend) ? 0 : INTEGER(AS_INTEGER(Sblend))[0],
+                                 INTEGER(AS_INTEGER(Sdevice))[0], &p));
+    return wrap_plan(p, rank);
+}
+
+SEXP R_plan_fh_cuda(SEXP vals, SEXP grid, SEXP Sweights, SEXP Sdevice)
+{
+    SEXP dim = getAttrib(vals, R_DimSymbol);
+    const int rank = LENGTH(dim);
+    int siz = 1;
+    if (rank <= 0 || rank > CHEBPOL_CUDA_MAXRANK) error("rank must be positive");
+    for (int i = 0; i < rank; i++) siz *= INTEGER(dim)[i];
+    if (LENGTH(vals) != siz) error("coefficient length(%d) does not match data length(%d)", LENGTH(vals), siz);
+    if (LENGTH(grid) != rank || LENGTH(Sweights) != rank) error("There must be one value for each knot");
+    const double *knots[CHEBPOL_CUDA_MAXRANK], *weights[CHEBPOL_CUDA_MAXRANK];
+    for (int i = 0; i < rank; i++) {
+        knots[i] = REAL(VECTOR_ELT(grid, i));
+        weights[i] = REAL(VECTOR_ELT(Sweights, i));
+    }
+    chebpol_cuda_plan *p = NULL;
+    raise(chebpol_cuda_plan_fh(REAL(vals), knots, weights, INTEGER(dim), rank, INTEGER(AS_INTEGER(Sdevice))[0], &p));
+    return wrap_plan(p, rank);
+}
+
+/* evaluate a resident interpolant: x is the K x P matrix (or length-K vector) the closure received;
+ * Sblend (multilinear plans; NULL keeps the plan's blend) is the per-call blend of R/multilinear.R:64-66 */
+SEXP R_plan_eval_cuda(SEXP plan, SEXP x, SEXP Sblend)
+{
+    chebpol_cuda_plan *p = (chebpol_cuda_plan *)R_ExternalPtrAddr(plan);
+    if (!p) error("the interpolant's device copy has been released (a closure restored by load() must be re-planned)");
+    if (!IS_NUMERIC(x)) error("argument x must be numeric");
+    int64_t rank = 0;
+    raise(chebpol_cuda_plan_get(p, CHEBPOL_CUDA_GET_RANK, &rank));
+    if (isMatrix(x) ? (nrows(x) != rank) : (LENGTH(x) != rank))
+        error("coefficient rank(%d) does not match argument length(%d)", (int)rank, isMatrix(x) ? nrows(x) : LENGTH(x));
+    if (!isNull(Sblend)) raise(chebpol_cuda_plan_set(p, CHEBPOL_CUDA_OPT_BLEND, INTEGER(AS_INTEGER(Sblend))[0]));
+    const R_xlen_t numvec = isMatrix(x) ? ncols(x) : 1;
+    SEXP resvec = PROTECT(NEW_NUMERIC(numvec));
+    const int rc = chebpol_cuda_plan_eval_host(p, REAL(x), (int64_t)numvec, REAL(resvec));
+    UNPROTECT(1);
+    raise(rc);
+    return resvec;
+}
+
+SEXP R_plan_free_cuda(SEXP plan)
+{
+    plan_finalizer(plan);
+    return R_NilValue;
+}
+
 /* rows to append to R_CallMethodDef callMethods[] (src/chebpol.c:943-967), same arities
  * as "evalcheb", "evalmlip", "FH" */
 const R_CallMethodDef chebpol_cuda_callMethods[] = {
@@ -423,4 +533,9 @@ const R_CallMethodDef chebpol_cuda_callMethods[] = {
     {"evalstalker_cuda", (DL_FUNC)&R_evalstalker_cuda, 5},
     {"evalsl_cuda", (DL_FUNC)&R_evalsl_cuda, 8},
     {"analyzesimplex_cuda", (DL_FUNC)&R_analyzesimplex_cuda, 3},
+    {"plan_cheb_cuda", (DL_FUNC)&R_plan_cheb_cuda, 3},
+    {"plan_mlip_cuda", (DL_FUNC)&R_plan_mlip_cuda, 4},
+    {"plan_fh_cuda", (DL_FUNC)&R_plan_fh_cuda, 4},
+    {"plan_eval_cuda", (DL_FUNC)&R_plan_eval_cuda, 3},
+    {"plan_free_cuda", (DL_FUNC)&R_plan_free_cuda, 1},
     {NULL, NULL, 0}};

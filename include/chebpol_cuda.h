@@ -149,6 +149,7 @@ CHEBPOL_CUDA_API int chebpol_cuda_plan_eval_host(chebpol_cuda_plan *plan, const 
 #define CHEBPOL_CUDA_GET_DEVICE 104
 #define CHEBPOL_CUDA_GET_SMEM_BYTES 105   /* dynamic smem of the most recent launch       */
 #define CHEBPOL_CUDA_GET_GRID 106         /* grid size of the most recent launch          */
+#define CHEBPOL_CUDA_GET_RANK 107         /* number of coordinates per point               */
 
 /* kernel selection.  AUTO picks the fastest kernel that supports the shape.
  * STRICT is the reference's operation order with no fused multiply-add:

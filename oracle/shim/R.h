@@ -58,6 +58,12 @@ SEXP VECTOR_ELT(SEXP, R_xlen_t);
 SEXP STRING_ELT(SEXP, R_xlen_t);
 const char *CHAR(SEXP);
 SEXP SET_VECTOR_ELT(SEXP, R_xlen_t, SEXP);
+/* external pointers (declarations only: used by the compile check of chebpol_b200/csrc/r_glue.c) */
+typedef void (*R_CFinalizer_t)(SEXP);
+SEXP R_MakeExternalPtr(void *p, SEXP tag, SEXP prot);
+void *R_ExternalPtrAddr(SEXP s);
+void R_ClearExternalPtr(SEXP s);
+void R_RegisterCFinalizerEx(SEXP s, R_CFinalizer_t fun, Rboolean onexit);
 void SET_STRING_ELT(SEXP, R_xlen_t, SEXP);
 SEXP Rf_mkChar(const char *);
 #define mkChar Rf_mkChar

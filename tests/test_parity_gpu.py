@@ -335,6 +335,31 @@ def test_mlip_binned_path_handles_clustered_and_ragged_batches(gpu_ok, port):
     plan.close()
 
 
+@pytest.mark.parametrize("dims,m", [((9, 8, 7, 6), 3), ((9, 8, 7, 6), 2), ((6, 5, 4, 5, 4), 3), ((6, 5, 4, 5, 4), 4), ((4, 3, 4, 3, 3, 3), 3),
+                                    ((7, 6, 5), 1), ((7, 6, 5), 2)])
+def test_mlip_bricks_partial_cell_major(gpu_ok, port, monkeypatch, dims, m):
+    """Bricks: only the first m dimensions expanded (2^m x the table instead of 2^D x), a point reads
+    2^(D-m) bricks.  Same kernel, same results as the full cell-major table."""
+    monkeypatch.setenv("CHEBPOL_CUDA_CELL_M", str(m))
+    grid, values = cases.mlip_case(dims, uniform=False)
+    x = cases.points(20_011, len(dims), lo=-1.2, hi=1.2)
+    x[:40, 0] = np.resize(grid[0], 40)
+    x[40:80, -1] = np.resize(grid[-1], 40)
+    plan = _lib.Plan.mlip(grid, values, 0)
+    b0 = plan.get(_lib.GET_TENSOR_BYTES)
+    got, k = eval_plan(plan, x, _lib.KERNEL_AUTO, _lib.VARIANT_MLIP_CELL)
+    assert k == "mlip_cell"
+    bricks = int(np.prod([n - 1 for n in dims[:m]]) * np.prod(dims[m:], dtype=np.int64))
+    assert plan.get(_lib.GET_TENSOR_BYTES) - b0 == bricks * 2 ** m * 8
+    assert_close(got, port.evalmlip(grid, values, x, threads=4), TOL_REL)
+    for blend in (1, 3, 4):
+        xi = cases.points(5000, len(dims), seed=blend)
+        plan.set(_lib.OPT_BLEND, blend)
+        gi, _ = eval_plan(plan, xi, _lib.KERNEL_AUTO, _lib.VARIANT_MLIP_CELL)
+        assert_close(gi, port.evalmlip(grid, values, xi, blend=blend, threads=4), TOL_REL)
+    plan.close()
+
+
 def test_mlip_golden_and_blend_names(gpu_ok):
     """chebpol-Ex.Rout.save:451-452: ml1(su) - exp(su)."""
     import math
