@@ -576,14 +576,6 @@ extern "C" int chebpol_cuda_plan_mlip(const double *const *grid, const int *dims
         }
     }
     p->quad_bytes = mlip_quad_bytes(rank, dims);
-    // A random gather wants the smallest DRAM fetch the L2 offers: with the default granularity every
-    // missed 16-byte pair costs 64 bytes of HBM traffic.  A hint, per device; streaming kernels do not care.
-    {
-        size_t gran = 32;
-        if (const char *env = getenv("CHEBPOL_CUDA_L2_FETCH")) gran = (size_t)atoi(env);
-        if (gran) (void)cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran);
-        (void)cudaGetLastError();
-    }
     *plan = p;
     return plan_ready(plan);
 }
@@ -1032,39 +1024,6 @@ static int launch_plan(chebpol_cuda_plan *p, const double *d_x, int64_t npts, do
             e = launch_cheb_strict(a, s, &li);
         }
     } else if (p->kind == PLAN_MLIP) {
-        // experiment switch: pin as much of the value table as the device allows in the persisting part of L2
-        static const int persist_mb = getenv("CHEBPOL_CUDA_MLIP_PERSIST_MB") ? atoi(getenv("CHEBPOL_CUDA_MLIP_PERSIST_MB")) : 0;
-        struct WindowGuard {
-            cudaStream_t s;
-            bool on = false;
-            ~WindowGuard()
-            {
-                if (!on) return;
-                cudaStreamAttrValue av;
-                memset(&av, 0, sizeof av);
-                cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &av);
-            }
-        } guard{s};
-        if (persist_mb > 0) {
-            int max_persist = 0, max_window = 0;
-            cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, p->device);
-            cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, p->device);
-            size_t want = (size_t)persist_mb << 20;
-            if (want > (size_t)max_persist) want = (size_t)max_persist;
-            cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
-            const double *tab = p->d_quads ? p->d_quads : p->d_tensor;
-            size_t bytes = p->d_quads ? (size_t)p->quad_bytes : (size_t)p->nelem * 8;
-            if (bytes > (size_t)max_window) bytes = (size_t)max_window;
-            cudaStreamAttrValue av;
-            memset(&av, 0, sizeof av);
-            av.accessPolicyWindow.base_ptr = const_cast<double *>(tab);
-            av.accessPolicyWindow.num_bytes = bytes;
-            av.accessPolicyWindow.hitRatio = bytes ? (float)((double)want / (double)bytes > 1.0 ? 1.0 : (double)want / (double)bytes) : 0.f;
-            av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-            av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-            if (cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &av) == cudaSuccess) guard.on = true;
-            (void)cudaGetLastError();
-        }
         MlipArgs a;
         a.values = p->d_tensor;
         a.grid = p->d_grid;

@@ -133,55 +133,6 @@ __device__ __forceinline__ void fh_basis(double *col, int n, double x, const dou
     }
 }
 
-// The same basis computed by the FOUR lanes of a quad for one point (warp-private prologue): lane t
-// takes the knots i = t, t+4, ...; the partial sums and the first knot hit are combined by shuffles
-// inside the quad.  Every lane of the warp must call it (full-mask shuffles); `live` is false for the
-// lanes of points beyond the batch, which then only write zeros.
-template <int NPT>
-__device__ __forceinline__ void fh_basis_quad(double *col, int n, double x, const double *__restrict__ kn,
-                                              const double *__restrict__ w, int t, bool live)
-{
-    int hit = n;
-    double den = 0.0;
-    if (live) {
-#pragma unroll 2
-        for (int i = t; i < n; i += 4) {
-            const double d = x - __ldg(kn + i);
-            const double p = __ldg(w + i) * fast_rcp(d);
-            col[(size_t)i * NPT] = p;
-            den += p;
-            hit = (fabs(d) < 10.0 * DBL_EPSILON && i < hit) ? i : hit;
-        }
-    }
-    den += __shfl_xor_sync(0xffffffffu, den, 1);
-    den += __shfl_xor_sync(0xffffffffu, den, 2);
-    hit = min(hit, __shfl_xor_sync(0xffffffffu, hit, 1));
-    hit = min(hit, __shfl_xor_sync(0xffffffffu, hit, 2));
-    if (!live) {
-        for (int i = t; i < n; i += 4) col[(size_t)i * NPT] = 0.0;
-        return;
-    }
-    if (hit < n || x != x) {
-        for (int i = t; i < n; i += 4) col[(size_t)i * NPT] = (i == hit) ? 1.0 : ((x != x) ? x : 0.0);
-        return;
-    }
-    const double r = 1.0 / den;
-    if (isfinite(r)) {
-#pragma unroll 2
-        for (int i = t; i < n; i += 4) col[(size_t)i * NPT] *= r;
-    } else if (t == 0) {
-        // the sum cancelled to zero or left the range (extreme extrapolation): one lane redoes it with
-        // IEEE divisions in the reference's order, so the result is finite exactly when the reference's is
-        double dsum = 0.0;
-        for (int j = 0; j < n; ++j) {
-            const double p = __ldg(w + j) / (x - __ldg(kn + j));
-            col[(size_t)j * NPT] = p;
-            dsum += p;
-        }
-        for (int j = 0; j < n; ++j) col[(size_t)j * NPT] /= dsum;
-    }
-}
-
 // KC: K/4 (padded); MT: 8-point tiles per warp; NW: warps; NTB: N-tiles (level-A indices) per step.
 template <int KC, int MT, int NW, int NTB>
 __global__ void __launch_bounds__(NW * 32, 1) contract_mma_kernel(const __grid_constant__ MmaArgs a)
@@ -229,27 +180,6 @@ __global__ void __launch_bounds__(NW * 32, 1) contract_mma_kernel(const __grid_c
     uint32_t round = 0;
     int64_t fill = 0;
 
-#ifdef MMA_WP
-    // Warp-private passes: a warp computes the basis vectors of ITS OWN MT*8 points (it is the only
-    // reader of those columns of Tb), so a pass needs no CTA-wide barrier and the warps drift apart:
-    // while one warp is in its prologue the other warps of its scheduler keep the FP64 pipe busy.
-    // The tensor ring is the only thing they share; it bounds the drift to ns - 1 slabs.
-    constexpr int kRankMax = 3 + kLevMax;
-    double xw[MT][kRankMax];
-    auto prefetch_xw = [&](int64_t tile) {
-#pragma unroll
-        for (int mt = 0; mt < MT; ++mt) {
-            const int64_t p = tile * NPT + (warp * MT + mt) * 8 + g;
-#pragma unroll
-            for (int L = 0; L < kRankMax; ++L) {
-                const bool mine = a.kind == 1 || (L & 3) == t;
-                xw[mt][L] = (L < rank && mine && tile < ntiles && p < a.npts) ? ldg_stream_f64(a.x + p * rank + L) : 0.0;
-            }
-        }
-    };
-    prefetch_xw(blockIdx.x);
-    __syncthreads();  // barrier initialisation and the ones row are visible
-#endif
     // coordinates of the next pass are fetched (into registers) while the current pass
     // computes, so the basis prologue never waits on DRAM
     constexpr int kMaxTasks = (NPT * (3 + kLevMax) + NT - 1) / NT;  // rank <= nfold(3) + kLevMax
@@ -263,37 +193,9 @@ __global__ void __launch_bounds__(NW * 32, 1) contract_mma_kernel(const __grid_c
             xpre[q] = (task < NPT * rank && tile < ntiles && p < a.npts) ? ldg_stream_f64(a.x + p * rank + L) : 0.0;
         }
     };
-#ifndef MMA_WP
     prefetch_x(blockIdx.x);
-#endif
 
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-#ifdef MMA_WP
-        __syncwarp();  // every lane has finished reading the previous pass's basis columns
-#pragma unroll
-        for (int mt = 0; mt < MT; ++mt) {
-            const int pt = (warp * MT + mt) * 8 + g;
-            const bool live = tile * NPT + pt < a.npts;
-            if (a.kind == 1) {
-#pragma unroll
-                for (int L = 0; L < kRankMax; ++L)
-                    if (L < rank)
-                        fh_basis_quad<NPT>(Tb + (size_t)a.boff[L] * NPT + pt, a.dims[L], xw[mt][L], a.grid + a.goff[L],
-                                           a.weights + a.goff[L], t, live);
-            } else {
-#pragma unroll
-                for (int L = 0; L < kRankMax; ++L)
-                    if (L < rank && (L & 3) == t) {
-                        double *col = Tb + (size_t)a.boff[L] * NPT + pt;
-                        if (live) cheb_basis<NPT>(col, a.dims[L], premap_coord(a.pm, L, xw[mt][L]));
-                        else
-                            for (int i = 0; i < a.dims[L]; ++i) col[(size_t)i * NPT] = 0.0;
-                    }
-            }
-        }
-        prefetch_xw(tile + gridDim.x);
-        __syncwarp();
-#else
         __syncthreads();  // previous pass has finished reading Tb (and, first time, barrier init is visible)
         // ---- 1. basis vectors of this pass's points
 #pragma unroll
@@ -318,7 +220,6 @@ __global__ void __launch_bounds__(NW * 32, 1) contract_mma_kernel(const __grid_c
         }
         prefetch_x(tile + gridDim.x);
         __syncthreads();
-#endif
 
         // ---- 2. A fragments: A[mt][kc] = prod_{l < nfold} Tb_l[digit_l(k)][point], k = 4*kc + t;
         //         the digit rows come from a host-built table (no integer division here)

@@ -13,8 +13,11 @@
 //     Q[((r*(n1-1) + i1)*n0 + i0)*2 + j] = V[i0, i1+j, r],          2*(n1-1)/n1 of the table,
 // so the four corners of a cell in dims (0,1) -- V[c0,c1], V[c0,c1+1], V[c0+1,c1], V[c0+1,c1+1] --
 // are 32 contiguous, 16-byte aligned bytes: a point reads 2^(D-2) quads instead of 2^(D-1) pairs,
-// half the wavefronts and (at the 32-byte sector granularity the plan asks the L2 for,
-// cudaLimitMaxL2FetchGranularity) 1.5 sectors per quad on average instead of 2.5 per two pairs.
+// half the L1 wavefronts and 1.25 sixty-four-byte DRAM bursts per 32 useful bytes instead of 2.25
+// per two pairs.  (B200's L2 fetches 64 bytes from HBM whatever cudaLimitMaxL2FetchGranularity says:
+// 32 / 64 / 128 measured identical, as did a persisting-L2 window on the table and CTAs per SM;
+// profiles/mlip_variants_r02.jsonl.)  Measured on the 64^4 table: 1.51e10 evaluations/s against
+// 1.14e10 for the pair gather, 5.2e9 against 2.7e9 on a 48^5 table (2 GB, far beyond L2 and TLB reach).
 //
 // Mapping: two adjacent lanes share a point; lane h loads the 16 bytes of dim-0 corner h of every
 // quad (one LDG.128 per quad and lane, both lanes of a point in the same line), computes the cell

@@ -1,9 +1,9 @@
 #!/usr/bin/env python
-"""Multilinear kernel variants on tables larger than L2: pair gather on the values as
-given, row-pair-interleaved quads (2x), cell-major (2^D x), each under the L2 fetch granularity given by
-CHEBPOL_CUDA_L2_FETCH (set before the plan is made).  One process per setting:
+"""Multilinear kernel variants on tables larger than L2: 1 pair gather on the values as
+given, 3 row-pair-interleaved quads (2x), 4 binned / cache-blocked path (1x + workspace), 2 bricks of 2^m corners
+(2^m x; CHEBPOL_CUDA_CELL_M pins m, m = rank is the cell-major table).  One process per setting:
 
-    CHEBPOL_CUDA_L2_FETCH=32 python tools/mlip_variants.py [--shape 64,64,64,64] [--points 5e7] [--variants 1,3,2]
+    CHEBPOL_CUDA_CELL_M=3 python tools/mlip_variants.py [--shape 64,64,64,64] [--points 5e7] [--variants 1,3,4,2]
 """
 import argparse
 import json
@@ -65,8 +65,8 @@ def main():
         print(json.dumps({"shape": dims, "points": npts, "variant": v, "kernel": plan.kernel_used, "ms": ms, "evals_per_s": rate,
                           "alg_GBs": rate * alg / 1e9, "frac_of_6450.9": rate * alg / 1e9 / 6450.9, "max_abs_err": err,
                           "table_MB": values.nbytes / 1e6, "plan_MB": plan.get(_lib.GET_TENSOR_BYTES) / 1e6,
-                          "l2_fetch": os.environ.get("CHEBPOL_CUDA_L2_FETCH", "32 (default)"),
-                          "persist_mb": os.environ.get("CHEBPOL_CUDA_MLIP_PERSIST_MB", "0")}), flush=True)
+                          "cell_m": os.environ.get("CHEBPOL_CUDA_CELL_M", "auto"),
+                          "cell_max_gb": os.environ.get("CHEBPOL_CUDA_CELL_MAX_GB", "16 (default)")}), flush=True)
     plan.close()
 
 
