@@ -549,7 +549,7 @@ extern "C" int chebpol_cuda_plan_mlip(const double *const *grid, const int *dims
         if (e != cudaSuccess) return bail(cuda_fail(e, "cudaMemcpy(lut)"));
     }
     // cell-major expansion (mlip_cell.cu) is built lazily, on the first evaluation large
-    // enough to amortise it; capped by CHEBPOL_CUDA_CELL_MAX_GB (default 16) and free memory
+    // enough to amortise it; capped by CHEBPOL_CUDA_CELL_MAX_GB (default: a quarter of the device) and free memory
     // The largest expansion that fits the cap: all rank dimensions (cell-major, 2^rank x the table),
     // else bricks over the first m >= 3 of them (2^m x; 64-byte bricks are the DRAM access
     // granularity, smaller ones waste half of every burst -- the 2 x quad table covers that end).
@@ -558,6 +558,11 @@ extern "C" int chebpol_cuda_plan_mlip(const double *const *grid, const int *dims
     for (int d = 0; d < rank; ++d) p->ncells *= dims[d] - 1;
     {
         double cap_gb = 16.0;
+        {
+            size_t free_b = 0, total_b = 0;  // default cap: a quarter of the device (45 GB on a B200)
+            if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) cap_gb = 0.25 * (double)total_b / 1e9;
+            (void)cudaGetLastError();
+        }
         if (const char *env = getenv("CHEBPOL_CUDA_CELL_MAX_GB")) cap_gb = atof(env);
         int m_lo = rank < 3 ? rank : 3, m_hi = rank;
         if (const char *env = getenv("CHEBPOL_CUDA_CELL_M")) {
@@ -1035,15 +1040,18 @@ static int launch_plan(chebpol_cuda_plan *p, const double *d_x, int64_t npts, do
         a.out = d_out;
         a.lut = p->d_lut;
         for (int i = 0; i < p->rank; ++i) { a.loff[i] = p->loff[i]; a.nb[i] = p->nbk[i]; a.lscale[i] = p->lscale[i]; }
-        // variant: 0 auto, 1 pair-gather kernel, 2 cell-major kernel (always expand), 3 quad kernel
-        // (always expand), 20..199 cell-major kernel with layout code warps*10 + stages,
+        // variant: 0 auto, 1 pair-gather kernel, 2 brick / cell-major kernel (always expand), 3 quad kernel
+        // (always expand), 4 binned path, 20..199 brick kernel with layout code warps*10 + stages,
         // 300+c quad kernel with c CTAs per SM.
-        // AUTO: the cell-major table (2^D x the values) when it fits and the batch has at least
-        // cells/8 points; else the row-pair-interleaved table (2 x) once a batch has at least
-        // half as many points as the table has values; else the pair gather on the values as given.
-        // 4: binned path (no extra table memory: the points are reordered so that a bin's sub-table
-        // is staged in shared memory); AUTO takes it, when the cell-major table is not available,
-        // for batches with enough points per bin to pay for the staging.
+        // AUTO climbs a ladder of table memory against speed (what decides is how many
+        // DRAM pages a point opens -- B200 serves about 4e10 random accesses a second whatever their
+        // size -- 1 for the cell-major table, 2^(D-m) for bricks, 2^(D-2) for quads, 2^(D-1) for pairs):
+        //   bricks over the first m dims, the largest 3 <= m <= D that fits the cap (m = D: cell-major),
+        //     once a batch has at least cells/8 points;
+        //   else the row-pair-interleaved quad table (2 x) once a batch has at least half as many
+        //     points as the table has values;
+        //   else, if even that cannot be allocated, the binned path (no extra table memory);
+        //   else the pair gather on the values as given.
         const bool want_quad = p->variant == 3 || (p->variant >= 300 && p->variant < 400);
         const bool want_bin = p->variant == 4;
         const bool allow_cell = p->variant == 0 || p->variant == 2 || (p->variant >= 20 && p->variant < 200);
@@ -1068,21 +1076,6 @@ static int launch_plan(chebpol_cuda_plan *p, const double *d_x, int64_t npts, do
             }
         }
         if (want_fast && allow_cell && p->d_cells) e = launch_mlip_cell(a, p->d_cells, p->cell_m, p->variant, p->num_sms, s, &li);
-        if (e == cudaErrorNotSupported && want_fast && (want_bin || p->variant == 0) && !p->bin_failed && aligned16 &&
-            (want_bin || p->nelem * 8 > (48ll << 20)) && mlip_bin_supported(p->rank, p->dims, npts, p->blend, want_bin)) {
-            cudaError_t ce = mlip_bin_prepare(&p->bin, p->rank, p->dims, npts);
-            if (ce == cudaSuccess) {
-                int nl = 0;
-                e = launch_mlip_bin(a, p->bin, p->num_sms, s, &li, &nl);
-                if (e == cudaSuccess && nl > 1) {
-                    p->launches += nl - 1;
-                    g_launches.fetch_add(nl - 1);
-                }
-            } else {
-                (void)cudaGetLastError();
-                if (ce != cudaErrorNotSupported) p->bin_failed = true;  // no room for the workspace
-            }
-        }
         if (e == cudaErrorNotSupported && want_fast && (want_quad || p->variant == 0) && p->quad_bytes > 0 && !p->quads_failed) {
             if (!p->d_quads && (want_quad || npts >= p->nelem / 2)) {
                 size_t free_b = 0, total_b = 0;
@@ -1104,6 +1097,21 @@ static int launch_plan(chebpol_cuda_plan *p, const double *d_x, int64_t npts, do
                 }
             }
             if (p->d_quads) e = launch_mlip_quad(a, p->d_quads, want_quad && p->variant >= 300 ? p->variant - 300 : 0, p->num_sms, s, &li);
+        }
+        if (e == cudaErrorNotSupported && want_fast && (want_bin || (p->variant == 0 && p->quads_failed)) && !p->bin_failed && aligned16 &&
+            (want_bin || p->nelem * 8 > (48ll << 20)) && mlip_bin_supported(p->rank, p->dims, npts, p->blend, want_bin)) {
+            cudaError_t ce = mlip_bin_prepare(&p->bin, p->rank, p->dims, npts);
+            if (ce == cudaSuccess) {
+                int nl = 0;
+                e = launch_mlip_bin(a, p->bin, p->num_sms, s, &li, &nl);
+                if (e == cudaSuccess && nl > 1) {
+                    p->launches += nl - 1;
+                    g_launches.fetch_add(nl - 1);
+                }
+            } else {
+                (void)cudaGetLastError();
+                if (ce != cudaErrorNotSupported) p->bin_failed = true;  // no room for the workspace
+            }
         }
         if (e == cudaErrorNotSupported && want_fast && p->variant < 2 && aligned16 && mlip_pair_supported(p->rank, p->blend))
             e = launch_mlip_pair(a, p->variant, p->num_sms, s, &li);
@@ -1509,7 +1517,7 @@ extern "C" int chebpol_cuda_plan_eval_host(chebpol_cuda_plan *p, const double *x
 // hits, and a modified tensor never does.  A hit is verified: entries up to 32 MB keep a host copy
 // of their defining arrays and the bytes are compared; larger ones rely on the 128-bit fingerprint
 // (collision probability ~2^-128 per pair, see hash128.h).  Per device at most 8 entries and
-// CHEBPOL_CUDA_CACHE_MAX_GB (default 16) of device memory, least recently used out first.
+// CHEBPOL_CUDA_CACHE_MAX_GB (default 64) of device memory, least recently used out first.
 // CHEBPOL_CUDA_PLAN_CACHE=0 disables the cache.
 #include "hash128.h"
 #include <memory>
@@ -1558,7 +1566,7 @@ static int64_t cache_budget_bytes()
 {
     static int64_t b = -1;
     if (b < 0) {
-        double gb = 16.0;
+        double gb = 64.0;  // per device; a multilinear plan with its expanded table can hold a quarter of a B200
         if (const char *e = getenv("CHEBPOL_CUDA_CACHE_MAX_GB")) gb = atof(e);
         b = gb > 0 ? (int64_t)(gb * 1e9) : 0;
     }

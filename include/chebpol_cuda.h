@@ -305,7 +305,7 @@ CHEBPOL_CUDA_API int chebpol_cuda_synth_points(uint64_t seed, int64_t first_poin
  * Returns TFLOP/s (2 flop/FMA). */
 CHEBPOL_CUDA_API int chebpol_cuda_fp64_peak(int device, int repeats, double *tflops);
 /* The stateless entry points keep interpolants resident between calls (per device up to 8
- * entries and CHEBPOL_CUDA_CACHE_MAX_GB, default 16, of device memory; least recently used out
+ * entries and CHEBPOL_CUDA_CACHE_MAX_GB, default 64, of device memory; least recently used out
  * first), so the closure that re-passes its tensor on every call (src/chebpol.c:340-381) does not
  * re-upload it, and a multilinear plan keeps its expanded cell table.  The key is the CONTENT:
  * kind, device, dims, byte count and a 128-bit fingerprint of every defining array (tensor,
