@@ -5,6 +5,7 @@
 #include "common.cuh"
 
 #include <atomic>
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -1401,6 +1402,11 @@ extern "C" int chebpol_cuda_plan_eval_host(chebpol_cuda_plan *p, const double *x
     int rc = ensure_pipeline(p, chunk);
     if (rc) { if (stg) staging_put(stg); return rc; }
     const int nthreads = p->host_threads > 0 ? p->host_threads : staging_threads();
+    // CHEBPOL_CUDA_TRACE=1: where the host thread of a staged call spends its time (stderr, one line per call)
+    static const bool trace = getenv("CHEBPOL_CUDA_TRACE") && atoi(getenv("CHEBPOL_CUDA_TRACE")) != 0;
+    double t_in = 0, t_out = 0, t_wait_buf = 0, t_wait_res = 0;
+    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_begin = trace ? now() : 0.0;
     if (stg) {
         // chunk c: threads fill in[b]; H2D -> kernel -> D2H into out[b]; chunk c-1 is drained to
         // the caller's buffer while chunk c runs on the GPU
@@ -1416,19 +1422,25 @@ extern "C" int chebpol_cuda_plan_eval_host(chebpol_cuda_plan *p, const double *x
         auto drain = [&](int64_t c) -> int {
             const int b = (int)(c & 1);
             const int64_t off = c * chunk, n = (off + chunk <= npts) ? chunk : npts - off;
+            const double t0 = trace ? now() : 0.0;
             cudaError_t e = cudaEventSynchronize(p->ev_out[b]);
             if (e != cudaSuccess) return cuda_fail(e, "D2H (staged)");
+            const double t1 = trace ? now() : 0.0;
             par_memcpy(out + off, stg->out[b], sizeof(double) * n, nthreads);
+            if (trace) { t_wait_res += t1 - t0; t_out += now() - t1; }
             return CHEBPOL_CUDA_OK;
         };
         for (int64_t c = 0; c < nch; ++c) {
             const int b = (int)(c & 1);
             const int64_t off = c * chunk, n = (off + chunk <= npts) ? chunk : npts - off;
+            const double t0 = trace ? now() : 0.0;
             if (c >= 2) {
                 cudaError_t e = cudaEventSynchronize(p->ev_in[b]);  // staging buffer b has been read
                 if (e != cudaSuccess) return bail(cuda_fail(e, "H2D (staged)"));
             }
+            const double t1 = trace ? now() : 0.0;
             par_memcpy(stg->in[b], x + off * p->rank, sizeof(double) * n * p->rank, nthreads);
+            if (trace) { t_wait_buf += t1 - t0; t_in += now() - t1; }
             cudaError_t e = cudaSuccess;
             if (c >= 2) e = cudaStreamWaitEvent(p->st_in, p->ev_k[b], 0);
             if (e == cudaSuccess) e = cudaMemcpyAsync(p->d_x[b], stg->in[b], sizeof(double) * n * p->rank, cudaMemcpyHostToDevice, p->st_in);
@@ -1449,6 +1461,12 @@ extern "C" int chebpol_cuda_plan_eval_host(chebpol_cuda_plan *p, const double *x
             }
         }
         rc = drain(nch - 1);
+        if (trace)
+            fprintf(stderr, "chebpol_cuda trace: device %d, %lld points in %lld chunks, %d host threads: total %.1f ms = copy-in %.1f (%.1f GB/s) + "
+                            "copy-out %.1f + wait for a free staging buffer %.1f + wait for results %.1f + enqueue/other %.1f\n",
+                    p->device, (long long)npts, (long long)nch, nthreads, 1e3 * (now() - t_begin), 1e3 * t_in,
+                    t_in > 0 ? npts * p->rank * 8.0 / t_in / 1e9 : 0.0, 1e3 * t_out, 1e3 * t_wait_buf, 1e3 * t_wait_res,
+                    1e3 * (now() - t_begin - t_in - t_out - t_wait_buf - t_wait_res));
         return bail(rc);
     }
     const int64_t nchunks = (npts + chunk - 1) / chunk;

@@ -2,7 +2,10 @@
 """Distil an .ncu-rep (captured on the GPU box, read here with `ncu -i`) into a small text
 summary for profiles/: key raw metrics, stall mix and the hottest SASS lines.
 
-    python tools/ncu_summary.py gpurun_out/prof.ncu-rep profiles/prof_r01.txt [units_per_launch]
+    python tools/ncu_summary.py gpurun_out/prof.ncu-rep profiles/prof_r01.txt [units_per_launch [launch_index]]
+
+launch_index picks one launch of a report that holds several (0 = the first); the output file is appended to
+when launch_index > 0, so a report of a multi-kernel path becomes one summary file.
 """
 import csv
 import io
@@ -32,8 +35,9 @@ def ncu_csv(rep, page):
 def main():
     rep, dst = sys.argv[1], sys.argv[2]
     units = float(sys.argv[3]) if len(sys.argv) > 3 else None
+    which = int(sys.argv[4]) if len(sys.argv) > 4 else 0
     raw = ncu_csv(rep, "raw")
-    hdr, unit, val = raw[0], raw[1], raw[2]
+    hdr, unit, val = raw[0], raw[1], raw[2 + which]
     m = {h: (v, u) for h, u, v in zip(hdr, unit, val)}
     lines = [f"# ncu summary of {rep.split('/')[-1]} (ncu --set full --clock-control none, one launch)",
              f"kernel: {m.get('Kernel Name', ('?',))[0]}", ""]
@@ -60,7 +64,11 @@ def main():
         lines += ["", f"units (points) in this launch: {units:.0f}",
                   f"DRAM traffic per launch: {tr:.4g} B = {tr / units:.1f} B/point"]
     src = ncu_csv(rep, "source")
-    shdr, data = src[1], src[2:]
+    starts = [i for i, r in enumerate(src) if r and r[0] == "Kernel Name"]
+    lo = starts[which] if which < len(starts) else 0
+    hi = starts[which + 1] if which + 1 < len(starts) else len(src)
+    src = src[lo:hi]
+    shdr, data = src[1], [r for r in src[2:] if len(r) > 10]
     ix = {h: i for i, h in enumerate(shdr)}
     tot = sum(int(r[ix["# Samples"]] or 0) for r in data)
     lines += ["", f"hottest SASS lines (of {tot} warp samples):"]
@@ -78,7 +86,7 @@ def main():
     lines += ["", "samples by opcode:"]
     for k, v in sorted(byop.items(), key=lambda kv: -kv[1])[:14]:
         lines.append(f"  {100.0 * v / max(tot, 1):5.2f}%  {k}")
-    open(dst, "w").write("\n".join(lines) + "\n")
+    open(dst, "a" if which > 0 else "w").write("\n".join(lines) + "\n\n")
     print("\n".join(lines[:40]))
 
 
