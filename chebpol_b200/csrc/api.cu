@@ -1671,8 +1671,10 @@ static void make_identity(Identity &id, int kind, const int *dims, int rank, uin
 }
 
 // does a cached entry hold exactly the interpolant of this call?
-static bool identity_matches(Identity &id, const CacheKey &ekey, const KeptBytes &ekept)
+static bool identity_matches(Identity &id, const CacheKey &ekey_in, const KeptBytes &ekept)
 {
+    CacheKey ekey = ekey_in;
+    ekey.device = id.key.device;  // the identity describes the interpolant; entries of every device are candidates
     if (!(ekey == id.key)) return false;
     if (!ekept) return true;  // fingerprint-only entry
     {
@@ -1895,19 +1897,28 @@ static int run_sharded(int rank, const double *x, int64_t npts, int ngpus, doubl
     if (per_dev_threads < 1) per_dev_threads = 1;
     if (per_dev_threads > 8) per_dev_threads = 8;
 
+    static const bool trace = getenv("CHEBPOL_CUDA_TRACE") && atoi(getenv("CHEBPOL_CUDA_TRACE")) != 0;
+    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_call = trace ? now() : 0.0;
     auto on_device = [&](int dev, const double *xs, int64_t n, double *os) -> int {
+        const double t0 = trace ? now() : 0.0;
         chebpol_cuda_plan *p = cacheable ? cache_take(id, dev) : nullptr;
         int r = CHEBPOL_CUDA_OK;
         if (!p) r = make_plan(dev, &p);
         if (!r && blend >= 0) p->blend = blend;  // per-call argument of the multilinear closure, not part of the key
         if (!r && epol >= 0) p->epol = epol;
         if (!r) p->host_threads = per_dev_threads;
+        const double t1 = trace ? now() : 0.0;
         if (!r && n > 0) r = chebpol_cuda_plan_eval_host(p, xs, n, os);
+        const double t2 = trace ? now() : 0.0;
         if (p) {
             if (cacheable && !r) cache_put(id, dev, p);
             else if (cacheable) cache_drop(p);  // failed: remove it from the cache if it came from there
             else chebpol_cuda_plan_destroy(p);
         }
+        if (trace)
+            fprintf(stderr, "chebpol_cuda trace: sharded call, device %d: thread started %.1f ms into the call, plan %.1f ms, evaluation %.1f ms, "
+                            "hand-back %.1f ms\n", dev, 1e3 * (t0 - t_call), 1e3 * (t1 - t0), 1e3 * (t2 - t1), 1e3 * (now() - t2));
         return r;
     };
 
@@ -1925,6 +1936,7 @@ static int run_sharded(int rank, const double *x, int64_t npts, int ngpus, doubl
         });
     }
     for (auto &t : th) t.join();
+    if (trace) fprintf(stderr, "chebpol_cuda trace: sharded call over %d devices took %.1f ms\n", ngpus, 1e3 * (now() - t_call));
     for (int g = 0; g < ngpus; ++g)
         if (rcs[g]) {
             g_last_error = "GPU " + std::to_string(g) + ": " + msgs[g];

@@ -1,6 +1,7 @@
 // contract_mma.cu -- configuration and dispatch of the DMMA contraction engine
 // (kernel: contract_mma.cuh; instantiations: contract_mma_inst*.cu).
 #include "common.cuh"
+#include <cstdlib>
 
 namespace {
 constexpr int kMaxStages = 8;
@@ -191,7 +192,9 @@ bool mma_fit_ring(MmaArgs &a, int npt)
     const int left = budget - kBarBytes - (a.sumn + 1) * npt * 8;
     if (left <= 0) return false;
     const int row_bytes = a.rs * 8;
-    int slab_cap = left / 3;
+    // tuning aid: CHEBPOL_CUDA_MMA_RINGDIV = how many slabs the ring space is divided into (default 3)
+    static const int ringdiv = [] { const char *e = getenv("CHEBPOL_CUDA_MMA_RINGDIV"); const int v = e ? atoi(e) : 3; return v >= 2 && v <= 8 ? v : 3; }();
+    int slab_cap = left / ringdiv;
     if (slab_cap > 64 * 1024) slab_cap = 64 * 1024;
     const int step_rows = 8 * a.ntb;
     int64_t rps = slab_cap / row_bytes / step_rows * step_rows;
