@@ -344,8 +344,7 @@ static int configure_mma(chebpol_cuda_plan *p, int kind, const double *host_tens
     MmaArgs &m = p->mma;
     m.pm = p->pm;
     // rows ordered (r'-tile of 8, level-A index, r' within the tile); zero rows pad level A to an
-    // even count and r' to a multiple of 8; the basis-table rows of r's group-level digits
-    // (int32) follow the coefficients of every row
+    // even count and r' to a multiple of 8
     const size_t rows = (size_t)m.nrows, rs = (size_t)m.rs, K = (size_t)m.K;
     std::vector<double> padded(rows * rs, 0.0);
     const int ng = m.nrows / (m.nAp * 8);
@@ -356,13 +355,6 @@ static int configure_mma(chebpol_cuda_plan *p, int kind, const double *host_tens
                 const int rp = 8 * g + u;
                 if (rp < m.nrp && ia < m.nA)
                     memcpy(&padded[dst * rs], host_tensor + ((size_t)ia + (size_t)m.nA * rp) * K, sizeof(double) * K);
-                int *info = reinterpret_cast<int *>(&padded[dst * rs + m.kp]);
-                size_t rem = rp < m.nrp ? (size_t)rp : 0;
-                for (int l = 0; l < m.nlg; ++l) {
-                    const int d = m.nfold + 1 + l;
-                    info[l] = m.boff[d] + (int)(rem % (size_t)m.dims[d]);
-                    rem /= (size_t)m.dims[d];
-                }
             }
     std::vector<int> ktab((size_t)m.kp * 3, -1);
     for (int k = 0; k < m.K; ++k) {
@@ -372,11 +364,24 @@ static int configure_mma(chebpol_cuda_plan *p, int kind, const double *host_tens
             rem /= m.dims[l];
         }
     }
+    // basis-table rows of the group-level digits of every r' (the ones row for absent levels and for the
+    // r' that pad the last tile): read once per group by close_group
+    const size_t ktab_ints = ktab.size();
+    ktab.resize(ktab_ints + (size_t)ng * 8 * 3, m.sumn);
+    for (int rp = 0; rp < m.nrp; ++rp) {
+        size_t rem = (size_t)rp;
+        for (int l = 0; l < m.nlg; ++l) {
+            const int d = m.nfold + 1 + l;
+            ktab[ktab_ints + (size_t)rp * 3 + l] = m.boff[d] + (int)(rem % (size_t)m.dims[d]);
+            rem /= (size_t)m.dims[d];
+        }
+    }
     cudaError_t ek = cudaMalloc(&p->d_ktab, sizeof(int) * ktab.size());
     if (ek != cudaSuccess) return cuda_fail(ek, "cudaMalloc(ktab)");
     ek = cudaMemcpy(p->d_ktab, ktab.data(), sizeof(int) * ktab.size(), cudaMemcpyHostToDevice);
     if (ek != cudaSuccess) return cuda_fail(ek, "cudaMemcpy(ktab)");
     m.ktab = p->d_ktab;
+    m.ginfo = p->d_ktab + ktab_ints;
     cudaError_t e = cudaMalloc(&p->d_mma, sizeof(double) * rows * rs);
     if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(mma tensor)");
     e = cudaMemcpy(p->d_mma, padded.data(), sizeof(double) * rows * rs, cudaMemcpyHostToDevice);

@@ -215,7 +215,7 @@ struct MmaArgs {
     int nfold;             // leading dims folded into K
     int K;                 // prod of folded dims
     int rs;                // row stride in doubles (== 4 or 12 mod 16: conflict-free B loads)
-    int kp;                // 4*KC: padded K; the row's group-level table rows (int32) start there
+    int kp;                // 4*KC: padded K
     int nlev;              // rank - nfold: unfolded dims
     int nA, nAp;           // size of level A (1 if absent) and its padding to a multiple of ntb
     int occ;               // CTAs per SM the ring is sized for (1 or 2)
@@ -225,6 +225,7 @@ struct MmaArgs {
     int nlg;               // group levels: max(nlev - 1, 0) <= 3
     int nrows;             // tensor rows: ceil(nrp/8) * nAp * 8 (a multiple of 8*ntb)
     const int *ktab;       // [kp][3] basis-table rows of the folded dims for each k (-1: padding)
+    const int *ginfo;      // [8*ceil(nrp/8)][3] basis-table rows of the group levels of each r' (ones row: absent / padding)
     int rows_per_slab;     // multiple of 8*ntb
     int nslabs, ns, stage_bytes, resident;
     const double *x;

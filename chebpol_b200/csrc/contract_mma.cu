@@ -262,7 +262,7 @@ bool mma_configure(MmaArgs &a, int kind, int rank, const int *dims, int *kc_out)
     const int64_t nrows = (nrp + 7) / 8 * a.nAp * 8;
     if (nrows >= (int64_t(1) << 31)) return false;
     a.nrows = (int)nrows;
-    int rs = a.kp + (a.nlg + 1) / 2;  // coefficients, then nlg int32 table rows
+    int rs = a.kp;  // coefficients only (the group-level table rows live in MmaArgs::ginfo)
     while (rs % 16 != 4 && rs % 16 != 12) ++rs;
     a.rs = rs;
     // some layout must fit

@@ -52,16 +52,6 @@ __device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double
                  : "d"(a), "d"(b));
 }
 
-// two independent DMMAs (the two N-tiles of a step) in one statement, so that their accumulator chains
-// are issued interleaved
-__device__ __forceinline__ void dmma884x2(double &d0, double &d1, double &e0, double &e1, double a, double b0, double b1)
-{
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%4}, {%5}, {%0,%1};\n\t"
-                 "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%2,%3}, {%4}, {%6}, {%2,%3};"
-                 : "+d"(d0), "+d"(d1), "+d"(e0), "+d"(e1)
-                 : "d"(a), "d"(b0), "d"(b1));
-}
-
 // ---- per-point, per-dimension basis vectors into shared memory -------------------
 // column layout: col[i*NPT] for i = 0..n-1
 template <int NPT>
@@ -264,10 +254,9 @@ __global__ void __launch_bounds__(NW * 32, 1) contract_mma_kernel(const __grid_c
         // a step's D tiles and what the epilogue needs to know about them
         struct Step {
             double D[NTB][MT][2];
-            int iA;          // level-A index of the first N-tile
-            bool end;        // the step closes its group
-            int info[2][3];  // basis-table rows of the group levels of this lane's two columns
-            bool valid[2];   // the columns exist (r' < nrp)
+            int iA;    // level-A index of the first N-tile
+            bool end;  // the step closes its group ...
+            int g8;    // ... which is this one (eight r' columns)
         };
         Step P0, P1;  // the step loop is unrolled by two: the roles (in flight / pending) alternate
 #pragma unroll
@@ -276,11 +265,7 @@ __global__ void __launch_bounds__(NW * 32, 1) contract_mma_kernel(const __grid_c
             for (int mt = 0; mt < MT; ++mt) P1.D[j][mt][0] = P1.D[j][mt][1] = 0.0;
         P1.iA = 0;
         P1.end = false;
-        P1.valid[0] = P1.valid[1] = false;
-#pragma unroll
-        for (int e = 0; e < 2; ++e)
-#pragma unroll
-            for (int l = 0; l < 3; ++l) P1.info[e][l] = a.sumn;
+        P1.g8 = 0;
         const double *tcol = Tb + warp * MT * 8 + g;
         const int nA1 = a.nA - 1;
 
@@ -304,54 +289,42 @@ __global__ void __launch_bounds__(NW * 32, 1) contract_mma_kernel(const __grid_c
         // weights go out together (absent levels read the ones row), so the exposed latency is one
         // shared-memory round trip and three dependent multiplies, not a chain per level.
         auto close_group = [&](const Step &P) {
+            // basis-table rows of the group levels of this lane's two columns (padding columns and absent
+            // levels name the ones row; the accumulated value of a padding column is zero: its tensor rows are)
+            const int *gi = a.ginfo + (size_t)(8 * P.g8 + 2 * t) * 3;
+            int info[2][3];
+#pragma unroll
+            for (int e = 0; e < 2; ++e)
+#pragma unroll
+                for (int l = 0; l < 3; ++l) info[e][l] = __ldg(gi + 3 * e + l);
             double w[2][MT][3];
 #pragma unroll
             for (int e = 0; e < 2; ++e)
 #pragma unroll
                 for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-                    for (int l = 0; l < 3; ++l) w[e][mt][l] = tcol[(size_t)P.info[e][l] * NPT + mt * 8];
+                    for (int l = 0; l < 3; ++l) w[e][mt][l] = tcol[(size_t)info[e][l] * NPT + mt * 8];
 #pragma unroll
             for (int e = 0; e < 2; ++e)
 #pragma unroll
                 for (int mt = 0; mt < MT; ++mt) {
                     const double ww = w[e][mt][0] * w[e][mt][1] * w[e][mt][2];
-                    acc[mt] = fma(P.valid[e] ? ww : 0.0, acc2[e][mt], acc[mt]);
+                    acc[mt] = fma(ww, acc2[e][mt], acc[mt]);
                     acc2[e][mt] = 0.0;
                 }
         };
 
         int sg = 0, g8 = 0;  // step within the group, group index
         // one step: issue the DMMAs of rows [r16, r16 + ROWS_STEP) into C while P is folded in
-#ifndef MMA_EXP
-#define MMA_EXP 0
-#endif
-        constexpr int PF = 2;  // MMA_EXP & 1: B fragments of the next step's first PF k-chunks are fetched in this step
-        double bq[NTB][PF];
-        auto load_first = [&](const double *slab, int r16) {
-            const double *bp = slab + (size_t)(r16 + g) * a.rs + t;
-#pragma unroll
-            for (int j = 0; j < NTB; ++j)
-#pragma unroll
-                for (int i = 0; i < PF; ++i) bq[j][i] = bp[(size_t)j * 8 * a.rs + 4 * i];
-        };
         auto step = [&](Step &C, const Step &P, const double *slab, int r16) {
 #pragma unroll
             for (int j = 0; j < NTB; ++j)
 #pragma unroll
                 for (int mt = 0; mt < MT; ++mt) C.D[j][mt][0] = C.D[j][mt][1] = 0.0;
             const double *bp = slab + (size_t)(r16 + g) * a.rs + t;
-            // bookkeeping: the group-level rows of this lane's columns ride at the end of the
-            // tensor rows of the first N-tile
             C.end = (sg == spg - 1);
             C.iA = NTB * sg;
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const int *info = reinterpret_cast<const int *>(slab + (size_t)(r16 + 2 * t + e) * a.rs + a.kp);
-                C.valid[e] = (8 * g8 + 2 * t + e) < a.nrp;
-#pragma unroll
-                for (int l = 0; l < 3; ++l) C.info[e][l] = (C.end && l < a.nlg) ? info[l] : a.sumn;
-            }
+            C.g8 = g8;
 #pragma unroll
             for (int kc = 0; kc < KC; ++kc) {
                 double b[NTB];
@@ -359,25 +332,12 @@ __global__ void __launch_bounds__(NW * 32, 1) contract_mma_kernel(const __grid_c
 #if defined(MMA_ABL) && (MMA_ABL & 4)
                 for (int j = 0; j < NTB; ++j) b[j] = bp[(size_t)j * 8 * a.rs];
 #else
-                for (int j = 0; j < NTB; ++j)
-                    b[j] = ((MMA_EXP & 1) && kc < PF && KC > 2 * PF) ? bq[j][kc < PF ? kc : 0] : bp[(size_t)j * 8 * a.rs + 4 * kc];
+                for (int j = 0; j < NTB; ++j) b[j] = bp[(size_t)j * 8 * a.rs + 4 * kc];
 #endif
 #pragma unroll
-                for (int mt = 0; mt < MT; ++mt) {
-                    if ((MMA_EXP & 2) && NTB == 2) {
-                        dmma884x2(C.D[0][mt][0], C.D[0][mt][1], C.D[1][mt][0], C.D[1][mt][1], A[mt][kc], b[0], b[NTB - 1]);
-                    } else {
+                for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-                        for (int j = 0; j < NTB; ++j) dmma884(C.D[j][mt][0], C.D[j][mt][1], A[mt][kc], b[j]);
-                    }
-                }
-                if ((MMA_EXP & 1) && KC > 2 * PF && kc >= KC - PF) {
-                    // the rows after this step's (the next step of the slab; past the slab's end the values are not used:
-                    // the ring is followed by the basis table, so the address is inside the shared-memory window)
-                    const int i = kc - (KC - PF);
-#pragma unroll
-                    for (int j = 0; j < NTB; ++j) bq[j][i < 0 ? 0 : i] = bp[(size_t)(j * 8 + ROWS_STEP) * a.rs + 4 * (i < 0 ? 0 : i)];
-                }
+                    for (int j = 0; j < NTB; ++j) dmma884(C.D[j][mt][0], C.D[j][mt][1], A[mt][kc], b[j]);
             }
 #if defined(MMA_ABL) && (MMA_ABL & 1)
 #pragma unroll
@@ -397,7 +357,6 @@ __global__ void __launch_bounds__(NW * 32, 1) contract_mma_kernel(const __grid_c
 
             // pending is P1 on entry and on exit
             int r16 = 0;
-            if (MMA_EXP & 1) load_first(slab, 0);
             for (; r16 + 2 * ROWS_STEP <= rows; r16 += 2 * ROWS_STEP) {
                 step(P0, P1, slab, r16);
                 step(P1, P0, slab, r16 + ROWS_STEP);

@@ -440,30 +440,6 @@ def test_fh_fast(gpu_ok, port, dims, kind, d):
     plan.close()
 
 
-@pytest.mark.parametrize("groups", [1, 2, 4])
-@pytest.mark.parametrize("basis,dims", [("cheb", (10,) * 5), ("cheb", (40, 40, 40)), ("cheb", (12, 12, 12, 3)), ("cheb", (6, 5, 4, 3, 2, 2)),
-                                        ("cheb", (40, 7)), ("cheb", (9, 9, 9, 9)), ("fh", (40, 40, 40)), ("fh", (12, 9)),
-                                        ("fh", (7, 6, 5, 6)), ("fh", (50, 30, 20))])
-def test_mma_staggered_warp_groups(gpu_ok, port, basis, dims, groups):
-    """The DMMA engine's warp groups begin their passes at different tensor rows (csrc/contract_mma.cuh):
-    every CTA gets several passes here so that head, steady state and tail of the stagger all run, the
-    batch is ragged (last pass partial), and the result must equal the strict kernel's to the fast bar
-    whether the geometry allows the requested number of groups or falls back to fewer."""
-    n = 148 * 128 * 5 + 77
-    x = cases.points(n, len(dims), seed=91)
-    if basis == "cheb":
-        plan = _lib.Plan.cheb(cases.cheb_fitted(dims))
-    else:
-        vals, grid, weights = cases.fh_case(dims, d=3)
-        plan = _lib.Plan.fh(vals, grid, weights)
-    want, ks = eval_plan(plan, x, _lib.KERNEL_STRICT)
-    got, k = eval_plan(plan, x, _lib.KERNEL_FAST, _lib.VARIANT_MMA + 1000000 * groups)
-    assert k in ("cheb_mma", "fh_mma") and ks.endswith("strict")
-    rel = np.abs(got - want).max() / np.abs(want).max()
-    assert rel <= TOL_REL, rel
-    plan.close()
-
-
 def test_fh_long_grid_falls_back_to_strict(gpu_ok, port):
     """dims[0] > 192 exceeds the folded K of the DMMA engine: AUTO must serve it with the strict kernel."""
     vals, grid, weights = cases.fh_case((200, 3), d=4)

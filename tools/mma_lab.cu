@@ -1,0 +1,154 @@
+// tools/mma_lab.cu -- the step loop of the DMMA contraction engine (csrc/contract_mma.cuh) in isolation:
+// B fragments from a shared-memory slab, A fragments in registers, two 8-row N-tiles per step, the
+// per-step fold (acc2 += bA * D) -- without the TMA ring, the per-pass prologue and the barriers.
+// Separates what the loop itself costs on the FP64 pipe from what the pass structure costs
+// (the FH 40^3 shape: KC = 10).
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/bin/mma_lab tools/mma_lab.cu
+#include <cstdio>
+#include <cstdlib>
+#include <cuda_runtime.h>
+
+__device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(d0), "+d"(d1)
+                 : "d"(a), "d"(b));
+}
+
+// EPI: 0 none (D summed into acc at the end of a step with one add), 1 the engine's fold (bA from shared
+// memory, 4 DFMA per step), 2 fold software-pipelined one step behind (as the engine does)
+// ILV: 0 source order kc-major (two chains alternate), 1 chain-major (all of N-tile 0, then N-tile 1)
+// SYNC: 0 none, 1 __syncwarp + lane-0 atomic + spin on a shared flag every SLAB_STEPS steps (the ring hand-shake)
+template <int KC, int NW, int EPI, int ILV, int SYNC, int KEEP = 0, int BREG = 0>
+__global__ void __launch_bounds__(NW * 32, 1) lab(double *sink, int passes, int steps_per_pass, int rs, int slab_steps, int nA)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    double *slab = reinterpret_cast<double *>(smem);            // [slab_steps*16][rs]
+    double *Tb = slab + (size_t)slab_steps * 16 * rs;           // [nA][NW*8]
+    int *cnt = reinterpret_cast<int *>(Tb + (size_t)nA * NW * 8);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+    for (int i = tid; i < slab_steps * 16 * rs; i += NW * 32) slab[i] = 1.0 / (1 + (i % 97));
+    for (int i = tid; i < nA * NW * 8; i += NW * 32) Tb[i] = 1.0 / (3 + (i % 31));
+    if (tid == 0) cnt[0] = 0;
+    __syncthreads();
+    double A[KC];
+#pragma unroll
+    for (int kc = 0; kc < KC; ++kc) A[kc] = 1.0 + 1e-3 * (kc + t) + 1e-4 * g;
+    const double *tcol = Tb + warp * 8 + g;
+    double total = 0.0;
+    for (int pass = 0; pass < passes; ++pass) {
+        double acc2[2] = {0.0, 0.0};
+        double PD[2][2] = {{0, 0}, {0, 0}};
+        int piA = 0;
+        int sstep = 0;
+        for (int s = 0; s < steps_per_pass; ++s) {
+            const int r16 = sstep * 16;
+            const double *bp = slab + (size_t)(r16 + g) * rs + t;
+            double D[2][2] = {{0, 0}, {0, 0}};
+            if (KEEP) { D[0][0] = PD[0][0]; D[0][1] = PD[0][1]; D[1][0] = PD[1][0]; D[1][1] = PD[1][1]; }
+            if (BREG) {
+                const double b0 = bp[0], b1 = bp[(size_t)8 * rs];
+#pragma unroll
+                for (int kc = 0; kc < KC; ++kc) {
+                    dmma884(D[0][0], D[0][1], A[kc], b0);
+                    dmma884(D[1][0], D[1][1], A[kc], b1);
+                }
+            } else if (ILV == 0) {
+#pragma unroll
+                for (int kc = 0; kc < KC; ++kc) {
+                    const double b0 = bp[4 * kc], b1 = bp[(size_t)8 * rs + 4 * kc];
+                    dmma884(D[0][0], D[0][1], A[kc], b0);
+                    dmma884(D[1][0], D[1][1], A[kc], b1);
+                }
+            } else {
+#pragma unroll
+                for (int kc = 0; kc < KC; ++kc) dmma884(D[0][0], D[0][1], A[kc], bp[4 * kc]);
+#pragma unroll
+                for (int kc = 0; kc < KC; ++kc) dmma884(D[1][0], D[1][1], A[kc], bp[(size_t)8 * rs + 4 * kc]);
+            }
+            const int iA = (2 * s) % nA;
+            if (KEEP) {
+                PD[0][0] = D[0][0]; PD[0][1] = D[0][1]; PD[1][0] = D[1][0]; PD[1][1] = D[1][1];
+            } else if (EPI == 0) {
+                acc2[0] += D[0][0] + D[1][0];
+                acc2[1] += D[0][1] + D[1][1];
+            } else if (EPI == 1) {
+                const double bA0 = tcol[(size_t)iA * NW * 8], bA1 = tcol[(size_t)(iA + 1) * NW * 8];
+                acc2[0] = fma(bA0, D[0][0], acc2[0]);
+                acc2[1] = fma(bA0, D[0][1], acc2[1]);
+                acc2[0] = fma(bA1, D[1][0], acc2[0]);
+                acc2[1] = fma(bA1, D[1][1], acc2[1]);
+            } else {
+                const double bA0 = tcol[(size_t)piA * NW * 8], bA1 = tcol[(size_t)(piA + 1) * NW * 8];
+                acc2[0] = fma(bA0, PD[0][0], acc2[0]);
+                acc2[1] = fma(bA0, PD[0][1], acc2[1]);
+                acc2[0] = fma(bA1, PD[1][0], acc2[0]);
+                acc2[1] = fma(bA1, PD[1][1], acc2[1]);
+                PD[0][0] = D[0][0]; PD[0][1] = D[0][1]; PD[1][0] = D[1][0]; PD[1][1] = D[1][1];
+                piA = iA;
+            }
+            if (++sstep == slab_steps) {
+                sstep = 0;
+                if (SYNC == 1) {
+                    __syncwarp();
+                    if (lane == 0) {
+                        __threadfence_block();
+                        atomicAdd(&cnt[0], 1);
+                    }
+                }
+            }
+        }
+        total += acc2[0] + acc2[1] + PD[0][0] + PD[1][1];
+    }
+    if (total == 1.2345e-300) sink[0] = total;
+}
+
+template <int KC, int NW, int EPI, int ILV, int SYNC, int KEEP = 0, int BREG = 0>
+void run(const char *name, double *sink, int slab_steps, int rs, double peak)
+{
+    const int passes = 40, steps = 100, nA = 40;
+    const size_t smem = (size_t)slab_steps * 16 * rs * 8 + (size_t)nA * NW * 8 * 8 + 64;
+    auto k = lab<KC, NW, EPI, ILV, SYNC, KEEP, BREG>;
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    k<<<148, NW * 32, smem>>>(sink, 4, steps, rs, slab_steps, nA);
+    cudaEventRecord(e0);
+    k<<<148, NW * 32, smem>>>(sink, passes, steps, rs, slab_steps, nA);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double flop = 148.0 * NW * passes * steps * 2 * KC * 2.0 * 8 * 8 * 4;
+    const double tf = flop / (ms * 1e-3) / 1e12;
+    printf("{\"variant\": \"%s\", \"KC\": %d, \"warps\": %d, \"epilogue\": %d, \"chain_major\": %d, \"slab_sync\": %d, \"slab_steps\": %d, \"ms\": %.4f, "
+           "\"dmma_TFLOPs\": %.2f, \"frac_of_peak\": %.4f, \"err\": \"%s\"}\n",
+           name, KC, NW, EPI, ILV, SYNC, slab_steps, ms, tf, tf / peak, cudaGetErrorString(cudaGetLastError()));
+    fflush(stdout);
+}
+
+int main(int argc, char **argv)
+{
+    const double peak = argc > 1 ? atof(argv[1]) : 37.1;
+    double *sink;
+    cudaMalloc(&sink, 8);
+    run<10, 16, 0, 0, 0>("skeleton, no epilogue", sink, 5, 44, peak);
+    run<10, 16, 0, 1, 0>("skeleton, chain-major source", sink, 5, 44, peak);
+    run<10, 16, 1, 0, 0>("fold in step", sink, 5, 44, peak);
+    run<10, 16, 2, 0, 0>("fold one step behind", sink, 5, 44, peak);
+    run<10, 16, 2, 0, 1>("fold behind + slab hand-shake", sink, 5, 44, peak);
+    run<10, 8, 2, 0, 0>("fold behind, 8 warps", sink, 5, 44, peak);
+    run<10, 12, 2, 0, 0>("fold behind, 12 warps", sink, 5, 44, peak);
+    run<25, 16, 0, 0, 0>("KC 25 skeleton", sink, 4, 108, peak);
+    run<25, 16, 2, 0, 0>("KC 25 fold behind", sink, 4, 108, peak);
+    run<10, 16, 0, 0, 0, 1, 0>("skeleton, accumulators carried across steps (no chain restart)", sink, 5, 44, peak);
+    run<10, 16, 0, 0, 0, 0, 1>("skeleton, B from registers (one LDS pair per step)", sink, 5, 44, peak);
+    run<10, 16, 0, 0, 0, 1, 1>("carried accumulators + B from registers", sink, 5, 44, peak);
+    run<5, 16, 0, 0, 0>("KC 5 skeleton", sink, 5, 28, peak);
+    run<20, 16, 0, 0, 0>("KC 20 skeleton", sink, 4, 84, peak);
+    run<40, 16, 0, 0, 0>("KC 40 skeleton", sink, 2, 164, peak);
+    run<10, 16, 0, 0, 0>("skeleton, row stride 41 (bank conflicts)", sink, 5, 41, peak);
+    run<10, 16, 0, 0, 0>("skeleton, row stride 52", sink, 5, 52, peak);
+    return 0;
+}
