@@ -353,8 +353,12 @@ static int configure_mma(chebpol_cuda_plan *p, int kind, const double *host_tens
             for (int u = 0; u < 8; ++u) {
                 const size_t dst = ((size_t)g * m.nAp + ia) * 8 + u;
                 const int rp = 8 * g + u;
-                if (rp < m.nrp && ia < m.nA)
-                    memcpy(&padded[dst * rs], host_tensor + ((size_t)ia + (size_t)m.nA * rp) * K, sizeof(double) * K);
+                if (rp < m.nrp && ia < m.nA) {
+                    const double *src = host_tensor + ((size_t)ia + (size_t)m.nA * rp) * K;
+                    if (!mma_pair_rows(kc)) memcpy(&padded[dst * rs], src, sizeof(double) * K);
+                    else
+                        for (size_t k = 0; k < K; ++k) padded[dst * rs + (size_t)mma_row_pos(kc, (int)k)] = src[k];
+                }
             }
     std::vector<int> ktab((size_t)m.kp * 3, -1);
     for (int k = 0; k < m.K; ++k) {

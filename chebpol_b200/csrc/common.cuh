@@ -236,6 +236,16 @@ struct MmaArgs {
     const double *weights;
     int goff[CP_MAXR];
 };
+// Rows of long K store the coefficients of two consecutive k-chunks pair-interleaved, so that one LDS.128
+// fetches a lane's B fragments of both (position of k = 4*kc + t: 8*(kc/2) + 2*t + kc%2; an odd last chunk
+// stays in place); the row stride is then 8 mod 16 doubles (conflict-free 128-bit loads).  Measured on the
+// step loop in isolation (tools/mma_lab.cu): KC = 25 0.948 -> 0.965 of the FP64 peak, KC = 10 0.928 -> 0.923.
+__host__ __device__ constexpr bool mma_pair_rows(int kc) { return kc >= 20; }
+__host__ __device__ constexpr int mma_row_pos(int kc_total, int k)
+{
+    const int kc = k / 4, t = k % 4;
+    return (mma_pair_rows(kc_total) && kc < (kc_total & ~1)) ? 8 * (kc / 2) + 2 * t + (kc & 1) : k;
+}
 bool mma_configure(MmaArgs &a, int kind, int rank, const int *dims, int *kc_out);
 cudaError_t launch_contract_mma(const MmaArgs &a, int variant, int num_sms, cudaStream_t s, LaunchInfo *li);
 

@@ -263,7 +263,8 @@ bool mma_configure(MmaArgs &a, int kind, int rank, const int *dims, int *kc_out)
     if (nrows >= (int64_t(1) << 31)) return false;
     a.nrows = (int)nrows;
     int rs = a.kp;  // coefficients only (the group-level table rows live in MmaArgs::ginfo)
-    while (rs % 16 != 4 && rs % 16 != 12) ++rs;
+    if (mma_pair_rows(kc)) while (rs % 16 != 8) ++rs;   // 128-bit B loads: two rows fill the 32 banks
+    else while (rs % 16 != 4 && rs % 16 != 12) ++rs;    // 64-bit B loads: eight rows x four k
     a.rs = rs;
     // some layout must fit
     for (const auto &i : kInsts) {

@@ -325,19 +325,46 @@ __global__ void __launch_bounds__(NW * 32, 1) contract_mma_kernel(const __grid_c
             C.end = (sg == spg - 1);
             C.iA = NTB * sg;
             C.g8 = g8;
+            if constexpr (mma_pair_rows(KC)) {
+                // pair-interleaved rows: one LDS.128 per N-tile holds this lane's B fragments of two k-chunks
+                const double *bq = slab + (size_t)(r16 + g) * a.rs + 2 * t;
 #pragma unroll
-            for (int kc = 0; kc < KC; ++kc) {
-                double b[NTB];
+                for (int kc = 0; kc + 1 < KC; kc += 2) {
+                    double2 b[NTB];
+#pragma unroll
+                    for (int j = 0; j < NTB; ++j) b[j] = *reinterpret_cast<const double2 *>(bq + (size_t)j * 8 * a.rs + 4 * kc);
+#pragma unroll
+                    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                        for (int j = 0; j < NTB; ++j) dmma884(C.D[j][mt][0], C.D[j][mt][1], A[mt][kc], b[j].x);
+#pragma unroll
+                    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                        for (int j = 0; j < NTB; ++j) dmma884(C.D[j][mt][0], C.D[j][mt][1], A[mt][kc + 1], b[j].y);
+                }
+                if constexpr (KC & 1) {
+#pragma unroll
+                    for (int j = 0; j < NTB; ++j) {
+                        const double b = bp[(size_t)j * 8 * a.rs + 4 * (KC - 1)];
+#pragma unroll
+                        for (int mt = 0; mt < MT; ++mt) dmma884(C.D[j][mt][0], C.D[j][mt][1], A[mt][KC - 1], b);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int kc = 0; kc < KC; ++kc) {
+                    double b[NTB];
 #pragma unroll
 #if defined(MMA_ABL) && (MMA_ABL & 4)
-                for (int j = 0; j < NTB; ++j) b[j] = bp[(size_t)j * 8 * a.rs];
+                    for (int j = 0; j < NTB; ++j) b[j] = bp[(size_t)j * 8 * a.rs];
 #else
-                for (int j = 0; j < NTB; ++j) b[j] = bp[(size_t)j * 8 * a.rs + 4 * kc];
+                    for (int j = 0; j < NTB; ++j) b[j] = bp[(size_t)j * 8 * a.rs + 4 * kc];
 #endif
 #pragma unroll
-                for (int mt = 0; mt < MT; ++mt)
+                    for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-                    for (int j = 0; j < NTB; ++j) dmma884(C.D[j][mt][0], C.D[j][mt][1], A[mt][kc], b[j]);
+                        for (int j = 0; j < NTB; ++j) dmma884(C.D[j][mt][0], C.D[j][mt][1], A[mt][kc], b[j]);
+                }
             }
 #if defined(MMA_ABL) && (MMA_ABL & 1)
 #pragma unroll

@@ -128,6 +128,116 @@ void run(const char *name, double *sink, int slab_steps, int rs, double peak)
     fflush(stdout);
 }
 
+
+// ---- second family: NTB N-tiles per step, fold one step behind, options:
+//   B128: B fragments of two consecutive k-chunks fetched by one LDS.128 (rows stored pair-interleaved)
+//   A128: the NTB(=2) level-A basis values of a step fetched by one LDS.128 (level-A table stored [point][iA])
+template <int KC, int NW, int NTB, int B128, int A128>
+__global__ void __launch_bounds__(NW * 32, 1) lab2(double *sink, int passes, int steps_per_pass, int rs, int slab_steps, int nA)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    double *slab = reinterpret_cast<double *>(smem);                  // [slab_steps*8*NTB][rs]
+    double *Tb = slab + (size_t)slab_steps * 8 * NTB * rs;            // [nA][NW*8] or [NW*8][nA+2]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+    for (int i = tid; i < slab_steps * 8 * NTB * rs; i += NW * 32) slab[i] = 1.0 / (1 + (i % 97));
+    for (int i = tid; i < (nA + 2) * NW * 8; i += NW * 32) Tb[i] = 1.0 / (3 + (i % 31));
+    __syncthreads();
+    double A[KC];
+#pragma unroll
+    for (int kc = 0; kc < KC; ++kc) A[kc] = 1.0 + 1e-3 * (kc + t) + 1e-4 * g;
+    const int pt = warp * 8 + g;
+    const double *tcol = A128 ? Tb + (size_t)pt * (nA + 2) : Tb + pt;
+    const size_t tstride = A128 ? 1 : (size_t)NW * 8;
+    double total = 0.0;
+    for (int pass = 0; pass < passes; ++pass) {
+        double acc2[2] = {0.0, 0.0};
+        double PD[NTB][2];
+#pragma unroll
+        for (int j = 0; j < NTB; ++j) PD[j][0] = PD[j][1] = 0.0;
+        int piA = 0, sstep = 0, iA = 0;
+        for (int s = 0; s < steps_per_pass; ++s) {
+            const double *bp = slab + (size_t)(sstep * 8 * NTB + g) * rs + (B128 ? 2 * t : t);
+            double D[NTB][2];
+#pragma unroll
+            for (int j = 0; j < NTB; ++j) D[j][0] = D[j][1] = 0.0;
+            if (B128) {
+#pragma unroll
+                for (int kc = 0; kc + 1 < KC; kc += 2) {
+                    double2 b[NTB];
+#pragma unroll
+                    for (int j = 0; j < NTB; ++j) b[j] = *reinterpret_cast<const double2 *>(bp + (size_t)j * 8 * rs + 4 * kc);
+#pragma unroll
+                    for (int j = 0; j < NTB; ++j) dmma884(D[j][0], D[j][1], A[kc], b[j].x);
+#pragma unroll
+                    for (int j = 0; j < NTB; ++j) dmma884(D[j][0], D[j][1], A[kc + 1], b[j].y);
+                }
+                if (KC & 1) {
+#pragma unroll
+                    for (int j = 0; j < NTB; ++j) dmma884(D[j][0], D[j][1], A[KC - 1], bp[(size_t)j * 8 * rs + 4 * (KC - 1)]);
+                }
+            } else {
+#pragma unroll
+                for (int kc = 0; kc < KC; ++kc) {
+                    double b[NTB];
+#pragma unroll
+                    for (int j = 0; j < NTB; ++j) b[j] = bp[(size_t)j * 8 * rs + 4 * kc];
+#pragma unroll
+                    for (int j = 0; j < NTB; ++j) dmma884(D[j][0], D[j][1], A[kc], b[j]);
+                }
+            }
+            // fold the previous step
+            double bA[NTB];
+            if (A128 && NTB == 2) {
+                const double2 v = *reinterpret_cast<const double2 *>(tcol + piA);
+                bA[0] = v.x;
+                bA[NTB - 1] = v.y;
+            } else {
+#pragma unroll
+                for (int j = 0; j < NTB; ++j) bA[j] = tcol[(size_t)(piA + j) * tstride];
+            }
+#pragma unroll
+            for (int j = 0; j < NTB; ++j) {
+                acc2[0] = fma(bA[j], PD[j][0], acc2[0]);
+                acc2[1] = fma(bA[j], PD[j][1], acc2[1]);
+                PD[j][0] = D[j][0];
+                PD[j][1] = D[j][1];
+            }
+            piA = iA;
+            iA += NTB;
+            if (iA + NTB > nA) iA = 0;
+            if (++sstep == slab_steps) sstep = 0;
+        }
+        total += acc2[0] + acc2[1] + PD[0][0] + PD[NTB - 1][1];
+    }
+    if (total == 1.2345e-300) sink[0] = total;
+}
+
+template <int KC, int NW, int NTB, int B128, int A128>
+void run2(const char *name, double *sink, int slab_steps, int rs, double peak)
+{
+    const int passes = 40, nA = 40;
+    const int steps = 200 / NTB;
+    const size_t smem = (size_t)slab_steps * 8 * NTB * rs * 8 + (size_t)(nA + 2) * NW * 8 * 8 + 64;
+    auto k = lab2<KC, NW, NTB, B128, A128>;
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    k<<<148, NW * 32, smem>>>(sink, 4, steps, rs, slab_steps, nA);
+    cudaEventRecord(e0);
+    k<<<148, NW * 32, smem>>>(sink, passes, steps, rs, slab_steps, nA);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double flop = 148.0 * NW * passes * steps * NTB * KC * 2.0 * 8 * 8 * 4;
+    const double tf = flop / (ms * 1e-3) / 1e12;
+    printf("{\"variant\": \"%s\", \"KC\": %d, \"warps\": %d, \"ntb\": %d, \"b128\": %d, \"a128\": %d, \"rs\": %d, \"ms\": %.4f, "
+           "\"dmma_TFLOPs\": %.2f, \"frac_of_peak\": %.4f, \"err\": \"%s\"}\n",
+           name, KC, NW, NTB, B128, A128, rs, ms, tf, tf / peak, cudaGetErrorString(cudaGetLastError()));
+    fflush(stdout);
+}
+
 int main(int argc, char **argv)
 {
     const double peak = argc > 1 ? atof(argv[1]) : 37.1;
@@ -150,5 +260,16 @@ int main(int argc, char **argv)
     run<40, 16, 0, 0, 0>("KC 40 skeleton", sink, 2, 164, peak);
     run<10, 16, 0, 0, 0>("skeleton, row stride 41 (bank conflicts)", sink, 5, 41, peak);
     run<10, 16, 0, 0, 0>("skeleton, row stride 52", sink, 5, 52, peak);
+    run2<10, 16, 2, 0, 0>("lab2 baseline: 2 N-tiles, LDS.64", sink, 5, 44, peak);
+    run2<10, 16, 2, 1, 0>("B by LDS.128, rs 40", sink, 5, 40, peak);
+    run2<10, 16, 2, 1, 0>("B by LDS.128, rs 44", sink, 5, 44, peak);
+    run2<10, 16, 2, 0, 1>("bA by LDS.128", sink, 5, 44, peak);
+    run2<10, 16, 2, 1, 1>("B and bA by LDS.128, rs 40", sink, 5, 40, peak);
+    run2<10, 16, 1, 0, 0>("1 N-tile per step", sink, 10, 44, peak);
+    run2<10, 16, 3, 0, 0>("3 N-tiles per step", sink, 3, 44, peak);
+    run2<10, 16, 4, 0, 0>("4 N-tiles per step", sink, 2, 44, peak);
+    run2<10, 16, 4, 1, 0>("4 N-tiles per step, B by LDS.128 rs 40", sink, 2, 40, peak);
+    run2<25, 16, 2, 0, 0>("KC 25 baseline", sink, 4, 100, peak);
+    run2<25, 16, 2, 1, 0>("KC 25 B by LDS.128 rs 104", sink, 4, 104, peak);
     return 0;
 }
