@@ -95,7 +95,8 @@ def load_traffic(kernel, cfg_id, npts):
     for name in TRAFFIC_FILES:
         try:
             with open(os.path.join(ROOT, "profiles", name)) as f:
-                t = json.load(f).get(kernel)
+                tab = json.load(f)
+            t = tab.get(f"{kernel}@{cfg_id}") or tab.get(kernel)
             if t and t.get("cfg") == cfg_id:
                 return t["bytes_per_point"] * npts, f"profiles/{name} (static: ncu dram__bytes per point of this kernel on this config x points per launch; not measured in this run)"
         except (OSError, ValueError):

@@ -269,6 +269,12 @@ int main(int argc, char **argv)
     run2<10, 16, 3, 0, 0>("3 N-tiles per step", sink, 3, 44, peak);
     run2<10, 16, 4, 0, 0>("4 N-tiles per step", sink, 2, 44, peak);
     run2<10, 16, 4, 1, 0>("4 N-tiles per step, B by LDS.128 rs 40", sink, 2, 40, peak);
+    run2<12, 16, 2, 0, 0>("KC 12 baseline", sink, 5, 52, peak);
+    run2<12, 16, 2, 1, 0>("KC 12 B by LDS.128 rs 56", sink, 5, 56, peak);
+    run2<16, 16, 2, 0, 0>("KC 16 baseline", sink, 4, 68, peak);
+    run2<16, 16, 2, 1, 0>("KC 16 B by LDS.128 rs 72", sink, 4, 72, peak);
+    run2<20, 16, 2, 0, 0>("KC 20 baseline", sink, 4, 84, peak);
+    run2<20, 16, 2, 1, 0>("KC 20 B by LDS.128 rs 88", sink, 4, 88, peak);
     run2<25, 16, 2, 0, 0>("KC 25 baseline", sink, 4, 100, peak);
     run2<25, 16, 2, 1, 0>("KC 25 B by LDS.128 rs 104", sink, 4, 104, peak);
     return 0;
