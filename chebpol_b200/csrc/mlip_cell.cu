@@ -74,6 +74,11 @@ __device__ __forceinline__ void cp_async16(void *dst_smem, const void *src)
 {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
 }
+// bricks of at most 64 bytes: ask for the 64-byte L2 fill (the default fills the 128-byte line from DRAM)
+__device__ __forceinline__ void cp_async16_fill64(void *dst_smem, const void *src)
+{
+    asm volatile("cp.async.cg.shared.global.L2::64B [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -176,7 +181,9 @@ __global__ void __launch_bounds__(512) mlip_cell_kernel(const __grid_constant__ 
             for (int k = 0; k < CH; ++k) {
                 const int pt = lane / CH + PPI * k;  // the lane whose point this lane serves in round k
                 const unsigned long long b = __shfl_sync(full, base, pt);
-                cp_async16(st + (size_t)pt * rowb + 16 * (lane % CH), reinterpret_cast<const void *>(b + lane_off));
+                void *dst = st + (size_t)pt * rowb + 16 * (lane % CH);
+                if (m <= 3) cp_async16_fill64(dst, reinterpret_cast<const void *>(b + lane_off));  // warp-uniform
+                else cp_async16(dst, reinterpret_cast<const void *>(b + lane_off));
             }
 #pragma unroll
             for (int d = 0; d < RANK; ++d) xcur[d] = xnext[d];
