@@ -1243,7 +1243,8 @@ struct Staging {
 };
 static std::vector<Staging *> g_staging_free;
 static std::mutex g_staging_mu;
-static const size_t kStageInBytes = 32u << 20;  // per input staging buffer
+static const size_t kStageInBytes = 32u << 20;   // per input staging buffer
+static const size_t kStageOutBytes = 16u << 20;  // per result staging buffer (rank 1 is limited by this one)
 
 static Staging *staging_get(size_t in_bytes, size_t out_bytes)
 {
@@ -1275,10 +1276,24 @@ static Staging *staging_get(size_t in_bytes, size_t out_bytes)
 
 static void staging_put(Staging *s)
 {
-    std::lock_guard<std::mutex> lk(g_staging_mu);
-    if (g_staging_free.size() < 8) { g_staging_free.push_back(s); return; }
-    for (int i = 0; i < 2; ++i) { cudaFreeHost(s->in[i]); cudaFreeHost(s->out[i]); }
-    delete s;
+    Staging *victim = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(g_staging_mu);
+        if (g_staging_free.size() < 8) { g_staging_free.push_back(s); return; }
+        // full: keep the larger buffers (a pool of sets that are too small for the next caller would make
+        // every call pin and unpin its own -- cudaHostAlloc costs tens of milliseconds)
+        size_t small = 0;
+        for (size_t i = 1; i < g_staging_free.size(); ++i)
+            if (g_staging_free[i]->in_bytes + g_staging_free[i]->out_bytes < g_staging_free[small]->in_bytes + g_staging_free[small]->out_bytes) small = i;
+        if (g_staging_free[small]->in_bytes + g_staging_free[small]->out_bytes < s->in_bytes + s->out_bytes) {
+            victim = g_staging_free[small];
+            g_staging_free[small] = s;
+        } else {
+            victim = s;
+        }
+    }
+    for (int i = 0; i < 2; ++i) { cudaFreeHost(victim->in[i]); cudaFreeHost(victim->out[i]); }
+    delete victim;
 }
 
 static int staging_threads()
@@ -1399,8 +1414,10 @@ extern "C" int chebpol_cuda_plan_eval_host(chebpol_cuda_plan *p, const double *x
     // large pageable batches: our own multi-threaded pinned staging (smaller chunks)
     Staging *stg = nullptr;
     if (chunk <= 0 && (size_t)npts * p->rank * 8 >= (16u << 20) && (is_pageable(x) || is_pageable(out))) {
-        const int64_t sc = (int64_t)(kStageInBytes / (8 * (size_t)p->rank));
-        stg = staging_get((size_t)sc * p->rank * 8, (size_t)sc * 8);
+        // every staging set has the same size, whatever the rank, so that any set serves any plan
+        int64_t sc = (int64_t)(kStageInBytes / (8 * (size_t)p->rank));
+        if (sc > (int64_t)(kStageOutBytes / 8)) sc = (int64_t)(kStageOutBytes / 8);
+        stg = staging_get(kStageInBytes, kStageOutBytes);
         if (stg) chunk = sc;
     }
     if (chunk <= 0) {
