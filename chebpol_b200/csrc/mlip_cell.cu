@@ -102,9 +102,17 @@ __global__ void __launch_bounds__(512) mlip_cell_kernel(const __grid_constant__ 
     constexpr int NLOW = 1 << LOWD;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *sgrid = reinterpret_cast<double *>(smem_raw);
-    int *slut = reinterpret_cast<int *>(smem_raw + (size_t)grid_elems * 8);
-    const int head_bytes = (grid_elems * 8 + lut_elems * 4 + 15) & ~15;
-    for (int i = threadIdx.x; i < grid_elems; i += blockDim.x) sgrid[i] = a.grid[i];
+    // 1 / (g[i] - g[i-1]) beside the knots: with linear blending the weight (x - g0) / (g1 - g0) becomes one
+    // multiply (<= 1.5 ulp from the quotient, the blend is continuous: far inside the fast kernels' 1e-12 bar);
+    // the other blends keep the division -- blend 4 is a step at w = 1/2, where one ulp decides the corner
+    double *srinv = sgrid + grid_elems;
+    int *slut = reinterpret_cast<int *>(smem_raw + (size_t)grid_elems * 16);
+    const int head_bytes = (grid_elems * 16 + lut_elems * 4 + 15) & ~15;
+    for (int i = threadIdx.x; i < grid_elems; i += blockDim.x) {
+        const double gi = a.grid[i];
+        sgrid[i] = gi;
+        srinv[i] = i > 0 ? 1.0 / (gi - a.grid[i - 1]) : 0.0;  // entries at the first knot of a dimension are never read
+    }
     for (int i = threadIdx.x; i < lut_elems; i += blockDim.x) slut[i] = a.lut[i];
     __syncthreads();
 
@@ -171,7 +179,8 @@ __global__ void __launch_bounds__(512) mlip_cell_kernel(const __grid_constant__ 
                 nn |= (v != v);
                 double g0, g1;
                 const int hi = cell_search(sgrid + a.goff[d], a.dims[d], slut + a.loff[d], a.nb[d], a.lscale[d], v, g0, g1);
-                wrow[d] = (v - g0) / (g1 - g0);
+                if constexpr (LINEAR) wrow[d] = v == g1 ? 1.0 : (v - g0) * srinv[a.goff[d] + hi];  // knots reproduce exactly
+                else wrow[d] = (v - g0) / (g1 - g0);
                 cell += bstr[d] * (hi - 1);
             }
             if (nn) wrow[0] = __longlong_as_double(0x7ff8000000000000LL);  // NaN in -> NaN out, whatever the blend
@@ -271,7 +280,7 @@ cudaError_t launch_rank(const MlipArgs &a, const double *cells, int m, int varia
 {
     int grid_elems = 0, lut_elems = 0;
     for (int d = 0; d < RANK; ++d) { grid_elems += a.dims[d]; lut_elems += a.nb[d]; }
-    const int head_bytes = (grid_elems * 8 + lut_elems * 4 + 15) & ~15;
+    const int head_bytes = (grid_elems * 16 + lut_elems * 4 + 15) & ~15;  // knots, reciprocal spacings, bucket tables
     const int rowb = stage_row_bytes(RANK);
     if ((((uintptr_t)a.x) & 15) != 0 || !a.lut || m < 1 || m > RANK) return cudaErrorNotSupported;
     // layout: `warps` warps per CTA, S stages each; tuning code = warps*10 + S (0: default)
