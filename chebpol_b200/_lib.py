@@ -23,6 +23,7 @@ _vp = C.c_void_p
 OPT_KERNEL, OPT_BLEND, OPT_CHUNK_POINTS, OPT_VARIANT = 1, 2, 3, 4
 OPT_EPOL, OPT_SL_CELLS = 5, 6
 GET_KERNEL_USED, GET_LAUNCHES, GET_TENSOR_BYTES, GET_DEVICE, GET_SMEM_BYTES, GET_GRID = 101, 102, 103, 104, 105, 106
+GET_RANK, GET_MMA_MACS = 107, 108
 KERNEL_AUTO, KERNEL_STRICT, KERNEL_FAST = 0, 1, 2
 VARIANT_AUTO, VARIANT_SLAB, VARIANT_MMA = 0, 1, 100000  # OPT_VARIANT families (csrc/api.cu: launch_plan)
 VARIANT_MLIP_PAIR, VARIANT_MLIP_CELL, VARIANT_MLIP_QUAD, VARIANT_MLIP_BIN = 1, 2, 3, 4

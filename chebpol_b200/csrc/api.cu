@@ -951,6 +951,9 @@ extern "C" int chebpol_cuda_plan_get(chebpol_cuda_plan *p, int what, int64_t *va
     case CHEBPOL_CUDA_GET_SMEM_BYTES: *value = p->last.smem; break;
     case CHEBPOL_CUDA_GET_GRID: *value = p->last.grid; break;
     case CHEBPOL_CUDA_GET_RANK: *value = p->rank; break;
+    case CHEBPOL_CUDA_GET_MMA_MACS:
+        *value = p->mma_ok ? (int64_t)p->mma.nrows * p->mma.kp + p->mma.nrows + (int64_t)(p->mma.nrows / (p->mma.nAp > 0 ? p->mma.nAp : 1)) : 0;
+        break;
     default: return fail(CHEBPOL_CUDA_EINVAL, "unknown query %d", what);
     }
     return CHEBPOL_CUDA_OK;

@@ -192,10 +192,15 @@ bool mma_fit_ring(MmaArgs &a, int npt)
     const int left = budget - kBarBytes - (a.sumn + 1) * npt * 8;
     if (left <= 0) return false;
     const int row_bytes = a.rs * 8;
-    // tuning aid: CHEBPOL_CUDA_MMA_RINGDIV = how many slabs the ring space is divided into (default 3)
-    static const int ringdiv = [] { const char *e = getenv("CHEBPOL_CUDA_MMA_RINGDIV"); const int v = e ? atoi(e) : 3; return v >= 2 && v <= 8 ? v : 3; }();
+    // Two large slabs (the ring space halved, at most 128 KB each) beat three smaller ones on every shape of
+    // tools/ring_sweep.py (profiles/ring_sweep_r02.jsonl: cfg2 0.954 -> 0.958, FH 40^3 0.840 -> 0.854,
+    // 12^6 0.998 -> 1.047 of the FP64 peak): fewer hand-shakes per pass, and a warp can run ahead of the
+    // slowest one by one slab only, which shortens the drain at the end of a pass.
+    // Tuning aids: CHEBPOL_CUDA_MMA_RINGDIV (2..8 parts), CHEBPOL_CUDA_MMA_SLAB_KB (8..200).
+    static const int ringdiv = [] { const char *e = getenv("CHEBPOL_CUDA_MMA_RINGDIV"); const int v = e ? atoi(e) : 2; return v >= 2 && v <= 8 ? v : 2; }();
     int slab_cap = left / ringdiv;
-    if (slab_cap > 64 * 1024) slab_cap = 64 * 1024;
+    static const int slab_max = [] { const char *e = getenv("CHEBPOL_CUDA_MMA_SLAB_KB"); const int v = e ? atoi(e) : 128; return (v >= 8 && v <= 200 ? v : 128) * 1024; }();
+    if (slab_cap > slab_max) slab_cap = slab_max;
     const int step_rows = 8 * a.ntb;
     int64_t rps = slab_cap / row_bytes / step_rows * step_rows;
     if (rps < step_rows) rps = step_rows;

@@ -150,6 +150,11 @@ CHEBPOL_CUDA_API int chebpol_cuda_plan_eval_host(chebpol_cuda_plan *plan, const 
 #define CHEBPOL_CUDA_GET_SMEM_BYTES 105   /* dynamic smem of the most recent launch       */
 #define CHEBPOL_CUDA_GET_GRID 106         /* grid size of the most recent launch          */
 #define CHEBPOL_CUDA_GET_RANK 107         /* number of coordinates per point               */
+#define CHEBPOL_CUDA_GET_MMA_MACS 108     /* multiply-adds per point the DMMA engine executes for this plan (tensor-core
+                                             MACs incl. padding, plus the per-row fold and per-column close); 0 if the
+                                             plan has no DMMA configuration.  The reference's Clenshaw count is
+                                             S = sum_k prod_{j>=k} n_j; the engine needs fewer when it folds two or more
+                                             dimensions into K, so an algorithmic roofline fraction can exceed 1 */
 
 /* kernel selection.  AUTO picks the fastest kernel that supports the shape.
  * STRICT is the reference's operation order with no fused multiply-add:
