@@ -108,6 +108,7 @@ struct chebpol_cuda_plan {
     int kernel_opt = CHEBPOL_CUDA_KERNEL_AUTO;
     int variant = 0;
     int64_t chunk_points = 0;
+    int64_t call_points = 0;  // points of the host call in progress (a chunk is launched on fewer): what the lazily built tables amortise over
     // slab configuration (Chebyshev DFMA fast path)
     bool slab_ok = false;
     SlabArgs slab;
@@ -1069,7 +1070,7 @@ static int launch_plan(chebpol_cuda_plan *p, const double *d_x, int64_t npts, do
         const bool want_bin = p->variant == 4;
         const bool allow_cell = p->variant == 0 || p->variant == 2 || (p->variant >= 20 && p->variant < 200);
         if (want_fast && allow_cell && p->cell_bytes > 0 && !p->d_cells && !p->cells_failed &&
-            (p->variant >= 2 || npts >= p->ncells / 8)) {
+            (p->variant >= 2 || (npts > p->call_points ? npts : p->call_points) >= p->ncells / 8)) {
             size_t free_b = 0, total_b = 0;
             cudaError_t ce = cudaMemGetInfo(&free_b, &total_b);
             if (ce == cudaSuccess && (size_t)p->cell_bytes < free_b / 2) ce = cudaMalloc(&p->d_cells, (size_t)p->cell_bytes);
@@ -1090,7 +1091,7 @@ static int launch_plan(chebpol_cuda_plan *p, const double *d_x, int64_t npts, do
         }
         if (want_fast && allow_cell && p->d_cells) e = launch_mlip_cell(a, p->d_cells, p->cell_m, p->variant, p->num_sms, s, &li);
         if (e == cudaErrorNotSupported && want_fast && (want_quad || p->variant == 0) && p->quad_bytes > 0 && !p->quads_failed) {
-            if (!p->d_quads && (want_quad || npts >= p->nelem / 2)) {
+            if (!p->d_quads && (want_quad || (npts > p->call_points ? npts : p->call_points) >= p->nelem / 2)) {
                 size_t free_b = 0, total_b = 0;
                 cudaError_t ce = cudaMemGetInfo(&free_b, &total_b);
                 if (ce == cudaSuccess && (size_t)p->quad_bytes < free_b / 2) ce = cudaMalloc(&p->d_quads, (size_t)p->quad_bytes);
@@ -1413,6 +1414,11 @@ extern "C" int chebpol_cuda_plan_eval_host(chebpol_cuda_plan *p, const double *x
     CU(cudaGetDevice(&cur));
     if (cur != p->device) CU(cudaSetDevice(p->device));
 
+    struct CallPoints {  // the whole call's size, visible to launch_plan while the chunks run
+        chebpol_cuda_plan *p;
+        CallPoints(chebpol_cuda_plan *q, int64_t n) : p(q) { p->call_points = n; }
+        ~CallPoints() { p->call_points = 0; }
+    } call_points(p, npts);
     int64_t chunk = p->chunk_points;
     // large pageable batches: our own multi-threaded pinned staging (smaller chunks)
     Staging *stg = nullptr;
@@ -1426,6 +1432,11 @@ extern "C" int chebpol_cuda_plan_eval_host(chebpol_cuda_plan *p, const double *x
     if (chunk <= 0) {
         chunk = (int64_t(128) << 20) / (8 * p->rank);
         if (chunk < (1 << 20)) chunk = 1 << 20;
+        // the first chunk's upload and the last chunk's download are not overlapped with anything: at least
+        // eight chunks (of at least 2^18 points) keep that below an eighth of the copy time
+        int64_t c8 = (npts + 7) / 8;
+        if (c8 < (1 << 18)) c8 = 1 << 18;
+        if (chunk > c8) chunk = c8;
     }
     if (chunk > npts) chunk = npts;
     int rc = ensure_pipeline(p, chunk);
