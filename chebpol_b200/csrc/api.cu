@@ -361,7 +361,7 @@ static int configure_mma(chebpol_cuda_plan *p, int kind, const double *host_tens
                         for (size_t k = 0; k < K; ++k) padded[dst * rs + (size_t)mma_row_pos(kc, (int)k)] = src[k];
                 }
             }
-    std::vector<int> ktab((size_t)m.kp * 3, -1);
+    std::vector<int> ktab((size_t)m.kp * 3, m.sumn);  // padding k and absent folded dims name the ones row (the padded coefficients are zero)
     for (int k = 0; k < m.K; ++k) {
         int rem = k;
         for (int l = 0; l < m.nfold; ++l) {

@@ -224,8 +224,10 @@ struct MmaArgs {
     int nrp;               // number of r' values (prod of the dims after level A; 1 if none)
     int nlg;               // group levels: max(nlev - 1, 0) <= 3
     int nrows;             // tensor rows: ceil(nrp/8) * nAp * 8 (a multiple of 8*ntb)
-    const int *ktab;       // [kp][3] basis-table rows of the folded dims for each k (-1: padding)
+    const int *ktab;       // [kp][3] basis-table rows of the folded dims for each k (the ones row: padding k, absent dims)
     const int *ginfo;      // [8*ceil(nrp/8)][3] basis-table rows of the group levels of each r' (ones row: absent / padding)
+    int fh_local, gi_local; // set by the launcher: FH knots + weights / the ginfo table are copied to shared memory (they fit
+                           // the few KB beside the ring budget); otherwise they are read from global memory
     int rows_per_slab;     // multiple of 8*ntb
     int nslabs, ns, stage_bytes, resident;
     const double *x;

@@ -37,6 +37,18 @@
 #include "common.cuh"
 #include "ptx.cuh"
 #include <float.h>
+#include <cstdio>
+
+#ifdef MMA_TIMING
+// debug build only (-DMMA_TIMING): clock64() of CTA 0's warps at the phases of their first passes,
+// [pass < 16][warp < 16][stamp < 8]: 0 pass begin (before barrier 1), 1 after barrier 1, 2 basis done (before
+// barrier 2), 3 after barrier 2, 4 A fragments built, 5 first slab arrived, 6 last step issued, 7 pass stored.
+// (ptxas hoists the clock reads that follow a barrier above it: "after barrier" stamps read as "arrived at".)
+static __device__ long long g_mma_timing[16 * 16 * 8];
+#define MMA_STAMP(k) do { if (blockIdx.x == 0 && lane == 0 && tpass < 16 && warp < 16) g_mma_timing[(tpass * 16 + warp) * 8 + (k)] = clock64(); } while (0)
+#else
+#define MMA_STAMP(k) do { } while (0)
+#endif
 
 namespace mma_detail {
 
@@ -95,8 +107,8 @@ __device__ __forceinline__ void fh_basis(double *col, int n, double x, const dou
     int i = 0;
 #pragma unroll 2
     for (; i + 1 < n; i += 2) {
-        const double d0 = x - __ldg(kn + i), d1 = x - __ldg(kn + i + 1);
-        const double p0 = __ldg(w + i) * fast_rcp(d0), p1 = __ldg(w + i + 1) * fast_rcp(d1);
+        const double d0 = x - kn[i], d1 = x - kn[i + 1];
+        const double p0 = w[i] * fast_rcp(d0), p1 = w[i + 1] * fast_rcp(d1);
         col[(size_t)i * NPT] = p0;
         col[(size_t)(i + 1) * NPT] = p1;
         den0 += p0;
@@ -105,8 +117,8 @@ __device__ __forceinline__ void fh_basis(double *col, int n, double x, const dou
         hit = (fabs(d0) < 10.0 * DBL_EPSILON && i < hit) ? i : hit;
     }
     if (i < n) {
-        const double d0 = x - __ldg(kn + i);
-        const double p0 = __ldg(w + i) * fast_rcp(d0);
+        const double d0 = x - kn[i];
+        const double p0 = w[i] * fast_rcp(d0);
         col[(size_t)i * NPT] = p0;
         den0 += p0;
         hit = (fabs(d0) < 10.0 * DBL_EPSILON && i < hit) ? i : hit;
@@ -125,7 +137,7 @@ __device__ __forceinline__ void fh_basis(double *col, int n, double x, const dou
         // divisions in the reference's order, so the result is finite exactly when the reference's is
         double dsum = 0.0;
         for (int j = 0; j < n; ++j) {
-            const double p = __ldg(w + j) / (x - __ldg(kn + j));
+            const double p = w[j] / (x - kn[j]);
             col[(size_t)j * NPT] = p;
             dsum += p;
         }
@@ -144,6 +156,16 @@ __global__ void __launch_bounds__(NW * 32, 1) contract_mma_kernel(const __grid_c
     int *done_cnt = reinterpret_cast<int *>(smem + kMaxStages * 8);
     unsigned char *ring = smem + kBarBytes;
     double *Tb = reinterpret_cast<double *>(ring + (size_t)a.ns * a.stage_bytes);
+    // Small tables copied to shared memory once (read from global memory they cost an L2 round trip each at
+    // every pass, all warps at the same time): the digit rows of the folded dims for each k; the
+    // Floater-Hormann knots and weights and the group-level table when the launcher found room for them.
+    int *sktab = reinterpret_cast<int *>(Tb + (size_t)(a.sumn + 1) * NPT);
+    double *sknots = reinterpret_cast<double *>(sktab + 4 * KC * 3);
+    const bool fh_local = a.fh_local != 0;
+    const double *fh_grid = fh_local ? sknots : a.grid, *fh_w = fh_local ? sknots + a.sumn : a.weights;
+    int *sginfo = reinterpret_cast<int *>(sknots + (fh_local ? 2 * a.sumn : 0));
+    const int ngi = (a.nrp + 7) / 8 * 8 * 3;
+    const int *ginfo = a.gi_local ? sginfo : a.ginfo;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
@@ -175,6 +197,11 @@ __global__ void __launch_bounds__(NW * 32, 1) contract_mma_kernel(const __grid_c
     }
     // the ones row of the basis table (absent levels)
     for (int i = tid; i < NPT; i += NT) Tb[(size_t)a.sumn * NPT + i] = 1.0;
+    for (int i = tid; i < 4 * KC * 3; i += NT) sktab[i] = a.ktab[i];
+    if (fh_local)
+        for (int i = tid; i < a.sumn; i += NT) { sknots[i] = a.grid[i]; sknots[a.sumn + i] = a.weights[i]; }
+    if (a.gi_local)
+        for (int i = tid; i < ngi; i += NT) sginfo[i] = a.ginfo[i];
 
     int stage = 0;
     uint32_t round = 0;
@@ -195,8 +222,16 @@ __global__ void __launch_bounds__(NW * 32, 1) contract_mma_kernel(const __grid_c
     };
     prefetch_x(blockIdx.x);
 
+#ifdef MMA_TIMING
+    int tpass = -1;
+#endif
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+#ifdef MMA_TIMING
+        ++tpass;
+#endif
+        MMA_STAMP(0);
         __syncthreads();  // previous pass has finished reading Tb (and, first time, barrier init is visible)
+        MMA_STAMP(1);
         // ---- 1. basis vectors of this pass's points
 #pragma unroll
         for (int q = 0; q < kMaxTasks; ++q) {
@@ -213,31 +248,48 @@ __global__ void __launch_bounds__(NW * 32, 1) contract_mma_kernel(const __grid_c
 #endif
                 const double xv = xpre[q];
                 if (a.kind == 0) cheb_basis<NPT>(col, n, premap_coord(a.pm, L, xv));
-                else fh_basis<NPT>(col, n, xv, a.grid + a.goff[L], a.weights + a.goff[L]);
+                else fh_basis<NPT>(col, n, xv, fh_grid + a.goff[L], fh_w + a.goff[L]);
             } else {
                 for (int i = 0; i < n; ++i) col[(size_t)i * NPT] = 0.0;
             }
         }
         prefetch_x(tile + gridDim.x);
+        MMA_STAMP(2);
         __syncthreads();
+        MMA_STAMP(3);
 
         // ---- 2. A fragments: A[mt][kc] = prod_{l < nfold} Tb_l[digit_l(k)][point], k = 4*kc + t;
         //         the digit rows come from a host-built table (no integer division here)
         double A[MT][KC];
+        // (straight-line per number of folded dims, padding k and absent dims naming the ones row: every load of
+        //  the pass's A fragments is in flight at once; the branchy per-k form with the digit rows in global memory
+        //  took 6.3 k cycles of a 238 k-cycle pass on cfg2, all warps at the same time)
+        {
+            const double *tb = Tb + warp * MT * 8 + g;
+            if (a.nfold == 1) {
 #pragma unroll
-        for (int kc = 0; kc < KC; ++kc) {
-            const int *kt = a.ktab + (4 * kc + t) * 3;
-            const int r0 = __ldg(kt), r1 = __ldg(kt + 1), r2 = __ldg(kt + 2);
+                for (int kc = 0; kc < KC; ++kc) {
+                    const int r0 = sktab[(4 * kc + t) * 3];
 #pragma unroll
-            for (int mt = 0; mt < MT; ++mt) {
-                const int pt = (warp * MT + mt) * 8 + g;
-                double v = 0.0;
-                if (r0 >= 0) {
-                    v = Tb[(size_t)r0 * NPT + pt];
-                    if (r1 >= 0) v *= Tb[(size_t)r1 * NPT + pt];
-                    if (r2 >= 0) v *= Tb[(size_t)r2 * NPT + pt];
+                    for (int mt = 0; mt < MT; ++mt) A[mt][kc] = tb[(size_t)r0 * NPT + mt * 8];
                 }
-                A[mt][kc] = v;
+            } else if (a.nfold == 2) {
+#pragma unroll
+                for (int kc = 0; kc < KC; ++kc) {
+                    const int *kt = sktab + (4 * kc + t) * 3;
+                    const int r0 = kt[0], r1 = kt[1];
+#pragma unroll
+                    for (int mt = 0; mt < MT; ++mt) A[mt][kc] = tb[(size_t)r0 * NPT + mt * 8] * tb[(size_t)r1 * NPT + mt * 8];
+                }
+            } else {
+#pragma unroll
+                for (int kc = 0; kc < KC; ++kc) {
+                    const int *kt = sktab + (4 * kc + t) * 3;
+                    const int r0 = kt[0], r1 = kt[1], r2 = kt[2];
+#pragma unroll
+                    for (int mt = 0; mt < MT; ++mt)
+                        A[mt][kc] = tb[(size_t)r0 * NPT + mt * 8] * tb[(size_t)r1 * NPT + mt * 8] * tb[(size_t)r2 * NPT + mt * 8];
+                }
             }
         }
 
@@ -291,12 +343,12 @@ __global__ void __launch_bounds__(NW * 32, 1) contract_mma_kernel(const __grid_c
         auto close_group = [&](const Step &P) {
             // basis-table rows of the group levels of this lane's two columns (padding columns and absent
             // levels name the ones row; the accumulated value of a padding column is zero: its tensor rows are)
-            const int *gi = a.ginfo + (size_t)(8 * P.g8 + 2 * t) * 3;
+            const int *gi = ginfo + (size_t)(8 * P.g8 + 2 * t) * 3;
             int info[2][3];
 #pragma unroll
             for (int e = 0; e < 2; ++e)
 #pragma unroll
-                for (int l = 0; l < 3; ++l) info[e][l] = __ldg(gi + 3 * e + l);
+                for (int l = 0; l < 3; ++l) info[e][l] = gi[3 * e + l];
             double w[2][MT][3];
 #pragma unroll
             for (int e = 0; e < 2; ++e)
@@ -376,9 +428,11 @@ __global__ void __launch_bounds__(NW * 32, 1) contract_mma_kernel(const __grid_c
             if (++sg == spg) { sg = 0; ++g8; }
         };
 
+        MMA_STAMP(4);
         for (int s = 0; s < a.nslabs; ++s) {
             const int st = a.resident ? s : stage;
             mbar_wait(&full_bar[st], a.resident ? 0u : (round & 1));
+            if (s == 0) MMA_STAMP(5);
             const double *slab = reinterpret_cast<const double *>(ring + (size_t)st * a.stage_bytes);
             const int rows = slab_rows(s);
 
@@ -412,6 +466,7 @@ __global__ void __launch_bounds__(NW * 32, 1) contract_mma_kernel(const __grid_c
                 if (++stage == ns) { stage = 0; ++round; }
             }
         }
+        MMA_STAMP(6);
         fold_pending(P1);  // drain: the last step always closes its group
         close_group(P1);
 
@@ -424,6 +479,7 @@ __global__ void __launch_bounds__(NW * 32, 1) contract_mma_kernel(const __grid_c
             const int64_t p = tile * NPT + (warp * MT + mt) * 8 + g;
             if (t == 0 && p < a.npts) a.out[p] = v;
         }
+        MMA_STAMP(7);
     }
 }
 
@@ -438,7 +494,15 @@ cudaError_t launch_one(const MmaArgs &a_in, int num_sms, cudaStream_t s, LaunchI
     constexpr int NPT = NW * MT * 8;
     MmaArgs a = a_in;
     if (a.ntb != NTB || !mma_fit_ring(a, NPT)) return cudaErrorNotSupported;
-    const int smem = kBarBytes + a.ns * a.stage_bytes + (a.sumn + 1) * NPT * 8;
+    // beside the ring budget (220 KB of the 227 KB a CTA may have): the k digit rows, and when they fit the
+    // remaining 4.5 KB the FH knots + weights and the group-level table
+    int extra = 4 * KC * 3 * 4, room = 4608;
+    a.fh_local = (a.kind == 1 && 2 * a.sumn * 8 <= room) ? 1 : 0;
+    if (a.fh_local) { extra += 2 * a.sumn * 8; room -= 2 * a.sumn * 8; }
+    const int gi_bytes = (a.nrp + 7) / 8 * 8 * 3 * 4;
+    a.gi_local = gi_bytes <= room ? 1 : 0;
+    if (a.gi_local) extra += gi_bytes;
+    const int smem = kBarBytes + a.ns * a.stage_bytes + (a.sumn + 1) * NPT * 8 + extra;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     const int64_t ntiles = (a.npts + NPT - 1) / NPT;
@@ -446,6 +510,35 @@ cudaError_t launch_one(const MmaArgs &a_in, int num_sms, cudaStream_t s, LaunchI
     int grid = (int)(ntiles < ctas ? ntiles : ctas);
     if (grid < 1) grid = 1;
     kern<<<grid, NW * 32, smem, s>>>(a);
+#ifdef MMA_TIMING
+    {
+        static long long h[16 * 16 * 8];
+        cudaStreamSynchronize(s);
+        cudaMemcpyFromSymbol(h, g_mma_timing, sizeof h);
+        const int np = (int)((ntiles + grid - 1) / grid) < 16 ? (int)((ntiles + grid - 1) / grid) : 16;
+        static const char *names[7] = {"wait at barrier 1", "basis", "wait at barrier 2", "A fragments", "first slab wait", "step loop", "drain + store"};
+        fprintf(stderr, "mma timing <KC %d, MT %d, NW %d>: %d slabs of %d rows, %d stages; cycles per phase, CTA 0, passes 2..%d: mean over warps [min, max]\n",
+                KC, MT, NW, a.nslabs, a.rows_per_slab, a.ns, np - 1);
+        for (int ph = 0; ph < 7; ++ph) {
+            double sum = 0; long long mn = 1ll << 60, mx = 0; int cnt = 0;
+            for (int p = 2; p < np; ++p)
+                for (int w = 0; w < NW && w < 16; ++w) {
+                    const long long d = h[(p * 16 + w) * 8 + ph + 1] - h[(p * 16 + w) * 8 + ph];
+                    sum += d; mn = d < mn ? d : mn; mx = d > mx ? d : mx; ++cnt;
+                }
+            if (cnt) fprintf(stderr, "  %-18s %9.0f [%lld, %lld]\n", names[ph], sum / cnt, mn, mx);
+        }
+        for (int p = 2; p < np && p < 6; ++p) {
+            long long a0 = 1ll << 60, e0 = 1ll << 60, e1 = 0, b0 = 1ll << 60, pe0 = 1ll << 60;
+            for (int w = 0; w < NW && w < 16; ++w) {
+                const long long *q = h + (p * 16 + w) * 8, v = h[((p - 1) * 16 + w) * 8 + 6];
+                a0 = q[0] < a0 ? q[0] : a0; e0 = q[6] < e0 ? q[6] : e0; e1 = q[6] > e1 ? q[6] : e1; b0 = q[4] < b0 ? q[4] : b0; pe0 = v < pe0 ? v : pe0;
+            }
+            fprintf(stderr, "  pass %d: warps reach the pass end over %lld cycles; from the first warp leaving the previous step loop to the first warp entering this one: %lld; pass length %lld\n",
+                    p, e1 - e0, b0 - pe0, e1 - a0);
+        }
+    }
+#endif
     if (li) { li->grid = grid; li->block = NW * 32; li->smem = smem; li->kernel = a.kind == 0 ? K_CHEB_MMA : K_FH_MMA; }
     return cudaGetLastError();
 }
