@@ -264,7 +264,24 @@ __global__ void __launch_bounds__(NW * 32, 1) contract_mma_kernel(const __grid_c
         // (straight-line per number of folded dims, padding k and absent dims naming the ones row: every load of
         //  the pass's A fragments is in flight at once; the branchy per-k form with the digit rows in global memory
         //  took 6.3 k cycles of a 238 k-cycle pass on cfg2, all warps at the same time)
-        {
+        if constexpr (KC * MT >= 60) {
+            // instantiations that hold 60 or more A fragments per lane (cfg5: <36, 2, 8>, 243 registers) keep the
+            // per-k form: the straight-line build costs them 2.3 % in the step loop's register allocation
+            // (5.98e6 vs 5.85e6 evals/s on 12^6), and their passes are hundreds of slabs long
+#pragma unroll
+            for (int kc = 0; kc < KC; ++kc) {
+                const int *kt = a.ktab + (4 * kc + t) * 3;
+                const int r0 = __ldg(kt), r1 = __ldg(kt + 1), r2 = __ldg(kt + 2);
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) {
+                    const int pt = (warp * MT + mt) * 8 + g;
+                    double v = Tb[(size_t)r0 * NPT + pt];
+                    if (r1 != a.sumn) v *= Tb[(size_t)r1 * NPT + pt];
+                    if (r2 != a.sumn) v *= Tb[(size_t)r2 * NPT + pt];
+                    A[mt][kc] = v;
+                }
+            }
+        } else {
             const double *tb = Tb + warp * MT * 8 + g;
             if (a.nfold == 1) {
 #pragma unroll
