@@ -633,6 +633,34 @@ def measure_workload(ctx, cfg_id, headline):
     parity = {**par, "ranks_checked": world, "n_all_ranks": n_all, "worst_rel_err_over_ranks": worst,
               "worst_abs_err_over_ranks": worst_abs, "all_ranks_ok": bool(all_ok), "checksum": checksum}
 
+    # ---- multilinear only (rank 0, after the timed region): the same batch through the layouts that need less table
+    # memory than the one AUTO picked, so that the memory / throughput ladder of DESIGN 3.3 is in the driver-run line
+    layouts = None
+    if cfg["kind"] == "mlip" and rank == 0 and not args.variant and not args.strict:
+        layouts = []
+        byts = 8.0 * (k + 1 + 2 ** k)
+        for var, name, mem in ((_lib.VARIANT_MLIP_QUAD, "quads (dim-1 row pairs interleaved)", "2 x the table"),
+                               (_lib.VARIANT_MLIP_PAIR, "the R layout as given, lane-pair gather", "1 x the table")):
+            try:
+                plan.set(_lib.OPT_VARIANT, var)
+                for _ in range(2):
+                    plan.eval_device_ptr(x.data_ptr(), npts, out.data_ptr(), stream.cuda_stream)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                for _ in range(5):
+                    plan.eval_device_ptr(x.data_ptr(), npts, out.data_ptr(), stream.cuda_stream)
+                e1.record(stream)
+                torch.cuda.synchronize(dev)
+                ms = e0.elapsed_time(e1) / 5
+                layouts.append({"layout": name, "table_memory": mem, "kernel": plan.kernel_used, "kernel_ms": ms,
+                                "value": npts / (ms * 1e-3), "unit": UNIT,
+                                "frac_of_hbm_peak": byts * npts / (ms * 1e-3) / 1e9 / ctx.peaks["hbm_gbs"]})
+            except Exception as ex:  # reported, never hidden
+                layouts.append({"layout": name, "error": f"{type(ex).__name__}: {ex}"})
+        plan.set(_lib.OPT_VARIANT, 0)
+        plan.eval_device_ptr(x.data_ptr(), npts, out.data_ptr(), stream.cuda_stream)  # `out` holds AUTO's results again
+        torch.cuda.synchronize(dev)
+
     # ---- end to end through the host-pointer C ABI, pinned host buffers
     e2e_steps = max(1, args.e2e_steps)
     epts = npts
@@ -697,6 +725,7 @@ def measure_workload(ctx, cfg_id, headline):
                    else "inputs smaller than L2 (latency regime, reported not targeted)"},
         "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roof,
         "cpu_baseline": cpu_baseline, "parity": parity,
+        **({"other_layouts": layouts} if layouts else {}),
     }
     return rec
 
@@ -802,6 +831,7 @@ def run_ours(args, cfg_id):
             "config": head["config"], "e2e": head["e2e"], "gpu_launches": head["gpu_launches"],
             "clocks": head["clocks"], "roofline": head["roofline"], "cpu_baseline": head["cpu_baseline"],
             "parity": head["parity"],
+            **({"other_layouts": head["other_layouts"]} if head.get("other_layouts") else {}),
             "workloads": subs, "e2e_dropin": dropin,
         }
         print(json.dumps(line), flush=True)
