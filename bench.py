@@ -26,7 +26,12 @@ Fields of a record
              the points and D2H of the results are inside the timed region
   roofline   the dominant kernel against the FP64-FMA roofline (Chebyshev, FH; peak measured in-run
              with DFMA / DMMA-only kernels because MEASURED_PEAKS.json has no FP64 figure) or the
-             HBM roofline (multilinear; peak from MEASURED_PEAKS.json)
+             HBM roofline (multilinear; peak from MEASURED_PEAKS.json).  `frac` counts the reference's
+             flop (2*S, the Clenshaw recursion); `pipe_frac` what the DMMA engine executes (it needs
+             fewer multiply-adds once two dimensions are folded into K, so `frac` can pass 1);
+             `frac_best` is the fastest single launch (the multilinear kernel runs into the 1 kW power
+             cap inside the >= 2.6 s loop); `traffic` is static (ncu, profiles/traffic_r02.json)
+  other_layouts  (multilinear record) the same batch through the layouts that need less table memory
   parity     every rank compares >= 1e5 strided points of ITS shard with the CPU oracle (the
              reference's own C, oracle/_ref); worst error over ranks; plus an order-independent
              checksum of all results (wrapping 64-bit sum of the bit patterns, summed over ranks)
