@@ -212,6 +212,25 @@ __global__ void __launch_bounds__(NW * 32, MINB) cheb_slab_kernel(const __grid_c
     uint32_t round = 0;
     int64_t fill = 0;  // index of the fill being consumed
 
+    // 1-D and 2-D tensors (the latency regime: a tile is a few microseconds of arithmetic, two warps per
+    // scheduler): the next tile's coordinates are fetched while the current tile computes, so that a tile does
+    // not begin with a DRAM round trip.  Only the instantiations with few points per thread carry the registers.
+    constexpr bool kPrefetch = PT <= 3;
+    const bool pre = kPrefetch && a.rank <= 2;
+    double xn[kPrefetch ? PT : 1][2];
+    auto fetch_x = [&](int64_t tile) {
+        if constexpr (kPrefetch) {
+#pragma unroll
+            for (int p = 0; p < PT; ++p) {
+                const int64_t idx = tile * TP + (int64_t)p * (NW * 32) + tid;
+                const bool ok = tile < ntiles && idx < a.npts;
+                xn[p][0] = ok ? ldg_stream_f64(a.x + idx * a.rank) : 0.0;
+                xn[p][1] = (ok && a.rank > 1) ? ldg_stream_f64(a.x + idx * a.rank + 1) : 0.0;
+            }
+        }
+    };
+    if (pre) fetch_x(blockIdx.x);
+
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         RowEval<N0P, PT> re;
         double tx1[PT], tx2[PT];       // 2*x for the in-slab levels 1, 2
@@ -225,6 +244,12 @@ __global__ void __launch_bounds__(NW * 32, MINB) cheb_slab_kernel(const __grid_c
                 pidx[p] = tile * TP + (int64_t)p * (NW * 32) + tid;
                 const bool ok = pidx[p] < a.npts;
                 const double *xp = a.x + pidx[p] * rank;
+                if (kPrefetch && pre) {
+                    x0[p] = ok ? premap_coord(a.pm, 0, xn[kPrefetch ? p : 0][0]) : 0.0;
+                    tx1[p] = (ok && rank > 1) ? 2.0 * premap_coord(a.pm, 1, xn[kPrefetch ? p : 0][1]) : 0.0;
+                    tx2[p] = 0.0;
+                    continue;
+                }
                 x0[p] = ok ? premap_coord(a.pm, 0, xp[0]) : 0.0;
                 tx1[p] = (ok && rank > 1) ? 2.0 * premap_coord(a.pm, 1, xp[1]) : 0.0;
                 tx2[p] = (ok && rank > 2) ? 2.0 * premap_coord(a.pm, 2, xp[2]) : 0.0;
@@ -235,6 +260,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) cheb_slab_kernel(const __grid_c
                 }
             }
             re.init(x0, a.n0);
+            if (pre) fetch_x(tile + gridDim.x);
         }
 
         double res[PT];
