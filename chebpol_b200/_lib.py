@@ -39,7 +39,7 @@ EXPORTS = [
     "chebpol_cuda_plan_cheb", "chebpol_cuda_plan_mlip", "chebpol_cuda_plan_fh",
     "chebpol_cuda_plan_destroy", "chebpol_cuda_plan_eval_device", "chebpol_cuda_plan_eval_host",
     "chebpol_cuda_plan_set", "chebpol_cuda_plan_get", "chebpol_cuda_fp64_peak",
-    "chebpol_cuda_launch_count", "chebpol_cuda_cache_clear", "chebpol_cuda_chebcoef", "chebpol_cuda_fhweights",
+    "chebpol_cuda_launch_count", "chebpol_cuda_cache_clear", "chebpol_cuda_debug_mma_geometry", "chebpol_cuda_debug_mma_row_pos", "chebpol_cuda_chebcoef", "chebpol_cuda_fhweights",
     "chebpol_cuda_evalgrid_cheb", "chebpol_cuda_evalgrid_mlip", "chebpol_cuda_evalgrid_fh",
     "chebpol_cuda_evalpolyh", "chebpol_cuda_plan_polyh",
     "chebpol_cuda_evalstalk", "chebpol_cuda_evalhyp", "chebpol_cuda_plan_stalk",

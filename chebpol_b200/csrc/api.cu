@@ -1879,6 +1879,25 @@ extern "C" int chebpol_cuda_debug_cache_stats(int64_t *entries, int64_t *hits, i
 
 extern "C" void chebpol_cuda_debug_cache_weak_hash(int on) { g_weak_hash.store(on ? 1 : 0); }
 
+bool mma_fit_ring(MmaArgs &a, int npt);
+extern "C" int chebpol_cuda_debug_mma_geometry(int kind, const int *dims, int rank, int npt, int64_t *out)
+{
+    if (!dims || !out || rank < 1 || rank > CP_MAXR || npt < 8 || npt % 8) return fail(CHEBPOL_CUDA_EINVAL, "mma geometry: bad arguments");
+    for (int i = 0; i < 16; ++i) out[i] = 0;
+    MmaArgs a = {};
+    int kc = 0;
+    if (!mma_configure(a, kind, rank, dims, &kc)) return CHEBPOL_CUDA_OK;
+    a.occ = 1;
+    if (!mma_fit_ring(a, npt)) return CHEBPOL_CUDA_OK;
+    out[0] = 1; out[1] = a.nfold; out[2] = a.K; out[3] = kc; out[4] = a.rs; out[5] = a.nrows;
+    out[6] = a.rows_per_slab; out[7] = a.nslabs; out[8] = a.ns; out[9] = a.stage_bytes; out[10] = a.resident;
+    out[11] = mma_pair_rows(kc) ? 1 : 0;
+    out[12] = 128 + (int64_t)a.ns * a.stage_bytes + (int64_t)(a.sumn + 1) * npt * 8;
+    out[13] = a.nA; out[14] = a.nAp; out[15] = a.nrp;
+    return CHEBPOL_CUDA_OK;
+}
+extern "C" int chebpol_cuda_debug_mma_row_pos(int kc, int k) { return mma_row_pos(kc, k); }
+
 extern "C" int chebpol_cuda_debug_fingerprint(const void *data, int64_t nbytes, int threads, uint64_t *out2)
 {
     if (!out2 || nbytes < 0 || (nbytes > 0 && !data)) return fail(CHEBPOL_CUDA_EINVAL, "NULL argument");

@@ -333,6 +333,15 @@ CHEBPOL_CUDA_API int chebpol_cuda_debug_fingerprint(const void *data, int64_t nb
  * retain = 0 models an entry above the 32 MB retention limit (fingerprint only) */
 CHEBPOL_CUDA_API int chebpol_cuda_debug_cache_would_hit(const void *a, int64_t na, const void *b, int64_t nb,
                                                         int retain, int *hit);
+/* host only (no device needed): the geometry the DMMA contraction engine chooses for a Chebyshev (kind 0) or
+ * Floater-Hormann (kind 1) tensor and `npt` points per pass (a multiple of 8, e.g. 128).  out[16]:
+ * 0 engine takes the shape (0/1), 1 folded dims, 2 K, 3 k-chunks KC, 4 row stride rs (doubles), 5 rows,
+ * 6 rows per slab, 7 slabs, 8 ring stages, 9 stage bytes, 10 tensor resident in shared memory (0/1),
+ * 11 rows stored pair-interleaved (0/1), 12 dynamic shared memory of the ring + basis table (bytes),
+ * 13 level-A size, 14 level-A size padded, 15 r' columns.  Used by the layout tests. */
+CHEBPOL_CUDA_API int chebpol_cuda_debug_mma_geometry(int kind, const int *dims, int rank, int npt, int64_t *out16);
+/* host only: position inside a stored row of coefficient k of a tensor with `kc` k-chunks */
+CHEBPOL_CUDA_API int chebpol_cuda_debug_mma_row_pos(int kc, int k);
 /* total kernels launched by this library in this process */
 CHEBPOL_CUDA_API int64_t chebpol_cuda_launch_count(void);
 

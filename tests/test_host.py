@@ -395,3 +395,49 @@ def test_sl_rejects_malformed_pivots(port):
     with pytest.raises(_lib.ChebpolCudaError) as ei:
         _lib.Plan.sl(kn, dtri, (lu, bad, bb), kv)
     assert ei.value.code == 1 and "pivot" in str(ei.value)
+
+
+def test_mma_engine_geometry_invariants():
+    """Host-only layout logic of the DMMA contraction engine (csrc/contract_mma.cu), over a few hundred shapes:
+    whatever it chooses must cover every tensor row exactly once, fit the shared memory of a CTA, keep the B-fragment
+    loads conflict-free (row stride rule) and give every k of a row its own position."""
+    import ctypes as C
+
+    L = _lib.lib()
+    L.chebpol_cuda_debug_mma_geometry.argtypes = [C.c_int, C.POINTER(C.c_int), C.c_int, C.c_int, C.POINTER(C.c_int64)]
+    L.chebpol_cuda_debug_mma_row_pos.argtypes = [C.c_int, C.c_int]
+    rng = np.random.default_rng(7)
+    shapes = [(10,) * 5, (12,) * 6, (40, 40, 40), (20, 20), (100, 100), (150, 3), (192,), (193,), (8,) * 6, (6,) * 7,
+              (16,) * 4, (24,) * 3, (3, 3, 3, 3, 3), (1, 4), (4, 1, 3), (2,) * 7, (33, 5), (12, 12, 12, 3), (77, 2), (80, 2)]
+    shapes += [tuple(int(v) for v in rng.integers(1, 41, int(rng.integers(1, 7)))) for _ in range(300)]
+    taken = 0
+    for kind in (0, 1):
+        for dims in shapes:
+            if np.prod(dims, dtype=np.float64) > 5e6:
+                continue
+            for npt in (32, 64, 96, 128, 256):
+                out = (C.c_int64 * 16)()
+                d = (C.c_int * len(dims))(*dims)
+                assert L.chebpol_cuda_debug_mma_geometry(kind, d, len(dims), npt, out) == 0
+                ok, nfold, K, kc, rs, rows, rps, nslabs, ns, stage, resident, pairs, smem, nA, nAp, nrp = (int(v) for v in out)
+                if not ok:
+                    continue
+                taken += 1
+                assert 1 <= nfold <= 3 and K == int(np.prod(dims[:nfold])) and K <= 192 and 4 * kc >= K
+                assert len(dims) - nfold <= 4
+                assert nA == (dims[nfold] if nfold < len(dims) else 1) and nAp % 2 == 0 and nA <= nAp <= nA + 1
+                assert nrp == int(np.prod(dims[nfold + 1:])) and rows == -(-nrp // 8) * nAp * 8
+                assert rs >= 4 * kc and rs % 16 == (8 if pairs else rs % 16) and (pairs or rs % 16 in (4, 12))
+                assert pairs == (kc >= 20)
+                assert rps % 16 == 0 or rps == rows
+                assert (nslabs - 1) * rps < rows <= nslabs * rps            # the slabs cover every row once
+                assert stage == rps * rs * 8 and ns >= (nslabs if resident else 2) and ns <= 8
+                assert smem <= 220 * 1024                                   # ring + basis table inside the budget
+                # every coefficient of a row has its own position inside the row's stride
+                pos = [L.chebpol_cuda_debug_mma_row_pos(kc, k) for k in range(4 * kc)]
+                assert sorted(pos) == list(range(4 * kc)) and max(pos) < rs
+                if pairs:   # lane t of a quad finds chunks 2q and 2q+1 side by side
+                    for q in range(kc // 2):
+                        for t in range(4):
+                            assert pos[4 * (2 * q) + t] == 8 * q + 2 * t and pos[4 * (2 * q + 1) + t] == 8 * q + 2 * t + 1
+    assert taken > 500
